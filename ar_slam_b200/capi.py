@@ -1,0 +1,211 @@
+"""ctypes mirror of include/ar_slam_b200.h (the C-ABI a ROS2 / CLI host binds).
+
+Argument meaning and error behaviour follow the header; Python only moves numpy
+arrays across the boundary.  If the shared library is missing this module
+raises -- there is deliberately no fallback implementation.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ELIM_AUTO, ELIM_TAGS, ELIM_CAPTURES = 0, 1, 2
+LINSOLVE_AUTO, LINSOLVE_DENSE, LINSOLVE_PCG = 0, 1, 2
+CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
+REASONS = {1: "gradient", 2: "parameter", 3: "function", 4: "min_radius", 5: "max_iterations",
+           6: "invalid_steps"}
+ERR_NO_DEVICE = -3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class ArslamError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("arslam error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32),
+                ("jacobi_scaling", C.c_int32), ("elimination", C.c_int32), ("linear_solver", C.c_int32),
+                ("pcg_max_iterations", C.c_int32), ("num_intrinsics", C.c_int32), ("verbose", C.c_int32),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+                ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("pcg_tolerance", C.c_double), ("tag_size", C.c_double),
+                ("dense_max_dim", C.c_int64)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("num_successful_steps", C.c_int32),
+                ("num_unsuccessful_steps", C.c_int32), ("termination", C.c_int32), ("reason", C.c_int32),
+                ("eliminated_side", C.c_int32), ("linear_solver", C.c_int32), ("reduced_dim", C.c_int32),
+                ("num_jacobian_evals", C.c_int64), ("num_cost_evals", C.c_int64),
+                ("linear_solver_iterations", C.c_int64), ("gpu_launches", C.c_int64),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double),
+                ("gradient_max_norm", C.c_double), ("total_ms", C.c_double), ("eval_ms", C.c_double),
+                ("linsolve_ms", C.c_double)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["reason_name"] = REASONS.get(self.reason, "?")
+        return d
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("total_ms", C.c_double), ("launches", C.c_int64),
+                ("algorithmic_bytes", C.c_double)]
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libar_slam_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ArslamError(-2, "%s is missing: run `python -m ar_slam_b200.build` "
+                                  "(there is no CPU fallback)" % path)
+        lib = C.CDLL(path)
+        lib.arslam_last_error.restype = C.c_char_p
+        lib.arslam_last_error.argtypes = [C.c_void_p]
+        lib.arslam_create.argtypes = [C.c_int, C.POINTER(Options), C.POINTER(C.c_void_p)]
+        lib.arslam_destroy.argtypes = [C.c_void_p]
+        lib.arslam_destroy.restype = None
+        _lib = lib
+    return _lib
+
+
+def default_options(**kw):
+    o = Options()
+    load_library().arslam_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Solver:
+    """One `arslam_solver` handle (== the `problem_` member of one ArSlamSolver)."""
+
+    def __init__(self, device=0, options=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.options = options or default_options()
+        rc = self._lib.arslam_create(C.c_int(device), C.byref(self.options), C.byref(self._h))
+        if rc != 0:
+            raise ArslamError(rc, (self._lib.arslam_last_error(None) or b"").decode())
+        self.n_cap = self.n_tag = self.n_blk = 0
+
+    def close(self):
+        if self._h:
+            self._lib.arslam_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise ArslamError(rc, (self._lib.arslam_last_error(self._h) or b"").decode())
+        return rc
+
+    def set_options(self, options):
+        self.options = options
+        self._check(self._lib.arslam_set_options(self._h, C.byref(options)))
+
+    def set_profiling(self, on):
+        self._check(self._lib.arslam_set_profiling(self._h, C.c_int(1 if on else 0)))
+
+    def kernel_times(self):
+        buf = (KernelTime * 64)()
+        n = self._check(self._lib.arslam_kernel_times(self._h, buf, C.c_int32(64)))
+        return [{"name": buf[i].name.decode(), "total_ms": buf[i].total_ms, "launches": buf[i].launches,
+                 "algorithmic_bytes": buf[i].algorithmic_bytes} for i in range(n)]
+
+    def set_problem(self, n_cap, n_tag, cap_idx, tag_idx, rect8):
+        cap_idx, tag_idx, rect8 = _i32(cap_idx), _i32(tag_idx), _f64(rect8).reshape(-1)
+        if rect8.size != 8 * len(cap_idx) or len(tag_idx) != len(cap_idx):
+            raise ValueError("cap_idx, tag_idx and rect8 disagree on the number of blocks")
+        self._check(self._lib.arslam_set_problem(self._h, C.c_int64(n_cap), C.c_int64(n_tag),
+                                                 C.c_int64(len(cap_idx)), _p(cap_idx, C.c_int32),
+                                                 _p(tag_idx, C.c_int32), _p(rect8)))
+        self.n_cap, self.n_tag, self.n_blk = int(n_cap), int(n_tag), len(cap_idx)
+
+    def set_params(self, cam, cap, tag):
+        cam, cap, tag = _f64(cam), _f64(cap).reshape(-1), _f64(tag).reshape(-1)
+        if cam.size != 3 or cap.size != 6 * self.n_cap or tag.size != 6 * self.n_tag:
+            raise ValueError("parameter array sizes do not match the problem")
+        self._check(self._lib.arslam_set_params(self._h, _p(cam), _p(cap), _p(tag)))
+
+    def get_params(self):
+        cam, cap, tag = np.zeros(3), np.zeros((self.n_cap, 6)), np.zeros((self.n_tag, 6))
+        self._check(self._lib.arslam_get_params(self._h, _p(cam), _p(cap), _p(tag)))
+        return cam, cap, tag
+
+    def evaluate(self, jacobians=True, residuals=True):
+        nb = self.n_blk
+        res = np.zeros((nb, 8)) if residuals else None
+        jc = np.zeros((nb, 8, 3)) if jacobians else None
+        jp = np.zeros((nb, 8, 6)) if jacobians else None
+        ja = np.zeros((nb, 8, 6)) if jacobians else None
+        cost = C.c_double(0)
+        self._check(self._lib.arslam_evaluate(self._h, C.byref(cost), _p(res), _p(jc), _p(jp), _p(ja)))
+        return cost.value, res, jc, jp, ja
+
+    def solve(self, log=True):
+        s = Summary()
+        rows = self.options.max_num_iterations + 2
+        lg = np.full((rows, 8), np.nan) if log else None
+        self._check(self._lib.arslam_solve(self._h, C.byref(s), _p(lg), C.c_int32(rows if log else 0)))
+        return s.as_dict(), (lg[: s.iterations + 1] if log else None)
+
+    def localize_batch(self, blk_offsets, tag_idx, rect8, seed_block, cam, tag_pose):
+        blk_offsets, tag_idx, seed_block = _i32(blk_offsets), _i32(tag_idx), _i32(seed_block)
+        rect8, cam, tag_pose = _f64(rect8).reshape(-1), _f64(cam), _f64(tag_pose).reshape(-1)
+        n = len(blk_offsets) - 1
+        pose = np.zeros((n, 6))
+        its = np.zeros(n, dtype=np.int32)
+        cost = np.zeros(n)
+        term = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.arslam_localize_batch(
+            self._h, C.c_int64(n), _p(blk_offsets, C.c_int32), _p(tag_idx, C.c_int32), _p(rect8),
+            _p(seed_block, C.c_int32), C.c_int64(tag_pose.size // 6), _p(cam), _p(tag_pose), _p(pose),
+            _p(its, C.c_int32), _p(cost), _p(term, C.c_int32)))
+        return pose, its, cost, term
+
+    # multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = load_library().arslam_comm_unique_id(buf)
+        if rc != 0:
+            raise ArslamError(rc, (load_library().arslam_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, world, uid):
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        self._check(self._lib.arslam_comm_init(self._h, C.c_int(rank), C.c_int(world), buf))

@@ -1,0 +1,956 @@
+// arslam.cu -- host side of libar_slam_b200.so: the C-ABI of
+// include/ar_slam_b200.h, device memory, the LM control loop and NCCL.
+//
+// Replaces ArSlamSolver::optimize / resetProblem / the AddResidualBlock sites
+// and localizeOne's per-capture solve (reference
+// ar_slam/src/ar_slam_util.cpp:720-727, 829-836, 903-979, 1001-1025).
+// There is no CPU fallback: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/ar_slam_b200.h"
+#include "cholesky.cuh"
+#include "kernels.cuh"
+#include "localize.cuh"
+#include "pcg.cuh"
+#include "schur.cuh"
+
+using namespace ars;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- NCCL through dlopen: no link-time dependency, and inside a torch
+// process the already loaded libnccl.so.2 is reused. -------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, const void* /* by value, see call */, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    for (const char* n : names) {
+      if (lib) break;
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(void**, int, const void*, int))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl misses symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+struct NcclId { char bytes[128]; };
+constexpr int kNcclDouble = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (stable enum values)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+struct Profiler {
+  bool on = false;
+  struct Rec { int id; cudaEvent_t a, b; };
+  std::vector<std::string> names;
+  std::vector<double> bytes, total_ms;
+  std::vector<long long> count;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  int id_of(const char* n, double b) {
+    for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) { bytes[i] = b; return (int)i; }
+    names.push_back(n); bytes.push_back(b); total_ms.push_back(0); count.push_back(0);
+    return (int)names.size() - 1;
+  }
+  cudaEvent_t ev() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void clear() {
+    for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); }
+    recs.clear(); names.clear(); bytes.clear(); total_ms.clear(); count.clear();
+  }
+  void resolve() {
+    for (auto& r : recs) {
+      float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+      total_ms[r.id] += ms; count[r.id]++;
+      pool.push_back(r.a); pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  ~Profiler() { for (auto e : pool) cudaEventDestroy(e); for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+};
+
+}  // namespace
+
+struct arslam_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  arslam_options opt;
+  std::string err;
+  // problem
+  int n_cap = 0, n_tag = 0, n_blk = 0, plane = 0, n_warp = 0;
+  bool have_problem = false, have_params = false;
+  std::vector<double> h_cam, h_cap, h_tag;  // host mirror of the parameters
+  // original order (evaluate API)
+  DevBuf<int32_t> o_cap, o_tag;
+  DevBuf<double> o_obs;
+  // sorted copies: side 0 capture-sorted, side 1 tag-sorted
+  DevBuf<int32_t> s_own[2], s_oth[2], s_off[2];
+  DevBuf<double> s_obs[2];
+  std::vector<int32_t> h_off[2];
+  // parameters: two sets (current / candidate)
+  DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2];
+  int cur = 0;
+  // normal equations
+  DevBuf<double> H[2], partial[2], W, Y, Z, YB, seg_cam, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
+  DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
+  DevBuf<double> eval_out, small;
+  double* h_sc = nullptr;  // pinned
+  long long ld = 0;
+  int n_pad = 0;
+  // pcg
+  PcgWorkspace pcg;
+  // comm
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  // stats
+  long long launches = 0;
+  Profiler prof;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return s->fail(ARSLAM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+// launch wrapper: counts, and brackets with events when profiling
+#define LAUNCH(name, bytes, ...)                                                              \
+  do {                                                                                        \
+    if (s->prof.on) {                                                                         \
+      Profiler::Rec r__{s->prof.id_of(name, (double)(bytes)), s->prof.ev(), s->prof.ev()};    \
+      cudaEventRecord(r__.a, s->stream);                                                      \
+      __VA_ARGS__;                                                                            \
+      cudaEventRecord(r__.b, s->stream);                                                      \
+      s->prof.recs.push_back(r__);                                                            \
+    } else {                                                                                  \
+      __VA_ARGS__;                                                                            \
+    }                                                                                         \
+    ++s->launches;                                                                            \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+extern "C" {
+
+int arslam_abi_version(void) { return ARSLAM_ABI_VERSION; }
+
+void arslam_default_options(arslam_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 50;  // ar_slam_util.cpp:1004
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->elimination = ARSLAM_ELIM_AUTO;
+  o->linear_solver = ARSLAM_LINSOLVE_AUTO;  // ar_slam_util.cpp:1011 DENSE_SCHUR where it is dense
+  o->pcg_max_iterations = 500;
+  o->num_intrinsics = 1;
+  o->verbose = 0;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->pcg_tolerance = 1e-8;
+  o->tag_size = 0.0635;  // ar_slam_util.hpp:319
+  o->dense_max_dim = 16384;
+}
+
+const char* arslam_last_error(const arslam_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
+  if (!out) return ARSLAM_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) +
+                     "); this solver has no CPU fallback";
+    cudaGetLastError();
+    return ARSLAM_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) { g_create_error = "device ordinal out of range"; return ARSLAM_ERR_INVALID; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10) {
+    g_create_error = "device is not sm_100 class; kernels are built for sm_100a only";
+    return ARSLAM_ERR_NO_DEVICE;
+  }
+  arslam_solver* s = new arslam_solver();
+  s->device = device;
+  if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&s->h_sc, 64 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
+      pcg_init() != cudaSuccess) {
+    g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete s;
+    return ARSLAM_ERR_CUDA;
+  }
+  for (auto& ev : s->ev) cudaEventCreate(&ev);
+  *out = s;
+  return ARSLAM_OK;
+}
+
+void arslam_destroy(arslam_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+  if (s->h_sc) cudaFreeHost(s->h_sc);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int arslam_set_options(arslam_solver* s, const arslam_options* opt) {
+  if (!s || !opt) return ARSLAM_ERR_INVALID;
+  if (opt->num_intrinsics != 1)
+    return s->fail(ARSLAM_ERR_UNSUPPORTED, "num_intrinsics=%d: only the reference's focal-only model is built", opt->num_intrinsics);
+  s->opt = *opt;
+  return ARSLAM_OK;
+}
+
+int arslam_set_profiling(arslam_solver* s, int on) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  s->prof.on = on != 0;
+  return ARSLAM_OK;
+}
+
+int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  int n = 0;
+  for (size_t i = 0; i < s->prof.names.size() && n < cap; ++i, ++n) {
+    std::memset(&out[n], 0, sizeof(out[n]));
+    std::snprintf(out[n].name, sizeof(out[n].name), "%s", s->prof.names[i].c_str());
+    out[n].total_ms = s->prof.total_ms[i];
+    out[n].launches = s->prof.count[i];
+    out[n].algorithmic_bytes = s->prof.bytes[i];
+  }
+  return n;
+}
+
+// Stable counting sort of block ids by key.
+static void counting_sort(const std::vector<int32_t>& in_order, const int32_t* key, int n_key,
+                          std::vector<int32_t>& out_order, std::vector<int32_t>* offsets) {
+  std::vector<int32_t> cnt(n_key + 1, 0);
+  for (int32_t b : in_order) cnt[key[b] + 1]++;
+  for (int i = 0; i < n_key; ++i) cnt[i + 1] += cnt[i];
+  if (offsets) *offsets = cnt;
+  std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+  out_order.resize(in_order.size());
+  for (int32_t b : in_order) out_order[pos[key[b]]++] = b;
+}
+
+int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk, const int32_t* cap_idx,
+                       const int32_t* tag_idx, const double* rect8) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (n_cap <= 0 || n_tag <= 0 || n_blk <= 0 || !cap_idx || !tag_idx || !rect8)
+    return s->fail(ARSLAM_ERR_INVALID, "set_problem: empty problem or null pointer");
+  if (n_blk > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
+    return s->fail(ARSLAM_ERR_INVALID, "set_problem: problem too large for 32-bit block indices");
+  for (int64_t b = 0; b < n_blk; ++b)
+    if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
+      return s->fail(ARSLAM_ERR_INVALID, "set_problem: block %lld has an index out of range", (long long)b);
+  CU(cudaSetDevice(s->device));
+  s->have_problem = false;
+  s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk = (int)n_blk;
+  s->plane = ((int)n_blk + 31) / 32 * 32;
+  s->n_warp = s->plane / 32;
+  const int nb = s->n_blk, plane = s->plane;
+  CU(s->o_cap.ensure(nb)); CU(s->o_tag.ensure(nb)); CU(s->o_obs.ensure((size_t)nb * 8));
+  CU(cudaMemcpyAsync(s->o_cap.p, cap_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->o_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->o_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
+  std::vector<int32_t> ident(nb), tmp, order;
+  for (int b = 0; b < nb; ++b) ident[b] = b;
+  std::vector<int32_t> own(plane), oth(plane);
+  std::vector<double> obs((size_t)8 * plane);
+  for (int side = 0; side < 2; ++side) {
+    const int32_t* k_own = side == 0 ? cap_idx : tag_idx;
+    const int32_t* k_oth = side == 0 ? tag_idx : cap_idx;
+    const int n_own = side == 0 ? s->n_cap : s->n_tag, n_oth = side == 0 ? s->n_tag : s->n_cap;
+    counting_sort(ident, k_oth, n_oth, tmp, nullptr);
+    counting_sort(tmp, k_own, n_own, order, &s->h_off[side]);
+    std::fill(obs.begin(), obs.end(), 0.0);
+    for (int p = 0; p < nb; ++p) {
+      const int b = order[p];
+      own[p] = k_own[b];
+      oth[p] = k_oth[b];
+      for (int k = 0; k < 8; ++k) obs[(size_t)k * plane + p] = rect8[8 * (size_t)b + k];
+    }
+    CU(s->s_own[side].ensure(plane)); CU(s->s_oth[side].ensure(plane)); CU(s->s_off[side].ensure(n_own + 1));
+    CU(s->s_obs[side].ensure((size_t)8 * plane));
+    CU(cudaMemcpyAsync(s->s_own[side].p, own.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->s_oth[side].p, oth.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->s_off[side].p, s->h_off[side].data(), sizeof(int32_t) * (n_own + 1), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->s_obs[side].p, obs.data(), sizeof(double) * 8 * plane, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));  // host staging buffers are reused
+    CU(s->H[side].ensure((size_t)n_own * NV));
+    CU(s->partial[side].ensure((size_t)s->n_warp * 2 * NV));
+    CU(s->d_pose[side].ensure((size_t)6 * n_own));
+    CU(s->warp_norm[side].ensure((size_t)8 * cdiv(n_own, 128) + 8));
+    CU(s->warp_gmax[side].ensure((size_t)4 * cdiv(n_own, 128) + 4));
+  }
+  for (int k = 0; k < 2; ++k) {
+    CU(s->cam[k].ensure(4)); CU(s->cap[k].ensure((size_t)6 * s->n_cap)); CU(s->tag[k].ensure((size_t)6 * s->n_tag));
+    CU(s->cap_pre[k].ensure((size_t)kCapPre * s->n_cap)); CU(s->tag_pre[k].ensure((size_t)kTagPre * s->n_tag));
+  }
+  CU(s->W.ensure((size_t)36 * plane)); CU(s->Y.ensure((size_t)36 * plane));
+  CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp));
+  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(16)); CU(s->cam_minus.ensure(4));
+  s->have_problem = true;
+  return ARSLAM_OK;
+}
+
+int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6, const double* tag_pose6) {
+  if (!s || !camera3 || !cap_pose6 || !tag_pose6) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem) return s->fail(ARSLAM_ERR_INVALID, "set_params before set_problem");
+  s->h_cam.assign(camera3, camera3 + 3);
+  s->h_cap.assign(cap_pose6, cap_pose6 + (size_t)6 * s->n_cap);
+  s->h_tag.assign(tag_pose6, tag_pose6 + (size_t)6 * s->n_tag);
+  s->have_params = true;
+  return ARSLAM_OK;
+}
+
+int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, double* tag_pose6) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (!s->have_params) return s->fail(ARSLAM_ERR_INVALID, "get_params before set_params");
+  if (camera3) std::memcpy(camera3, s->h_cam.data(), 3 * sizeof(double));
+  if (cap_pose6) std::memcpy(cap_pose6, s->h_cap.data(), sizeof(double) * 6 * s->n_cap);
+  if (tag_pose6) std::memcpy(tag_pose6, s->h_tag.data(), sizeof(double) * 6 * s->n_tag);
+  return ARSLAM_OK;
+}
+
+static int upload_params(arslam_solver* s, int k) {
+  double cam4[4] = {s->h_cam[0], s->h_cam[1], s->h_cam[2], 0.0};
+  CU(cudaMemcpyAsync(s->cam[k].p, cam4, sizeof(cam4), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->cap[k].p, s->h_cap.data(), sizeof(double) * 6 * s->n_cap, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->tag[k].p, s->h_tag.data(), sizeof(double) * 6 * s->n_tag, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));  // cam4 is on the stack
+  return ARSLAM_OK;
+}
+
+static int launch_prep(arslam_solver* s, int k) {
+  LAUNCH("prep_captures", 48.0 * s->n_cap + 8.0 * kCapPre * s->n_cap,
+         prep_captures_kernel<<<cdiv(s->n_cap, 128), 128, 0, s->stream>>>(s->n_cap, s->cap[k].p, s->cap_pre[k].p));
+  LAUNCH("prep_tags", 48.0 * s->n_tag + 8.0 * kTagPre * s->n_tag,
+         prep_tags_kernel<<<cdiv(s->n_tag, 128), 128, 0, s->stream>>>(s->n_tag, s->tag[k].p, s->opt.tag_size, s->tag_pre[k].p));
+  return ARSLAM_OK;
+}
+
+int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* jac_cam, double* jac_cap, double* jac_tag) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem || !s->have_params) return s->fail(ARSLAM_ERR_INVALID, "evaluate needs set_problem and set_params");
+  CU(cudaSetDevice(s->device));
+  s->prof.clear();
+  const int nb = s->n_blk, nc = 4 * nb;
+  const int nwarp = cdiv(nc, 256) * 8;
+  int rc = upload_params(s, 0);
+  if (rc) return rc;
+  launch_prep(s, 0);
+  // outputs live in one scratch allocation: res 8 | jc 24 | jp 48 | ja 48 per block, then warp costs
+  const size_t per_blk = 8 + 24 + 48 + 48;
+  CU(s->eval_out.ensure(per_blk * nb + nwarp + 8));
+  double* d_res = s->eval_out.p;
+  double* d_jc = d_res + (size_t)8 * nb;
+  double* d_jp = d_jc + (size_t)24 * nb;
+  double* d_ja = d_jp + (size_t)48 * nb;
+  double* d_wc = d_ja + (size_t)48 * nb;
+  double* d_cost = d_wc + nwarp;
+  const bool want_j = jac_cam || jac_cap || jac_tag;
+  LAUNCH("eval_jacobian", (want_j ? 274.0 : 34.0) * nc,
+         eval_jacobian_kernel<<<cdiv(nc, 256), 256, 0, s->stream>>>(
+             nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
+             s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
+             want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
+  LAUNCH("colsum", 8.0 * nwarp, colsum_kernel<<<1, 1024, 0, s->stream>>>(nwarp, 1, d_wc, d_cost));
+  CU(cudaGetLastError());
+  double h_cost = 0.0;
+  CU(cudaMemcpyAsync(&h_cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (residuals) CU(cudaMemcpyAsync(residuals, d_res, sizeof(double) * 8 * nb, cudaMemcpyDeviceToHost, s->stream));
+  if (jac_cam) CU(cudaMemcpyAsync(jac_cam, d_jc, sizeof(double) * 24 * nb, cudaMemcpyDeviceToHost, s->stream));
+  if (jac_cap) CU(cudaMemcpyAsync(jac_cap, d_jp, sizeof(double) * 48 * nb, cudaMemcpyDeviceToHost, s->stream));
+  if (jac_tag) CU(cudaMemcpyAsync(jac_tag, d_ja, sizeof(double) * 48 * nb, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->prof.resolve();
+  if (cost) *cost = 0.5 * h_cost;
+  return ARSLAM_OK;
+}
+
+// ------------------------------------------------------------------ solve ---
+namespace {
+
+// ---- multi-GPU helpers (one process per GPU; captures are sharded) ----------
+__global__ void small_pack_kernel(const double* sc, double* buf, int rank, int world) {
+  const int i = threadIdx.x;
+  if (i < 6) buf[i] = sc[4 + i];
+  if (i >= 8 && i < 8 + world) buf[i] = (i - 8 == rank) ? sc[10] : 0.0;
+}
+__global__ void small_unpack_kernel(double* sc, const double* buf, int world) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6; ++i) sc[4 + i] = buf[i];
+    double m = 0.0;
+    for (int r = 0; r < world; ++r) m = fmax(m, buf[8 + r]);
+    sc[10] = m;
+  }
+}
+__global__ void axpy_kernel(int n, const double* a, const double* b, double sign, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + sign * b[i];
+}
+
+int nccl_sum(arslam_solver* s, double* buf, size_t count) {
+  const int rc = g_nccl.AllReduce(buf, buf, count, kNcclDouble, kNcclSum, s->comm, s->stream);
+  if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return ARSLAM_OK;
+}
+
+// sums [model, cand_r2, step2_e, xnorm2_e, step2_f, xnorm2_f]; max of gmax_e via per-rank slots
+int small_allreduce(arslam_solver* s, double* sc) {
+  CU(s->small.ensure(8 + s->world));
+  LAUNCH("small_pack", 128.0, small_pack_kernel<<<1, 64 + s->world, 0, s->stream>>>(sc, s->small.p, s->rank, s->world));
+  int rc = nccl_sum(s, s->small.p, 8 + s->world);
+  if (rc) return rc;
+  LAUNCH("small_unpack", 128.0, small_unpack_kernel<<<1, 32, 0, s->stream>>>(sc, s->small.p, s->world));
+  return ARSLAM_OK;
+}
+
+// every capture is moved by exactly one rank: pose = initial + sum over ranks (pose_r - initial)
+int gather_captures(arslam_solver* s, int k) {
+  const int n = 6 * s->n_cap;
+  double* init = s->d_pose[0].p;
+  double* diff = s->cap[1 - k].p;
+  CU(cudaMemcpyAsync(init, s->h_cap.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+  LAUNCH("axpy", 24.0 * n, axpy_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->cap[k].p, init, -1.0, diff));
+  int rc = nccl_sum(s, diff, n);
+  if (rc) return rc;
+  LAUNCH("axpy", 24.0 * n, axpy_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, init, diff, 1.0, s->cap[k].p));
+  return ARSLAM_OK;
+}
+
+// ---- PCG hooks (filled in by pcg.cuh's kernels) -------------------------------
+int pcg_prepare(PcgWorkspace&, int, int, int, const int32_t*, const int32_t*, cudaStream_t, std::string& err) {
+  err = "PCG linear solver not built yet; raise dense_max_dim or use ARSLAM_LINSOLVE_DENSE";
+  return ARSLAM_ERR_UNSUPPORTED;
+}
+int pcg_launch_eliminate(arslam_solver* s, const SchurArgs&, double*) { return s->fail(ARSLAM_ERR_UNSUPPORTED, "PCG not built"); }
+int pcg_launch_solve(arslam_solver* s, int, double*, const double*, const LmScalars*, const double*, double, double*, long long*) {
+  return s->fail(ARSLAM_ERR_UNSUPPORTED, "PCG not built");
+}
+
+struct Sides {
+  int e, f;        // side index (0 capture, 1 tag) of the eliminated / retained poses
+  int n_e, n_f;
+};
+
+int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, double* sc) {
+  const int nb = s->n_blk, plane = s->plane, grid = cdiv(plane, kAccumThreads);
+  for (int pass = 0; pass < 2; ++pass) {
+    const int side = pass == 0 ? sd.e : sd.f;
+    const int n_own = side == 0 ? s->n_cap : s->n_tag;
+    AccumArgs a;
+    a.n_blk = nb; a.plane = plane;
+    a.own_idx = s->s_own[side].p; a.oth_idx = s->s_oth[side].p; a.obs = s->s_obs[side].p;
+    a.cap_pre = s->cap_pre[k].p; a.tag_pre = s->tag_pre[k].p; a.cam = s->cam[k].p;
+    a.out_seg = pass == 0 ? s->H[side].p : HF;
+    a.partial = s->partial[side].p;
+    a.W = s->W.p; a.warp_cam = s->warp_cam.p;
+    const double bytes_e = (4.0 * 18.0 + 288.0) * nb + 264.0 * n_own;
+    const double bytes_f = (4.0 * 18.0) * nb + 264.0 * n_own;
+    if (pass == 0) {
+      if (side == 0) LAUNCH("accum_E", bytes_e, accum_kernel<0, true><<<grid, kAccumThreads, 0, s->stream>>>(a));
+      else LAUNCH("accum_E", bytes_e, accum_kernel<1, true><<<grid, kAccumThreads, 0, s->stream>>>(a));
+    } else {
+      if (side == 0) LAUNCH("accum_F", bytes_f, accum_kernel<0, false><<<grid, kAccumThreads, 0, s->stream>>>(a));
+      else LAUNCH("accum_F", bytes_f, accum_kernel<1, false><<<grid, kAccumThreads, 0, s->stream>>>(a));
+    }
+    LAUNCH("seg_fixup", 8.0 * NV * n_own,
+           seg_fixup_kernel<<<cdiv((long long)n_own * NV, 256), 256, 0, s->stream>>>(n_own, s->s_off[side].p, s->partial[side].p, a.out_seg));
+  }
+  LAUNCH("colsum", 32.0 * s->n_warp, colsum_kernel<<<1, 1024, 0, s->stream>>>(s->n_warp, 4, s->warp_cam.p, sc));
+  return ARSLAM_OK;
+}
+
+__global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled) {
+  const double sg = enabled ? 1.0 / (1.0 + sqrt(sc[0])) : 1.0;
+  sc[14] = sg;
+  *sigF_cam = sg;
+}
+__global__ void cam_step_kernel(const double* uF_cam, const double* cam, double* cam_c, double* d_cam, double* sc) {
+  const double d = -uF_cam[0];
+  d_cam[0] = d; d_cam[1] = 0.0; d_cam[2] = 0.0;
+  cam_c[0] = cam[0] + d; cam_c[1] = cam[1]; cam_c[2] = cam[2];
+  sc[13] = cam[0] - (cam[0] + d);
+  sc[15] = cam[0];
+}
+__global__ void collect_fail_kernel(int n_e, const double* Z, double* sc) {
+  // any E pose whose damped 6x6 block was not positive definite
+  double f = 0.0;
+  for (int i = threadIdx.x; i < n_e; i += blockDim.x) f = fmax(f, Z[8 * (size_t)i + 6]);
+  f = warp_max(f);
+  if ((threadIdx.x & 31) == 0 && f != 0.0) sc[12] = 1.0;
+}
+
+}  // namespace
+
+int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, int32_t log_rows) {
+  if (!s || !summary) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem || !s->have_params) return s->fail(ARSLAM_ERR_INVALID, "solve needs set_problem and set_params");
+  CU(cudaSetDevice(s->device));
+  const double t_start = wall_ms();
+  const arslam_options& o = s->opt;
+  std::memset(summary, 0, sizeof(*summary));
+  s->launches = 0;
+  s->prof.clear();
+
+  // ---- which pose side is eliminated
+  Sides sd;
+  int elim = o.elimination;
+  if (elim == ARSLAM_ELIM_AUTO) elim = (s->n_cap >= s->n_tag) ? ARSLAM_ELIM_CAPTURES : ARSLAM_ELIM_TAGS;
+  if (s->world > 1 && elim != ARSLAM_ELIM_CAPTURES)
+    return s->fail(ARSLAM_ERR_UNSUPPORTED, "multi-GPU solve shards captures and must eliminate them");
+  sd.e = elim == ARSLAM_ELIM_CAPTURES ? 0 : 1;
+  sd.f = 1 - sd.e;
+  sd.n_e = sd.e == 0 ? s->n_cap : s->n_tag;
+  sd.n_f = sd.f == 0 ? s->n_cap : s->n_tag;
+  const int n = 6 * sd.n_f + 1;  // reduced dimension (F poses + focal)
+  const int cam_row = n - 1, rhs_row = n;
+  int lin = o.linear_solver;
+  if (lin == ARSLAM_LINSOLVE_AUTO) lin = (n <= o.dense_max_dim) ? ARSLAM_LINSOLVE_DENSE : ARSLAM_LINSOLVE_PCG;
+  summary->eliminated_side = elim;
+  summary->linear_solver = lin;
+  summary->reduced_dim = n;
+
+  // ---- buffers that depend on the roles
+  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * sd.n_e)); CU(s->seg_cam.ensure((size_t)2 * sd.n_e));
+  CU(s->sigE.ensure((size_t)6 * sd.n_e)); CU(s->sigF.ensure((size_t)n + 1)); CU(s->uF.ensure((size_t)n + 1));
+  size_t s_elems = 0;
+  if (lin == ARSLAM_LINSOLVE_DENSE) {
+    s->n_pad = (n + 1 + CB - 1) / CB * CB;
+    s->ld = s->n_pad;
+    s_elems = (size_t)s->n_pad * s->ld;
+    CU(s->yF.ensure((size_t)s->n_pad));
+  } else {
+    int rc = pcg_prepare(s->pcg, sd.n_e, sd.n_f, s->n_blk, s->h_off[sd.e].data(), s->s_oth[sd.e].p, s->stream, s->err);
+    if (rc) return rc;
+    s_elems = s->pcg.value_count();  // block values + border + rhs
+    CU(s->yF.ensure((size_t)n + 1));
+  }
+  // reduction buffer: [S or sparse values | cam_minus (4) | HF (n_f NV) | scalar head (4)]
+  const size_t red_tail = 4 + (size_t)sd.n_f * NV + 4;
+  CU(s->red.ensure(s_elems + red_tail));
+  double* S = s->red.p;
+  double* cam_minus = S + s_elems;
+  double* HF = cam_minus + 4;
+  double* sc_head = HF + (size_t)sd.n_f * NV;  // cam_H, cam_g, sum_r2, 0 : summed across ranks
+  double* sc = s->sc.p;
+  CU(cudaMemsetAsync(sc, 0, 16 * sizeof(double), s->stream));
+
+  int rc = upload_params(s, 0);
+  if (rc) return rc;
+  s->cur = 0;
+  launch_prep(s, 0);
+  launch_accumulate(s, sd, 0, HF, sc_head);
+
+  double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
+  bool have_sigma = false, last_successful = true, fresh_linearisation = true, pending_acc = false;
+  int iteration = 0, invalid = 0;
+  int termination = ARSLAM_NO_CONVERGENCE, reason = ARSLAM_REASON_MAX_ITERATIONS;
+  double x_cost = 0.0, grad_max = 0.0, x_norm = 0.0;
+  double eval_ms = 0.0, lin_ms = 0.0;
+  summary->num_jacobian_evals = 1;
+  summary->num_successful_steps = 1;
+  const int ne_warps = cdiv(sd.n_e, 32), nf_warps = cdiv(sd.n_f, 32);
+
+  auto log_iter = [&](int it, double cost, double cost_change, double step_norm, double rho, int valid, int ok) {
+    if (iter_log && it < log_rows) {
+      double* L = iter_log + 8 * (size_t)it;
+      L[0] = cost; L[1] = cost_change; L[2] = grad_max; L[3] = step_norm;
+      L[4] = rho; L[5] = radius; L[6] = valid; L[7] = ok;
+    }
+    if (o.verbose)
+      std::printf("%4d  cost %.6e  change %.3e  |grad| %.3e  |step| %.3e  rho %.3e  radius %.3e%s\n", it, cost,
+                  cost_change, grad_max, step_norm, rho, radius, valid ? (ok ? "" : "  (rejected)") : "  (invalid)");
+  };
+
+  while (true) {
+    // FinalizeIterationAndCheckIfMinimizerCanContinue, the tests that need no new data
+    if (iteration >= o.max_num_iterations && iteration > 0) {
+      termination = ARSLAM_NO_CONVERGENCE; reason = ARSLAM_REASON_MAX_ITERATIONS; break; }
+    if (radius <= o.min_trust_region_radius) {
+      termination = ARSLAM_CONVERGENCE; reason = ARSLAM_REASON_MIN_RADIUS; break; }
+    const bool stop_after_readback = iteration >= o.max_num_iterations;  // max_num_iterations == 0
+
+    // ---------------- linear solve for this radius (speculative; see below)
+    const int k = s->cur, kc = 1 - s->cur;
+    cudaEventRecord(s->ev[0], s->stream);
+    if (!have_sigma) {
+      LAUNCH("sigma", 8.0 * 12 * sd.n_e,
+             sigma_pose_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->H[sd.e].p, o.jacobi_scaling, s->sigE.p));
+    }
+    {
+      SchurArgs a;
+      a.n_e = sd.n_e; a.plane = s->plane;
+      a.e_off = s->s_off[sd.e].p; a.f_idx = s->s_oth[sd.e].p;
+      a.HE = s->H[sd.e].p; a.W = s->W.p; a.sig_e = s->sigE.p;
+      a.radius = radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
+      a.Y = s->Y.p; a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p;
+      a.S = nullptr; a.ld = s->ld; a.cam_row = cam_row; a.rhs_row = rhs_row;
+      CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
+      CU(cudaMemsetAsync(sc + 12, 0, sizeof(double), s->stream));
+      if (lin == ARSLAM_LINSOLVE_DENSE) {
+        a.S = S;
+        LAUNCH("schur_eliminate", (288.0 * 2 + 4) * s->n_blk + (264.0 + 128) * sd.n_e,
+               schur_eliminate_kernel<<<cdiv((long long)sd.n_e * 32, 128), 128, 0, s->stream>>>(a));
+      } else {
+        rc = pcg_launch_eliminate(s, a, S);
+        if (rc) return rc;
+      }
+      LAUNCH("collect_fail", 8.0 * sd.n_e, collect_fail_kernel<<<1, 1024, 0, s->stream>>>(sd.n_e, s->Z.p, sc));
+      LAUNCH("colsum", 16.0 * sd.n_e, colsum_kernel<<<1, 1024, 0, s->stream>>>(sd.n_e, 2, s->seg_cam.p, cam_minus));
+    }
+    if (s->world > 1) {
+      // one allreduce per linearisation: partial Schur terms (+ on a fresh
+      // linearisation the partial tag blocks, focal terms and cost)
+      const size_t cnt = fresh_linearisation ? s_elems + red_tail : s_elems + 4;
+      rc = nccl_sum(s, S, cnt);
+      if (rc) return rc;
+    }
+    if (fresh_linearisation) {
+      CU(cudaMemcpyAsync(sc, sc_head, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p));
+      LAUNCH("colmax", 8.0 * ne_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, s->warp_gmax[sd.e].p, sc + 10));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p));
+      LAUNCH("colmax", 8.0 * nf_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_f, 128) * 4, s->warp_gmax[sd.f].p, sc + 11));
+    }
+    if (!have_sigma) {
+      LAUNCH("sigma", 8.0 * 12 * sd.n_f,
+             sigma_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, o.jacobi_scaling, s->sigF.p));
+      LAUNCH("cam_sigma", 16.0, cam_sigma_kernel<<<1, 1, 0, s->stream>>>(sc, s->sigF.p + cam_row, o.jacobi_scaling));
+      have_sigma = true;
+    }
+    if (lin == ARSLAM_LINSOLVE_DENSE) {
+      dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n + 1, 8));
+      LAUNCH("dense_scale", 8.0 * n * n, dense_scale_kernel<<<grd, blk, 0, s->stream>>>(S, s->ld, rhs_row, s->sigF.p));
+      LAUNCH("dense_add_pose", 8.0 * NV * sd.n_f,
+             dense_add_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, s->sigF.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row));
+      LAUNCH("dense_add_camera", 64.0,
+             dense_add_camera_kernel<<<cdiv(std::max(1, s->n_pad - rhs_row - 1), 128), 128, 0, s->stream>>>(
+                 reinterpret_cast<const LmScalars*>(sc), cam_minus, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row, s->n_pad));
+      if (s->prof.on) {
+        Profiler::Rec r{s->prof.id_of("dense_cholesky", 0.0), s->prof.ev(), s->prof.ev()};
+        cudaEventRecord(r.a, s->stream);
+        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, sc + 12, s->stream);
+        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
+        cudaEventRecord(r.b, s->stream);
+        s->prof.recs.push_back(r);
+      } else {
+        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, sc + 12, s->stream);
+        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
+      }
+    } else {
+      long long its = 0;
+      rc = pcg_launch_solve(s, sd.n_f, S, HF, reinterpret_cast<const LmScalars*>(sc), cam_minus, radius, s->yF.p, &its);
+      if (rc) return rc;
+    }
+    LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
+    {
+      BacksubArgs b;
+      b.n_e = sd.n_e; b.plane = s->plane; b.e_off = s->s_off[sd.e].p; b.f_idx = s->s_oth[sd.e].p;
+      b.Y = s->Y.p; b.Z = s->Z.p; b.YB = s->YB.p; b.sig_e = s->sigE.p; b.uF = s->uF.p; b.cam_row = cam_row;
+      b.d_e = s->d_pose[sd.e].p;
+      LAUNCH("backsub", 292.0 * s->n_blk + 200.0 * sd.n_e,
+             backsub_kernel<<<cdiv((long long)sd.n_e * 32, 128), 128, 0, s->stream>>>(b));
+    }
+    double* x_e = sd.e == 0 ? s->cap[k].p : s->tag[k].p;
+    double* x_f = sd.f == 0 ? s->cap[k].p : s->tag[k].p;
+    double* xc_e = sd.e == 0 ? s->cap[kc].p : s->tag[kc].p;
+    double* xc_f = sd.f == 0 ? s->cap[kc].p : s->tag[kc].p;
+    {
+      ApplyArgs ap;
+      ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
+      ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
+      LAUNCH("apply_step", 144.0 * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
+      LAUNCH("colsum", 16.0 * ne_warps, colsum_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, 2, s->warp_norm[sd.e].p, sc + 6));
+      ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
+      ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
+      ap.count_norms = (s->rank == 0) ? 1 : 0;
+      LAUNCH("apply_step", 144.0 * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
+      LAUNCH("colsum", 16.0 * nf_warps, colsum_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_f, 128) * 4, 2, s->warp_norm[sd.f].p, sc + 8));
+      LAUNCH("cam_step", 64.0, cam_step_kernel<<<1, 1, 0, s->stream>>>(s->uF.p + cam_row, s->cam[k].p, s->cam[kc].p, s->d_cam.p, sc));
+    }
+    cudaEventRecord(s->ev[1], s->stream);
+    // ---------------- candidate point: model cost change and cost at x + delta
+    launch_prep(s, kc);
+    {
+      CandArgs c;
+      c.n_blk = s->n_blk; c.plane = s->plane;
+      c.own_idx = s->s_own[sd.e].p; c.oth_idx = s->s_oth[sd.e].p; c.obs = s->s_obs[sd.e].p;
+      c.cap_pre = s->cap_pre[k].p; c.tag_pre = s->tag_pre[k].p; c.cap_pre_c = s->cap_pre[kc].p; c.tag_pre_c = s->tag_pre[kc].p;
+      c.cam = s->cam[k].p; c.cam_c = s->cam[kc].p; c.d_cam = s->d_cam.p;
+      c.d_cap = s->d_pose[0].p; c.d_tag = s->d_pose[1].p; c.warp_out = s->warp_cand.p;
+      const int grid = cdiv(s->plane, 128);
+      if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0><<<grid, 128, 0, s->stream>>>(c));
+      else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1><<<grid, 128, 0, s->stream>>>(c));
+      LAUNCH("colsum", 16.0 * s->n_warp, colsum_kernel<<<1, 1024, 0, s->stream>>>(s->n_warp, 2, s->warp_cand.p, sc + 4));
+    }
+    if (s->world > 1) {
+      // small allreduce: sums [model, cand_r2, step2_e, xnorm2_e, step2_f, xnorm2_f] and
+      // max of gmax_e through per-rank slots
+      rc = small_allreduce(s, sc);
+      if (rc) return rc;
+    }
+    cudaEventRecord(s->ev[2], s->stream);
+    CU(cudaMemcpyAsync(s->h_sc, sc, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, s->ev[0], s->ev[1]);
+      cudaEventElapsedTime(&b, s->ev[1], s->ev[2]);
+      lin_ms += a; eval_ms += b;
+    }
+    const double* h = s->h_sc;
+    if (fresh_linearisation) {
+      x_cost = 0.5 * h[2];
+      grad_max = std::max(std::max(h[10], h[11]), std::fabs(h[1]));
+      if (iteration == 0) { summary->initial_cost = x_cost; log_iter(0, x_cost, 0.0, 0.0, 0.0, 1, 1); }
+    }
+    fresh_linearisation = false;
+    // the data-dependent test of FinalizeIteration...: the speculative work above is discarded
+    if (last_successful && grad_max <= o.gradient_tolerance) {
+      termination = ARSLAM_CONVERGENCE; reason = ARSLAM_REASON_GRADIENT; break; }
+    if (stop_after_readback) { termination = ARSLAM_NO_CONVERGENCE; reason = ARSLAM_REASON_MAX_ITERATIONS; break; }
+    ++iteration;
+    last_successful = false;
+    const double f_cur = h[15];
+    x_norm = std::sqrt(h[7] + h[9] + f_cur * f_cur + s->h_cam[1] * s->h_cam[1] + s->h_cam[2] * s->h_cam[2]);
+    const double step_norm = std::sqrt(h[6] + h[8] + h[13] * h[13]);
+    const double model_cost_change = -h[4];
+    const double cand_cost_raw = 0.5 * h[5];
+    const bool lin_ok = (h[12] == 0.0) && std::isfinite(step_norm) && std::isfinite(h[4]);
+    if (!lin_ok || !(model_cost_change > 0.0)) {
+      // HandleInvalidStep
+      summary->num_unsuccessful_steps++;
+      if (++invalid >= o.max_num_consecutive_invalid_steps) {
+        termination = ARSLAM_FAILURE; reason = ARSLAM_REASON_INVALID_STEPS; break; }
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      log_iter(iteration, x_cost, 0.0, 0.0, 0.0, 0, 0);
+      continue;
+    }
+    invalid = 0;
+    summary->num_cost_evals++;
+    const double cand_cost = std::isfinite(cand_cost_raw) ? cand_cost_raw : std::numeric_limits<double>::max();
+    const double cost_change = x_cost - cand_cost;
+    if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) {
+      termination = ARSLAM_CONVERGENCE; reason = ARSLAM_REASON_PARAMETER;
+      log_iter(iteration, x_cost, cost_change, step_norm, 0.0, 1, 0);
+      break;
+    }
+    if (std::fabs(cost_change) <= o.function_tolerance * x_cost) {
+      termination = ARSLAM_CONVERGENCE; reason = ARSLAM_REASON_FUNCTION;
+      log_iter(iteration, x_cost, cost_change, step_norm, 0.0, 1, 0);
+      break;
+    }
+    const double rho = cost_change / model_cost_change;
+    if (rho > o.min_relative_decrease) {
+      // HandleSuccessfulStep: the candidate becomes the current point
+      s->cur = kc;
+      if (pending_acc) {  // timing of the previous accumulate is resolved now (the stream is idle)
+        float a_ms = 0; cudaEventElapsedTime(&a_ms, s->ev[3], s->ev[4]); eval_ms += a_ms;
+      }
+      cudaEventRecord(s->ev[3], s->stream);
+      launch_accumulate(s, sd, kc, HF, sc_head);
+      cudaEventRecord(s->ev[4], s->stream);
+      pending_acc = true;
+      summary->num_jacobian_evals++;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3));
+      radius = std::min(o.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      last_successful = true;
+      fresh_linearisation = true;
+      summary->num_successful_steps++;
+      x_cost = cand_cost;  // re-evaluated value arrives with the next readback
+      log_iter(iteration, cand_cost, cost_change, step_norm, rho, 1, 1);
+    } else {
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      summary->num_unsuccessful_steps++;
+      log_iter(iteration, cand_cost, cost_change, step_norm, rho, 1, 0);
+    }
+  }
+  // ---- results: current parameter set back to the host mirror
+  {
+    const int k = s->cur;
+    CU(cudaMemcpyAsync(s->h_sc + 32, s->cam[k].p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_sc + 40, sc_head, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (s->world > 1) {
+      rc = gather_captures(s, k);
+      if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(s->h_cap.data(), s->cap[k].p, sizeof(double) * 6 * s->n_cap, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_tag.data(), s->tag[k].p, sizeof(double) * 6 * s->n_tag, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    s->h_cam[0] = s->h_sc[32];
+    if (pending_acc) { float a_ms = 0; cudaEventElapsedTime(&a_ms, s->ev[3], s->ev[4]); eval_ms += a_ms; }
+    // a successful last step was re-linearised but not read back yet: exact cost of the final point
+    if (fresh_linearisation && iteration > 0 && s->world == 1) x_cost = 0.5 * s->h_sc[42];
+  }
+  s->prof.resolve();
+  summary->iterations = iteration;
+  summary->termination = termination;
+  summary->reason = reason;
+  summary->final_cost = x_cost;
+  summary->final_radius = radius;
+  summary->gradient_max_norm = grad_max;
+  summary->gpu_launches = s->launches;
+  summary->linear_solver_iterations = s->pcg.total_iterations;
+  summary->eval_ms = eval_ms;
+  summary->linsolve_ms = lin_ms;
+  summary->total_ms = wall_ms() - t_start;
+  return ARSLAM_OK;
+}
+
+// -------------------------------------------------------------- localise ---
+int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_offsets, const int32_t* tag_idx,
+                          const double* rect8, const int32_t* seed_block, int64_t n_tag, const double* camera3,
+                          const double* tag_pose6, double* cap_pose6, int32_t* iterations, double* final_cost,
+                          int32_t* termination) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (n_loc <= 0 || !blk_offsets || !tag_idx || !rect8 || !seed_block || n_tag <= 0 || !camera3 || !tag_pose6 || !cap_pose6)
+    return s->fail(ARSLAM_ERR_INVALID, "localize_batch: null pointer or empty batch");
+  const int64_t nb = blk_offsets[n_loc];
+  if (blk_offsets[0] != 0 || nb < 0 || nb > (1LL << 28)) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: bad block offsets");
+  for (int64_t i = 0; i < n_loc; ++i) {
+    const int32_t k = blk_offsets[i + 1] - blk_offsets[i];
+    if (k < 0 || seed_block[i] >= k) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: capture %lld has bad offsets/seed", (long long)i);
+  }
+  for (int64_t b = 0; b < nb; ++b)
+    if (tag_idx[b] < 0 || tag_idx[b] >= n_tag) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: tag index out of range");
+  CU(cudaSetDevice(s->device));
+  s->prof.clear();
+  s->launches = 0;
+  DevBuf<int32_t> d_off, d_tag, d_seed, d_it, d_term;
+  DevBuf<double> d_obs, d_tagpose, d_tagpre, d_pose, d_cost;
+  CU(d_off.ensure(n_loc + 1)); CU(d_tag.ensure(nb)); CU(d_seed.ensure(n_loc)); CU(d_it.ensure(n_loc)); CU(d_term.ensure(n_loc));
+  CU(d_obs.ensure((size_t)8 * nb)); CU(d_tagpose.ensure((size_t)6 * n_tag)); CU(d_tagpre.ensure((size_t)kTagPre * n_tag));
+  CU(d_pose.ensure((size_t)6 * n_loc)); CU(d_cost.ensure(n_loc));
+  CU(cudaMemcpyAsync(d_off.p, blk_offsets, sizeof(int32_t) * (n_loc + 1), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_seed.p, seed_block, sizeof(int32_t) * n_loc, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_tagpose.p, tag_pose6, sizeof(double) * 6 * n_tag, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(d_pose.p, cap_pose6, sizeof(double) * 6 * n_loc, cudaMemcpyHostToDevice, s->stream));
+  LAUNCH("prep_tags", 8.0 * (6 + kTagPre) * n_tag,
+         prep_tags_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>((int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p));
+  LocArgs a;
+  a.n_loc = (int)n_loc; a.blk_off = d_off.p; a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
+  a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p; a.focal = camera3[0];
+  const arslam_options& o = s->opt;
+  a.o.max_num_iterations = o.max_num_iterations; a.o.max_invalid = o.max_num_consecutive_invalid_steps;
+  a.o.jacobi_scaling = o.jacobi_scaling; a.o.initial_radius = o.initial_trust_region_radius;
+  a.o.max_radius = o.max_trust_region_radius; a.o.min_radius = o.min_trust_region_radius;
+  a.o.min_relative_decrease = o.min_relative_decrease; a.o.min_diag = o.min_lm_diagonal; a.o.max_diag = o.max_lm_diagonal;
+  a.o.function_tolerance = o.function_tolerance; a.o.gradient_tolerance = o.gradient_tolerance;
+  a.o.parameter_tolerance = o.parameter_tolerance; a.o.tag_size = o.tag_size;
+  a.pose = d_pose.p; a.iterations = d_it.p; a.final_cost = d_cost.p; a.termination = d_term.p;
+  LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc,
+         localize_kernel<<<cdiv(n_loc * 32, 128), 128, 0, s->stream>>>(a));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cap_pose6, d_pose.p, sizeof(double) * 6 * n_loc, cudaMemcpyDeviceToHost, s->stream));
+  if (iterations) CU(cudaMemcpyAsync(iterations, d_it.p, sizeof(int32_t) * n_loc, cudaMemcpyDeviceToHost, s->stream));
+  if (final_cost) CU(cudaMemcpyAsync(final_cost, d_cost.p, sizeof(double) * n_loc, cudaMemcpyDeviceToHost, s->stream));
+  if (termination) CU(cudaMemcpyAsync(termination, d_term.p, sizeof(int32_t) * n_loc, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->prof.resolve();
+  return ARSLAM_OK;
+}
+
+// ------------------------------------------------------------------ comm ----
+int arslam_comm_unique_id(void* id128) {
+  if (!id128) return ARSLAM_ERR_INVALID;
+  std::string err;
+  if (!g_nccl.load(err)) { g_create_error = err; return ARSLAM_ERR_NCCL; }
+  NcclId id;
+  std::memset(&id, 0, sizeof(id));
+  if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return ARSLAM_ERR_NCCL; }
+  std::memcpy(id128, &id, 128);
+  return ARSLAM_OK;
+}
+
+int arslam_comm_init(arslam_solver* s, int rank, int world_size, const void* id128) {
+  if (!s || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return ARSLAM_ERR_INVALID;
+  std::string err;
+  if (!g_nccl.load(err)) return s->fail(ARSLAM_ERR_NCCL, "%s", err.c_str());
+  CU(cudaSetDevice(s->device));
+  NcclId id;
+  std::memcpy(&id, id128, 128);
+  // ncclCommInitRank takes the id BY VALUE (128-byte struct, passed in memory by the SysV ABI)
+  typedef int (*init_fn)(void**, int, NcclId, int);
+  init_fn init = reinterpret_cast<init_fn>(reinterpret_cast<void*>(g_nccl.CommInitRank));
+  int rc = init(&s->comm, world_size, id, rank);
+  if (rc != 0) return s->fail(ARSLAM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  s->rank = rank;
+  s->world = world_size;
+  return ARSLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// kernels.cuh -- bundle-adjustment kernels (sm_100a).
+//
+// Terminology: the two pose sets (captures, tags) play two roles per solve:
+// the E side is eliminated by the Schur complement, the F side (plus the
+// camera intrinsics) is retained.  Residual blocks are kept twice in HBM,
+// once sorted by E pose and once sorted by F pose, as structure-of-arrays
+// planes, so that each pass sees every pose's blocks as one contiguous
+// segment and can reduce J^T J / J^T r inside the CTA (warp-shuffle + shared
+// memory staging) instead of with global atomics.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "model.cuh"
+
+namespace ars {
+
+constexpr int NV = 33;         // per-pose normal-equation record: H upper (21) | g (6) | H_pose,f (6)
+constexpr int kAccumThreads = 128;
+constexpr int kAccumWarps = kAccumThreads / 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------- prep -----
+__global__ void prep_captures_kernel(int n, const double* __restrict__ pose, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[6], rec[kCapPre];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p[k] = pose[6 * (size_t)i + k];
+  prep_capture(p, rec);
+  double2* o = reinterpret_cast<double2*>(out + (size_t)kCapPre * i);
+#pragma unroll
+  for (int k = 0; k < kCapPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+}
+__global__ void prep_tags_kernel(int n, const double* __restrict__ pose, double tag_size,
+                                 double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[6], rec[kTagPre];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p[k] = pose[6 * (size_t)i + k];
+  prep_tag(p, tag_size, rec);
+  double2* o = reinterpret_cast<double2*>(out + (size_t)kTagPre * i);
+#pragma unroll
+  for (int k = 0; k < kTagPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+}
+
+// ------------------------------------------------ kernel (1): evaluate -----
+// One thread per observation corner, original block order.  Writes what
+// ceres::Problem::Evaluate would: residuals and the three Jacobian blocks in
+// Ceres' row-major layout.  Thread (b, i) owns rows 2i, 2i+1 of block b, i.e.
+// 16 B of residuals, 48 B of jac_cam, 96 B of jac_cap and of jac_tag, all
+// contiguous across consecutive threads (coalesced 128-bit stores).
+// Algorithmic bytes per corner: 16 obs + 2 idx + 16 r + 240 J = 274.
+__global__ void __launch_bounds__(256)
+eval_jacobian_kernel(int n_corner, const int32_t* __restrict__ cap_idx, const int32_t* __restrict__ tag_idx,
+                     const double2* __restrict__ obs /* [n_corner] (x,y) */,
+                     const double* __restrict__ cap_pre, const double* __restrict__ tag_pre,
+                     const double* __restrict__ cam, double2* __restrict__ res /* may be null */,
+                     double2* __restrict__ jac_cam, double2* __restrict__ jac_cap,
+                     double2* __restrict__ jac_tag, double* __restrict__ warp_cost) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double rr = 0.0;
+  if (t < n_corner) {
+    const int b = t >> 2, i = t & 3;
+    const double f = cam[0];
+    const double2 o = obs[t];
+    const double* cp = cap_pre + (size_t)kCapPre * cap_idx[b];
+    const double* tp = tag_pre + (size_t)kTagPre * tag_idx[b] + 12 * i;
+    CornerJ j;
+    corner_jacobian(cp, tp, f, o.x, o.y, j);
+    rr = j.r[0] * j.r[0] + j.r[1] * j.r[1];
+    if (res) res[t] = make_double2(j.r[0], j.r[1]);
+    if (jac_cam) {
+      double2* d = jac_cam + 3 * (size_t)t;
+      d[0] = make_double2(j.K[0], 0.0);
+      d[1] = make_double2(0.0, j.K[1]);
+      d[2] = make_double2(0.0, 0.0);
+    }
+    if (jac_cap) {
+      double2* d = jac_cap + 6 * (size_t)t;
+      d[0] = make_double2(j.A[0][0], j.A[0][1]);
+      d[1] = make_double2(j.A[0][2], j.B[0][0]);
+      d[2] = make_double2(j.B[0][1], j.B[0][2]);
+      d[3] = make_double2(j.A[1][0], j.A[1][1]);
+      d[4] = make_double2(j.A[1][2], j.B[1][0]);
+      d[5] = make_double2(j.B[1][1], j.B[1][2]);
+    }
+    if (jac_tag) {
+      double2* d = jac_tag + 6 * (size_t)t;
+      d[0] = make_double2(j.A[0][0], j.A[0][1]);
+      d[1] = make_double2(j.A[0][2], j.C[0][0]);
+      d[2] = make_double2(j.C[0][1], j.C[0][2]);
+      d[3] = make_double2(j.A[1][0], j.A[1][1]);
+      d[4] = make_double2(j.A[1][2], j.C[1][0]);
+      d[5] = make_double2(j.C[1][1], j.C[1][2]);
+    }
+  }
+  rr = warp_sum(rr);
+  if ((threadIdx.x & 31) == 0) warp_cost[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = rr;
+}
+
+// -------------------------------------- kernels (1)+(2) fused: accumulate --
+// One thread per residual block (4 corners), blocks sorted by the "own" pose
+// side of this pass (SIDE 0: capture-sorted, SIDE 1: tag-sorted).  Per thread:
+// evaluate the Jacobian pieces of its 4 corners in registers and accumulate
+// the Gram entries it needs; then
+//   * WITH_W: write the 6x6 cross block W = J_own^T J_other (36 coalesced
+//     plane stores) and the warp's camera/cost partial;
+//   * reduce the per-pose record (H_own,own upper | g_own | H_own,f; NV = 33
+//     doubles) over the segment of threads that share the pose: values are
+//     staged transposed in shared memory ([value][lane], padded), then lane v
+//     walks the 32 columns and flushes a sum at every segment boundary.
+//     Segments inside a warp are written straight to out_seg; pieces that
+//     straddle warps go to `partial` and are summed in a fixed order by
+//     seg_fixup_kernel, so the result is bit-reproducible.  No global atomics.
+// J never touches HBM.  Algorithmic bytes per corner (E pass): 16 obs + 2 idx
+// in, 72 W out; per pose 264 out.  (F pass: 18 in, 264 per pose out.)
+struct AccumArgs {
+  int n_blk;                 // blocks in this pass (sorted order)
+  int plane;                 // plane stride (n_blk rounded up to 32)
+  const int32_t* own_idx;    // [n_blk] pose index on the sorted side
+  const int32_t* oth_idx;    // [n_blk] pose index on the other side
+  const double* obs;         // 8 planes [k][plane]: x0,y0,x1,y1,x2,y2,x3,y3
+  const double* cap_pre;
+  const double* tag_pre;
+  const double* cam;
+  double* out_seg;           // [n_pose][NV]
+  double* partial;           // [n_warp][2][NV]
+  double* W;                 // 36 planes [e][plane] (WITH_W)
+  double* warp_cam;          // [n_warp][4]: sum K^2, sum K r, sum r^2, 0 (WITH_W)
+};
+
+template <int SIDE, bool WITH_W>
+__global__ void __launch_bounds__(kAccumThreads, 2) accum_kernel(const AccumArgs a) {
+  __shared__ double stage[kAccumWarps][NV][33];
+  __shared__ int sseg[kAccumWarps][36];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int pos = blockIdx.x * kAccumThreads + threadIdx.x;
+  const int gwarp = pos >> 5;
+  const bool valid = pos < a.n_blk;
+  const int own = valid ? a.own_idx[pos] : -1;
+  const int oth = valid ? a.oth_idx[pos] : 0;
+  sseg[wid][lane + 1] = own;
+  if (lane == 0) {
+    const int w0 = gwarp << 5;
+    sseg[wid][0] = (w0 > 0 && w0 - 1 < a.n_blk) ? a.own_idx[w0 - 1] : -2;
+    sseg[wid][33] = (w0 + 32 < a.n_blk) ? a.own_idx[w0 + 32] : -1;
+  }
+
+  // Gram accumulators.  own = [A | O2], other = [A | X2]; SIDE 0: O2 = B
+  // (capture rotation), X2 = C (tag rotation); SIDE 1 the other way round.
+  double AA[6] = {0, 0, 0, 0, 0, 0}, AO[9], OO[6] = {0, 0, 0, 0, 0, 0};
+  double AX[9], OX[9];
+  double Ar[3] = {0, 0, 0}, Or[3] = {0, 0, 0}, AK[3] = {0, 0, 0}, OK[3] = {0, 0, 0};
+  double KK = 0.0, Kr = 0.0, rr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { AO[i] = 0.0; AX[i] = 0.0; OX[i] = 0.0; }
+
+  if (valid) {
+    const int cap = SIDE == 0 ? own : oth;
+    const int tag = SIDE == 0 ? oth : own;
+    const double f = a.cam[0];
+    double cp[kCapPre];
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.cap_pre + (size_t)kCapPre * cap);
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const double2 v = __ldg(src + k);
+        cp[2 * k] = v.x;
+        cp[2 * k + 1] = v.y;
+      }
+    }
+    const double2* tsrc = reinterpret_cast<const double2*>(a.tag_pre + (size_t)kTagPre * tag);
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      double tp[12];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double2 v = __ldg(tsrc + 6 * i + k);
+        tp[2 * k] = v.x;
+        tp[2 * k + 1] = v.y;
+      }
+      const double ox = a.obs[(size_t)(2 * i) * a.plane + pos];
+      const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
+      CornerJ j;
+      corner_jacobian(cp, tp, f, ox, oy, j);
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const double* A = j.A[row];
+        const double* O = SIDE == 0 ? j.B[row] : j.C[row];
+        const double* X = SIDE == 0 ? j.C[row] : j.B[row];
+        const double r = j.r[row], K = j.K[row];
+        AA[0] += A[0] * A[0]; AA[1] += A[0] * A[1]; AA[2] += A[0] * A[2];
+        AA[3] += A[1] * A[1]; AA[4] += A[1] * A[2]; AA[5] += A[2] * A[2];
+        OO[0] += O[0] * O[0]; OO[1] += O[0] * O[1]; OO[2] += O[0] * O[2];
+        OO[3] += O[1] * O[1]; OO[4] += O[1] * O[2]; OO[5] += O[2] * O[2];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            AO[p * 3 + q] += A[p] * O[q];
+            if (WITH_W) {
+              AX[p * 3 + q] += A[p] * X[q];
+              OX[p * 3 + q] += O[p] * X[q];
+            }
+          }
+          Ar[p] += A[p] * r;
+          Or[p] += O[p] * r;
+          AK[p] += A[p] * K;
+          OK[p] += O[p] * K;
+        }
+        if (WITH_W) {
+          KK += K * K;
+          Kr += K * r;
+          rr += r * r;
+        }
+      }
+    }
+    if (WITH_W) {
+      // W = own^T other = [A^T A, A^T X2 ; O2^T A, O2^T X2], row-major 6x6 planes
+      double* w = a.W + pos;
+      const size_t ps = a.plane;
+      const double aa[9] = {AA[0], AA[1], AA[2], AA[1], AA[3], AA[4], AA[2], AA[4], AA[5]};
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          w[(size_t)(p * 6 + q) * ps] = aa[p * 3 + q];
+          w[(size_t)(p * 6 + 3 + q) * ps] = AX[p * 3 + q];
+          w[(size_t)((p + 3) * 6 + q) * ps] = AO[q * 3 + p];
+          w[(size_t)((p + 3) * 6 + 3 + q) * ps] = OX[p * 3 + q];
+        }
+    }
+  }
+  if (WITH_W) {
+    KK = warp_sum(KK);
+    Kr = warp_sum(Kr);
+    rr = warp_sum(rr);
+    if (lane == 0) {
+      double* wc = a.warp_cam + 4 * (size_t)gwarp;
+      wc[0] = KK; wc[1] = Kr; wc[2] = rr; wc[3] = 0.0;
+    }
+  }
+  // stage the per-pose record, transposed: stage[v][lane]
+  {
+    double(*st)[33] = stage[wid];
+    // H upper packed, own = [A(0..2) | O2(3..5)]
+    st[tri6(0, 0)][lane] = AA[0]; st[tri6(0, 1)][lane] = AA[1]; st[tri6(0, 2)][lane] = AA[2];
+    st[tri6(1, 1)][lane] = AA[3]; st[tri6(1, 2)][lane] = AA[4]; st[tri6(2, 2)][lane] = AA[5];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) st[tri6(p, 3 + q)][lane] = AO[p * 3 + q];
+    st[tri6(3, 3)][lane] = OO[0]; st[tri6(3, 4)][lane] = OO[1]; st[tri6(3, 5)][lane] = OO[2];
+    st[tri6(4, 4)][lane] = OO[3]; st[tri6(4, 5)][lane] = OO[4]; st[tri6(5, 5)][lane] = OO[5];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      st[21 + p][lane] = Ar[p];
+      st[24 + p][lane] = Or[p];
+      st[27 + p][lane] = AK[p];
+      st[30 + p][lane] = OK[p];
+    }
+  }
+  __syncwarp();
+  const int* sg = sseg[wid];
+  for (int v = lane; v < NV; v += 32) {
+    const double* col = stage[wid][v];
+    double acc = 0.0;
+    int run_start = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int sj = sg[j + 1], sn = sg[j + 2];
+      acc += col[j];
+      if (sn != sj) {
+        if (sj >= 0) {
+          const bool starts_before = (run_start == 0) && (sg[0] == sj);
+          if (!starts_before) a.out_seg[(size_t)sj * NV + v] = acc;
+          else a.partial[((size_t)gwarp * 2 + 0) * NV + v] = acc;
+        }
+        acc = 0.0;
+        run_start = j + 1;
+      } else if (j == 31 && sj >= 0) {
+        a.partial[((size_t)gwarp * 2 + (run_start == 0 ? 0 : 1)) * NV + v] = acc;
+      }
+    }
+  }
+}
+
+// Sums the pieces of poses whose blocks straddle warps (fixed order), and
+// zero-fills poses without blocks.  One thread per (pose, value).
+__global__ void seg_fixup_kernel(int n_pose, const int32_t* __restrict__ seg_off,
+                                 const double* __restrict__ partial, double* __restrict__ out_seg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pose * NV) return;
+  const int s = t / NV, v = t - s * NV;
+  const int b0 = seg_off[s], b1 = seg_off[s + 1];
+  if (b1 == b0) { out_seg[t] = 0.0; return; }
+  const int w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
+  if (w0 == w1) return;
+  double acc = 0.0;
+  for (int w = w0; w <= w1; ++w) {
+    const int slot = (w == w0 && (b0 & 31) != 0) ? 1 : 0;
+    acc += partial[((size_t)w * 2 + slot) * NV + v];
+  }
+  out_seg[t] = acc;
+}
+
+// Deterministic column sums of a [n][m] array (m <= 8) into out[m]; one CTA.
+__global__ void __launch_bounds__(1024) colsum_kernel(int n, int m, const double* __restrict__ in,
+                                                      double* __restrict__ out) {
+  __shared__ double sm[1024];
+  for (int c = 0; c < m; ++c) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) acc += in[(size_t)i * m + c];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = sm[0];
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------- candidate / model -----
+// One thread per block (E-sorted order).  At the current point x: model
+// residual J*delta per row, accumulated as sum (J d)(r + J d / 2) (Ceres'
+// model_cost_change, trust_region_minimizer.cc).  At the candidate x + delta:
+// sum r^2.  warp partials -> colsum_kernel.  Bytes per corner: 18 in.
+struct CandArgs {
+  int n_blk, plane;
+  const int32_t* own_idx;
+  const int32_t* oth_idx;
+  const double* obs;
+  const double* cap_pre;   // at x (full records)
+  const double* tag_pre;
+  const double* cap_pre_c; // at x + delta
+  const double* tag_pre_c;
+  const double* cam;       // at x
+  const double* cam_c;     // at x + delta
+  const double* d_cam;     // step, unscaled: [3]
+  const double* d_cap;     // [6 n_cap]
+  const double* d_tag;     // [6 n_tag]
+  double* warp_out;        // [n_warp][2]: model term, candidate sum r^2
+};
+template <int SIDE>
+__global__ void __launch_bounds__(128) candidate_kernel(const CandArgs a) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0, c2 = 0.0;
+  if (pos < a.n_blk) {
+    const int own = a.own_idx[pos], oth = a.oth_idx[pos];
+    const int cap = SIDE == 0 ? own : oth, tag = SIDE == 0 ? oth : own;
+    const double f = a.cam[0], fc = a.cam_c[0], df = a.d_cam[0];
+    double dc[6], da[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      dc[k] = a.d_cap[6 * (size_t)cap + k];
+      da[k] = a.d_tag[6 * (size_t)tag + k];
+    }
+    const double dt[3] = {dc[0] + da[0], dc[1] + da[1], dc[2] + da[2]};
+    const double* cp = a.cap_pre + (size_t)kCapPre * cap;
+    const double* tp = a.tag_pre + (size_t)kTagPre * tag;
+    const double* cpc = a.cap_pre_c + (size_t)kCapPre * cap;
+    const double* tpc = a.tag_pre_c + (size_t)kTagPre * tag;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const double ox = a.obs[(size_t)(2 * i) * a.plane + pos];
+      const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
+      CornerJ j;
+      corner_jacobian(cp, tp + 12 * i, f, ox, oy, j);
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        double jd = j.K[row] * df;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          jd += j.A[row][k] * dt[k] + j.B[row][k] * dc[3 + k] + j.C[row][k] * da[3 + k];
+        m += jd * (j.r[row] + jd * 0.5);
+      }
+      double rc[2];
+      corner_residual(cpc, tpc + 12 * i, fc, ox, oy, rc);
+      c2 += rc[0] * rc[0] + rc[1] * rc[1];
+    }
+  }
+  m = warp_sum(m);
+  c2 = warp_sum(c2);
+  if ((threadIdx.x & 31) == 0) {
+    double* o = a.warp_out + 2 * (size_t)(pos >> 5);
+    o[0] = m;
+    o[1] = c2;
+  }
+}
+
+// ------------------------------------------------------------ LM vectors ---
+// sigma = 1 / (1 + sqrt(H_jj)) once at iteration 0 (Ceres jacobi_scaling).
+// One thread per pose; rec = out_seg layout.
+__global__ void sigma_pose_kernel(int n_pose, const double* __restrict__ rec, int enabled,
+                                  double* __restrict__ sigma) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pose) return;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double h = rec[(size_t)i * NV + tri6(k, k)];
+    sigma[6 * (size_t)i + k] = enabled ? 1.0 / (1.0 + sqrt(h)) : 1.0;
+  }
+}
+
+// Small device-resident scalar block shared by the LM kernels (16 doubles;
+// the colsum / colmax reductions write straight into its fields).
+struct LmScalars {
+  double cam_H;      // [0] sum K^2   (J^T J of the focal length)
+  double cam_g;      // [1] sum K r
+  double sum_r2;     // [2] sum r^2 at x
+  double unused0;    // [3]
+  double model;      // [4] sum (J d)(r + J d/2)
+  double cand_r2;    // [5] sum r^2 at x + delta
+  double step2_e;    // [6] ||delta||^2, E poses
+  double xnorm2_e;   // [7] ||x||^2, E poses that own blocks
+  double step2_f;    // [8]
+  double xnorm2_f;   // [9]
+  double gmax_e;     // [10] max |g_i|, E poses
+  double gmax_f;     // [11]
+  double chol_fail;  // [12] != 0: a factorisation failed (non-positive pivot)
+  double d_cam;      // [13] step of the focal length
+  double sigma_f;    // [14] Jacobi scale of the focal length
+  double unused1;    // [15]
+};
+
+}  // namespace ars

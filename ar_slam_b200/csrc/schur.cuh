@@ -1,0 +1,335 @@
+// schur.cuh -- kernels (3)/(4): Schur complement of the E poses, dense
+// reduced system assembly, back-substitution and the LM step vectors.
+//
+// Replaces Ceres' SchurEliminator::Eliminate / BackSubstitute and
+// LevenbergMarquardtStrategy's damping (reached from ceres::Solve,
+// reference ar_slam/src/ar_slam_util.cpp:1011-1015).
+//
+// Scaled, damped normal equations (Jacobi scaling sigma, LM diagonal D):
+//   Ht = Sig H Sig + D^2,  gt = Sig g,  solve Ht y = gt,  delta = -Sig y.
+// Reduced system ordering: F pose f -> rows 6f..6f+5, focal length -> row
+// cam_row = 6 n_f, right-hand side -> extra row rhs_row = cam_row + 1 of the
+// same lower-triangular array, so that the Cholesky sweep also performs the
+// forward substitution.
+#pragma once
+#include "kernels.cuh"
+
+namespace ars {
+
+struct SchurArgs {
+  int n_e, plane;
+  const int32_t* e_off;   // [n_e + 1] block offsets (E-sorted order)
+  const int32_t* f_idx;   // [n_blk]   F pose per E-sorted block
+  const double* HE;       // [n_e][NV]
+  const double* W;        // 36 planes
+  const double* sig_e;    // [6 n_e]
+  double radius, min_diag, max_diag;
+  double* Y;              // 36 planes: Ht_ee^-1 (sig_e W)
+  double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
+  double* YB;             // [n_e][6]: Ht_ee^-1 sig_e H_e,f
+  double* seg_cam;        // [n_e][2]: (sig_e H_e,f).yb , (sig_e H_e,f).z
+  double* S;              // dense lower-triangular accumulation target (+=), or null
+  long long ld;
+  int cam_row, rhs_row;
+};
+
+// decode p -> (i <= j) with p = j (j + 1) / 2 + i
+__device__ __forceinline__ void tri_decode(int p, int& i, int& j) {
+  j = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+  while ((j + 1) * (j + 2) / 2 <= p) ++j;
+  while (j * (j + 1) / 2 > p) --j;
+  i = p - j * (j + 1) / 2;
+}
+
+__device__ __forceinline__ void load_scaled_E(const SchurArgs& a, int e, double L[36], double g[6],
+                                              double hk[6], double s[6]) {
+  const double* rec = a.HE + (size_t)e * NV;
+  const double radius = a.radius;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s[i] = a.sig_e[6 * (size_t)e + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      const double h = rec[tri6(i, j)] * s[i] * s[j];
+      L[i * 6 + j] = h;
+      L[j * 6 + i] = h;
+    }
+    const double d = fmin(fmax(L[i * 6 + i], a.min_diag), a.max_diag);
+    L[i * 6 + i] += d / radius;
+    g[i] = rec[21 + i] * s[i];
+    hk[i] = rec[27 + i] * s[i];
+  }
+}
+
+// One warp per E pose.  6x6 Cholesky in registers (every lane holds the same
+// factor), then lanes take the pose's blocks / block pairs.
+__global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= a.n_e) return;
+  const int beg = a.e_off[e], k = a.e_off[e + 1] - beg;
+  double L[36], z[6], yb[6], s[6], hk[6];
+  load_scaled_E(a, e, L, z, hk, s);
+  const bool ok = chol6(L);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) yb[i] = hk[i];
+  chol6_solve(L, z);
+  chol6_solve(L, yb);
+  if (lane == 0) {
+    double* zo = a.Z + 8 * (size_t)e;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      zo[i] = z[i];
+      a.YB[6 * (size_t)e + i] = yb[i];
+      c0 += hk[i] * yb[i];
+      c1 += hk[i] * z[i];
+    }
+    zo[6] = (ok || k == 0) ? 0.0 : 1.0;
+    zo[7] = 0.0;
+    a.seg_cam[2 * (size_t)e] = c0;
+    a.seg_cam[2 * (size_t)e + 1] = c1;
+  }
+  const size_t ps = a.plane;
+  for (int j = lane; j < k; j += 32) {
+    const int blk = beg + j;
+    double Wt[36];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Wt[i * 6 + c] = a.W[(size_t)(i * 6 + c) * ps + blk] * s[i];
+    const int f = a.f_idx[blk];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double col[6];
+      double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        col[i] = Wt[i * 6 + c];
+        b0 += col[i] * yb[i];
+        b1 += col[i] * z[i];
+      }
+      chol6_solve(L, col);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) a.Y[(size_t)(i * 6 + c) * ps + blk] = col[i];
+      if (a.S) {
+        atomicAdd(a.S + (size_t)a.cam_row * a.ld + 6 * f + c, b0);
+        atomicAdd(a.S + (size_t)a.rhs_row * a.ld + 6 * f + c, b1);
+      }
+    }
+  }
+  if (!a.S) return;
+  __syncwarp();
+  const int npairs = k * (k + 1) / 2;
+  for (int p = lane; p < npairs; p += 32) {
+    int i, j;
+    tri_decode(p, i, j);
+    const int bi = beg + i, bj = beg + j;
+    const int fi = a.f_idx[bi], fj = a.f_idx[bj];  // fi <= fj (sorted within the segment)
+    double Wi[36], Yj[36];
+#pragma unroll
+    for (int m = 0; m < 6; ++m)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
+        Yj[m * 6 + c] = a.Y[(size_t)(m * 6 + c) * ps + bj];
+      }
+    double M[36];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) acc += Wi[m * 6 + r] * Yj[m * 6 + c];
+        M[r * 6 + c] = acc;  // block (fi, fj) of sum W~^T Y
+      }
+    if (fi != fj) {
+      // lower-triangular storage: element (6 fj + c, 6 fi + r)
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          atomicAdd(a.S + (size_t)(6 * fj + c) * a.ld + 6 * fi + r, M[r * 6 + c]);
+    } else {
+      const bool twice = (i != j);  // same F pose seen twice by this E pose
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+          const double v = twice ? (M[r * 6 + c] + M[c * 6 + r]) : M[r * 6 + c];
+          atomicAdd(a.S + (size_t)(6 * fi + r) * a.ld + 6 * fi + c, v);
+        }
+    }
+  }
+}
+
+// S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
+__global__ void dense_scale_kernel(double* __restrict__ S, long long ld, int n /* = rhs_row */,
+                                   const double* __restrict__ sigF) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > n || j >= n || j > i) return;
+  const double si = (i == n) ? 1.0 : sigF[i];
+  S[(size_t)i * ld + j] = -si * sigF[j] * S[(size_t)i * ld + j];
+}
+
+// Adds the F-pose diagonal blocks sig H_ff sig + D^2, the camera border and
+// the gradient to the dense system.  One thread per F pose.
+__global__ void dense_add_pose_kernel(int n_f, const double* __restrict__ HF, const double* __restrict__ sigF,
+                                      double radius, double min_diag, double max_diag,
+                                      double* __restrict__ S, long long ld, int cam_row, int rhs_row) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_f) return;
+  const double* rec = HF + (size_t)f * NV;
+  const double sc_cam = sigF[cam_row];
+  double s[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s[i] = sigF[6 * f + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double h = rec[tri6(j, i)] * s[i] * s[j];
+      if (i == j) h += fmin(fmax(h, min_diag), max_diag) / radius;
+      S[(size_t)(6 * f + i) * ld + 6 * f + j] += h;
+    }
+    S[(size_t)cam_row * ld + 6 * f + i] += rec[27 + i] * s[i] * sc_cam;
+    S[(size_t)rhs_row * ld + 6 * f + i] += rec[21 + i] * s[i];
+  }
+}
+
+// Camera row / rhs tail / identity padding.  cam_minus = column sums of seg_cam.
+__global__ void dense_add_camera_kernel(const LmScalars* __restrict__ sc, const double* __restrict__ cam_minus,
+                                        double radius, double min_diag, double max_diag, double* __restrict__ S,
+                                        long long ld, int cam_row, int rhs_row, int n_pad) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double sf = sc->sigma_f;
+    const double h = sc->cam_H * sf * sf;
+    const double d = fmin(fmax(h, min_diag), max_diag) / radius;
+    S[(size_t)cam_row * ld + cam_row] = sf * sf * (sc->cam_H - cam_minus[0]) + d;
+    S[(size_t)rhs_row * ld + cam_row] = sf * (sc->cam_g - cam_minus[1]);
+    S[(size_t)rhs_row * ld + rhs_row] = 1e300;
+  }
+  const int i = rhs_row + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) S[(size_t)i * ld + i] = 1.0;
+}
+
+// uF = sigF * yF (the unscaled, un-negated F step); yF is row rhs_row of the
+// factored array after back substitution.
+__global__ void scale_uF_kernel(int n, const double* __restrict__ y, const double* __restrict__ sigF,
+                                double* __restrict__ uF) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) uF[i] = y[i] * sigF[i];
+}
+
+// Back substitution of the E poses: y_e = z - sum_j Y_j uF[f_j] - yb uF[cam];
+// delta_e = -sig_e y_e.  One warp per E pose, lanes over its blocks.
+struct BacksubArgs {
+  int n_e, plane;
+  const int32_t* e_off;
+  const int32_t* f_idx;
+  const double* Y;
+  const double* Z;
+  const double* YB;
+  const double* sig_e;
+  const double* uF;   // [6 n_f + 1]
+  int cam_row;
+  double* d_e;        // [6 n_e] step of the E poses
+};
+__global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= a.n_e) return;
+  const int beg = a.e_off[e], k = a.e_off[e + 1] - beg;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const size_t ps = a.plane;
+  for (int j = lane; j < k; j += 32) {
+    const int blk = beg + j;
+    const int f = a.f_idx[blk];
+    double u[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) u[c] = a.uF[6 * (size_t)f + c];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[i] += a.Y[(size_t)(i * 6 + c) * ps + blk] * u[c];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane < 6) {
+    const double uc = a.uF[a.cam_row];
+    const double y = a.Z[8 * (size_t)e + lane] - acc[lane] - a.YB[6 * (size_t)e + lane] * uc;
+    a.d_e[6 * (size_t)e + lane] = (k > 0) ? -a.sig_e[6 * (size_t)e + lane] * y : 0.0;
+  }
+}
+
+// delta_F = -uF ; candidate = x + delta on both pose sides and the camera;
+// per-warp partials of ||delta||^2 and ||x||^2 over poses that own blocks.
+struct ApplyArgs {
+  int n_pose;
+  const int32_t* seg_off;   // [n_pose + 1] (sorted by this side)
+  const double* x;          // [6 n_pose]
+  const double* step;       // [6 n_pose]: d_e (already the step) or uF (to be negated)
+  int negate;
+  double* delta;            // [6 n_pose] out (unscaled step)
+  double* x_cand;           // [6 n_pose] out
+  double* warp_out;         // [n_warp][2]: sum delta^2, sum x^2
+  int count_norms;          // 0: this rank does not own the norms of this side (multi-GPU)
+};
+__global__ void apply_step_kernel(const ApplyArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0, x2 = 0.0;
+  if (i < a.n_pose) {
+    const bool active = a.seg_off[i + 1] > a.seg_off[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double x = a.x[6 * (size_t)i + k];
+      double d = a.step[6 * (size_t)i + k];
+      d = active ? (a.negate ? -d : d) : 0.0;
+      const double xc = x + d;
+      a.delta[6 * (size_t)i + k] = d;
+      a.x_cand[6 * (size_t)i + k] = xc;
+      if (active && a.count_norms) {
+        const double dd = x - xc;  // Ceres: (x - candidate_x).norm()
+        d2 += dd * dd;
+        x2 += x * x;
+      }
+    }
+  }
+  d2 = warp_sum(d2);
+  x2 = warp_sum(x2);
+  if ((threadIdx.x & 31) == 0) {
+    double* o = a.warp_out + 2 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    o[0] = d2;
+    o[1] = x2;
+  }
+}
+
+// max |g| over poses that own blocks -> per-warp maxima
+__global__ void gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
+                               double* __restrict__ warp_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (i < n_pose && seg_off[i + 1] > seg_off[i]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(rec[(size_t)i * NV + 21 + k]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) warp_out[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = m;
+}
+__global__ void __launch_bounds__(1024) colmax_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
+  __shared__ double sm[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc = fmax(acc, in[i]);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+}  // namespace ars

@@ -1,0 +1,159 @@
+"""Synthetic maps of the BASELINE shapes.
+
+Tags lie in a planar-ish slab on a jittered grid (0.3 m pitch, the demo's
+spacing), each rotated by up to 30 degrees off the common normal; tag side
+0.0635 m (reference ar_slam_util.hpp:319).  Captures look at the slab from
+1 - 2.5 m with up to 30 degrees of tilt and a random roll; f = 760 px, image
+1020 x 768 (the demo's values).  Every capture observes the `tags_per_capture`
+tags nearest to its look-at point that project inside the image; observations
+are the exact projection + N(0, noise_px) and go through a float32 round trip
+like geometry_msgs/Point32 (ar_slam_interfaces/msg/Detection.msg).
+Everything derives from one Philox stream keyed by `seed`, so every rank can
+regenerate the same map.
+
+The projection below is plain numpy and only generates data; it is not a
+solver path.
+"""
+import numpy as np
+from scipy.spatial import cKDTree
+
+TAG_SIZE = 0.0635
+IMG_W, IMG_H = 1020, 768
+F_TRUE = 760.0
+_DIRS = np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0]])
+
+
+def rodrigues(aa):
+    """Rotation matrices [n,3,3] of angle-axis vectors [n,3]."""
+    aa = np.asarray(aa, dtype=np.float64).reshape(-1, 3)
+    th = np.linalg.norm(aa, axis=1)
+    safe = np.where(th > 1e-12, th, 1.0)
+    k = aa / safe[:, None]
+    K = np.zeros((len(aa), 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -k[:, 2], k[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = k[:, 2], -k[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -k[:, 1], k[:, 0]
+    s, c = np.sin(th)[:, None, None], np.cos(th)[:, None, None]
+    R = np.eye(3)[None] + s * K + (1 - c) * (K @ K)
+    R[th <= 1e-12] = np.eye(3)
+    return R
+
+
+def matrix_to_aa(R):
+    """Angle-axis vectors [n,3] of rotation matrices [n,3,3] (angles < pi)."""
+    R = np.asarray(R).reshape(-1, 3, 3)
+    c = np.clip((np.trace(R, axis1=1, axis2=2) - 1) / 2, -1, 1)
+    th = np.arccos(c)
+    v = np.stack([R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]], axis=1)
+    s = 2 * np.sin(th)
+    out = np.where(s[:, None] > 1e-12, v / np.where(s > 1e-12, s, 1.0)[:, None] * th[:, None], v / 2)
+    return out
+
+
+def project(cam, cap_pose, tag_pose, tag_size=TAG_SIZE):
+    """Corner pixels [n,4,2] and depths [n,4] of n (capture, tag) pairs."""
+    Ra, Rc = rodrigues(tag_pose[:, 3:]), rodrigues(cap_pose[:, 3:])
+    m = np.zeros((4, 3))
+    m[:, :2] = 0.5 * tag_size * _DIRS
+    pw = np.einsum("nij,kj->nki", Ra, m) + tag_pose[:, None, :3]
+    q = pw + cap_pose[:, None, :3]
+    p = np.einsum("nij,nkj->nki", Rc, q)
+    uv = cam[0] * p[..., :2] / p[..., 2:3]
+    return uv, p[..., 2]
+
+
+class SynthMap:
+    pass
+
+
+def make_map(n_cap, n_tag, tags_per_capture=8, seed=0xA55A0002, noise_px=0.3, pitch=0.3,
+             init_noise_t=0.02, init_noise_r_deg=2.0, f_init=800.0):
+    """Returns a SynthMap with ground truth, observations and a perturbed initial state."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed)))
+    # ---- tags on a jittered grid
+    side = int(np.ceil(np.sqrt(n_tag)))
+    gi, gj = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    grid = np.stack([gi.ravel(), gj.ravel()], axis=1)[:n_tag].astype(np.float64)
+    tag_t = np.zeros((n_tag, 3))
+    tag_t[:, :2] = grid * pitch + rng.uniform(-0.3 * pitch, 0.3 * pitch, (n_tag, 2))
+    tag_t[:, 2] = rng.uniform(-0.1, 0.1, n_tag)
+    axis = rng.normal(size=(n_tag, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    tag_w = axis * rng.uniform(0, np.deg2rad(30.0), (n_tag, 1))
+    tag_pose = np.concatenate([tag_t, tag_w], axis=1)
+    extent = side * pitch
+    tree = cKDTree(tag_t[:, :2])
+    cam_true = np.array([F_TRUE, 0.0, 0.0])
+
+    cap_pose = np.zeros((n_cap, 6))
+    blk_cap, blk_tag, blk_obs = [], [], []
+    todo = np.arange(n_cap)
+    kq = min(n_tag, max(3 * tags_per_capture, 24))
+    for _ in range(50):
+        if len(todo) == 0:
+            break
+        n = len(todo)
+        look = np.zeros((n, 3))
+        look[:, :2] = rng.uniform(0.1 * extent, 0.9 * extent, (n, 2)) if extent > 2.0 else \
+            rng.uniform(0, extent, (n, 2))
+        h = rng.uniform(1.0, 2.5, n)
+        tilt_axis = rng.normal(size=(n, 3))
+        tilt_axis[:, 2] = 0
+        tilt_axis /= np.linalg.norm(tilt_axis, axis=1, keepdims=True)
+        tilt = rodrigues(tilt_axis * rng.uniform(0, np.deg2rad(30.0), (n, 1)))
+        roll = rodrigues(np.stack([np.zeros(n), np.zeros(n), rng.uniform(-np.pi, np.pi, n)], axis=1))
+        Rc = roll @ tilt  # world -> camera
+        # camera centre: back off from the look-at point along the optical axis
+        zc = Rc[:, 2, :]  # optical axis in world coordinates
+        centre = look - zc * h[:, None]
+        pose = np.concatenate([-centre, matrix_to_aa(Rc)], axis=1)
+        _, nn = tree.query(look[:, :2], k=kq)
+        nn = nn.reshape(n, kq)
+        uv, z = project(cam_true, np.repeat(pose, kq, axis=0), tag_pose[nn.ravel()])
+        uv, z = uv.reshape(n, kq, 4, 2), z.reshape(n, kq, 4)
+        inside = (np.abs(uv[..., 0]) < 0.5 * IMG_W - 4).all(-1) & (np.abs(uv[..., 1]) < 0.5 * IMG_H - 4).all(-1) \
+            & (z > 0.2).all(-1)
+        rank = np.cumsum(inside, axis=1)
+        take = inside & (rank <= tags_per_capture)
+        ok = take.sum(1) >= tags_per_capture
+        for ci in np.nonzero(ok)[0]:
+            c = todo[ci]
+            cap_pose[c] = pose[ci]
+            sel = np.nonzero(take[ci])[0]
+            blk_cap.append(np.full(len(sel), c))
+            blk_tag.append(nn[ci, sel])
+            blk_obs.append(uv[ci, sel].reshape(len(sel), 8))
+        todo = todo[~ok]
+    if len(todo):
+        raise RuntimeError("could not place %d captures" % len(todo))
+    blk_cap = np.concatenate(blk_cap).astype(np.int32)
+    order = np.argsort(blk_cap, kind="stable")
+    blk_cap = blk_cap[order]
+    blk_tag = np.concatenate(blk_tag).astype(np.int32)[order]
+    obs = np.concatenate(blk_obs)[order]
+    obs = obs + rng.normal(0, noise_px, obs.shape)
+    obs = obs.astype(np.float32).astype(np.float64)  # Point32 round trip
+
+    m = SynthMap()
+    m.n_cap, m.n_tag = n_cap, n_tag
+    m.cap_idx, m.tag_idx, m.obs = blk_cap, blk_tag, np.ascontiguousarray(obs)
+    m.cam_true, m.cap_true, m.tag_true = cam_true, cap_pose, tag_pose
+    # ---- initial state: ground truth perturbed by init_noise_t metres / init_noise_r_deg degrees
+    m.cam0 = np.array([f_init, 0.0, 0.0])
+    m.cap0 = cap_pose + np.concatenate([rng.normal(0, init_noise_t, (n_cap, 3)),
+                                        rng.normal(0, np.deg2rad(init_noise_r_deg), (n_cap, 3))], axis=1)
+    m.tag0 = tag_pose + np.concatenate([rng.normal(0, init_noise_t, (n_tag, 3)),
+                                        rng.normal(0, np.deg2rad(init_noise_r_deg), (n_tag, 3))], axis=1)
+    used = np.zeros(n_tag, bool)
+    used[blk_tag] = True
+    m.tags_used = int(used.sum())
+    return m
+
+
+def make_localization_batch(n_loc, n_tag, tags_per_capture=8, seed=0xA55A0004, noise_px=0.3):
+    """Config 4: captures to localise against the fixed ground-truth map."""
+    m = make_map(n_loc, n_tag, tags_per_capture, seed=seed, noise_px=noise_px)
+    counts = np.bincount(m.cap_idx, minlength=n_loc)
+    m.blk_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    m.seed_block = np.zeros(n_loc, dtype=np.int32)  # first block: every tag is in the map
+    return m

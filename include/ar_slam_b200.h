@@ -1,0 +1,189 @@
+/* ar_slam_b200.h -- C-ABI of the B200-native solver for ar_slam's optimisation
+ * hot path.
+ *
+ * The reference has no FFI: its seam is the C++ class ArSlamSolver
+ * (ar_slam/include/ar_slam/ar_slam_util.hpp:367-497).  This header is what a
+ * maintainer binds in place of the `ceres::Problem problem_` member
+ * (ar_slam_util.hpp:473) and of the Ceres calls in ar_slam_util.cpp; each entry
+ * point names the reference code it replaces.  Plain pointers and sizes only,
+ * no C++ or torch types, no exceptions across the boundary: every call returns
+ * ARSLAM_OK (0) or a negative error code and leaves a message in
+ * arslam_last_error().
+ *
+ * Threading (ar_slam/src/ar_slam.cpp:87,93-98): one caller at a time per
+ * handle, from any thread; every entry binds the handle's CUDA device first.
+ * Handles share no mutable state.
+ *
+ * Conventions:
+ *   camera   [f, l1, l2]                        (ar_slam_util.hpp:64-76)
+ *   capture  [tx,ty,tz, wx,wy,wz]  inverse pose, p_cam = R(w)(p_world + t)
+ *   tag      [tx,ty,tz, wx,wy,wz]  forward pose, p_world = R(w) c + t
+ *   rect     x0,y0,x1,y1,x2,y2,x3,y3 centred pixels, TL,TR,BR,BL
+ *                                                (ar_slam_util.hpp:266-293,335-345)
+ */
+#ifndef AR_SLAM_B200_H_
+#define AR_SLAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARSLAM_ABI_VERSION 1
+
+enum {
+  ARSLAM_OK = 0,
+  ARSLAM_ERR_INVALID = -1,    /* bad argument / bad index / call order     */
+  ARSLAM_ERR_CUDA = -2,       /* CUDA runtime error (message has details)  */
+  ARSLAM_ERR_NO_DEVICE = -3,  /* no usable sm_100 device: there is NO CPU fallback */
+  ARSLAM_ERR_NCCL = -4,
+  ARSLAM_ERR_UNSUPPORTED = -5
+};
+
+/* Mirrors ceres::TerminationType as far as the reference can observe it. */
+enum { ARSLAM_CONVERGENCE = 0, ARSLAM_NO_CONVERGENCE = 1, ARSLAM_FAILURE = 2 };
+enum {
+  ARSLAM_REASON_GRADIENT = 1, ARSLAM_REASON_PARAMETER = 2, ARSLAM_REASON_FUNCTION = 3,
+  ARSLAM_REASON_MIN_RADIUS = 4, ARSLAM_REASON_MAX_ITERATIONS = 5, ARSLAM_REASON_INVALID_STEPS = 6
+};
+
+enum { ARSLAM_ELIM_AUTO = 0, ARSLAM_ELIM_TAGS = 1, ARSLAM_ELIM_CAPTURES = 2 };
+enum { ARSLAM_LINSOLVE_AUTO = 0, ARSLAM_LINSOLVE_DENSE = 1, ARSLAM_LINSOLVE_PCG = 2 };
+
+/* Solver options.  Defaults (arslam_default_options) are exactly what
+ * ArSlamSolver::optimize sets (ar_slam_util.cpp:1003-1012: 50 iterations,
+ * DENSE_SCHUR) plus the Ceres 2.0.0 Solver::Options defaults it leaves alone. */
+typedef struct arslam_options {
+  int32_t max_num_iterations;                /* 50  (ar_slam_util.cpp:1004) */
+  int32_t max_num_consecutive_invalid_steps; /* 5   */
+  int32_t jacobi_scaling;                    /* 1   */
+  int32_t elimination;                       /* ARSLAM_ELIM_*; AUTO eliminates the larger pose set */
+  int32_t linear_solver;                     /* ARSLAM_LINSOLVE_*; AUTO: dense Cholesky when the
+                                                reduced system is small/dense, PCG otherwise   */
+  int32_t pcg_max_iterations;                /* 500 */
+  int32_t num_intrinsics;                    /* 1: focal only (the reference's live model,
+                                                ar_slam_util.cpp:160-162); 3 reserved for the
+                                                radial TODO model (:164-171)                  */
+  int32_t verbose;                           /* 0; 1 prints the per-iteration table like
+                                                minimizer_progress_to_stdout (:1012)          */
+  double initial_trust_region_radius;        /* 1e4   */
+  double max_trust_region_radius;            /* 1e16  */
+  double min_trust_region_radius;            /* 1e-32 */
+  double min_relative_decrease;              /* 1e-3  */
+  double min_lm_diagonal;                    /* 1e-6  */
+  double max_lm_diagonal;                    /* 1e32  */
+  double function_tolerance;                 /* 1e-6  */
+  double gradient_tolerance;                 /* 1e-10 */
+  double parameter_tolerance;                /* 1e-8  */
+  double pcg_tolerance;                      /* 1e-8: relative residual ||S y - b|| / ||b||    */
+  double tag_size;                           /* 0.0635 m (ar_slam_util.hpp:319)                */
+  int64_t dense_max_dim;                     /* AUTO picks dense Cholesky up to this reduced
+                                                dimension (default 16384)                      */
+} arslam_options;
+
+/* What ceres::Solver::Summary would have told the reference had it looked
+ * (ar_slam_util.cpp:1013-1017 discards it). */
+typedef struct arslam_summary {
+  int32_t iterations;             /* LM iterations run (successful + unsuccessful + invalid) */
+  int32_t num_successful_steps;   /* includes iteration 0, like Ceres */
+  int32_t num_unsuccessful_steps;
+  int32_t termination;            /* ARSLAM_CONVERGENCE / NO_CONVERGENCE / FAILURE */
+  int32_t reason;                 /* ARSLAM_REASON_* */
+  int32_t eliminated_side;        /* ARSLAM_ELIM_TAGS or ARSLAM_ELIM_CAPTURES actually used */
+  int32_t linear_solver;          /* ARSLAM_LINSOLVE_DENSE or _PCG actually used */
+  int32_t reduced_dim;            /* dimension of the reduced (Schur) system */
+  int64_t num_jacobian_evals;     /* residual+Jacobian+accumulation evaluations */
+  int64_t num_cost_evals;         /* candidate (residual-only) evaluations */
+  int64_t linear_solver_iterations; /* total PCG iterations (0 for dense) */
+  int64_t gpu_launches;           /* kernels launched by this solve */
+  double initial_cost, final_cost;
+  double final_radius;
+  double gradient_max_norm;
+  double total_ms;                /* host wall time of the call */
+  double eval_ms, linsolve_ms;    /* device time (CUDA events) of the two phases */
+} arslam_summary;
+
+typedef struct arslam_solver arslam_solver; /* opaque; owns all device memory */
+
+void arslam_default_options(arslam_options* opt);
+int arslam_abi_version(void);
+
+/* Lifetime == lifetime of the ArSlamSolver that owns `problem_`
+ * (ar_slam_util.hpp:473).  `device` is a CUDA ordinal.  Fails with
+ * ARSLAM_ERR_NO_DEVICE when there is no GPU: no CPU path exists. */
+int arslam_create(int device, const arslam_options* opt, arslam_solver** out);
+void arslam_destroy(arslam_solver* s);
+const char* arslam_last_error(const arslam_solver* s); /* s may be NULL: creation errors */
+int arslam_set_options(arslam_solver* s, const arslam_options* opt);
+
+/* Replaces resetProblem (ar_slam_util.cpp:1021-1025) + the AddResidualBlock
+ * loops (:720-727, :829-836): defines the whole set of residual blocks.
+ * Block b couples camera, capture cap_idx[b] and tag tag_idx[b]; rect8 holds
+ * 8 doubles per block (ArucoRect order).  Copies everything to HBM in
+ * structure-of-arrays form, sorted once per pose side.  Under
+ * arslam_comm_init every rank passes only ITS blocks (all blocks of a capture
+ * on one rank) with GLOBAL n_cap / n_tag and global indices. */
+int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk,
+                       const int32_t* cap_idx, const int32_t* tag_idx, const double* rect8);
+
+/* Parameter blocks live in the caller's Capture::inv_pose / Aruco::pose /
+ * camera_.params (ar_slam_util.hpp:72,208,237); Ceres updated them in place
+ * through raw pointers, here they are copied in before and out after. */
+int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6,
+                      const double* tag_pose6);
+int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, double* tag_pose6);
+
+/* What ceres::Problem::Evaluate would return for the current parameters:
+ * cost = 1/2 sum r^2, residuals [8 n_blk] (x0,y0,..,y3 per block,
+ * ar_slam_util.cpp:207-208) and the AutoDiffCostFunction<..,8,3,6,6>
+ * Jacobians (:722), row-major per parameter block: jac_cam [n_blk][8][3],
+ * jac_cap [n_blk][8][6], jac_tag [n_blk][8][6].  Any output may be NULL.
+ * Host pointers. */
+int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* jac_cam,
+                    double* jac_cap, double* jac_tag);
+
+/* Replaces ArSlamSolver::optimize == ceres::Solve (ar_slam_util.cpp:1001-1018)
+ * on the blocks of arslam_set_problem, starting from arslam_set_params.
+ * iter_log (optional, host): log_rows x 8 doubles per iteration: cost,
+ * cost_change, gradient_max_norm, step_norm, relative_decrease, radius,
+ * step_is_valid, step_is_successful. */
+int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, int32_t log_rows);
+
+/* Replaces localizeMany / localizeOne (ar_slam_util.cpp:888-979) for a batch
+ * of independent captures against the fixed map given by camera3 / tag_pose6
+ * (n_tag tags).  Capture i owns blocks blk_offsets[i] .. blk_offsets[i+1];
+ * seed_block[i] is the index (within the capture) of the block whose tag is
+ * shared with the map (:911-927) and seeds the pose through initCapturePose
+ * (:91-108); seed_block[i] < 0 leaves capture i untouched (:929-933).
+ * cap_pose6 [6 n_loc] out; iterations / final_cost / termination are optional
+ * per-capture outputs (host pointers). */
+int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_offsets,
+                          const int32_t* tag_idx, const double* rect8, const int32_t* seed_block,
+                          int64_t n_tag, const double* camera3, const double* tag_pose6,
+                          double* cap_pose6, int32_t* iterations, double* final_cost,
+                          int32_t* termination);
+
+/* Multi-GPU (new; the reference is single-threaded): one process per GPU.
+ * Rank 0 calls arslam_comm_unique_id, ships the 128 bytes to the other ranks
+ * by any means (torch.distributed, MPI, a file), then every rank calls
+ * arslam_comm_init.  Afterwards arslam_solve sums the per-rank partial normal
+ * equations with one ncclAllReduce per linearisation over NVLink. */
+int arslam_comm_unique_id(void* id128);
+int arslam_comm_init(arslam_solver* s, int rank, int world_size, const void* id128);
+
+/* Device-side timing of the last arslam_solve / arslam_localize_batch /
+ * arslam_evaluate, for bench.py: fills up to `cap` (name,ms,launches) rows. */
+typedef struct arslam_kernel_time {
+  char name[48];
+  double total_ms;
+  int64_t launches;
+  double algorithmic_bytes; /* per launch, by the formulas in DESIGN.md */
+} arslam_kernel_time;
+int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch with CUDA events */
+int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap); /* returns rows */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AR_SLAM_B200_H_ */

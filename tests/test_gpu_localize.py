@@ -1,0 +1,57 @@
+"""Parity of kernel (5), batched localisation, with the oracle's restated
+localizeOne (ar_slam_util.cpp:903-979), through the C-ABI."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_demo_img4(gpu_solver_cls, oracle):
+    """BASELINE config 1b: ar_loc of img4 against the map built from img1-3."""
+    from oracle import schedule
+    m = schedule.MapData()
+    m.load_yaml(os.path.join(GOLD, "demo_map_detections.yaml"))
+    sch = schedule.Scheduler(m)
+    sch.solve()
+    cam = m.cam.copy()
+    m.load_yaml(os.path.join(GOLD, "demo_loc_detections.yaml"))
+    m.cam[:] = cam   # loadYaml of the detections overwrote the camera (ar_slam_util.cpp:357-367)
+    blocks = m.cap_blocks[3]
+    tag_idx = [m.blk_tag[b] for b in blocks]
+    obs = np.array([m.blk_rect[b] for b in blocks])
+    s = gpu_solver_cls()
+    pose, its, cost, term = s.localize_batch([0, len(blocks)], tag_idx, obs, [0], m.cam, np.array(m.tag_pose))
+    s.close()
+    sch.localize_many(3)
+    so = m.solve_log[-1]
+    assert its[0] == so["iterations"] and term[0] == 0
+    assert abs(cost[0] - so["final_cost"]) <= 1e-9 * so["final_cost"]
+    assert abs(cost[0] - 31.6121425) < 1e-5
+    assert np.abs(pose[0] - m.cap_pose[3]).max() < 1e-9
+
+
+def test_batch_matches_oracle(gpu_solver_cls, oracle):
+    from ar_slam_b200 import synth
+    m = synth.make_localization_batch(20000, 500, seed=5)
+    # ragged input: drop a few blocks, mark some captures as not localisable
+    seed = m.seed_block.copy()
+    seed[::97] = -1
+    seed[5::13] = 3
+    s = gpu_solver_cls()
+    pose, its, cost, term = s.localize_batch(m.blk_offsets, m.tag_idx, m.obs, seed, m.cam_true, m.tag_true)
+    s.close()
+    po, io, co, to = oracle.localize_batch(m.blk_offsets, m.tag_idx, m.obs, seed, m.cam_true, m.tag_true,
+                                           num_threads=4)
+    assert np.array_equal(its < 0, io < 0) and np.all(its[::97] == -1)
+    ok = io >= 0
+    same = its[ok] == io[ok]
+    assert same.mean() > 0.999            # identical LM trajectory length
+    assert np.array_equal(term[ok], to[ok])
+    assert np.allclose(cost[ok][same], co[ok][same], rtol=1e-9)
+    assert np.abs(pose[ok][same] - po[ok][same]).max() < 1e-8
+    # and the answer is right: close to the ground-truth pose
+    err = np.abs(pose[ok] - m.cap_true[ok])
+    assert np.median(err[:, :3]) < 5e-3 and np.median(err[:, 3:]) < 5e-3
