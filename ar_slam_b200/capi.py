@@ -137,6 +137,10 @@ class Solver:
         self.options = options
         self._check(self._lib.arslam_set_options(self._h, C.byref(options)))
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer handle (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self._check(self._lib.arslam_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
     def set_profiling(self, on):
         self._check(self._lib.arslam_set_profiling(self._h, C.c_int(1 if on else 0)))
 

@@ -118,7 +118,7 @@ struct Profiler {
 
 struct arslam_solver {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
   arslam_options opt;
   std::string err;
   // problem
@@ -235,13 +235,14 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
   arslam_solver* s = new arslam_solver();
   s->device = device;
   if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&s->h_sc, 64 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
       pcg_init() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
     return ARSLAM_ERR_CUDA;
   }
+  s->stream = s->own_stream;
   for (auto& ev : s->ev) cudaEventCreate(&ev);
   *out = s;
   return ARSLAM_OK;
@@ -254,7 +255,7 @@ void arslam_destroy(arslam_solver* s) {
   if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->h_sc) cudaFreeHost(s->h_sc);
-  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
 }
 
@@ -263,6 +264,14 @@ int arslam_set_options(arslam_solver* s, const arslam_options* opt) {
   if (opt->num_intrinsics != 1)
     return s->fail(ARSLAM_ERR_UNSUPPORTED, "num_intrinsics=%d: only the reference's focal-only model is built", opt->num_intrinsics);
   s->opt = *opt;
+  return ARSLAM_OK;
+}
+
+int arslam_set_stream(arslam_solver* s, void* cuda_stream) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
   return ARSLAM_OK;
 }
 

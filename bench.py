@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ar_slam solver.
+
+A "step" is one Levenberg-Marquardt iteration (Jacobian evaluation +
+accumulation + Schur/linear solve + candidate cost + accept/reject) of the
+bundle adjustment on a synthetic map.  Default
+workload: BASELINE config 3, 100k captures x 5k tags, ~8 tags per capture
+(3.2 M observation corners), the shape the metric is quoted on.
+
+  python bench.py --gpus N --steps K --warmup W      (torchrun for N > 1)
+  python bench.py --impl reference ...               CPU restatement of the reference's Ceres path
+
+value  = observation corners processed per second by the whole job
+         (corners x LM iterations / device time, CUDA events on the solver's
+         stream, max over ranks), problem resident in HBM.
+e2e    = the same through the C-ABI with host buffers: set_problem +
+         set_params + solve + get_params inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (captures, tags, tags per capture, BASELINE config)
+    "ba_100k_5k": (100000, 5000, 8, 3),
+    "ba_1k_200": (1000, 200, 8, 2),
+    "ba_20k_2k": (20000, 2000, 8, 5),
+}
+ITERS_PER_SOLVE = 5  # LM iterations per solve call; the solve restarts from the same initial state
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def bench_options(ar, iters, args):
+    o = ar.default_options()
+    o.max_num_iterations = iters
+    # run exactly `iters` LM iterations: switch the convergence tests off
+    o.function_tolerance = 0.0
+    o.parameter_tolerance = 0.0
+    o.gradient_tolerance = 0.0
+    if args.linear_solver == "dense":
+        o.linear_solver = ar.LINSOLVE_DENSE
+        o.dense_max_dim = 1 << 20
+    elif args.linear_solver == "pcg":
+        o.linear_solver = ar.LINSOLVE_PCG
+    o.pcg_tolerance = args.pcg_tolerance
+    return o
+
+
+def shard(m, rank, world):
+    """Contiguous capture ranges balanced by block count (all blocks of a capture on one rank)."""
+    if world == 1:
+        return m.cap_idx, m.tag_idx, m.obs
+    nb = len(m.cap_idx)
+    counts = np.bincount(m.cap_idx, minlength=m.n_cap)
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    cuts = [int(np.searchsorted(cum, nb * r / world)) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, m.n_cap
+    lo, hi = cum[cuts[rank]], cum[cuts[rank + 1]]
+    return m.cap_idx[lo:hi], m.tag_idx[lo:hi], m.obs[lo:hi]
+
+
+def run_solves(s, m, total_iters):
+    """Runs solves of ITERS_PER_SOLVE iterations from the same start until total_iters are done."""
+    done, summaries = 0, []
+    while done < total_iters:
+        n = min(ITERS_PER_SOLVE, total_iters - done)
+        if s.options.max_num_iterations != n:
+            s.options.max_num_iterations = n
+            s.set_options(s.options)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        summ, _ = s.solve(log=False)
+        if summ["iterations"] != n:
+            raise RuntimeError("solve stopped after %d of %d iterations (%s)" % (summ["iterations"], n, summ["reason_name"]))
+        summaries.append(summ)
+        done += n
+    return summaries
+
+
+def cpu_baseline(args, steps, warmup, threads=None):
+    """Times the oracle (restated reference, not Ceres) on a bounded sample of the workload."""
+    from ar_slam_b200 import synth
+    from oracle import pyoracle as po
+    n_cap, n_tag, tpc, _ = WORKLOADS[args.workload]
+    scale = max(1, n_cap // args.cpu_sample_captures)
+    sc, st = max(50, n_cap // scale), max(10, n_tag // scale)
+    m = synth.make_map(sc, st, tpc, seed=0xA55A0000 + 100)
+    threads = threads or po.max_threads()
+    o = po.default_options(num_threads=threads, max_num_iterations=1, function_tolerance=0.0,
+                           parameter_tolerance=0.0, gradient_tolerance=0.0)
+    nc = 4 * len(m.cap_idx)
+
+    def run(iters):
+        o.max_num_iterations = iters
+        t = time.perf_counter()
+        _, _, _, summ, _ = po.solve(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs, m.cam0, m.cap0, m.tag0, options=o)
+        return time.perf_counter() - t, summ
+    if warmup:
+        run(min(warmup, 2))
+    dt, summ = run(steps)
+    its = max(1, summ["iterations"])
+    return {"value": nc * its / dt, "unit": "corners/s", "cores": threads, "kind": "port",
+            "lm_iters_per_sec": its / dt, "reduced_dim": summ["reduced_dim"],
+            "sample": "%d captures x %d tags (%d corners), same generator and density as %s, %d LM iterations, "
+                      "restated reference (not Ceres): Jet autodiff + dense Schur, OpenMP x%d"
+                      % (sc, st, nc, args.workload, its, threads)}, dt, its
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ba_100k_5k", choices=sorted(WORKLOADS))
+    ap.add_argument("--linear-solver", default="auto", choices=["auto", "dense", "pcg"])
+    ap.add_argument("--pcg-tolerance", type=float, default=1e-8)
+    ap.add_argument("--cpu-sample-captures", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_cap, n_tag, tpc, cfg_id = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, dt, its = cpu_baseline(args, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "observation_corners_per_sec", "value": cb["value"], "unit": "corners/s",
+                "n_gpus": args.gpus, "steps": its, "warmup": args.warmup, "ms_per_step": 1e3 * dt / its,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "lm_iters_per_sec": cb["lm_iters_per_sec"],
+                "config": {"workload": args.workload, "captures": n_cap, "tags": n_tag, "tags_per_capture": tpc,
+                           "note": "CPU arm runs the bounded sample described in cpu_baseline.sample"},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "corners/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import ar_slam_b200 as ar
+    from ar_slam_b200 import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.scaling == "weak":
+        n_cap *= world
+    m = synth.make_map(n_cap, n_tag, tpc, seed=0xA55A0000 + cfg_id)
+    cap_idx, tag_idx, obs = shard(m, rank, world)
+    n_corner_total = 4 * len(m.cap_idx)
+
+    opts = bench_options(ar, ITERS_PER_SOLVE, args)
+    s = ar.Solver(device=local_rank, options=opts)
+    stream = torch.cuda.Stream()
+    s.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(ar.Solver.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        s.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    s.set_problem(m.n_cap, m.n_tag, cap_idx, tag_idx, obs)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    if args.warmup > 0:
+        run_solves(s, m, args.warmup)
+    # ---- timed region: exactly --steps LM iterations, CUDA events on the solver's stream
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        summaries = run_solves(s, m, args.steps)
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    launches = int(sum(x["gpu_launches"] for x in summaries))
+    pcg_its = int(sum(x["linear_solver_iterations"] for x in summaries))
+    final_cost = summaries[-1]["final_cost"]
+
+    # ---- end to end through the C-ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        s.set_problem(m.n_cap, m.n_tag, cap_idx, tag_idx, obs)
+        e2e_sum = run_solves(s, m, args.steps)
+        cam, cap, tag = s.get_params()
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        n_solves = len(e2e_sum)
+        param_bytes = 8 * (3 + 6 * m.n_cap + 6 * m.n_tag)
+        h2d = (obs.nbytes + cap_idx.nbytes + tag_idx.nbytes) * 3 + n_solves * param_bytes
+        d2h = n_solves * param_bytes + 128 * args.steps
+        e2e = {"value": n_corner_total * args.steps / dt, "unit": "corners/s",
+               "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+               "lm_iters_per_sec": args.steps / dt,
+               "what": "arslam_set_problem + %d x (set_params, solve of %d LM iterations, get_params) from host "
+                       "arrays, wall clock" % (n_solves, ITERS_PER_SOLVE)}
+
+    # ---- per-kernel device times (separate profiled solve; events around every launch)
+    roofline = None
+    kernels = None
+    if rank == 0:
+        s.set_profiling(True)
+    if True:
+        run_solves(s, m, ITERS_PER_SOLVE)
+    if rank == 0:
+        kt = s.kernel_times()
+        s.set_profiling(False)
+        kernels = {k["name"]: {"ms_per_launch": k["total_ms"] / max(1, k["launches"]), "launches": k["launches"],
+                               "algorithmic_bytes": k["algorithmic_bytes"]} for k in kt}
+        peak, how = read_peaks()
+        cand = [k for k in kt if k["name"] in ("accum_E", "accum_F") and k["launches"] > 0]
+        if cand:
+            top = max(cand, key=lambda k: k["total_ms"])
+            sec = top["total_ms"] / top["launches"] * 1e-3
+            ach = top["algorithmic_bytes"] / sec / 1e9
+            roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": how,
+                        "us_per_launch": sec * 1e6}
+
+    if rank == 0:
+        cb = None
+        if not args.no_cpu_baseline and world == 1:
+            cb, _, _ = cpu_baseline(args, 2, 1)
+        value = n_corner_total * args.steps / (ms * 1e-3)
+        line = {"metric": "observation_corners_per_sec", "value": value, "unit": "corners/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "lm_iters_per_sec": args.steps / (ms * 1e-3),
+                "config": {"workload": args.workload, "captures": m.n_cap, "tags": m.n_tag, "tags_per_capture": tpc,
+                           "blocks": int(len(m.cap_idx)), "corners": int(n_corner_total),
+                           "linear_solver": {1: "dense_cholesky_dmma", 2: "pcg"}[summaries[0]["linear_solver"]],
+                           "eliminated": {1: "tags", 2: "captures"}[summaries[0]["eliminated_side"]],
+                           "reduced_dim": summaries[0]["reduced_dim"], "iters_per_solve": ITERS_PER_SOLVE,
+                           "l2_policy": "inputs larger than L2 (W + observations > 126 MB) for ba_100k_5k; "
+                                        "no explicit flush", "final_cost": final_cost,
+                           "pcg_iterations": pcg_its},
+                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
+                "kernels": kernels}
+        print(json.dumps(line))
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

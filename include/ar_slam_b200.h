@@ -116,6 +116,10 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out);
 void arslam_destroy(arslam_solver* s);
 const char* arslam_last_error(const arslam_solver* s); /* s may be NULL: creation errors */
 int arslam_set_options(arslam_solver* s, const arslam_options* opt);
+/* Run all work of this handle on the caller's CUDA stream (a cudaStream_t cast
+ * to void*; NULL restores the handle's own stream), e.g. to bracket calls with
+ * the caller's CUDA events. */
+int arslam_set_stream(arslam_solver* s, void* cuda_stream);
 
 /* Replaces resetProblem (ar_slam_util.cpp:1021-1025) + the AddResidualBlock
  * loops (:720-727, :829-836): defines the whole set of residual blocks.

@@ -46,7 +46,10 @@ def test_demo_map_build_matches_oracle(gpu_solver_cls, oracle, elim):
     for so, sg in zip(mo.solve_log, mg.solve_log):
         assert sg["termination"] == so["termination"] == 0
         assert abs(sg["iterations"] - so["iterations"]) <= 1
-        assert abs(sg["initial_cost"] - so["initial_cost"]) <= 1e-9 * so["initial_cost"]
+        # the first solve starts from identical numbers; later ones start from the previous
+        # solve's end point, which was cut off at function_tolerance 1e-6 on a gauge-free problem
+        tol = 1e-9 if so is mo.solve_log[0] else 1e-6
+        assert abs(sg["initial_cost"] - so["initial_cost"]) <= tol * so["initial_cost"]
         assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]
     assert abs(mg.cam[0] - mo.cam[0]) <= 1e-4 * mo.cam[0]
     assert abs(mg.cam[0] - 758.66) < 0.05 and mg.cam[1] == 0.0 and mg.cam[2] == 0.0
