@@ -131,7 +131,9 @@ struct arslam_solver {
   // sorted copies: side 0 capture-sorted, side 1 tag-sorted
   DevBuf<int32_t> s_own[2], s_oth[2], s_off[2];
   DevBuf<double> s_obs[2];
-  std::vector<int32_t> h_off[2];
+  std::vector<int32_t> h_off[2], h_oth[2];
+  long long problem_version = 0, pcg_version = -1;
+  int pcg_side = -1, n_sm = 0;
   // parameters: two sets (current / candidate)
   DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2];
   int cur = 0;
@@ -228,12 +230,14 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
   if (device < 0 || device >= count) { g_create_error = "device ordinal out of range"; return ARSLAM_ERR_INVALID; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
+  const int n_sm = prop.multiProcessorCount;
   if (prop.major < 10) {
     g_create_error = "device is not sm_100 class; kernels are built for sm_100a only";
     return ARSLAM_ERR_NO_DEVICE;
   }
   arslam_solver* s = new arslam_solver();
   s->device = device;
+  s->n_sm = n_sm;
   if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&s->h_sc, 64 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
@@ -345,6 +349,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
     }
     CU(s->s_own[side].ensure(plane)); CU(s->s_oth[side].ensure(plane)); CU(s->s_off[side].ensure(n_own + 1));
     CU(s->s_obs[side].ensure((size_t)8 * plane));
+    s->h_oth[side].assign(oth.begin(), oth.begin() + nb);
     CU(cudaMemcpyAsync(s->s_own[side].p, own.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->s_oth[side].p, oth.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->s_off[side].p, s->h_off[side].data(), sizeof(int32_t) * (n_own + 1), cudaMemcpyHostToDevice, s->stream));
@@ -364,6 +369,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp));
   CU(s->d_cam.ensure(4)); CU(s->sc.ensure(16)); CU(s->cam_minus.ensure(4));
   s->have_problem = true;
+  ++s->problem_version;
   return ARSLAM_OK;
 }
 
@@ -493,14 +499,65 @@ int gather_captures(arslam_solver* s, int k) {
   return ARSLAM_OK;
 }
 
-// ---- PCG hooks (filled in by pcg.cuh's kernels) -------------------------------
-int pcg_prepare(PcgWorkspace&, int, int, int, const int32_t*, const int32_t*, cudaStream_t, std::string& err) {
-  err = "PCG linear solver not built yet; raise dense_max_dim or use ARSLAM_LINSOLVE_DENSE";
-  return ARSLAM_ERR_UNSUPPORTED;
+// ---- PCG hooks ---------------------------------------------------------------
+int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
+  if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
+  std::string err;
+  const int rc = pcg_symbolic(s->pcg, n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), s->stream, err);
+  if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel, kPcgThreads, 0));
+  if (occ < 1) return s->fail(ARSLAM_ERR_CUDA, "pcg_kernel cannot be made resident");
+  s->pcg.grid = std::min(s->n_sm * std::min(occ, 2), 2048);
+  s->pcg_version = s->problem_version;
+  s->pcg_side = side_e;
+  return ARSLAM_OK;
 }
-int pcg_launch_eliminate(arslam_solver* s, const SchurArgs&, double*) { return s->fail(ARSLAM_ERR_UNSUPPORTED, "PCG not built"); }
-int pcg_launch_solve(arslam_solver* s, int, double*, const double*, const LmScalars*, const double*, double, double*, long long*) {
-  return s->fail(ARSLAM_ERR_UNSUPPORTED, "PCG not built");
+
+int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw) {
+  SparseTarget t;
+  t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx;
+  t.Sraw = Sraw;
+  t.borderm = Sraw + (size_t)36 * s->pcg.nnzb;
+  t.rhsm = t.borderm + (size_t)6 * s->pcg.n_f;
+  LAUNCH("schur_eliminate_sparse", (288.0 * 2 + 4) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
+         schur_eliminate_sparse_kernel<<<cdiv((long long)a.n_e * 32, 128), 128, 0, s->stream>>>(a, t));
+  return ARSLAM_OK;
+}
+
+int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, const double* sc, const double* cam_minus,
+                     double radius, double* x_out) {
+  PcgWorkspace& w = s->pcg;
+  const size_t nvec = (size_t)6 * n_f + 2;
+  double* v = w.vec;
+  CU(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), s->stream));
+  PcgFinalizeArgs f;
+  f.n_f = n_f; f.nnzb = w.nnzb; f.row_ptr = w.row_ptr; f.col_idx = w.col_idx; f.src_slot = w.src_slot;
+  f.Sraw = Sraw; f.borderm = Sraw + (size_t)36 * w.nnzb; f.rhsm = f.borderm + (size_t)6 * n_f;
+  f.HF = HF; f.sigF = s->sigF.p; f.sc = reinterpret_cast<const LmScalars*>(sc); f.cam_minus = cam_minus;
+  f.radius = radius; f.min_diag = s->opt.min_lm_diagonal; f.max_diag = s->opt.max_lm_diagonal;
+  f.Sfin = w.Sfin; f.Minv = w.Minv; f.border = v + 6 * nvec; f.rhs = v + 7 * nvec; f.scal = w.scal;
+  LAUNCH("pcg_finalize", 2.0 * 288.0 * w.nnzb + 8.0 * (NV + 36 + 24) * n_f,
+         pcg_finalize_kernel<<<cdiv(std::max(n_f, 1), 128), 128, 0, s->stream>>>(f));
+  PcgArgs a;
+  a.n_f = n_f; a.max_iter = s->opt.pcg_max_iterations; a.tol = s->opt.pcg_tolerance;
+  a.row_ptr = w.row_ptr; a.col_idx = w.col_idx; a.S = w.Sfin; a.Minv = w.Minv;
+  a.border = f.border; a.rhs = f.rhs;
+  a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
+  a.partial = w.partial; a.scal = w.scal;
+  void* args[] = {(void*)&a};
+  if (s->prof.on) {
+    Profiler::Rec r{s->prof.id_of("pcg_solve", 288.0 * w.nnzb), s->prof.ev(), s->prof.ev()};
+    cudaEventRecord(r.a, s->stream);
+    CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args, 0, s->stream));
+    cudaEventRecord(r.b, s->stream);
+    s->prof.recs.push_back(r);
+  } else {
+    CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args, 0, s->stream));
+  }
+  ++s->launches;
+  LAUNCH("pcg_publish", 32.0, pcg_publish_kernel<<<1, 1, 0, s->stream>>>(w.scal, const_cast<double*>(sc)));
+  return ARSLAM_OK;
 }
 
 struct Sides {
@@ -596,7 +653,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     s_elems = (size_t)s->n_pad * s->ld;
     CU(s->yF.ensure((size_t)s->n_pad));
   } else {
-    int rc = pcg_prepare(s->pcg, sd.n_e, sd.n_f, s->n_blk, s->h_off[sd.e].data(), s->s_oth[sd.e].p, s->stream, s->err);
+    int rc = pcg_prepare(s, sd.e, sd.n_e, sd.n_f);
     if (rc) return rc;
     s_elems = s->pcg.value_count();  // block values + border + rhs
     CU(s->yF.ensure((size_t)n + 1));
@@ -714,8 +771,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
       }
     } else {
-      long long its = 0;
-      rc = pcg_launch_solve(s, sd.n_f, S, HF, reinterpret_cast<const LmScalars*>(sc), cam_minus, radius, s->yF.p, &its);
+      rc = pcg_launch_solve(s, sd.n_f, S, HF, sc, cam_minus, radius, s->yF.p);
       if (rc) return rc;
     }
     LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
@@ -776,6 +832,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       lin_ms += a; eval_ms += b;
     }
     const double* h = s->h_sc;
+    if (lin == ARSLAM_LINSOLVE_PCG) summary->linear_solver_iterations += (long long)h[3];
     if (fresh_linearisation) {
       x_cost = 0.5 * h[2];
       grad_max = std::max(std::max(h[10], h[11]), std::fabs(h[1]));
@@ -871,7 +928,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   summary->final_radius = radius;
   summary->gradient_max_norm = grad_max;
   summary->gpu_launches = s->launches;
-  summary->linear_solver_iterations = s->pcg.total_iterations;
   summary->eval_ms = eval_ms;
   summary->linsolve_ms = lin_ms;
   summary->total_ms = wall_ms() - t_start;

@@ -89,13 +89,12 @@ def make_map(n_cap, n_tag, tags_per_capture=8, seed=0xA55A0002, noise_px=0.3, pi
     blk_cap, blk_tag, blk_obs = [], [], []
     todo = np.arange(n_cap)
     kq = min(n_tag, max(3 * tags_per_capture, 24))
-    for _ in range(50):
+    for _ in range(200):
         if len(todo) == 0:
             break
         n = len(todo)
         look = np.zeros((n, 3))
-        look[:, :2] = rng.uniform(0.1 * extent, 0.9 * extent, (n, 2)) if extent > 2.0 else \
-            rng.uniform(0, extent, (n, 2))
+        look[:, :2] = rng.uniform(-0.02 * extent, 1.0 * extent, (n, 2))
         h = rng.uniform(1.0, 2.5, n)
         tilt_axis = rng.normal(size=(n, 3))
         tilt_axis[:, 2] = 0
@@ -116,13 +115,11 @@ def make_map(n_cap, n_tag, tags_per_capture=8, seed=0xA55A0002, noise_px=0.3, pi
         rank = np.cumsum(inside, axis=1)
         take = inside & (rank <= tags_per_capture)
         ok = take.sum(1) >= tags_per_capture
-        for ci in np.nonzero(ok)[0]:
-            c = todo[ci]
-            cap_pose[c] = pose[ci]
-            sel = np.nonzero(take[ci])[0]
-            blk_cap.append(np.full(len(sel), c))
-            blk_tag.append(nn[ci, sel])
-            blk_obs.append(uv[ci, sel].reshape(len(sel), 8))
+        rows, cols = np.nonzero(take & ok[:, None])   # row-major: grouped by capture, nearest first
+        cap_pose[todo[ok]] = pose[ok]
+        blk_cap.append(todo[rows])
+        blk_tag.append(nn[rows, cols])
+        blk_obs.append(uv[rows, cols].reshape(len(rows), 8))
         todo = todo[~ok]
     if len(todo):
         raise RuntimeError("could not place %d captures" % len(todo))

@@ -121,3 +121,47 @@ def test_solve_is_deterministic(gpu_solver_cls):
         costs.append(summ["initial_cost"])
         s.close()
     assert costs[0] == costs[1]
+
+
+def test_pcg_matches_dense(gpu_solver_cls, oracle):
+    """The sparse reduced system + PCG (used where the reduced system is large) must walk the
+    same LM trajectory as the dense Cholesky path and the oracle when solved tightly."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(1000, 200)
+    res = {}
+    for name, ls in (("dense", ar_slam_b200.LINSOLVE_DENSE), ("pcg", ar_slam_b200.LINSOLVE_PCG)):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ls, pcg_tolerance=1e-12,
+                                                                 pcg_max_iterations=2000))
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        summ, log = s.solve()
+        res[name] = (summ, log, s.get_params())
+        s.close()
+    (sd, ld, pd), (sp, lp, pp) = res["dense"], res["pcg"]
+    assert sp["linear_solver"] == ar_slam_b200.LINSOLVE_PCG and sp["linear_solver_iterations"] > 0
+    assert sp["iterations"] == sd["iterations"] and sp["reason"] == sd["reason"]
+    assert np.allclose(lp[:, 0], ld[:, 0], rtol=1e-9)
+    assert np.allclose(lp[1:, 3], ld[1:, 3], rtol=1e-6)
+    assert abs(pp[0][0] - pd[0][0]) <= 1e-8 * pd[0][0]
+    assert np.abs(pp[1] - pd[1]).max() < 1e-7 and np.abs(pp[2] - pd[2]).max() < 1e-7
+    _, _, _, so, log_o = oracle.solve(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs, m.cam0, m.cap0, m.tag0,
+                                      options=oracle.default_options(num_threads=4))
+    assert sp["iterations"] == so["iterations"]
+    assert abs(sp["final_cost"] - so["final_cost"]) <= 1e-8 * so["final_cost"]
+
+
+def test_pcg_default_tolerance_converges_like_dense(gpu_solver_cls):
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(3000, 400, seed=21)
+    out = {}
+    for name, ls in (("dense", ar_slam_b200.LINSOLVE_DENSE), ("pcg", ar_slam_b200.LINSOLVE_PCG)):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ls))
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        out[name], _ = s.solve()
+        s.close()
+    assert out["pcg"]["termination"] == 0 and out["dense"]["termination"] == 0
+    assert abs(out["pcg"]["iterations"] - out["dense"]["iterations"]) <= 1
+    assert abs(out["pcg"]["final_cost"] - out["dense"]["final_cost"]) <= 1e-6 * out["dense"]["final_cost"]
