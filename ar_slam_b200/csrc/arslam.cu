@@ -508,20 +508,20 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel, kPcgThreads, 0));
   if (occ < 1) return s->fail(ARSLAM_ERR_CUDA, "pcg_kernel cannot be made resident");
-  s->pcg.grid = std::min(s->n_sm * std::min(occ, 2), 2048);
+  s->pcg.grid = std::min(s->n_sm * std::min(occ, 1), 1024);
   s->pcg_version = s->problem_version;
   s->pcg_side = side_e;
   return ARSLAM_OK;
 }
 
-int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw) {
+int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, const int32_t* e_idx) {
   SparseTarget t;
   t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx;
   t.Sraw = Sraw;
   t.borderm = Sraw + (size_t)36 * s->pcg.nnzb;
   t.rhsm = t.borderm + (size_t)6 * s->pcg.n_f;
-  LAUNCH("schur_eliminate_sparse", (288.0 * 2 + 4) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
-         schur_eliminate_sparse_kernel<<<cdiv((long long)a.n_e * 32, 128), 128, 0, s->stream>>>(a, t));
+  LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
+         schur_eliminate_kernel<SparseTarget><<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(a, t, s->n_blk, e_idx));
   return ARSLAM_OK;
 }
 
@@ -717,15 +717,16 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       a.HE = s->H[sd.e].p; a.W = s->W.p; a.sig_e = s->sigE.p;
       a.radius = radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
       a.Y = s->Y.p; a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p;
-      a.S = nullptr; a.ld = s->ld; a.cam_row = cam_row; a.rhs_row = rhs_row;
       CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
       CU(cudaMemsetAsync(sc + 12, 0, sizeof(double), s->stream));
+      LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(sd.n_e, 256), 256, 0, s->stream>>>(a));
       if (lin == ARSLAM_LINSOLVE_DENSE) {
-        a.S = S;
-        LAUNCH("schur_eliminate", (288.0 * 2 + 4) * s->n_blk + (264.0 + 128) * sd.n_e,
-               schur_eliminate_kernel<<<cdiv((long long)sd.n_e * 32, 128), 128, 0, s->stream>>>(a));
+        DenseTarget t;
+        t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
+        LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
+               schur_eliminate_kernel<DenseTarget><<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
       } else {
-        rc = pcg_launch_eliminate(s, a, S);
+        rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;
       }
       LAUNCH("collect_fail", 8.0 * sd.n_e, collect_fail_kernel<<<1, 1024, 0, s->stream>>>(sd.n_e, s->Z.p, sc));

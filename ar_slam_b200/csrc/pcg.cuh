@@ -19,7 +19,7 @@
 namespace ars {
 namespace cg = cooperative_groups;
 
-constexpr int kPcgThreads = 256;
+constexpr int kPcgThreads = 1024;  // one CTA per SM, ~one block row per warp
 constexpr int kPcgWarps = kPcgThreads / 32;
 
 struct PcgWorkspace {
@@ -106,103 +106,25 @@ struct SparseTarget {
   double* Sraw;     // [nnzb][36]
   double* borderm;  // [6 n_f]  sum W~^T yb
   double* rhsm;     // [6 n_f]  sum W~^T z
+  __device__ __forceinline__ void add_border(int f, int c, double b0, double b1) const {
+    atomicAdd(borderm + 6 * (size_t)f + c, b0);
+    atomicAdd(rhsm + 6 * (size_t)f + c, b1);
+  }
+  // lower block (row fj, col fi), found by bisection in the row's sorted column list
+  __device__ __forceinline__ double* block(int fi, int fj) const {
+    int lo = row_ptr[fj], hi = row_ptr[fj + 1] - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (col_idx[mid] < fi) lo = mid + 1; else hi = mid;
+    }
+    return Sraw + 36 * (size_t)lo;
+  }
+  __device__ __forceinline__ void add(double* blk, int r, int c, double v, bool diag, bool twice) const {
+    if (!diag) { atomicAdd(blk + c * 6 + r, v); return; }
+    atomicAdd(blk + r * 6 + c, v);
+    if (twice) atomicAdd(blk + c * 6 + r, v);
+  }
 };
-
-__device__ __forceinline__ int bsr_find(const SparseTarget& t, int row, int col) {
-  int lo = t.row_ptr[row], hi = t.row_ptr[row + 1] - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (t.col_idx[mid] < col) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-__global__ void __launch_bounds__(128) schur_eliminate_sparse_kernel(const SchurArgs a, const SparseTarget t) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= a.n_e) return;
-  const int beg = a.e_off[e], k = a.e_off[e + 1] - beg;
-  double L[36], z[6], yb[6], s[6], hk[6];
-  load_scaled_E(a, e, L, z, hk, s);
-  const bool ok = chol6(L);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) yb[i] = hk[i];
-  chol6_solve(L, z);
-  chol6_solve(L, yb);
-  if (lane == 0) {
-    double* zo = a.Z + 8 * (size_t)e;
-    double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      zo[i] = z[i];
-      a.YB[6 * (size_t)e + i] = yb[i];
-      c0 += hk[i] * yb[i];
-      c1 += hk[i] * z[i];
-    }
-    zo[6] = (ok || k == 0) ? 0.0 : 1.0;
-    zo[7] = 0.0;
-    a.seg_cam[2 * (size_t)e] = c0;
-    a.seg_cam[2 * (size_t)e + 1] = c1;
-  }
-  const size_t ps = a.plane;
-  for (int j = lane; j < k; j += 32) {
-    const int blk = beg + j;
-    double Wt[36];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) Wt[i * 6 + c] = a.W[(size_t)(i * 6 + c) * ps + blk] * s[i];
-    const int f = a.f_idx[blk];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      double col[6];
-      double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        col[i] = Wt[i * 6 + c];
-        b0 += col[i] * yb[i];
-        b1 += col[i] * z[i];
-      }
-      chol6_solve(L, col);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) a.Y[(size_t)(i * 6 + c) * ps + blk] = col[i];
-      atomicAdd(t.borderm + 6 * (size_t)f + c, b0);
-      atomicAdd(t.rhsm + 6 * (size_t)f + c, b1);
-    }
-  }
-  __syncwarp();
-  const int npairs = k * (k + 1) / 2;
-  for (int p = lane; p < npairs; p += 32) {
-    int i, j;
-    tri_decode(p, i, j);
-    const int bi = beg + i, bj = beg + j;
-    const int fi = a.f_idx[bi], fj = a.f_idx[bj];  // fi <= fj
-    double Wi[36], Yj[36];
-#pragma unroll
-    for (int m = 0; m < 6; ++m)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
-        Yj[m * 6 + c] = a.Y[(size_t)(m * 6 + c) * ps + bj];
-      }
-    double* dst = t.Sraw + 36 * (size_t)bsr_find(t, fj, fi);  // lower block (row fj, col fi)
-    const bool diag = fi == fj, twice = diag && (i != j);
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double acc = 0.0;  // M[r][c] = block (fi, fj) element
-#pragma unroll
-        for (int m = 0; m < 6; ++m) acc += Wi[m * 6 + r] * Yj[m * 6 + c];
-        if (!diag) {
-          atomicAdd(dst + c * 6 + r, acc);        // transposed into the lower block
-        } else {
-          atomicAdd(dst + r * 6 + c, acc);
-          if (twice) atomicAdd(dst + c * 6 + r, acc);
-        }
-      }
-  }
-}
 
 // ---- finalize: scale by sigma_F, add the F-pose diagonal blocks and damping,
 // mirror the upper blocks, invert the diagonal blocks for the preconditioner.
@@ -325,29 +247,34 @@ __device__ __forceinline__ void grid_sums(cg::grid_group& grid, double (&v)[NS],
 #pragma unroll
     for (int i = 0; i < NS; ++i) sm[wid * NS + i] = v[i];
   __syncthreads();
-  if (threadIdx.x < NS) {
-    double acc = 0.0;
-    for (int w = 0; w < kPcgWarps; ++w) acc += sm[w * NS + threadIdx.x];
-    partial[(size_t)blockIdx.x * 8 + threadIdx.x] = acc;
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      double acc = lane < kPcgWarps ? sm[lane * NS + i] : 0.0;
+      acc = warp_sum(acc);
+      if (lane == 0) partial[(size_t)blockIdx.x * 8 + i] = acc;
+    }
   }
   grid.sync();
-  if (threadIdx.x < 32) {
-    double acc[NS];
+  // every CTA reads all CTA partials (one load per thread) and reduces them in the same fixed tree
+  double acc[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) acc[i] = 0.0;
-    // lanes take CTAs round-robin, fixed order -> identical on every CTA
-    for (int b = lane; b < (int)gridDim.x; b += 32)
-#pragma unroll
-      for (int i = 0; i < NS; ++i) acc[i] += partial[(size_t)b * 8 + i];
+  for (int i = 0; i < NS; ++i) acc[i] = threadIdx.x < gridDim.x ? partial[(size_t)threadIdx.x * 8 + i] : 0.0;
+  const int nwarp_used = ((int)gridDim.x + 31) >> 5;
+  if (wid < nwarp_used) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) acc[i] = warp_sum(acc[i]);
     if (lane == 0)
 #pragma unroll
-      for (int i = 0; i < NS; ++i) sm[64 + i] = acc[i];
+      for (int i = 0; i < NS; ++i) sm[64 + wid * NS + i] = acc[i];
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NS; ++i) v[i] = sm[64 + i];
+  for (int i = 0; i < NS; ++i) {
+    double t = 0.0;
+    for (int w = 0; w < nwarp_used; ++w) t += sm[64 + w * NS + i];
+    v[i] = t;
+  }
   __syncthreads();
 }
 
@@ -356,9 +283,9 @@ __global__ void pcg_publish_kernel(const double* scal, double* sc) {
   if (scal[3] != 0.0) sc[12] = 1.0;      // failure -> invalid LM step
 }
 
-__global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgArgs a) {
+__global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[96];
+  __shared__ double sm[64 + 32 * 2 + 8];
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * kPcgThreads + threadIdx.x) >> 5, nw = (gridDim.x * kPcgThreads) >> 5;
   const int g = lane >> 3, rr_ = lane & 7;  // 4 block groups x 8 lanes (6 active rows)
@@ -413,18 +340,31 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgArgs a) {
     double sa[2] = {0.0, 0.0};
     const double pk = a.z[camrow] + beta * p_old[camrow];
     for (int f = gw; f < n_f; f += nw) {
-      double acc = 0.0;
+      double acc = 0.0, acc2 = 0.0;
       const int s0 = a.row_ptr[f], s1 = a.row_ptr[f + 1];
-      for (int s = s0 + g; s < s1; s += 4) {
+      for (int s = s0 + g; s < s1; s += 8) {   // two independent blocks in flight per lane group
+        const int sB = s + 4;
+        const bool hasB = sB < s1;
         const int c = a.col_idx[s];
+        const int cB = hasB ? a.col_idx[sB] : c;
         if (act) {
           const double* B = a.S + 36 * (size_t)s + rr_ * 6;
           const double* zc = a.z + 6 * (size_t)c;
           const double* pc = p_old + 6 * (size_t)c;
+          const double* B2 = a.S + 36 * (size_t)(hasB ? sB : s) + rr_ * 6;
+          const double* zc2 = a.z + 6 * (size_t)cB;
+          const double* pc2 = p_old + 6 * (size_t)cB;
+          double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) acc += B[j] * (zc[j] + beta * pc[j]);
+          for (int j = 0; j < 6; ++j) {
+            t1 += B[j] * (zc[j] + beta * pc[j]);
+            t2 += B2[j] * (zc2[j] + beta * pc2[j]);
+          }
+          acc += t1;
+          if (hasB) acc2 += t2;
         }
       }
+      acc += acc2;
       acc += __shfl_xor_sync(0xffffffffu, acc, 8);
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
       if (lane < 6) {

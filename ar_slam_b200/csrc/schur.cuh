@@ -28,9 +28,6 @@ struct SchurArgs {
   double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
   double* YB;             // [n_e][6]: Ht_ee^-1 sig_e H_e,f
   double* seg_cam;        // [n_e][2]: (sig_e H_e,f).yb , (sig_e H_e,f).z
-  double* S;              // dense lower-triangular accumulation target (+=), or null
-  long long ld;
-  int cam_row, rhs_row;
 };
 
 // decode p -> (i <= j) with p = j (j + 1) / 2 + i
@@ -62,13 +59,41 @@ __device__ __forceinline__ void load_scaled_E(const SchurArgs& a, int e, double 
   }
 }
 
-// One warp per E pose.  6x6 Cholesky in registers (every lane holds the same
-// factor), then lanes take the pose's blocks / block pairs.
-__global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= a.n_e) return;
-  const int beg = a.e_off[e], k = a.e_off[e + 1] - beg;
+// Where the Schur terms sum W~_i^T Y_j land: the dense lower-triangular array
+// (DenseTarget) or the block-sparse value array (SparseTarget, pcg.cuh).
+struct DenseTarget {
+  double* S;
+  long long ld;
+  int cam_row, rhs_row;
+  __device__ __forceinline__ void add_border(int f, int c, double b0, double b1) const {
+    atomicAdd(S + (size_t)cam_row * ld + 6 * f + c, b0);
+    atomicAdd(S + (size_t)rhs_row * ld + 6 * f + c, b1);
+  }
+  // M[r][c] = element (6 fi + r, 6 fj + c), fi <= fj, of sum W~^T Y; stored in the lower triangle
+  __device__ __forceinline__ double* block(int fi, int fj) const { return S + (size_t)(6 * fj) * ld + 6 * fi; }
+  __device__ __forceinline__ void add(double* blk, int r, int c, double v, bool diag, bool twice) const {
+    if (!diag) { atomicAdd(blk + (size_t)c * ld + r, v); return; }
+    // diagonal block: keep it fully symmetric
+    atomicAdd(blk + (size_t)r * ld + c, v);
+    if (twice) atomicAdd(blk + (size_t)c * ld + r, v);
+  }
+};
+
+// One thread per residual block (E-sorted order).  Thread j of a segment
+//   * rebuilds the segment's damped 6x6 block and factors it in registers
+//     (batched 6x6 Cholesky; the 8-fold redundancy inside a segment is cheaper
+//     than a shuffle broadcast of 21 + 12 doubles),
+//   * computes Y_j = Ht_ee^-1 (sig_e W_j) with coalesced plane loads/stores,
+//   * then walks its partners i <= j of the same segment (W_i is a warp-wide
+//     broadcast load) and adds W~_i^T Y_j to the reduced system.
+template <typename Target>
+__global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk,
+                                                              const int32_t* __restrict__ e_idx) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_blk) return;
+  const int e = e_idx[pos];
+  const int beg = a.e_off[e];
+  const int j = pos - beg;
   double L[36], z[6], yb[6], s[6], hk[6];
   load_scaled_E(a, e, L, z, hk, s);
   const bool ok = chol6(L);
@@ -76,7 +101,7 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a)
   for (int i = 0; i < 6; ++i) yb[i] = hk[i];
   chol6_solve(L, z);
   chol6_solve(L, yb);
-  if (lane == 0) {
+  if (j == 0) {
     double* zo = a.Z + 8 * (size_t)e;
     double c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -86,83 +111,62 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a)
       c0 += hk[i] * yb[i];
       c1 += hk[i] * z[i];
     }
-    zo[6] = (ok || k == 0) ? 0.0 : 1.0;
+    zo[6] = ok ? 0.0 : 1.0;
     zo[7] = 0.0;
     a.seg_cam[2 * (size_t)e] = c0;
     a.seg_cam[2 * (size_t)e + 1] = c1;
   }
   const size_t ps = a.plane;
-  for (int j = lane; j < k; j += 32) {
-    const int blk = beg + j;
-    double Wt[36];
+  const int fj = a.f_idx[pos];
+  double Y[36];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+  for (int c = 0; c < 6; ++c) {
+    double col[6];
+    double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) Wt[i * 6 + c] = a.W[(size_t)(i * 6 + c) * ps + blk] * s[i];
-    const int f = a.f_idx[blk];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      double col[6];
-      double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        col[i] = Wt[i * 6 + c];
-        b0 += col[i] * yb[i];
-        b1 += col[i] * z[i];
-      }
-      chol6_solve(L, col);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) a.Y[(size_t)(i * 6 + c) * ps + blk] = col[i];
-      if (a.S) {
-        atomicAdd(a.S + (size_t)a.cam_row * a.ld + 6 * f + c, b0);
-        atomicAdd(a.S + (size_t)a.rhs_row * a.ld + 6 * f + c, b1);
-      }
+    for (int i = 0; i < 6; ++i) {
+      col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
+      b0 += col[i] * yb[i];
+      b1 += col[i] * z[i];
     }
+    chol6_solve(L, col);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      Y[i * 6 + c] = col[i];
+      a.Y[(size_t)(i * 6 + c) * ps + pos] = col[i];
+    }
+    t.add_border(fj, c, b0, b1);
   }
-  if (!a.S) return;
-  __syncwarp();
-  const int npairs = k * (k + 1) / 2;
-  for (int p = lane; p < npairs; p += 32) {
-    int i, j;
-    tri_decode(p, i, j);
-    const int bi = beg + i, bj = beg + j;
-    const int fi = a.f_idx[bi], fj = a.f_idx[bj];  // fi <= fj (sorted within the segment)
-    double Wi[36], Yj[36];
+  for (int i = 0; i <= j; ++i) {
+    const int bi = beg + i;
+    const int fi = a.f_idx[bi];  // fi <= fj: blocks are sorted by F pose inside a segment
+    double Wi[36];
 #pragma unroll
     for (int m = 0; m < 6; ++m)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
-        Yj[m * 6 + c] = a.Y[(size_t)(m * 6 + c) * ps + bj];
-      }
-    double M[36];
+      for (int c = 0; c < 6; ++c) Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
+    double* blk = t.block(fi, fj);
+    const bool diag = fi == fj, twice = diag && (i != j);
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         double acc = 0.0;
 #pragma unroll
-        for (int m = 0; m < 6; ++m) acc += Wi[m * 6 + r] * Yj[m * 6 + c];
-        M[r * 6 + c] = acc;  // block (fi, fj) of sum W~^T Y
+        for (int m = 0; m < 6; ++m) acc += Wi[m * 6 + r] * Y[m * 6 + c];
+        t.add(blk, r, c, acc, diag, twice);
       }
-    if (fi != fj) {
-      // lower-triangular storage: element (6 fj + c, 6 fi + r)
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c < 6; ++c)
-          atomicAdd(a.S + (size_t)(6 * fj + c) * a.ld + 6 * fi + r, M[r * 6 + c]);
-    } else {
-      const bool twice = (i != j);  // same F pose seen twice by this E pose
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) {
-          const double v = twice ? (M[r * 6 + c] + M[c * 6 + r]) : M[r * 6 + c];
-          atomicAdd(a.S + (size_t)(6 * fi + r) * a.ld + 6 * fi + c, v);
-        }
-    }
   }
+}
+
+// E poses without blocks never reach schur_eliminate_kernel: clear their records.
+__global__ void schur_empty_kernel(const SchurArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n_e || a.e_off[e + 1] > a.e_off[e]) return;
+  for (int i = 0; i < 8; ++i) a.Z[8 * (size_t)e + i] = 0.0;
+  for (int i = 0; i < 6; ++i) a.YB[6 * (size_t)e + i] = 0.0;
+  a.seg_cam[2 * (size_t)e] = 0.0;
+  a.seg_cam[2 * (size_t)e + 1] = 0.0;
 }
 
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
