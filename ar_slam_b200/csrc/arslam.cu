@@ -138,9 +138,9 @@ struct arslam_solver {
   DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2];
   int cur = 0;
   // normal equations
-  DevBuf<double> H[2], partial[2], W, Y, Z, YB, seg_cam, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
+  DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
-  DevBuf<double> eval_out, small;
+  DevBuf<double> eval_out, small, colsum_part;
   double* h_sc = nullptr;  // pinned
   long long ld = 0;
   int n_pad = 0;
@@ -188,6 +188,8 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 extern "C" {
 
+namespace { int launch_colsum(arslam_solver* s, int n, int m, const double* in, double* out); }
+
 int arslam_abi_version(void) { return ARSLAM_ABI_VERSION; }
 
 void arslam_default_options(arslam_options* o) {
@@ -209,7 +211,7 @@ void arslam_default_options(arslam_options* o) {
   o->function_tolerance = 1e-6;
   o->gradient_tolerance = 1e-10;
   o->parameter_tolerance = 1e-8;
-  o->pcg_tolerance = 1e-8;
+  o->pcg_tolerance = 0.1;  // inexact-Newton forcing term, the value of Ceres' Solver::Options::eta
   o->tag_size = 0.0635;  // ar_slam_util.hpp:319
   o->dense_max_dim = 16384;
 }
@@ -240,7 +242,7 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
   s->n_sm = n_sm;
   if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(&s->h_sc, 64 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
+      cudaMallocHost(&s->h_sc, 128 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
       pcg_init() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -358,16 +360,16 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
     CU(s->H[side].ensure((size_t)n_own * NV));
     CU(s->partial[side].ensure((size_t)s->n_warp * 2 * NV));
     CU(s->d_pose[side].ensure((size_t)6 * n_own));
-    CU(s->warp_norm[side].ensure((size_t)8 * cdiv(n_own, 128) + 8));
+    CU(s->warp_norm[side].ensure((size_t)12 * cdiv(n_own, 128) + 12));
     CU(s->warp_gmax[side].ensure((size_t)4 * cdiv(n_own, 128) + 4));
   }
   for (int k = 0; k < 2; ++k) {
     CU(s->cam[k].ensure(4)); CU(s->cap[k].ensure((size_t)6 * s->n_cap)); CU(s->tag[k].ensure((size_t)6 * s->n_tag));
     CU(s->cap_pre[k].ensure((size_t)kCapPre * s->n_cap)); CU(s->tag_pre[k].ensure((size_t)kTagPre * s->n_tag));
   }
-  CU(s->W.ensure((size_t)36 * plane)); CU(s->Y.ensure((size_t)36 * plane));
-  CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp));
-  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(16)); CU(s->cam_minus.ensure(4));
+  CU(s->W.ensure((size_t)36 * plane));
+  CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp + 8));
+  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(4)); CU(s->colsum_part.ensure(4 * kColsumChunks));
   s->have_problem = true;
   ++s->problem_version;
   return ARSLAM_OK;
@@ -434,7 +436,7 @@ int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* j
              nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
              s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
              want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
-  LAUNCH("colsum", 8.0 * nwarp, colsum_kernel<<<1, 1024, 0, s->stream>>>(nwarp, 1, d_wc, d_cost));
+  launch_colsum(s, nwarp, 1, d_wc, d_cost);
   CU(cudaGetLastError());
   double h_cost = 0.0;
   CU(cudaMemcpyAsync(&h_cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -451,18 +453,29 @@ int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* j
 // ------------------------------------------------------------------ solve ---
 namespace {
 
+// deterministic column sums, two stages when the input is large
+int launch_colsum(arslam_solver* s, int n, int m, const double* in, double* out) {
+  if (n <= 8192) {
+    LAUNCH("colsum", 8.0 * n * m, colsum_kernel<<<1, 1024, 0, s->stream>>>(n, m, in, out));
+  } else {
+    LAUNCH("colsum", 8.0 * n * m, colsum_stage1_kernel<<<kColsumChunks, 256, 0, s->stream>>>(n, m, in, s->colsum_part.p));
+    LAUNCH("colsum2", 4096.0, colsum_stage2_kernel<<<1, 128, 0, s->stream>>>(kColsumChunks, m, s->colsum_part.p, out));
+  }
+  return ARSLAM_OK;
+}
+
 // ---- multi-GPU helpers (one process per GPU; captures are sharded) ----------
 __global__ void small_pack_kernel(const double* sc, double* buf, int rank, int world) {
   const int i = threadIdx.x;
-  if (i < 6) buf[i] = sc[4 + i];
-  if (i >= 8 && i < 8 + world) buf[i] = (i - 8 == rank) ? sc[10] : 0.0;
+  if (i < 8) buf[i] = sc[4 + i];   // cross, cand_r2, step2_e, xnorm2_e, mq_e, step2_f, xnorm2_f, mq_f
+  if (i >= 8 && i < 8 + world) buf[i] = (i - 8 == rank) ? sc[16] : 0.0;
 }
 __global__ void small_unpack_kernel(double* sc, const double* buf, int world) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 6; ++i) sc[4 + i] = buf[i];
+    for (int i = 0; i < 8; ++i) sc[4 + i] = buf[i];
     double m = 0.0;
     for (int r = 0; r < world; ++r) m = fmax(m, buf[8 + r]);
-    sc[10] = m;
+    sc[16] = m;
   }
 }
 __global__ void axpy_kernel(int n, const double* a, const double* b, double sign, double* out) {
@@ -476,7 +489,7 @@ int nccl_sum(arslam_solver* s, double* buf, size_t count) {
   return ARSLAM_OK;
 }
 
-// sums [model, cand_r2, step2_e, xnorm2_e, step2_f, xnorm2_f]; max of gmax_e via per-rank slots
+// sums the eight block-local LM scalars; max of gmax_e via per-rank slots
 int small_allreduce(arslam_solver* s, double* sc) {
   CU(s->small.ensure(8 + s->world));
   LAUNCH("small_pack", 128.0, small_pack_kernel<<<1, 64 + s->world, 0, s->stream>>>(sc, s->small.p, s->rank, s->world));
@@ -503,12 +516,21 @@ int gather_captures(arslam_solver* s, int k) {
 int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
   std::string err;
-  const int rc = pcg_symbolic(s->pcg, n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), s->stream, err);
+  const int rc = pcg_symbolic(s->pcg, n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), s->stream, err,
+                              s->n_sm, (size_t)227 * 1024 - 2048);
   if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel, kPcgThreads, 0));
   if (occ < 1) return s->fail(ARSLAM_ERR_CUDA, "pcg_kernel cannot be made resident");
   s->pcg.grid = std::min(s->n_sm * std::min(occ, 1), 1024);
+  if (s->pcg.pair_slot) {
+    SparseTarget t;
+    t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx; t.Sraw = nullptr; t.borderm = nullptr; t.rhsm = nullptr;
+    t.pair_slot = nullptr;
+    LAUNCH("pair_slot", 4.0 * s->pcg.n_pairs,
+           pair_slot_kernel<<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p,
+                                                                      s->s_oth[side_e].p, s->pcg.pair_off, t, s->pcg.pair_slot));
+  }
   s->pcg_version = s->problem_version;
   s->pcg_side = side_e;
   return ARSLAM_OK;
@@ -520,8 +542,11 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   t.Sraw = Sraw;
   t.borderm = Sraw + (size_t)36 * s->pcg.nnzb;
   t.rhsm = t.borderm + (size_t)6 * s->pcg.n_f;
+  t.pair_slot = s->pcg.pair_slot;
+  SchurArgs a2 = a;
+  a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
   LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
-         schur_eliminate_kernel<SparseTarget><<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(a, t, s->n_blk, e_idx));
+         schur_eliminate_kernel<SparseTarget><<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(a2, t, s->n_blk, e_idx));
   return ARSLAM_OK;
 }
 
@@ -537,23 +562,34 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   f.HF = HF; f.sigF = s->sigF.p; f.sc = reinterpret_cast<const LmScalars*>(sc); f.cam_minus = cam_minus;
   f.radius = radius; f.min_diag = s->opt.min_lm_diagonal; f.max_diag = s->opt.max_lm_diagonal;
   f.Sfin = w.Sfin; f.Minv = w.Minv; f.border = v + 6 * nvec; f.rhs = v + 7 * nvec; f.scal = w.scal;
-  LAUNCH("pcg_finalize", 2.0 * 288.0 * w.nnzb + 8.0 * (NV + 36 + 24) * n_f,
-         pcg_finalize_kernel<<<cdiv(std::max(n_f, 1), 128), 128, 0, s->stream>>>(f));
-  PcgArgs a;
+  LAUNCH("pcg_finalize_offdiag", 2.0 * 288.0 * w.nnzb,
+         pcg_finalize_offdiag_kernel<<<cdiv((long long)w.nnzb * 6, 256), 256, 0, s->stream>>>(f, w.slot_row));
+  LAUNCH("pcg_finalize", 8.0 * (NV + 36 + 36 + 36 + 24) * n_f,
+         pcg_finalize_kernel<<<cdiv(std::max(n_f, 1), 64), 64, 0, s->stream>>>(f, w.diag_slot));
+  PcgSmemArgs sa;
+  PcgArgs& a = sa.a;
   a.n_f = n_f; a.max_iter = s->opt.pcg_max_iterations; a.tol = s->opt.pcg_tolerance;
   a.row_ptr = w.row_ptr; a.col_idx = w.col_idx; a.S = w.Sfin; a.Minv = w.Minv;
   a.border = f.border; a.rhs = f.rhs;
   a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
   a.partial = w.partial; a.scal = w.scal;
-  void* args[] = {(void*)&a};
+  sa.cta_row = w.cta_row; sa.halo_ptr = w.halo_ptr; sa.halo_col = w.halo_col; sa.lcol = w.lcol;
+  sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots;
+  const bool use_smem = w.smem_ok && !getenv("ARSLAM_PCG_NO_SMEM");
+  void* args_g[] = {(void*)&a};
+  void* args_s[] = {(void*)&sa};
+  Profiler::Rec r{0, nullptr, nullptr};
   if (s->prof.on) {
-    Profiler::Rec r{s->prof.id_of("pcg_solve", 288.0 * w.nnzb), s->prof.ev(), s->prof.ev()};
+    r = Profiler::Rec{s->prof.id_of("pcg_solve", 288.0 * w.nnzb), s->prof.ev(), s->prof.ev()};
     cudaEventRecord(r.a, s->stream);
-    CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args, 0, s->stream));
+  }
+  if (use_smem)
+    CU(cudaLaunchCooperativeKernel((void*)pcg_smem_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
+  else
+    CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args_g, 0, s->stream));
+  if (s->prof.on) {
     cudaEventRecord(r.b, s->stream);
     s->prof.recs.push_back(r);
-  } else {
-    CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args, 0, s->stream));
   }
   ++s->launches;
   LAUNCH("pcg_publish", 32.0, pcg_publish_kernel<<<1, 1, 0, s->stream>>>(w.scal, const_cast<double*>(sc)));
@@ -589,7 +625,7 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
     LAUNCH("seg_fixup", 8.0 * NV * n_own,
            seg_fixup_kernel<<<cdiv((long long)n_own * NV, 256), 256, 0, s->stream>>>(n_own, s->s_off[side].p, s->partial[side].p, a.out_seg));
   }
-  LAUNCH("colsum", 32.0 * s->n_warp, colsum_kernel<<<1, 1024, 0, s->stream>>>(s->n_warp, 4, s->warp_cam.p, sc));
+  launch_colsum(s, s->n_warp, 4, s->warp_cam.p, sc);
   return ARSLAM_OK;
 }
 
@@ -644,7 +680,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   summary->reduced_dim = n;
 
   // ---- buffers that depend on the roles
-  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * sd.n_e)); CU(s->seg_cam.ensure((size_t)2 * sd.n_e));
+  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * sd.n_e)); CU(s->seg_cam.ensure((size_t)4 * sd.n_e));
+  CU(s->seg_cross.ensure((size_t)sd.n_e));
   CU(s->sigE.ensure((size_t)6 * sd.n_e)); CU(s->sigF.ensure((size_t)n + 1)); CU(s->uF.ensure((size_t)n + 1));
   size_t s_elems = 0;
   if (lin == ARSLAM_LINSOLVE_DENSE) {
@@ -666,7 +703,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   double* HF = cam_minus + 4;
   double* sc_head = HF + (size_t)sd.n_f * NV;  // cam_H, cam_g, sum_r2, 0 : summed across ranks
   double* sc = s->sc.p;
-  CU(cudaMemsetAsync(sc, 0, 16 * sizeof(double), s->stream));
+  CU(cudaMemsetAsync(sc, 0, kNumScalars * sizeof(double), s->stream));
 
   int rc = upload_params(s, 0);
   if (rc) return rc;
@@ -710,13 +747,15 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       LAUNCH("sigma", 8.0 * 12 * sd.n_e,
              sigma_pose_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->H[sd.e].p, o.jacobi_scaling, s->sigE.p));
     }
+    SchurArgs schur_args;
     {
       SchurArgs a;
       a.n_e = sd.n_e; a.plane = s->plane;
       a.e_off = s->s_off[sd.e].p; a.f_idx = s->s_oth[sd.e].p;
       a.HE = s->H[sd.e].p; a.W = s->W.p; a.sig_e = s->sigE.p;
       a.radius = radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
-      a.Y = s->Y.p; a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p;
+      a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr;
+      schur_args = a;
       CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
       CU(cudaMemsetAsync(sc + 12, 0, sizeof(double), s->stream));
       LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(sd.n_e, 256), 256, 0, s->stream>>>(a));
@@ -729,8 +768,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;
       }
-      LAUNCH("collect_fail", 8.0 * sd.n_e, collect_fail_kernel<<<1, 1024, 0, s->stream>>>(sd.n_e, s->Z.p, sc));
-      LAUNCH("colsum", 16.0 * sd.n_e, colsum_kernel<<<1, 1024, 0, s->stream>>>(sd.n_e, 2, s->seg_cam.p, cam_minus));
+      launch_colsum(s, sd.n_e, 4, s->seg_cam.p, cam_minus);
     }
     if (s->world > 1) {
       // one allreduce per linearisation: partial Schur terms (+ on a fresh
@@ -742,9 +780,9 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (fresh_linearisation) {
       CU(cudaMemcpyAsync(sc, sc_head, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
       LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p));
-      LAUNCH("colmax", 8.0 * ne_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, s->warp_gmax[sd.e].p, sc + 10));
+      LAUNCH("colmax", 8.0 * ne_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, s->warp_gmax[sd.e].p, sc + 16));
       LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p));
-      LAUNCH("colmax", 8.0 * nf_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_f, 128) * 4, s->warp_gmax[sd.f].p, sc + 11));
+      LAUNCH("colmax", 8.0 * nf_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_f, 128) * 4, s->warp_gmax[sd.f].p, sc + 17));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
@@ -759,7 +797,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
              dense_add_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, s->sigF.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row));
       LAUNCH("dense_add_camera", 64.0,
              dense_add_camera_kernel<<<cdiv(std::max(1, s->n_pad - rhs_row - 1), 128), 128, 0, s->stream>>>(
-                 reinterpret_cast<const LmScalars*>(sc), cam_minus, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row, s->n_pad));
+                 reinterpret_cast<LmScalars*>(sc), cam_minus, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row, s->n_pad));
       if (s->prof.on) {
         Profiler::Rec r{s->prof.id_of("dense_cholesky", 0.0), s->prof.ev(), s->prof.ev()};
         cudaEventRecord(r.a, s->stream);
@@ -778,11 +816,11 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
     {
       BacksubArgs b;
-      b.n_e = sd.n_e; b.plane = s->plane; b.e_off = s->s_off[sd.e].p; b.f_idx = s->s_oth[sd.e].p;
-      b.Y = s->Y.p; b.Z = s->Z.p; b.YB = s->YB.p; b.sig_e = s->sigE.p; b.uF = s->uF.p; b.cam_row = cam_row;
-      b.d_e = s->d_pose[sd.e].p;
-      LAUNCH("backsub", 292.0 * s->n_blk + 200.0 * sd.n_e,
-             backsub_kernel<<<cdiv((long long)sd.n_e * 32, 128), 128, 0, s->stream>>>(b));
+      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row;
+      b.d_e = s->d_pose[sd.e].p; b.seg_cross = s->seg_cross.p;
+      LAUNCH("backsub", 292.0 * s->n_blk + 400.0 * sd.n_e,
+             backsub_kernel<<<cdiv((long long)sd.n_e * kBsGroup, 128), 128, 0, s->stream>>>(b));
+      launch_colsum(s, sd.n_e, 1, s->seg_cross.p, sc + 4);
     }
     double* x_e = sd.e == 0 ? s->cap[k].p : s->tag[k].p;
     double* x_f = sd.f == 0 ? s->cap[k].p : s->tag[k].p;
@@ -790,31 +828,33 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     double* xc_f = sd.f == 0 ? s->cap[kc].p : s->tag[kc].p;
     {
       ApplyArgs ap;
+      ap.uF_cam = s->uF.p + cam_row;
       ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
+      ap.rec = s->H[sd.e].p;
       ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
-      LAUNCH("apply_step", 144.0 * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
-      LAUNCH("colsum", 16.0 * ne_warps, colsum_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, 2, s->warp_norm[sd.e].p, sc + 6));
+      LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
+      launch_colsum(s, cdiv(sd.n_e, 128) * 4, 3, s->warp_norm[sd.e].p, sc + 6);
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
+      ap.rec = HF;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
       ap.count_norms = (s->rank == 0) ? 1 : 0;
-      LAUNCH("apply_step", 144.0 * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
-      LAUNCH("colsum", 16.0 * nf_warps, colsum_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_f, 128) * 4, 2, s->warp_norm[sd.f].p, sc + 8));
+      LAUNCH("apply_step", 144.0 * sd.n_f + 8.0 * NV * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
+      launch_colsum(s, cdiv(sd.n_f, 128) * 4, 3, s->warp_norm[sd.f].p, sc + 9);
       LAUNCH("cam_step", 64.0, cam_step_kernel<<<1, 1, 0, s->stream>>>(s->uF.p + cam_row, s->cam[k].p, s->cam[kc].p, s->d_cam.p, sc));
     }
     cudaEventRecord(s->ev[1], s->stream);
-    // ---------------- candidate point: model cost change and cost at x + delta
+    // ---------------- candidate point: cost at x + delta (residuals only)
     launch_prep(s, kc);
     {
       CandArgs c;
       c.n_blk = s->n_blk; c.plane = s->plane;
       c.own_idx = s->s_own[sd.e].p; c.oth_idx = s->s_oth[sd.e].p; c.obs = s->s_obs[sd.e].p;
-      c.cap_pre = s->cap_pre[k].p; c.tag_pre = s->tag_pre[k].p; c.cap_pre_c = s->cap_pre[kc].p; c.tag_pre_c = s->tag_pre[kc].p;
-      c.cam = s->cam[k].p; c.cam_c = s->cam[kc].p; c.d_cam = s->d_cam.p;
-      c.d_cap = s->d_pose[0].p; c.d_tag = s->d_pose[1].p; c.warp_out = s->warp_cand.p;
-      const int grid = cdiv(s->plane, 128);
-      if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0><<<grid, 128, 0, s->stream>>>(c));
-      else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1><<<grid, 128, 0, s->stream>>>(c));
-      LAUNCH("colsum", 16.0 * s->n_warp, colsum_kernel<<<1, 1024, 0, s->stream>>>(s->n_warp, 2, s->warp_cand.p, sc + 4));
+      c.cap_pre_c = s->cap_pre[kc].p; c.tag_pre_c = s->tag_pre[kc].p; c.cam_c = s->cam[kc].p;
+      c.warp_out = s->warp_cand.p;
+      const int grid = cdiv(s->plane, 256);
+      if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0><<<grid, 256, 0, s->stream>>>(c));
+      else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1><<<grid, 256, 0, s->stream>>>(c));
+      launch_colsum(s, grid * 8, 1, s->warp_cand.p, sc + 5);
     }
     if (s->world > 1) {
       // small allreduce: sums [model, cand_r2, step2_e, xnorm2_e, step2_f, xnorm2_f] and
@@ -823,7 +863,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (rc) return rc;
     }
     cudaEventRecord(s->ev[2], s->stream);
-    CU(cudaMemcpyAsync(s->h_sc, sc, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_sc, sc, kNumScalars * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     {
@@ -833,10 +873,10 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       lin_ms += a; eval_ms += b;
     }
     const double* h = s->h_sc;
-    if (lin == ARSLAM_LINSOLVE_PCG) summary->linear_solver_iterations += (long long)h[3];
+    if (lin == ARSLAM_LINSOLVE_PCG) summary->linear_solver_iterations += (long long)h[18];
     if (fresh_linearisation) {
       x_cost = 0.5 * h[2];
-      grad_max = std::max(std::max(h[10], h[11]), std::fabs(h[1]));
+      grad_max = std::max(std::max(h[16], h[17]), std::fabs(h[1]));
       if (iteration == 0) { summary->initial_cost = x_cost; log_iter(0, x_cost, 0.0, 0.0, 0.0, 1, 1); }
     }
     fresh_linearisation = false;
@@ -847,11 +887,14 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     ++iteration;
     last_successful = false;
     const double f_cur = h[15];
-    x_norm = std::sqrt(h[7] + h[9] + f_cur * f_cur + s->h_cam[1] * s->h_cam[1] + s->h_cam[2] * s->h_cam[2]);
-    const double step_norm = std::sqrt(h[6] + h[8] + h[13] * h[13]);
-    const double model_cost_change = -h[4];
+    x_norm = std::sqrt(h[7] + h[10] + f_cur * f_cur + s->h_cam[1] * s->h_cam[1] + s->h_cam[2] * s->h_cam[2]);
+    const double step_norm = std::sqrt(h[6] + h[9] + h[13] * h[13]);
+    // model_cost_change = -(J d).(r + J d / 2) = -(g.d + d^T H d / 2), assembled from the block pieces
+    const double d_focal = -h[13];
+    const double model_sum = h[4] + h[8] + h[11] + h[1] * d_focal + 0.5 * h[0] * d_focal * d_focal;
+    const double model_cost_change = -model_sum;
     const double cand_cost_raw = 0.5 * h[5];
-    const bool lin_ok = (h[12] == 0.0) && std::isfinite(step_norm) && std::isfinite(h[4]);
+    const bool lin_ok = (h[12] == 0.0) && std::isfinite(step_norm) && std::isfinite(model_sum);
     if (!lin_ok || !(model_cost_change > 0.0)) {
       // HandleInvalidStep
       summary->num_unsuccessful_steps++;

@@ -316,7 +316,37 @@ __global__ void seg_fixup_kernel(int n_pose, const int32_t* __restrict__ seg_off
   out_seg[t] = acc;
 }
 
-// Deterministic column sums of a [n][m] array (m <= 8) into out[m]; one CTA.
+// Deterministic column sums of a [n][m] array (m <= 4) into out[m]: every CTA
+// reduces one contiguous chunk in a fixed order (stage 1), one CTA adds the
+// chunk sums (stage 2).  Same result on every run, no atomics.
+constexpr int kColsumChunks = 128;
+__global__ void __launch_bounds__(256) colsum_stage1_kernel(int n, int m, const double* __restrict__ in,
+                                                            double* __restrict__ part /* [chunks][4] */) {
+  __shared__ double sm[8][4];
+  const int chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  double acc[4] = {0, 0, 0, 0};
+  for (int i = lo + threadIdx.x; i < hi; i += 256)
+    for (int c = 0; c < m; ++c) acc[c] += in[(size_t)i * m + c];
+  for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+  if ((threadIdx.x & 31) == 0)
+    for (int c = 0; c < 4; ++c) sm[threadIdx.x >> 5][c] = acc[c];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+    part[blockIdx.x * 4 + threadIdx.x] = t;
+  }
+}
+__global__ void colsum_stage2_kernel(int chunks, int m, const double* __restrict__ part, double* __restrict__ out) {
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;  // one warp per column
+  if (c >= m) return;
+  double t = 0.0;
+  for (int i = lane; i < chunks; i += 32) t += part[i * 4 + c];
+  t = warp_sum(t);
+  if (lane == 0) out[c] = t;
+}
+// small inputs: one CTA
 __global__ void __launch_bounds__(1024) colsum_kernel(int n, int m, const double* __restrict__ in,
                                                       double* __restrict__ out) {
   __shared__ double sm[1024];
@@ -334,72 +364,50 @@ __global__ void __launch_bounds__(1024) colsum_kernel(int n, int m, const double
   }
 }
 
-// --------------------------------------------------- candidate / model -----
-// One thread per block (E-sorted order).  At the current point x: model
-// residual J*delta per row, accumulated as sum (J d)(r + J d / 2) (Ceres'
-// model_cost_change, trust_region_minimizer.cc).  At the candidate x + delta:
-// sum r^2.  warp partials -> colsum_kernel.  Bytes per corner: 18 in.
+// ------------------------------------------------------------ candidate -----
+// Cost at the candidate point x + delta: one thread per block (E-sorted order),
+// residuals only.  warp partials of sum r^2 -> colsum_kernel.  Bytes per corner: 18 in.
 struct CandArgs {
   int n_blk, plane;
   const int32_t* own_idx;
   const int32_t* oth_idx;
   const double* obs;
-  const double* cap_pre;   // at x (full records)
-  const double* tag_pre;
-  const double* cap_pre_c; // at x + delta
+  const double* cap_pre_c; // prep records at x + delta
   const double* tag_pre_c;
-  const double* cam;       // at x
-  const double* cam_c;     // at x + delta
-  const double* d_cam;     // step, unscaled: [3]
-  const double* d_cap;     // [6 n_cap]
-  const double* d_tag;     // [6 n_tag]
-  double* warp_out;        // [n_warp][2]: model term, candidate sum r^2
+  const double* cam_c;
+  double* warp_out;        // [n_warp]: candidate sum r^2
 };
 template <int SIDE>
-__global__ void __launch_bounds__(128) candidate_kernel(const CandArgs a) {
+__global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  double m = 0.0, c2 = 0.0;
+  double c2 = 0.0;
   if (pos < a.n_blk) {
     const int own = a.own_idx[pos], oth = a.oth_idx[pos];
     const int cap = SIDE == 0 ? own : oth, tag = SIDE == 0 ? oth : own;
-    const double f = a.cam[0], fc = a.cam_c[0], df = a.d_cam[0];
-    double dc[6], da[6];
+    const double fc = a.cam_c[0];
+    double cp[kCapPre];
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.cap_pre_c + (size_t)kCapPre * cap);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      dc[k] = a.d_cap[6 * (size_t)cap + k];
-      da[k] = a.d_tag[6 * (size_t)tag + k];
+      for (int k = 0; k < 11; ++k) {
+        const double2 v = __ldg(src + k);
+        cp[2 * k] = v.x;
+        cp[2 * k + 1] = v.y;
+      }
     }
-    const double dt[3] = {dc[0] + da[0], dc[1] + da[1], dc[2] + da[2]};
-    const double* cp = a.cap_pre + (size_t)kCapPre * cap;
-    const double* tp = a.tag_pre + (size_t)kTagPre * tag;
-    const double* cpc = a.cap_pre_c + (size_t)kCapPre * cap;
     const double* tpc = a.tag_pre_c + (size_t)kTagPre * tag;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
       const double ox = a.obs[(size_t)(2 * i) * a.plane + pos];
       const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
-      CornerJ j;
-      corner_jacobian(cp, tp + 12 * i, f, ox, oy, j);
-#pragma unroll
-      for (int row = 0; row < 2; ++row) {
-        double jd = j.K[row] * df;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          jd += j.A[row][k] * dt[k] + j.B[row][k] * dc[3 + k] + j.C[row][k] * da[3 + k];
-        m += jd * (j.r[row] + jd * 0.5);
-      }
+      double tp3[3] = {__ldg(tpc + 12 * i), __ldg(tpc + 12 * i + 1), __ldg(tpc + 12 * i + 2)};
       double rc[2];
-      corner_residual(cpc, tpc + 12 * i, fc, ox, oy, rc);
+      corner_residual(cp, tp3, fc, ox, oy, rc);
       c2 += rc[0] * rc[0] + rc[1] * rc[1];
     }
   }
-  m = warp_sum(m);
   c2 = warp_sum(c2);
-  if ((threadIdx.x & 31) == 0) {
-    double* o = a.warp_out + 2 * (size_t)(pos >> 5);
-    o[0] = m;
-    o[1] = c2;
-  }
+  if ((threadIdx.x & 31) == 0) a.warp_out[pos >> 5] = c2;
 }
 
 // ------------------------------------------------------------ LM vectors ---
@@ -416,25 +424,30 @@ __global__ void sigma_pose_kernel(int n_pose, const double* __restrict__ rec, in
   }
 }
 
-// Small device-resident scalar block shared by the LM kernels (16 doubles;
+// Small device-resident scalar block shared by the LM kernels (24 doubles;
 // the colsum / colmax reductions write straight into its fields).
 struct LmScalars {
   double cam_H;      // [0] sum K^2   (J^T J of the focal length)
   double cam_g;      // [1] sum K r
   double sum_r2;     // [2] sum r^2 at x
   double unused0;    // [3]
-  double model;      // [4] sum (J d)(r + J d/2)
+  double cross;      // [4] sum over blocks delta_e^T W delta_f
   double cand_r2;    // [5] sum r^2 at x + delta
   double step2_e;    // [6] ||delta||^2, E poses
   double xnorm2_e;   // [7] ||x||^2, E poses that own blocks
-  double step2_f;    // [8]
-  double xnorm2_f;   // [9]
-  double gmax_e;     // [10] max |g_i|, E poses
-  double gmax_f;     // [11]
+  double mq_e;       // [8] sum g.d + d^T H d / 2 + d_f H_e,f.d over E poses
+  double step2_f;    // [9]
+  double xnorm2_f;   // [10]
+  double mq_f;       // [11]
   double chol_fail;  // [12] != 0: a factorisation failed (non-positive pivot)
   double d_cam;      // [13] step of the focal length
   double sigma_f;    // [14] Jacobi scale of the focal length
-  double unused1;    // [15]
+  double focal;      // [15] current focal length
+  double gmax_e;     // [16] max |g_i|, E poses
+  double gmax_f;     // [17]
+  double pcg_iters;  // [18]
+  double pad[5];
 };
+constexpr int kNumScalars = 24;
 
 }  // namespace ars

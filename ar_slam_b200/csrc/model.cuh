@@ -310,9 +310,10 @@ ARS_HD void seed_capture_pose(const double rect[8], double focal, const double t
 }
 
 // Cholesky factor + solve of a 6x6 SPD system held in registers
-// ("batched 6x6 Cholesky in registers").  H is full row-major, L overwrites
-// the lower triangle of the same array.  Returns false on a non-positive
-// pivot (Eigen::LLT's failure condition).
+// ("batched 6x6 Cholesky in registers").  H is full row-major; the factor
+// overwrites the lower triangle of the same array, with the RECIPROCALS of the
+// pivots on the diagonal (the solves then need no division).  Returns false on
+// a non-positive pivot (Eigen::LLT's failure condition).
 ARS_HD bool chol6(double H[36]) {
   bool ok = true;
 #pragma unroll
@@ -321,9 +322,8 @@ ARS_HD bool chol6(double H[36]) {
 #pragma unroll
     for (int k = 0; k < j; ++k) d -= H[j * 6 + k] * H[j * 6 + k];
     ok = ok && (d > 0.0);
-    const double l = sqrt(d);
-    const double il = 1.0 / l;
-    H[j * 6 + j] = l;
+    const double il = 1.0 / sqrt(d);
+    H[j * 6 + j] = il;
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = H[i * 6 + j];
@@ -340,14 +340,14 @@ ARS_HD void chol6_solve(const double L[36], double b[6]) {
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
-    b[i] = s / L[i * 6 + i];
+    b[i] = s * L[i * 6 + i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = b[i];
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
-    b[i] = s / L[i * 6 + i];
+    b[i] = s * L[i * 6 + i];
   }
 }
 

@@ -34,10 +34,26 @@ struct PcgWorkspace {
   double* vec = nullptr;        // x | r | z | p0 | p1 | q | border | rhs : 8 x (6 n_f + 2)
   double* partial = nullptr;    // [grid][8]
   double* scal = nullptr;       // [16]: S_kk, 1/S_kk, iterations, fail, ...
+  // shared-memory resident variant: block rows are split into one contiguous range per CTA
+  bool smem_ok = false;
+  int smem_grid = 0, cap_slots = 0, max_halo = 0, max_slots = 0;
+  size_t smem_bytes = 0;
+  int32_t* cta_row = nullptr;   // [smem_grid + 1]
+  int32_t* halo_ptr = nullptr;  // [smem_grid + 1]
+  int32_t* halo_col = nullptr;  // distinct block columns each CTA reads
+  uint16_t* lcol = nullptr;     // [nnzb] column of a slot as an index into its CTA's halo list
+  int32_t* diag_slot = nullptr; // [n_f]
+  int32_t* slot_row = nullptr;  // [nnzb]
+  int32_t* pair_off = nullptr;  // [n_blk] (E-sorted) pairs before each block
+  int32_t* pair_slot = nullptr; // [n_pairs]
+  long long n_pairs = 0;
   size_t value_count() const { return (size_t)36 * nnzb + (size_t)12 * n_f; }
   void release() {
     cudaFree(row_ptr); cudaFree(col_idx); cudaFree(src_slot); cudaFree(Sfin); cudaFree(Minv);
     cudaFree(vec); cudaFree(partial); cudaFree(scal);
+    cudaFree(cta_row); cudaFree(halo_ptr); cudaFree(halo_col); cudaFree(lcol); cudaFree(diag_slot); cudaFree(slot_row); cudaFree(pair_off); cudaFree(pair_slot);
+    pair_off = pair_slot = nullptr;
+    cta_row = halo_ptr = halo_col = diag_slot = slot_row = nullptr; lcol = nullptr; smem_ok = false;
     row_ptr = col_idx = src_slot = nullptr; Sfin = Minv = vec = partial = scal = nullptr;
     valid = false;
   }
@@ -46,7 +62,7 @@ struct PcgWorkspace {
 
 // ---- symbolic phase (host): block pattern of sum_e W_e^T W_e over the E segments
 inline int pcg_symbolic(PcgWorkspace& ws, int n_e, int n_f, const int32_t* e_off, const int32_t* f_of_blk,
-                        cudaStream_t st, std::string& err) {
+                        cudaStream_t st, std::string& err, int n_sm, size_t smem_limit) {
   ws.release();
   std::vector<uint64_t> keys;
   keys.reserve((size_t)e_off[n_e] * 8);
@@ -76,6 +92,13 @@ inline int pcg_symbolic(PcgWorkspace& ws, int n_e, int n_f, const int32_t* e_off
     }
   ws.n_f = n_f;
   ws.nnzb = nnzb;
+  std::vector<int32_t> pair_off(std::max(e_off[n_e], 1));
+  {
+    long long acc = 0;
+    for (int e = 0; e < n_e; ++e)
+      for (int b = e_off[e]; b < e_off[e + 1]; ++b) { pair_off[b] = (int32_t)acc; acc += b - e_off[e] + 1; }
+    ws.n_pairs = acc;
+  }
   const size_t nvec = (size_t)6 * n_f + 2;
   cudaError_t ce = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, bytes); };
@@ -87,12 +110,85 @@ inline int pcg_symbolic(PcgWorkspace& ws, int n_e, int n_f, const int32_t* e_off
   A((void**)&ws.vec, sizeof(double) * 8 * nvec);
   A((void**)&ws.partial, sizeof(double) * 8 * 4096);
   A((void**)&ws.scal, sizeof(double) * 16);
+  if (ws.n_pairs < (1LL << 31)) {
+    A((void**)&ws.pair_off, sizeof(int32_t) * pair_off.size());
+    A((void**)&ws.pair_slot, sizeof(int32_t) * std::max<long long>(ws.n_pairs, 1));
+  }
   if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
   cudaMemcpyAsync(ws.row_ptr, row_ptr.data(), sizeof(int32_t) * (n_f + 1), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(ws.col_idx, col.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(ws.src_slot, src.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice, st);
+  if (ws.pair_off) cudaMemcpyAsync(ws.pair_off, pair_off.data(), sizeof(int32_t) * pair_off.size(), cudaMemcpyHostToDevice, st);
   ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) { err = std::string("pcg symbolic upload: ") + cudaGetErrorString(ce); return -2; }
+  // ---- one contiguous block-row range per SM, balanced by block count; the CTA keeps its
+  // slice of the matrix in shared memory for the whole solve (33 MB of SMEM across 148 SMs)
+  {
+    const int G = n_sm;
+    std::vector<int32_t> cta_row(G + 1, n_f), halo_ptr(G + 1, 0), halo_col, diag(n_f, 0);
+    std::vector<uint16_t> lcol(nnzb, 0);
+    cta_row[0] = 0;
+    {
+      int r = 0;
+      for (int c = 0; c < G; ++c) {
+        const long long target = (long long)nnzb * (c + 1) / G;
+        while (r < n_f && row_ptr[r + 1] <= target) ++r;
+        if (c == G - 1) r = n_f;
+        cta_row[c + 1] = r;
+      }
+    }
+    int max_halo = 0, max_slots = 0, max_rows = 0;
+    std::vector<int32_t> tmp;
+    for (int c = 0; c < G; ++c) {
+      const int s0 = row_ptr[cta_row[c]], s1 = row_ptr[cta_row[c + 1]];
+      tmp.assign(col.begin() + s0, col.begin() + s1);
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      for (int sl = s0; sl < s1; ++sl)
+        lcol[sl] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), col[sl]) - tmp.begin());
+      halo_ptr[c + 1] = halo_ptr[c] + (int)tmp.size();
+      halo_col.insert(halo_col.end(), tmp.begin(), tmp.end());
+      max_halo = std::max(max_halo, (int)tmp.size());
+      max_slots = std::max(max_slots, s1 - s0);
+      max_rows = std::max(max_rows, cta_row[c + 1] - cta_row[c]);
+    }
+    for (int r = 0; r < n_f; ++r)
+      diag[r] = (int32_t)(std::lower_bound(col.begin() + row_ptr[r], col.begin() + row_ptr[r + 1], r) - col.begin());
+    {
+      std::vector<int32_t> srow(nnzb);
+      for (int r = 0; r < n_f; ++r)
+        for (int sl = row_ptr[r]; sl < row_ptr[r + 1]; ++sl) srow[sl] = r;
+      if (ce == cudaSuccess) ce = cudaMalloc((void**)&ws.diag_slot, sizeof(int32_t) * std::max(n_f, 1));
+      if (ce == cudaSuccess) ce = cudaMalloc((void**)&ws.slot_row, sizeof(int32_t) * std::max(nnzb, 1));
+      if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+      cudaMemcpyAsync(ws.diag_slot, diag.data(), sizeof(int32_t) * n_f, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(ws.slot_row, srow.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice, st);
+      ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) { err = std::string("pcg symbolic upload: ") + cudaGetErrorString(ce); return -2; }
+    }
+    ws.smem_grid = G;
+    ws.max_halo = max_halo;
+    ws.max_slots = max_slots;
+    // dynamic shared memory: matrix slice | gathered halo vector | local column ids
+    const size_t fixed = (size_t)max_halo * 48 + (((size_t)max_slots * 2 + 15) / 16) * 16 + 2048;
+    ws.smem_ok = max_halo < 65535 && max_rows <= 64 && smem_limit > fixed + 288 * 16;
+    if (ws.smem_ok) {
+      ws.cap_slots = (int)std::min<size_t>((smem_limit - fixed) / 288, (size_t)max_slots);
+      ws.smem_bytes = (size_t)ws.cap_slots * 288 + fixed - 2048;
+      auto A2 = [&](void** p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
+      A2((void**)&ws.cta_row, sizeof(int32_t) * (G + 1));
+      A2((void**)&ws.halo_ptr, sizeof(int32_t) * (G + 1));
+      A2((void**)&ws.halo_col, sizeof(int32_t) * halo_col.size());
+      A2((void**)&ws.lcol, sizeof(uint16_t) * nnzb);
+      if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+      cudaMemcpyAsync(ws.cta_row, cta_row.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(ws.halo_ptr, halo_ptr.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(ws.halo_col, halo_col.data(), sizeof(int32_t) * halo_col.size(), cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(ws.lcol, lcol.data(), sizeof(uint16_t) * nnzb, cudaMemcpyHostToDevice, st);
+      ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) { err = std::string("pcg symbolic upload: ") + cudaGetErrorString(ce); return -2; }
+    }
+  }
   ws.valid = true;
   return 0;
 }
@@ -110,21 +206,32 @@ struct SparseTarget {
     atomicAdd(borderm + 6 * (size_t)f + c, b0);
     atomicAdd(rhsm + 6 * (size_t)f + c, b1);
   }
-  // lower block (row fj, col fi), found by bisection in the row's sorted column list
-  __device__ __forceinline__ double* block(int fi, int fj) const {
+  const int32_t* pair_slot;  // [n_pairs] precomputed slot of every (partner, block) pair, or null
+  // lower block (row fj, col fi): precomputed slot, else bisection in the row's sorted column list
+  __device__ __forceinline__ int find(int fi, int fj) const {
     int lo = row_ptr[fj], hi = row_ptr[fj + 1] - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (col_idx[mid] < fi) lo = mid + 1; else hi = mid;
     }
-    return Sraw + 36 * (size_t)lo;
+    return lo;
   }
-  __device__ __forceinline__ void add(double* blk, int r, int c, double v, bool diag, bool twice) const {
-    if (!diag) { atomicAdd(blk + c * 6 + r, v); return; }
-    atomicAdd(blk + r * 6 + c, v);
-    if (twice) atomicAdd(blk + c * 6 + r, v);
+  __device__ __forceinline__ double* block(int fi, int fj, long long pair) const {
+    return Sraw + 36 * (size_t)(pair_slot ? pair_slot[pair] : find(fi, fj));
   }
+  __device__ __forceinline__ double* elem(double* blk, int e) const { return blk + e; }
 };
+
+// fills pair_slot once per problem: thread per E-sorted block, loop over its partners
+__global__ void pair_slot_kernel(int n_blk, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
+                                 const int32_t* __restrict__ f_idx, const int32_t* __restrict__ pair_off,
+                                 SparseTarget t, int32_t* __restrict__ out) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_blk) return;
+  const int beg = e_off[e_idx[pos]];
+  const int fj = f_idx[pos];
+  for (int i = 0; i <= pos - beg; ++i) out[(size_t)pair_off[pos] + i] = t.find(f_idx[beg + i], fj);
+}
 
 // ---- finalize: scale by sigma_F, add the F-pose diagonal blocks and damping,
 // mirror the upper blocks, invert the diagonal blocks for the preconditioner.
@@ -149,8 +256,25 @@ struct PcgFinalizeArgs {
   double* scal;           // [0] S_kk  [1] 1/S_kk  [3] fail
 };
 
-__global__ void pcg_finalize_kernel(const PcgFinalizeArgs a) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per block row
+// off-diagonal blocks: one thread per (slot, block row i) -- 6 consecutive doubles each
+__global__ void pcg_finalize_offdiag_kernel(const PcgFinalizeArgs a, const int32_t* __restrict__ slot_row) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nnzb * 6) return;
+  const int s = t / 6, i = t - s * 6;
+  const int row = slot_row[s], col = a.col_idx[s];
+  if (col == row) return;
+  const double* src = a.Sraw + 36 * (size_t)a.src_slot[s];
+  double* dst = a.Sfin + 36 * (size_t)s + i * 6;
+  const double sri = a.sigF[6 * (size_t)row + i];
+  const bool tr = col > row;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    dst[j] = -sri * a.sigF[6 * (size_t)col + j] * (tr ? src[j * 6 + i] : src[i * 6 + j]);
+}
+
+// diagonal blocks, border, right-hand side and the block-Jacobi inverses: one thread per block row
+__global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __restrict__ diag_slot) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row == 0) {
     const double sf = a.sc->sigma_f;
     const double h = a.sc->cam_H * sf * sf;
@@ -159,7 +283,7 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a) {
     a.scal[0] = skk;
     a.scal[1] = 1.0 / skk;
     a.rhs[6 * (size_t)a.n_f] = sf * (a.sc->cam_g - a.cam_minus[1]);
-    if (!(skk > 0.0)) a.scal[3] = 1.0;
+    if (!(skk > 0.0) || a.cam_minus[2] != 0.0) a.scal[3] = 1.0;
   }
   if (row >= a.n_f) return;
   double sr[6];
@@ -172,45 +296,30 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a) {
     a.border[6 * (size_t)row + i] = sr[i] * scam * (rec[27 + i] - a.borderm[6 * (size_t)row + i]);
     a.rhs[6 * (size_t)row + i] = sr[i] * (rec[21 + i] - a.rhsm[6 * (size_t)row + i]);
   }
-  for (int s = a.row_ptr[row]; s < a.row_ptr[row + 1]; ++s) {
-    const int col = a.col_idx[s];
-    const double* src = a.Sraw + 36 * (size_t)a.src_slot[s];
-    double* dst = a.Sfin + 36 * (size_t)s;
-    if (col != row) {
-      double scl[6];
+  const int s = diag_slot[row];
+  const double* src = a.Sraw + 36 * (size_t)s;
+  double* dst = a.Sfin + 36 * (size_t)s;
+  double D[36];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) scl[i] = a.sigF[6 * (size_t)col + i];
-      const bool tr = col > row;
+  for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) dst[i * 6 + j] = -sr[i] * scl[j] * (tr ? src[j * 6 + i] : src[i * 6 + j]);
-    } else {
-      double D[36];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const double h = rec[i <= j ? tri6(i, j) : tri6(j, i)];
-          // the raw diagonal block holds its lower triangle (+ upper from the i != j duplicates): symmetrise from the lower part
-          const double m = i >= j ? src[i * 6 + j] : src[j * 6 + i];
-          double v = sr[i] * sr[j] * (h - m);
-          if (i == j) v += fmin(fmax(sr[i] * sr[i] * h, a.min_diag), a.max_diag) / a.radius;
-          D[i * 6 + j] = v;
-          dst[i * 6 + j] = v;
-        }
-      // inverse through the Cholesky factor (columns of the identity)
-      const bool ok = chol6(D);
-      if (!ok) a.scal[3] = 1.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double e[6] = {0, 0, 0, 0, 0, 0};
-        e[c] = 1.0;
-        chol6_solve(D, e);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) a.Minv[36 * (size_t)row + i * 6 + c] = e[i];
-      }
+    for (int j = 0; j < 6; ++j) {
+      const double h = rec[i <= j ? tri6(i, j) : tri6(j, i)];
+      const double m = i >= j ? src[i * 6 + j] : src[j * 6 + i];  // raw diagonal block is symmetric
+      double v = sr[i] * sr[j] * (h - m);
+      if (i == j) v += fmin(fmax(sr[i] * sr[i] * h, a.min_diag), a.max_diag) / a.radius;
+      D[i * 6 + j] = v;
+      dst[i * 6 + j] = v;
     }
+  const bool ok = chol6(D);
+  if (!ok) a.scal[3] = 1.0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double e[6] = {0, 0, 0, 0, 0, 0};
+    e[c] = 1.0;
+    chol6_solve(D, e);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.Minv[36 * (size_t)row + i * 6 + c] = e[i];
   }
 }
 
@@ -279,7 +388,7 @@ __device__ __forceinline__ void grid_sums(cg::grid_group& grid, double (&v)[NS],
 }
 
 __global__ void pcg_publish_kernel(const double* scal, double* sc) {
-  sc[3] = scal[2];                       // PCG iterations of this solve
+  sc[18] = scal[2];                      // PCG iterations of this solve
   if (scal[3] != 0.0) sc[12] = 1.0;      // failure -> invalid LM step
 }
 
@@ -427,6 +536,174 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
   }
 }
 
-inline cudaError_t pcg_init() { return cudaSuccess; }
+
+// ---- shared-memory resident variant -------------------------------------------
+// Each CTA owns a contiguous range of block rows and keeps that slice of the
+// matrix in shared memory across all iterations (config 3: 30.6 MB over 148 SMs
+// = 207 KB per SM); per iteration it gathers the ~250 neighbouring 6-vectors it
+// needs from L2 once, multiplies out of shared memory, and keeps x, r, q, p of
+// its own rows in registers.  HBM / L2 traffic per iteration is the halo only.
+struct PcgSmemArgs {
+  PcgArgs a;
+  const int32_t* cta_row;
+  const int32_t* halo_ptr;
+  const int32_t* halo_col;
+  const uint16_t* lcol;
+  int cap_slots, max_halo, max_slots;
+};
+
+__global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ double sm[64 + 32 * 2 + 8];
+  const PcgArgs& a = A.a;
+  double* Ss = reinterpret_cast<double*>(dyn);                       // [cap_slots][36]
+  double* xs = Ss + (size_t)A.cap_slots * 36;                        // [max_halo][6]
+  uint16_t* lc = reinterpret_cast<uint16_t*>(xs + (size_t)A.max_halo * 6);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 3, rr_ = lane & 7;
+  const bool act = rr_ < 6;
+  const int n_f = a.n_f, camrow = 6 * n_f;
+  const int r0 = A.cta_row[blockIdx.x], r1 = A.cta_row[blockIdx.x + 1];
+  const int s_beg = a.row_ptr[r0], s_end = a.row_ptr[r1];
+  const int nslot = s_end - s_beg, ncache = min(nslot, A.cap_slots);
+  const int h0 = A.halo_ptr[blockIdx.x], nhalo = A.halo_ptr[blockIdx.x + 1] - h0;
+  const double skk = a.scal[0], iskk = a.scal[1];
+  const bool is_cam_owner = (blockIdx.x == 0 && tid == 0);
+  int parity = 0;
+  // matrix slice and local column ids -> shared memory (once)
+  {
+    const double2* src = reinterpret_cast<const double2*>(a.S + 36 * (size_t)s_beg);
+    double2* dst = reinterpret_cast<double2*>(Ss);
+    for (int i = tid; i < ncache * 18; i += kPcgThreads) dst[i] = src[i];
+    for (int i = tid; i < nslot; i += kPcgThreads) lc[i] = A.lcol[s_beg + i];
+  }
+  // this warp's rows (at most two), state in registers of lanes 0..5
+  const int rowA = r0 + wid, rowB = r0 + wid + 32;
+  const bool hasA = rowA < r1, hasB = rowB < r1;
+  double xA = 0.0, xB = 0.0, rA = 0.0, rB = 0.0, qA = 0.0, qB = 0.0, pA = 0.0, pB = 0.0;
+  double s2[2] = {0.0, 0.0};
+  auto precond = [&](int row, double rv) {
+    double zv = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double rc = __shfl_sync(0xffffffffu, rv, c);
+      if (lane < 6) zv += a.Minv[36 * (size_t)row + lane * 6 + c] * rc;
+    }
+    return zv;
+  };
+  if (hasA) {
+    if (lane < 6) rA = a.rhs[6 * (size_t)rowA + lane];
+    const double zv = precond(rowA, rA);
+    if (lane < 6) { a.z[6 * (size_t)rowA + lane] = zv; a.p0[6 * (size_t)rowA + lane] = 0.0; s2[0] += rA * zv; s2[1] += rA * rA; }
+  }
+  if (hasB) {
+    if (lane < 6) rB = a.rhs[6 * (size_t)rowB + lane];
+    const double zv = precond(rowB, rB);
+    if (lane < 6) { a.z[6 * (size_t)rowB + lane] = zv; a.p0[6 * (size_t)rowB + lane] = 0.0; s2[0] += rB * zv; s2[1] += rB * rB; }
+  }
+  double xk = 0.0, rk = 0.0;
+  if (is_cam_owner) {
+    rk = a.rhs[camrow];
+    const double zv = rk * iskk;
+    a.z[camrow] = zv; a.p0[camrow] = 0.0;
+    s2[0] += rk * zv;
+    s2[1] += rk * rk;
+  }
+  grid_sums<2>(grid, s2, a.partial, sm, parity);
+  double rz = s2[0];
+  const double bb = s2[1];
+  const double thresh = a.tol * a.tol * bb;
+  double beta = 0.0;
+  double* p_old = a.p0;
+  double* p_new = a.p1;
+  int it = 0;
+  bool fail = !(bb >= 0.0) || !isfinite(bb);
+  if (!(bb == 0.0 || fail)) {
+    while (it < a.max_iter) {
+      ++it;
+      // ---- phase A: gather p = z + beta p_old for the halo columns, q = S p from shared memory
+      const double pk = a.z[camrow] + beta * p_old[camrow];
+      for (int i = tid; i < nhalo * 6; i += kPcgThreads) {
+        const int c = A.halo_col[h0 + i / 6], k = i - (i / 6) * 6;
+        xs[i] = a.z[6 * (size_t)c + k] + beta * p_old[6 * (size_t)c + k];
+      }
+      __syncthreads();
+      double sa[2] = {0.0, 0.0};
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const int row = which == 0 ? rowA : rowB;
+        if (!(which == 0 ? hasA : hasB)) continue;
+        double acc = 0.0;
+        const int s0 = a.row_ptr[row] - s_beg, s1 = a.row_ptr[row + 1] - s_beg;
+        double pf = 0.0;
+        for (int s = s0 + g; s < s1; s += 4) {
+          if (act) {
+            const double* B = (s < ncache ? Ss + 36 * (size_t)s : a.S + 36 * (size_t)(s_beg + s)) + rr_ * 6;
+            const double* xv = xs + 6 * (int)lc[s];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc += B[j] * xv[j];
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane < 6) {
+          pf = a.z[6 * (size_t)row + lane] + beta * p_old[6 * (size_t)row + lane];
+          const double bd = a.border[6 * (size_t)row + lane];
+          const double qf = acc + bd * pk;
+          p_new[6 * (size_t)row + lane] = pf;
+          sa[0] += pf * qf;
+          sa[1] += bd * pf;
+          if (which == 0) { pA = pf; qA = qf; } else { pB = pf; qB = qf; }
+        }
+      }
+      grid_sums<2>(grid, sa, a.partial, sm, parity);
+      const double qk = sa[1] + skk * pk;
+      const double pq = sa[0] + pk * qk;
+      if (!(pq > 0.0) || !isfinite(pq)) { fail = true; break; }
+      const double alpha = rz / pq;
+      // ---- phase B: own rows only, state in registers
+      double sb[2] = {0.0, 0.0};
+      if (hasA) {
+        xA += alpha * pA;
+        rA -= alpha * qA;
+        const double zv = precond(rowA, rA);
+        if (lane < 6) { a.z[6 * (size_t)rowA + lane] = zv; sb[0] += rA * zv; sb[1] += rA * rA; }
+      }
+      if (hasB) {
+        xB += alpha * pB;
+        rB -= alpha * qB;
+        const double zv = precond(rowB, rB);
+        if (lane < 6) { a.z[6 * (size_t)rowB + lane] = zv; sb[0] += rB * zv; sb[1] += rB * rB; }
+      }
+      if (is_cam_owner) {
+        p_new[camrow] = pk;
+        xk += alpha * pk;
+        rk -= alpha * qk;
+        const double zv = rk * iskk;
+        a.z[camrow] = zv;
+        sb[0] += rk * zv;
+        sb[1] += rk * rk;
+      }
+      grid_sums<2>(grid, sb, a.partial, sm, parity);
+      beta = sb[0] / rz;
+      rz = sb[0];
+      double* t = p_old; p_old = p_new; p_new = t;
+      if (sb[1] <= thresh) break;
+      if (!isfinite(sb[1])) { fail = true; break; }
+    }
+  }
+  if (hasA && lane < 6) a.x[6 * (size_t)rowA + lane] = xA;
+  if (hasB && lane < 6) a.x[6 * (size_t)rowB + lane] = xB;
+  if (is_cam_owner) {
+    a.x[camrow] = xk;
+    a.scal[2] = (double)it;
+    if (fail) a.scal[3] = 1.0;
+  }
+}
+
+inline cudaError_t pcg_init() {
+  return cudaFuncSetAttribute(pcg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+}
 
 }  // namespace ars

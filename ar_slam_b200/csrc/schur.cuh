@@ -20,14 +20,14 @@ struct SchurArgs {
   int n_e, plane;
   const int32_t* e_off;   // [n_e + 1] block offsets (E-sorted order)
   const int32_t* f_idx;   // [n_blk]   F pose per E-sorted block
+  const int32_t* pair_off; // [n_blk]  number of (partner, block) pairs before each block (sparse target)
   const double* HE;       // [n_e][NV]
   const double* W;        // 36 planes
   const double* sig_e;    // [6 n_e]
   double radius, min_diag, max_diag;
-  double* Y;              // 36 planes: Ht_ee^-1 (sig_e W)
   double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
   double* YB;             // [n_e][6]: Ht_ee^-1 sig_e H_e,f
-  double* seg_cam;        // [n_e][2]: (sig_e H_e,f).yb , (sig_e H_e,f).z
+  double* seg_cam;        // [n_e][4]: (sig_e H_e,f).yb , (sig_e H_e,f).z , factorisation failed, 0
 };
 
 // decode p -> (i <= j) with p = j (j + 1) / 2 + i
@@ -70,13 +70,9 @@ struct DenseTarget {
     atomicAdd(S + (size_t)rhs_row * ld + 6 * f + c, b1);
   }
   // M[r][c] = element (6 fi + r, 6 fj + c), fi <= fj, of sum W~^T Y; stored in the lower triangle
-  __device__ __forceinline__ double* block(int fi, int fj) const { return S + (size_t)(6 * fj) * ld + 6 * fi; }
-  __device__ __forceinline__ void add(double* blk, int r, int c, double v, bool diag, bool twice) const {
-    if (!diag) { atomicAdd(blk + (size_t)c * ld + r, v); return; }
-    // diagonal block: keep it fully symmetric
-    atomicAdd(blk + (size_t)r * ld + c, v);
-    if (twice) atomicAdd(blk + (size_t)c * ld + r, v);
-  }
+  __device__ __forceinline__ double* block(int fi, int fj, long long /*pair*/) const { return S + (size_t)(6 * fj) * ld + 6 * fi; }
+  // address of element e = 6 * row + col of a 6x6 block
+  __device__ __forceinline__ double* elem(double* blk, int e) const { return blk + (size_t)(e / 6) * ld + (e % 6); }
 };
 
 // One thread per residual block (E-sorted order).  Thread j of a segment
@@ -89,73 +85,110 @@ struct DenseTarget {
 template <typename Target>
 __global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk,
                                                               const int32_t* __restrict__ e_idx) {
+  __shared__ double stage[4][32][37];
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= n_blk) return;
-  const int e = e_idx[pos];
-  const int beg = a.e_off[e];
-  const int j = pos - beg;
-  double L[36], z[6], yb[6], s[6], hk[6];
-  load_scaled_E(a, e, L, z, hk, s);
-  const bool ok = chol6(L);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool valid = pos < n_blk;
+  const int e = valid ? e_idx[pos] : 0;
+  const int beg = valid ? a.e_off[e] : 0;
+  const int j = valid ? pos - beg : -1;
+  double Y[36], s[6];
+  int fj = 0;
+  if (valid) {
+    double L[36], z[6], yb[6], hk[6];
+    load_scaled_E(a, e, L, z, hk, s);
+    const bool ok = chol6(L);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) yb[i] = hk[i];
-  chol6_solve(L, z);
-  chol6_solve(L, yb);
-  if (j == 0) {
-    double* zo = a.Z + 8 * (size_t)e;
-    double c0 = 0.0, c1 = 0.0;
+    for (int i = 0; i < 6; ++i) yb[i] = hk[i];
+    chol6_solve(L, z);
+    chol6_solve(L, yb);
+    if (j == 0) {
+      double* zo = a.Z + 8 * (size_t)e;
+      double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      zo[i] = z[i];
-      a.YB[6 * (size_t)e + i] = yb[i];
-      c0 += hk[i] * yb[i];
-      c1 += hk[i] * z[i];
-    }
-    zo[6] = ok ? 0.0 : 1.0;
-    zo[7] = 0.0;
-    a.seg_cam[2 * (size_t)e] = c0;
-    a.seg_cam[2 * (size_t)e + 1] = c1;
-  }
-  const size_t ps = a.plane;
-  const int fj = a.f_idx[pos];
-  double Y[36];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    double col[6];
-    double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
-      b0 += col[i] * yb[i];
-      b1 += col[i] * z[i];
-    }
-    chol6_solve(L, col);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      Y[i * 6 + c] = col[i];
-      a.Y[(size_t)(i * 6 + c) * ps + pos] = col[i];
-    }
-    t.add_border(fj, c, b0, b1);
-  }
-  for (int i = 0; i <= j; ++i) {
-    const int bi = beg + i;
-    const int fi = a.f_idx[bi];  // fi <= fj: blocks are sorted by F pose inside a segment
-    double Wi[36];
-#pragma unroll
-    for (int m = 0; m < 6; ++m)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
-    double* blk = t.block(fi, fj);
-    const bool diag = fi == fj, twice = diag && (i != j);
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double acc = 0.0;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) acc += Wi[m * 6 + r] * Y[m * 6 + c];
-        t.add(blk, r, c, acc, diag, twice);
+      for (int i = 0; i < 6; ++i) {
+        zo[i] = z[i];
+        a.YB[6 * (size_t)e + i] = yb[i];
+        c0 += hk[i] * yb[i];
+        c1 += hk[i] * z[i];
       }
+      zo[6] = ok ? 0.0 : 1.0;
+      zo[7] = 0.0;
+      double* sg = a.seg_cam + 4 * (size_t)e;
+      sg[0] = c0; sg[1] = c1; sg[2] = ok ? 0.0 : 1.0; sg[3] = 0.0;
+    }
+    const size_t ps = a.plane;
+    fj = a.f_idx[pos];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double col[6];
+      double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
+        b0 += col[i] * yb[i];
+        b1 += col[i] * z[i];
+      }
+      chol6_solve(L, col);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) Y[i * 6 + c] = col[i];
+      t.add_border(fj, c, b0, b1);
+    }
+  }
+  // pair products W~_i^T Y_j for partners i <= j of the same segment.  Every lane stages its
+  // 6x6 product in shared memory; the warp then adds it to the reduced system with one
+  // atomic per lane on consecutive addresses (coalesced reductions at L2).
+  int tmax = j;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  const size_t ps = a.plane;
+  for (int i = 0; i <= tmax; ++i) {
+    const bool active = i <= j;
+    double* blk = nullptr;
+    if (active) {
+      const int bi = beg + i;
+      const int fi = a.f_idx[bi];  // fi <= fj: blocks are sorted by F pose inside a segment
+      double Wi[36];
+#pragma unroll
+      for (int m = 0; m < 6; ++m)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
+      blk = t.block(fi, fj, (a.pair_off ? (long long)a.pair_off[pos] : 0) + i);
+      const bool diag = fi == fj, twice = diag && (i != j);
+      double* st = stage[wid][lane];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double acc = 0.0;  // M[r][c] = element (6 fi + r, 6 fj + c)
+          double acct = 0.0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) {
+            acc += Wi[m * 6 + r] * Y[m * 6 + c];
+            if (twice) acct += Wi[m * 6 + c] * Y[m * 6 + r];
+          }
+          // lower-triangular storage: off-diagonal products land transposed in block (fj, fi)
+          if (!diag) st[c * 6 + r] = acc;
+          else st[r * 6 + c] = twice ? acc + acct : acc;
+        }
+    }
+    __syncwarp();
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    // lanes 0..31 of the warp add elements 0..31 of every staged block; the 4-element tails
+    // (elements 32..35) of eight blocks at a time share one more warp-wide atomic
+    for (int base = 0; base < 32; base += 8) {
+      if (!((m >> base) & 0xffu)) continue;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int src = base + q;
+        double* dst = reinterpret_cast<double*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(blk), src));
+        if ((m >> src) & 1u) atomicAdd(t.elem(dst, lane), stage[wid][src][lane]);
+      }
+      const int src = base + (lane >> 2);
+      double* dst = reinterpret_cast<double*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(blk), src));
+      if ((m >> src) & 1u) atomicAdd(t.elem(dst, 32 + (lane & 3)), stage[wid][src][32 + (lane & 3)]);
+    }
+    __syncwarp();
   }
 }
 
@@ -165,8 +198,7 @@ __global__ void schur_empty_kernel(const SchurArgs a) {
   if (e >= a.n_e || a.e_off[e + 1] > a.e_off[e]) return;
   for (int i = 0; i < 8; ++i) a.Z[8 * (size_t)e + i] = 0.0;
   for (int i = 0; i < 6; ++i) a.YB[6 * (size_t)e + i] = 0.0;
-  a.seg_cam[2 * (size_t)e] = 0.0;
-  a.seg_cam[2 * (size_t)e + 1] = 0.0;
+  for (int i = 0; i < 4; ++i) a.seg_cam[4 * (size_t)e + i] = 0.0;
 }
 
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
@@ -205,7 +237,7 @@ __global__ void dense_add_pose_kernel(int n_f, const double* __restrict__ HF, co
 }
 
 // Camera row / rhs tail / identity padding.  cam_minus = column sums of seg_cam.
-__global__ void dense_add_camera_kernel(const LmScalars* __restrict__ sc, const double* __restrict__ cam_minus,
+__global__ void dense_add_camera_kernel(LmScalars* __restrict__ sc, const double* __restrict__ cam_minus,
                                         double radius, double min_diag, double max_diag, double* __restrict__ S,
                                         long long ld, int cam_row, int rhs_row, int n_pad) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -215,6 +247,7 @@ __global__ void dense_add_camera_kernel(const LmScalars* __restrict__ sc, const 
     S[(size_t)cam_row * ld + cam_row] = sf * sf * (sc->cam_H - cam_minus[0]) + d;
     S[(size_t)rhs_row * ld + cam_row] = sf * (sc->cam_g - cam_minus[1]);
     S[(size_t)rhs_row * ld + rhs_row] = 1e300;
+    if (cam_minus[2] != 0.0) sc->chol_fail = 1.0;  // some E pose's damped 6x6 block was not positive definite
   }
   const int i = rhs_row + 1 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) S[(size_t)i * ld + i] = 1.0;
@@ -228,44 +261,77 @@ __global__ void scale_uF_kernel(int n, const double* __restrict__ y, const doubl
   if (i < n) uF[i] = y[i] * sigF[i];
 }
 
-// Back substitution of the E poses: y_e = z - sum_j Y_j uF[f_j] - yb uF[cam];
-// delta_e = -sig_e y_e.  One warp per E pose, lanes over its blocks.
+// Back substitution of the E poses and the cross term of the model cost change.
+//   y_e = z - Ht_ee^-1 (sum_j sig_e W_j uF[f_j]) - yb uF[cam],   delta_e = -sig_e y_e
+//   cross_e = sum_j delta_e^T W_j delta_f,   delta_f = -uF[f_j]
+// One warp per E pose, lanes over its blocks; the 6x6 factor is rebuilt in
+// registers from the pose record (cheaper than keeping Ht_ee^-1 W in HBM).
+// Bytes per corner: 72 (W) + 1 (index).
 struct BacksubArgs {
-  int n_e, plane;
-  const int32_t* e_off;
-  const int32_t* f_idx;
-  const double* Y;
-  const double* Z;
-  const double* YB;
-  const double* sig_e;
+  SchurArgs sa;       // HE, W, sig_e, radius, e_off, f_idx, Z, YB
   const double* uF;   // [6 n_f + 1]
   int cam_row;
   double* d_e;        // [6 n_e] step of the E poses
+  double* seg_cross;  // [n_e]
 };
+constexpr int kBsGroup = 8;  // lanes per E pose: four poses per warp (8 blocks per capture is the common case)
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = kBsGroup / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= a.n_e) return;
-  const int beg = a.e_off[e], k = a.e_off[e + 1] - beg;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  const size_t ps = a.plane;
-  for (int j = lane; j < k; j += 32) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gid / kBsGroup, gl = gid % kBsGroup;
+  const bool valid = e < a.sa.n_e;
+  const int beg = valid ? a.sa.e_off[e] : 0, k = valid ? a.sa.e_off[e + 1] - beg : 0;
+  double L[36], zt[6], hk[6], s[6];
+  if (k > 0) {
+    load_scaled_E(a.sa, e, L, zt, hk, s);
+    chol6(L);
+  }
+  const size_t ps = a.sa.plane;
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = gl; j < k; j += kBsGroup) {
     const int blk = beg + j;
-    const int f = a.f_idx[blk];
+    const int f = a.sa.f_idx[blk];
     double u[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) u[c] = a.uF[6 * (size_t)f + c];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) acc[i] += a.Y[(size_t)(i * 6 + c) * ps + blk] * u[c];
+      for (int c = 0; c < 6; ++c) t[i] += a.sa.W[(size_t)(i * 6 + c) * ps + blk] * u[c];
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane < 6) {
+  for (int i = 0; i < 6; ++i) t[i] = group_sum(t[i]);
+  double de[6] = {0, 0, 0, 0, 0, 0};
+  if (k > 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) t[i] *= s[i];
+    chol6_solve(L, t);
     const double uc = a.uF[a.cam_row];
-    const double y = a.Z[8 * (size_t)e + lane] - acc[lane] - a.YB[6 * (size_t)e + lane] * uc;
-    a.d_e[6 * (size_t)e + lane] = (k > 0) ? -a.sig_e[6 * (size_t)e + lane] * y : 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      de[i] = -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - a.sa.YB[6 * (size_t)e + i] * uc);
+  }
+  double cross = 0.0;
+  for (int j = gl; j < k; j += kBsGroup) {
+    const int blk = beg + j;
+    const int f = a.sa.f_idx[blk];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double w = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) w += de[i] * a.sa.W[(size_t)(i * 6 + c) * ps + blk];
+      cross -= w * a.uF[6 * (size_t)f + c];
+    }
+  }
+  cross = group_sum(cross);
+  if (valid && gl == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.d_e[6 * (size_t)e + i] = de[i];
+    a.seg_cross[e] = cross;
   }
 }
 
@@ -277,23 +343,27 @@ struct ApplyArgs {
   const double* x;          // [6 n_pose]
   const double* step;       // [6 n_pose]: d_e (already the step) or uF (to be negated)
   int negate;
+  const double* rec;        // [n_pose][NV] normal-equation records of this side (unscaled)
+  const double* uF_cam;     // -> uF[cam_row]; the focal step is its negative
   double* delta;            // [6 n_pose] out (unscaled step)
   double* x_cand;           // [6 n_pose] out
-  double* warp_out;         // [n_warp][2]: sum delta^2, sum x^2
-  int count_norms;          // 0: this rank does not own the norms of this side (multi-GPU)
+  double* warp_out;         // [n_warp][3]: sum delta^2, sum x^2, sum (g.d + d^T H d / 2 + d_cam H_pose,f.d)
+  int count_norms;          // 0: this rank does not own the sums of this side (multi-GPU)
 };
 __global__ void apply_step_kernel(const ApplyArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double d2 = 0.0, x2 = 0.0;
+  double d2 = 0.0, x2 = 0.0, mq = 0.0;
   if (i < a.n_pose) {
     const bool active = a.seg_off[i + 1] > a.seg_off[i];
+    double d[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const double x = a.x[6 * (size_t)i + k];
-      double d = a.step[6 * (size_t)i + k];
-      d = active ? (a.negate ? -d : d) : 0.0;
-      const double xc = x + d;
-      a.delta[6 * (size_t)i + k] = d;
+      double dk = a.step[6 * (size_t)i + k];
+      dk = active ? (a.negate ? -dk : dk) : 0.0;
+      d[k] = dk;
+      const double xc = x + dk;
+      a.delta[6 * (size_t)i + k] = dk;
       a.x_cand[6 * (size_t)i + k] = xc;
       if (active && a.count_norms) {
         const double dd = x - xc;  // Ceres: (x - candidate_x).norm()
@@ -301,13 +371,28 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
         x2 += x * x;
       }
     }
+    if (active && a.count_norms) {
+      const double* rec = a.rec + (size_t)i * NV;
+      const double dcam = -a.uF_cam[0];
+      double q = 0.0;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        double hd = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) hd += rec[p <= c ? tri6(p, c) : tri6(c, p)] * d[c];
+        q += d[p] * (rec[21 + p] + 0.5 * hd + dcam * rec[27 + p]);
+      }
+      mq = q;
+    }
   }
   d2 = warp_sum(d2);
   x2 = warp_sum(x2);
+  mq = warp_sum(mq);
   if ((threadIdx.x & 31) == 0) {
-    double* o = a.warp_out + 2 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    double* o = a.warp_out + 3 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     o[0] = d2;
     o[1] = x2;
+    o[2] = mq;
   }
 }
 

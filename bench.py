@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ba_100k_5k", choices=sorted(WORKLOADS))
     ap.add_argument("--linear-solver", default="auto", choices=["auto", "dense", "pcg"])
-    ap.add_argument("--pcg-tolerance", type=float, default=1e-8)
+    ap.add_argument("--pcg-tolerance", type=float, default=0.1)
     ap.add_argument("--cpu-sample-captures", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

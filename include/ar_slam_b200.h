@@ -76,7 +76,7 @@ typedef struct arslam_options {
   double function_tolerance;                 /* 1e-6  */
   double gradient_tolerance;                 /* 1e-10 */
   double parameter_tolerance;                /* 1e-8  */
-  double pcg_tolerance;                      /* 1e-8: relative residual ||S y - b|| / ||b||    */
+  double pcg_tolerance;                      /* 0.1: relative residual ||S y - b|| / ||b|| at which PCG stops (inexact Newton; Ceres' eta) */
   double tag_size;                           /* 0.0635 m (ar_slam_util.hpp:319)                */
   int64_t dense_max_dim;                     /* AUTO picks dense Cholesky up to this reduced
                                                 dimension (default 16384)                      */

@@ -163,5 +163,6 @@ def test_pcg_default_tolerance_converges_like_dense(gpu_solver_cls):
         out[name], _ = s.solve()
         s.close()
     assert out["pcg"]["termination"] == 0 and out["dense"]["termination"] == 0
-    assert abs(out["pcg"]["iterations"] - out["dense"]["iterations"]) <= 1
-    assert abs(out["pcg"]["final_cost"] - out["dense"]["final_cost"]) <= 1e-6 * out["dense"]["final_cost"]
+    # default pcg_tolerance 0.1 (inexact Newton, Ceres' eta): a couple more LM iterations, same minimum
+    assert 0 <= out["pcg"]["iterations"] - out["dense"]["iterations"] <= 3
+    assert abs(out["pcg"]["final_cost"] - out["dense"]["final_cost"]) <= 1e-5 * out["dense"]["final_cost"]
