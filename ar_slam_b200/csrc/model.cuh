@@ -273,6 +273,48 @@ ARS_HD void rotate_point(const double w[3], const double p[3], double out[3]) {
     out[2] = p[2] + (w[0] * p[1] - w[1] * p[0]);
   }
 }
+// calcInitValues (ar_slam_util.cpp:52-88): depth from the longest edge, centroid, in-plane yaw
+ARS_HD void seed_local_values(const double rect[8], double focal, double tag_size, double lp[3], double* yaw) {
+  double max_d2 = 0.0, ax = 0.0, ay = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    const double dx = rect[2 * i] - rect[2 * j], dy = rect[2 * i + 1] - rect[2 * j + 1];
+    const double d2 = dx * dx + dy * dy;
+    max_d2 = fmax(d2, max_d2);
+    ax += rect[2 * i];
+    ay += rect[2 * i + 1];
+  }
+  ax *= 0.25;
+  ay *= 0.25;
+  double avg = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double expected = atan2(corner_dy(i), corner_dx(i));
+    const double actual = atan2(rect[2 * i + 1] - ay, rect[2 * i] - ax);
+    const double delta = normalize_angle(actual - expected);
+    avg += normalize_angle(delta - avg) / (double)(i + 1);
+  }
+  const double lz = focal * tag_size / sqrt(max_d2);
+  lp[0] = ax * lz / focal;
+  lp[1] = ay * lz / focal;
+  lp[2] = lz;
+  *yaw = avg;
+}
+// initArPose (ar_slam_util.cpp:111-128): tag pose from one quad and the capture's pose
+ARS_HD void seed_tag_pose(const double rect[8], double focal, const double cap_pose[6], double tag_size,
+                          double out[6]) {
+  double lp[3], yaw;
+  seed_local_values(rect, focal, tag_size, lp, &yaw);
+  const double cap_rot[3] = {-cap_pose[3], -cap_pose[4], -cap_pose[5]};
+  double t[3];
+  rotate_point(cap_rot, lp, t);
+  out[0] = t[0] - cap_pose[0];
+  out[1] = t[1] - cap_pose[1];
+  out[2] = t[2] - cap_pose[2];
+  const double local_rot[3] = {0.0, 0.0, yaw};
+  compose_aa(cap_rot, local_rot, out + 3);
+}
 // rect: x0,y0,...,y3
 ARS_HD void seed_capture_pose(const double rect[8], double focal, const double tag_pose[6],
                               double tag_size, double out[6]) {

@@ -1,0 +1,468 @@
+// ar_slam_solver.cpp -- host data store, schedules and map.yaml of the drop-in
+// facade (see ar_slam_solver.hpp).  Follows the behaviour of the reference's
+// ar_slam/src/ar_slam_util.cpp: loadYaml :304-368, saveYaml :371-465,
+// addDetections :591-627, solveIncremental :629-678, solveCapture :680-742,
+// solve :744-866, addConnectedCaptures :869-885, localizeMany/One :888-979,
+// optimize :1001-1018, resetProblem :1021-1025 -- with the Ceres calls
+// replaced by the C-ABI of the CUDA library.
+#include "ar_slam_solver.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+#include "../csrc/model.cuh"  // host build of the seed heuristics (calcInitValues & co.)
+
+namespace {
+
+// ---- a reader for the subset of YAML that saveYaml / yaml-cpp emit -----------
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+  return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+std::string unquote(std::string s) {
+  s = trim(s);
+  if (s.size() >= 2 && ((s.front() == '"' && s.back() == '"') || (s.front() == '\'' && s.back() == '\''))) return s.substr(1, s.size() - 2);
+  return s;
+}
+std::vector<double> parse_flow_seq(const std::string& v) {
+  const size_t a = v.find('['), b = v.rfind(']');
+  if (a == std::string::npos || b == std::string::npos || b < a) throw std::runtime_error("expected a flow sequence: " + v);
+  std::vector<double> out;
+  std::stringstream ss(v.substr(a + 1, b - a - 1));
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    item = trim(item);
+    if (item.empty()) continue;
+    if (item == ".nan" || item == ".NaN") out.push_back(std::nan(""));
+    else if (item == ".inf") out.push_back(INFINITY);
+    else if (item == "-.inf") out.push_back(-INFINITY);
+    else out.push_back(std::strtod(item.c_str(), nullptr));
+  }
+  return out;
+}
+struct YLine { int indent; bool item; std::string key, value; };
+std::vector<YLine> read_lines(const std::string& fn) {
+  std::ifstream f(fn);
+  if (!f) throw std::runtime_error("cannot open " + fn);
+  std::vector<YLine> out;
+  std::string raw;
+  while (std::getline(f, raw)) {
+    std::string s = raw;
+    if (trim(s).empty() || trim(s)[0] == '#' || trim(s) == "---") continue;
+    YLine l;
+    l.indent = (int)s.find_first_not_of(' ');
+    std::string body = trim(s);
+    l.item = body.rfind("- ", 0) == 0;
+    if (l.item) { body = trim(body.substr(2)); l.indent += 2; }
+    const size_t c = body.find(':');
+    if (c == std::string::npos) throw std::runtime_error("cannot parse yaml line: " + raw);
+    l.key = unquote(body.substr(0, c));
+    l.value = trim(body.substr(c + 1));
+    out.push_back(l);
+  }
+  return out;
+}
+
+// yaml-cpp writes doubles with max_digits10 significant digits (lossless)
+std::string num(double v) {
+  if (std::isnan(v)) return ".nan";
+  if (std::isinf(v)) return v > 0 ? ".inf" : "-.inf";
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), "%.17g", v);
+  return buf;
+}
+
+void check(arslam_solver* s, int rc, const char* what) {
+  if (rc != ARSLAM_OK) throw std::runtime_error(std::string(what) + ": " + arslam_last_error(s));
+}
+
+}  // namespace
+
+bool endswith(const std::string& str, const std::string& suffix) {
+  return str.size() >= suffix.size() && str.compare(str.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+std::string filename_no_ext(std::string filepath) {
+  const size_t slash = filepath.find_last_of('/');
+  if (slash != std::string::npos) filepath = filepath.substr(slash + 1);
+  const size_t dot = filepath.find_last_of('.');
+  if (dot != std::string::npos) filepath = filepath.substr(0, dot);
+  return filepath;
+}
+
+ArSlamSolver::ArSlamSolver() { arslam_default_options(&options_); }
+ArSlamSolver::~ArSlamSolver() { if (gpu_) arslam_destroy(gpu_); }
+
+arslam_solver* ArSlamSolver::handle() {
+  if (!gpu_) {
+    const char* dev = std::getenv("ARSLAM_DEVICE");
+    const int rc = arslam_create(dev ? std::atoi(dev) : 0, &options_, &gpu_);
+    if (rc != ARSLAM_OK) throw std::runtime_error(std::string("arslam_create: ") + arslam_last_error(nullptr));
+  }
+  return gpu_;
+}
+
+Capture& ArSlamSolver::addCapture(CaptureUid cap_uid, std::string fn) {
+  CaptureHandle h(captures_.size());
+  if (!capture_map_.try_emplace(cap_uid, h).second) throw std::runtime_error("Capture with uid already added");
+  captures_.emplace_back(std::move(cap_uid), h, std::move(fn));
+  return captures_.back();
+}
+Aruco& ArSlamSolver::addAruco(ArucoId ar_id) {
+  ArucoHandle h(arucos_.size());
+  aruco_map_.try_emplace(ar_id, h);  // an existing id keeps its first handle, like the reference
+  arucos_.emplace_back(std::move(ar_id), h);
+  return arucos_.back();
+}
+Aruco& ArSlamSolver::getOrAddAruco(const ArucoId& ar_id) {
+  auto it = aruco_map_.find(ar_id);
+  return it == aruco_map_.end() ? addAruco(ar_id) : at(it->second);
+}
+Block& ArSlamSolver::addBlock(const ArucoRect& rect, CaptureHandle c, ArucoHandle a) {
+  BlockHandle h(blocks_.size());
+  blocks_.emplace_back(h, rect, c, a);
+  at(c).blocks.emplace_back(h);
+  at(a).blocks.emplace_back(h);
+  return blocks_.back();
+}
+
+CaptureUid ArSlamSolver::genUniqueCaptureUid() const {
+  const std::string base = "cap_" + std::to_string(captures_.size());
+  if (CaptureUid uid{base}; capture_map_.count(uid) == 0) return uid;
+  for (unsigned i = 0; i < 1000; ++i) {
+    CaptureUid uid{base + "_" + std::to_string(i)};
+    if (capture_map_.count(uid) == 0) return uid;
+  }
+  throw std::runtime_error("cannot generate unique id");
+}
+
+void ArSlamSolver::loadYaml(const std::string& fn) {
+  const std::vector<YLine> lines = read_lines(fn);
+  struct Blk { std::string cap, tag; std::vector<double> rect; bool has_rect = false; };
+  std::vector<Blk> blks;
+  std::vector<std::pair<std::string, std::pair<std::vector<double>, std::string>>> caps;
+  std::vector<std::pair<std::string, std::vector<double>>> tags;
+  std::vector<double> cam_params;
+  int width = -1, height = -1;
+  std::string section, entry;
+  for (const YLine& l : lines) {
+    if (l.indent == 0) { section = l.key; entry.clear(); continue; }
+    if (section == "blocks") {
+      if (l.item) blks.emplace_back();
+      if (blks.empty()) throw std::runtime_error("malformed blocks section in " + fn);
+      Blk& b = blks.back();
+      if (l.key == "capture") b.cap = unquote(l.value);
+      else if (l.key == "aruco") b.tag = unquote(l.value);
+      else if (l.key == "aruco_rect") { b.rect = parse_flow_seq(l.value); b.has_rect = true; }
+    } else if (section == "captures") {
+      if (l.indent == 2) { caps.push_back({l.key, {{}, ""}}); continue; }
+      if (caps.empty()) throw std::runtime_error("malformed captures section in " + fn);
+      if (l.key == "inv_pose") caps.back().second.first = parse_flow_seq(l.value);
+      else if (l.key == "img_fn") caps.back().second.second = unquote(l.value);
+    } else if (section == "arucos") {
+      if (l.indent == 2) { tags.push_back({l.key, {}}); continue; }
+      if (tags.empty()) throw std::runtime_error("malformed arucos section in " + fn);
+      if (l.key == "pose") tags.back().second = parse_flow_seq(l.value);
+    } else if (section == "camera") {
+      if (l.key == "params") cam_params = parse_flow_seq(l.value);
+      else if (l.key == "width") width = std::atoi(l.value.c_str());
+      else if (l.key == "height") height = std::atoi(l.value.c_str());
+    }
+  }
+  // same order as the reference: captures, arucos, blocks, camera
+  for (auto& c : caps) {
+    CaptureUid uid(c.first);
+    if (capture_map_.count(uid)) throw std::runtime_error("capture with id CaptureUid:" + c.first + " already exists");
+    Capture& cap = addCapture(uid, c.second.second);
+    if (c.second.first.size() < 6) throw std::runtime_error("inv_pose needs 6 values");
+    for (size_t i = 0; i < 6; ++i) cap.inv_pose.params[i] = c.second.first[i];
+  }
+  for (auto& t : tags) {
+    Aruco& a = addAruco(ArucoId(t.first));
+    if (t.second.size() < 6) throw std::runtime_error("pose needs 6 values");
+    for (size_t i = 0; i < 6; ++i) a.pose.params[i] = t.second[i];
+  }
+  for (auto& b : blks) {
+    auto ci = capture_map_.find(CaptureUid(b.cap));
+    auto ai = aruco_map_.find(ArucoId(b.tag));
+    if (ci == capture_map_.end() || ai == aruco_map_.end()) throw std::out_of_range("block refers to an unknown capture or aruco");
+    if (b.rect.size() != 8) throw std::runtime_error("aruco_rect has wrong number of values");
+    ArucoRect r;
+    for (unsigned i = 0; i < 4; ++i) { r.corners[i].x = b.rect[2 * i]; r.corners[i].y = b.rect[2 * i + 1]; }
+    addBlock(r, ci->second, ai->second);
+  }
+  if (width < 0 || height < 0) throw std::runtime_error("camera section needs width and height");
+  camera_.size = std::make_pair(width, height);
+  for (size_t i = 0; i < cam_params.size() && i < 3; ++i) camera_.params[i] = cam_params[i];
+}
+
+void ArSlamSolver::saveYaml(std::ostream& out) const {
+  auto seq = [](std::ostream& o, const double* v, size_t n) {
+    o << "[";
+    for (size_t i = 0; i < n; ++i) o << (i ? ", " : "") << num(v[i]);
+    o << "]";
+  };
+  out << "blocks:";
+  if (blocks_.empty()) out << "\n  []";
+  for (const Block& b : blocks_) {
+    double r[8];
+    for (unsigned i = 0; i < 4; ++i) { r[2 * i] = b.aruco_rect.corners[i].x; r[2 * i + 1] = b.aruco_rect.corners[i].y; }
+    out << "\n  - capture: " << at(b.capture).uid.uid << "\n    aruco: " << at(b.aruco).id.id << "\n    aruco_rect: ";
+    seq(out, r, 8);
+  }
+  out << "\ncaptures:";
+  if (captures_.empty()) out << "\n  {}";
+  for (const Capture& c : captures_) {
+    out << "\n  " << c.uid.uid << ":\n    inv_pose: ";
+    seq(out, c.inv_pose.params.data(), 6);
+    out << "\n    img_fn: " << c.img_fn;
+  }
+  out << "\narucos:";
+  if (arucos_.empty()) out << "\n  {}";
+  for (const Aruco& a : arucos_) {
+    out << "\n  " << a.id.id << ":\n    pose: ";
+    seq(out, a.pose.params.data(), 6);
+  }
+  out << "\ncamera:\n  params: ";
+  seq(out, camera_.params.data(), 3);
+  if (camera_.size.has_value()) out << "\n  width: " << camera_.size->first << "\n  height: " << camera_.size->second;
+  out << std::endl;
+  if (!out.good()) throw std::runtime_error("Yaml emit is not good");
+}
+
+void ArSlamSolver::printCameras() const {
+  std::cout << "\tf=" << camera_.params[0] << "\tl1=" << camera_.params[1] << "\tl1=" << camera_.params[2] << std::endl;
+}
+
+void ArSlamSolver::compareProjections() const {
+  // residual dump of every added block (reference :175-189, :576-589) from one GPU evaluation
+  std::vector<BlockHandle> added;
+  for (const Block& b : blocks_) if (b.added) added.push_back(b.handle);
+  if (added.empty()) return;
+  ArSlamSolver* self = const_cast<ArSlamSolver*>(this);
+  std::vector<BlockHandle> keep = self->problem_blocks_;
+  self->problem_blocks_ = added;
+  std::vector<int32_t> ci, ti;
+  std::vector<double> rect;
+  for (BlockHandle h : added) {
+    const Block& b = at(h);
+    ci.push_back(b.capture.idx); ti.push_back(b.aruco.idx);
+    for (const Point& p : b.aruco_rect.corners) { rect.push_back(p.x); rect.push_back(p.y); }
+  }
+  std::vector<double> cap(6 * captures_.size()), tag(6 * arucos_.size()), res(8 * added.size());
+  for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(captures_[i].data(), 6, cap.begin() + 6 * i);
+  for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(arucos_[i].data(), 6, tag.begin() + 6 * i);
+  arslam_solver* g = self->handle();
+  check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), added.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+  check(g, arslam_set_params(g, camera_.params.data(), cap.data(), tag.data()), "set_params");
+  double cost = 0;
+  check(g, arslam_evaluate(g, &cost, res.data(), nullptr, nullptr, nullptr), "evaluate");
+  for (size_t k = 0; k < added.size(); ++k) {
+    std::cout << "Block " << added[k].idx << std::endl;
+    for (unsigned i = 0; i < 4; ++i) {
+      const Point& c = at(added[k]).aruco_rect.corners[i];
+      std::cout << "  point " << i << std::endl
+                << "    x " << c.x << " dx " << res[8 * k + 2 * i] << std::endl
+                << "    y " << c.y << " dy " << res[8 * k + 2 * i + 1] << std::endl;
+    }
+  }
+  self->problem_blocks_ = keep;
+}
+
+std::optional<CaptureHandle> ArSlamSolver::addDetections(const ar_slam_interfaces::msg::Detections& d) {
+  if (d.detections.empty()) return std::nullopt;
+  const std::pair<int, int> image_size((int)d.image_width, (int)d.image_height);
+  if (camera_.size.has_value()) {
+    if (camera_.size.value() != image_size) {
+      std::cerr << "WARN Mismatched image size expected [" << camera_.size->first << " x " << camera_.size->second
+                << "] got [" << image_size.first << " x " << image_size.second << "]" << std::endl;
+      return std::nullopt;
+    }
+  } else {
+    camera_.size = image_size;
+  }
+  Capture& capture = addCapture(CaptureUid(d.capture_uid), d.image_path);  // throws on a duplicate uid (hpp:422-425)
+  for (const auto& det : d.detections) {
+    Aruco& aruco = getOrAddAruco(ArucoId(det.id));
+    addBlock(ArucoRect{det}, capture.handle, aruco.handle);
+  }
+  unsolved_captures_.insert(capture.handle);
+  return capture.handle;
+}
+
+void ArSlamSolver::addCaptureBlocksToProblem(Capture& capture) {
+  for (BlockHandle bh : capture.blocks) {
+    Block& block = at(bh);
+    Aruco& aruco = at(block.aruco);
+    double rect[8];
+    for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
+    if (!aruco.initialized) {
+      aruco.initialized = true;
+      ars::seed_tag_pose(rect, camera_.params[0], capture.data(), options_.tag_size, aruco.data());  // initArPose
+    }
+    if (block.added) throw std::runtime_error("block for capture was somehow already added?");
+    block.added = true;
+    problem_blocks_.push_back(bh);  // == problem_.AddResidualBlock(cost, nullptr, camera, capture, aruco)
+  }
+}
+
+void ArSlamSolver::solveCapture(Capture& capture, std::optional<BlockHandle> init_block_handle) {
+  if (init_block_handle.has_value()) {
+    const Block& block = at(init_block_handle.value());
+    double rect[8];
+    for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
+    ars::seed_capture_pose(rect, camera_.params[0], at(block.aruco).data(), options_.tag_size, capture.data());  // initCapturePose
+  }
+  addCaptureBlocksToProblem(capture);
+  optimize(capture);
+}
+
+void ArSlamSolver::solveIncremental() {
+  if (unsolved_captures_.size() == captures_.size() && !unsolved_captures_.empty()) {
+    CaptureHandle h = *unsolved_captures_.begin();
+    std::cout << "Solving initial capture " << h.idx << std::endl;
+    unsolved_captures_.erase(h);
+    solveCapture(at(h), std::nullopt);
+  }
+  std::cout << "Solve incremental with " << unsolved_captures_.size() << " unsolved captures" << std::endl;
+  bool repeat_solve = false;
+  do {
+    repeat_solve = false;
+    for (auto itr = unsolved_captures_.begin(); itr != unsolved_captures_.end(); ++itr) {
+      Capture& capture = at(*itr);
+      for (BlockHandle bh : capture.blocks) {
+        if (at(at(bh).aruco).initialized) {
+          std::cout << "Capture CaptureUid:" << capture.uid.uid << " can be solved through ArucoId:" << at(at(bh).aruco).id.id << std::endl;
+          repeat_solve = true;
+          itr = unsolved_captures_.erase(itr);
+          solveCapture(capture, bh);
+          break;
+        }
+      }
+      if (itr == unsolved_captures_.end()) break;
+    }
+  } while (repeat_solve);
+}
+
+void ArSlamSolver::solve() {
+  if (captures_.empty()) return;
+  std::deque<CaptureHandle> open_captures;
+  unsigned best_cap_idx = 0;
+  {
+    size_t best = captures_.front().blocks.size();
+    for (unsigned i = 1; i < captures_.size(); ++i)
+      if (captures_[i].blocks.size() > best) { best = captures_[i].blocks.size(); best_cap_idx = i; }
+    std::cout << "using best capture " << best_cap_idx << " with " << best << " tags" << std::endl;
+  }
+  Capture& best_capture = captures_[best_cap_idx];
+  best_capture.init_block = BlockHandle(~0u);  // prevents the capture from being queued again
+  open_captures.emplace_back(best_capture.handle);
+  while (!open_captures.empty()) {
+    CaptureHandle h = open_captures.front();
+    open_captures.pop_front();
+    std::cout << "Processing capture " << h.idx << std::endl;
+    Capture& capture = at(h);
+    if (h.idx != best_cap_idx) {
+      const Block& block = at(capture.init_block.value());
+      double rect[8];
+      for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
+      ars::seed_capture_pose(rect, camera_.params[0], at(block.aruco).data(), options_.tag_size, at(block.capture).data());
+    }
+    addCaptureBlocksToProblem(capture);
+    optimize(capture);
+    addConnectedCaptures(capture, open_captures);
+  }
+}
+
+void ArSlamSolver::addConnectedCaptures(const Capture& base, std::deque<CaptureHandle>& open_captures) {
+  for (BlockHandle bbh : base.blocks) {
+    Aruco& base_aruco = at(at(bbh).aruco);
+    for (BlockHandle bh : base_aruco.blocks) {
+      Capture& capture = at(at(bh).capture);
+      if (!capture.init_block.has_value()) {
+        capture.init_block = bh;
+        open_captures.emplace_back(capture.handle);
+      }
+    }
+  }
+}
+
+// One batched GPU call for all new captures: they are mutually independent
+// (tags and camera constant, ar_slam_util.cpp:965,972), so the reference's
+// serial loop (:897-900) and the batch give the same poses.
+void ArSlamSolver::localizeMany(unsigned first_loc_cap_idx) {
+  const size_t n_loc = captures_.size() > first_loc_cap_idx ? captures_.size() - first_loc_cap_idx : 0;
+  if (n_loc == 0) return;
+  resetProblem();
+  std::vector<int32_t> offsets(1, 0), tag_idx, seed(n_loc, -1);
+  std::vector<double> rect, tag(6 * arucos_.size()), pose(6 * n_loc);
+  for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(arucos_[i].data(), 6, tag.begin() + 6 * i);
+  for (size_t i = 0; i < n_loc; ++i) {
+    Capture& capture = captures_.at(first_loc_cap_idx + i);
+    std::copy_n(capture.data(), 6, pose.begin() + 6 * i);
+    int k = 0;
+    for (BlockHandle cbh : capture.blocks) {
+      Block& block = at(cbh);
+      if (seed[i] < 0) {  // first tag shared with one of the "mapping" captures (:911-927)
+        for (BlockHandle bh : at(block.aruco).blocks)
+          if (at(bh).capture.idx < first_loc_cap_idx) { seed[i] = k; break; }
+      }
+      tag_idx.push_back(block.aruco.idx);
+      for (const Point& p : block.aruco_rect.corners) { rect.push_back(p.x); rect.push_back(p.y); }
+      ++k;
+    }
+    offsets.push_back((int32_t)tag_idx.size());
+    if (seed[i] < 0) {
+      std::cout << "WARNING : Cannot find connected ar tags for capture " << capture.handle.idx << std::endl;
+    } else {
+      for (BlockHandle cbh : capture.blocks) {
+        if (at(cbh).added) throw std::runtime_error("block for capture was somehow already added?");
+        at(cbh).added = true;
+      }
+    }
+  }
+  if (tag_idx.empty()) return;
+  arslam_solver* g = handle();
+  check(g, arslam_set_options(g, &options_), "set_options");
+  check(g, arslam_localize_batch(g, n_loc, offsets.data(), tag_idx.data(), rect.data(), seed.data(), arucos_.size(),
+                                 camera_.params.data(), tag.data(), pose.data(), nullptr, nullptr, nullptr),
+        "localize_batch");
+  for (size_t i = 0; i < n_loc; ++i)
+    if (seed[i] >= 0) std::copy_n(pose.begin() + 6 * i, 6, captures_.at(first_loc_cap_idx + i).data());
+}
+
+// == ceres::Solve(options{max_num_iterations 50, DENSE_SCHUR}, &problem_, &summary)
+void ArSlamSolver::optimize(const Capture&) {
+  if (problem_blocks_.empty()) return;
+  std::vector<int32_t> ci, ti;
+  std::vector<double> rect;
+  ci.reserve(problem_blocks_.size()); ti.reserve(problem_blocks_.size()); rect.reserve(8 * problem_blocks_.size());
+  for (BlockHandle h : problem_blocks_) {
+    const Block& b = at(h);
+    ci.push_back(b.capture.idx);
+    ti.push_back(b.aruco.idx);
+    for (const Point& p : b.aruco_rect.corners) { rect.push_back(p.x); rect.push_back(p.y); }
+  }
+  std::vector<double> cap(6 * captures_.size()), tag(6 * arucos_.size());
+  for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(captures_[i].data(), 6, cap.begin() + 6 * i);
+  for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(arucos_[i].data(), 6, tag.begin() + 6 * i);
+  arslam_solver* g = handle();
+  std::cout << "Starting solver..." << std::endl;
+  check(g, arslam_set_options(g, &options_), "set_options");
+  check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), problem_blocks_.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+  check(g, arslam_set_params(g, camera_.params.data(), cap.data(), tag.data()), "set_params");
+  // like the reference, a solver that does not converge is not an error (summary discarded at :1013-1017);
+  // API misuse and CUDA failures are
+  check(g, arslam_solve(g, &last_summary_, nullptr, 0), "solve");
+  summaries_.push_back(last_summary_);
+  check(g, arslam_get_params(g, camera_.params.data(), cap.data(), tag.data()), "get_params");
+  for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(cap.begin() + 6 * i, 6, captures_[i].data());
+  for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(tag.begin() + 6 * i, 6, arucos_[i].data());
+}
+
+void ArSlamSolver::resetProblem() { problem_blocks_.clear(); }

@@ -34,6 +34,10 @@ void shim_seed_capture_pose(const double* rect8, double focal, const double* tag
                             double* out6) {
   ars::seed_capture_pose(rect8, focal, tag_pose, tag_size, out6);
 }
+void shim_seed_tag_pose(const double* rect8, double focal, const double* cap_pose, double tag_size,
+                        double* out6) {
+  ars::seed_tag_pose(rect8, focal, cap_pose, tag_size, out6);
+}
 int shim_chol6_solve(const double* H36, const double* b6, double* x6) {
   double L[36];
   for (int i = 0; i < 36; ++i) L[i] = H36[i];

@@ -72,6 +72,10 @@ def test_device_seed_matches_reference_heuristic(shim, oracle):
         shim.shim_seed_capture_pose(_p(rect), C.c_double(f), _p(tag), C.c_double(0.0635), _p(out))
         ref = oracle.init_capture_pose(rect, [f, 0, 0], tag)
         assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+        cap = np.concatenate([rng.normal(0, 1, 3), rng.normal(0, 0.7, 3)])
+        shim.shim_seed_tag_pose(_p(rect), C.c_double(f), _p(cap), C.c_double(0.0635), _p(out))
+        ref = oracle.init_tag_pose(rect, [f, 0, 0], cap)
+        assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
 def test_register_cholesky(shim):
