@@ -41,6 +41,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, const void* /* by value, see call */, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
@@ -58,14 +59,15 @@ struct NcclApi {
     CommInitRank = (int (*)(void**, int, const void*, int))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl misses symbols"; return false; }
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather) { err = "libnccl misses symbols"; return false; }
     return true;
   }
 };
 NcclApi g_nccl;
 struct NcclId { char bytes[128]; };
-constexpr int kNcclDouble = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (stable enum values)
+constexpr int kNcclDouble = 8, kNcclInt64 = 4, kNcclSum = 0, kNcclMax = 2;  // ncclFloat64, ncclInt64, ncclSum, ncclMax
 
 template <typename T>
 struct DevBuf {
@@ -513,10 +515,42 @@ int gather_captures(arslam_solver* s, int k) {
 }
 
 // ---- PCG hooks ---------------------------------------------------------------
+// Multi-GPU: every rank must use the same block pattern of the reduced system (the partial
+// values are summed element-wise), so the ranks' pair-key lists are all-gathered and united.
+int union_keys_across_ranks(arslam_solver* s, std::vector<uint64_t>& keys) {
+  if (s->world <= 1) return ARSLAM_OK;
+  DevBuf<long long> cnt, sendb, recvb;
+  CU(cnt.ensure(1));
+  long long n_local = (long long)keys.size(), n_max = 0;
+  CU(cudaMemcpyAsync(cnt.p, &n_local, sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+  int rc = g_nccl.AllReduce(cnt.p, cnt.p, 1, kNcclInt64, kNcclMax, s->comm, s->stream);
+  if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllReduce(max): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  CU(cudaMemcpyAsync(&n_max, cnt.p, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  std::vector<uint64_t> padded(keys);
+  padded.resize((size_t)n_max, ~0ull);
+  CU(sendb.ensure((size_t)n_max)); CU(recvb.ensure((size_t)n_max * s->world));
+  CU(cudaMemcpyAsync(sendb.p, padded.data(), sizeof(uint64_t) * n_max, cudaMemcpyHostToDevice, s->stream));
+  rc = g_nccl.AllGather(sendb.p, recvb.p, (size_t)n_max, kNcclInt64, s->comm, s->stream);
+  if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  std::vector<uint64_t> all((size_t)n_max * s->world);
+  CU(cudaMemcpyAsync(all.data(), recvb.p, sizeof(uint64_t) * all.size(), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  std::sort(all.begin(), all.end());
+  all.erase(std::unique(all.begin(), all.end()), all.end());
+  if (!all.empty() && all.back() == ~0ull) all.pop_back();
+  keys.swap(all);
+  return ARSLAM_OK;
+}
+
 int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
   std::string err;
-  const int rc = pcg_symbolic(s->pcg, n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), s->stream, err,
+  std::vector<uint64_t> keys;
+  pcg_collect_keys(n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), keys);
+  int urc = union_keys_across_ranks(s, keys);
+  if (urc) return urc;
+  const int rc = pcg_symbolic(s->pcg, keys, n_e, n_f, s->h_off[side_e].data(), s->stream, err,
                               s->n_sm, (size_t)227 * 1024 - 2048);
   if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
   int occ = 0;

@@ -61,11 +61,11 @@ struct PcgWorkspace {
 };
 
 // ---- symbolic phase (host): block pattern of sum_e W_e^T W_e over the E segments
-inline int pcg_symbolic(PcgWorkspace& ws, int n_e, int n_f, const int32_t* e_off, const int32_t* f_of_blk,
-                        cudaStream_t st, std::string& err, int n_sm, size_t smem_limit) {
-  ws.release();
-  std::vector<uint64_t> keys;
-  keys.reserve((size_t)e_off[n_e] * 8);
+// keys = (row << 32 | col) of every block of the reduced system this rank contributes to
+inline void pcg_collect_keys(int n_e, int n_f, const int32_t* e_off, const int32_t* f_of_blk,
+                             std::vector<uint64_t>& keys) {
+  keys.clear();
+  keys.reserve((size_t)e_off[n_e] * 8 + n_f);
   for (int e = 0; e < n_e; ++e)
     for (int i = e_off[e]; i < e_off[e + 1]; ++i)
       for (int j = e_off[e]; j < e_off[e + 1]; ++j)
@@ -73,6 +73,11 @@ inline int pcg_symbolic(PcgWorkspace& ws, int n_e, int n_f, const int32_t* e_off
   for (int f = 0; f < n_f; ++f) keys.push_back((uint64_t)(uint32_t)f << 32 | (uint32_t)f);  // every diagonal block exists
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+}
+
+inline int pcg_symbolic(PcgWorkspace& ws, const std::vector<uint64_t>& keys, int n_e, int n_f, const int32_t* e_off,
+                        cudaStream_t st, std::string& err, int n_sm, size_t smem_limit) {
+  ws.release();
   const int nnzb = (int)keys.size();
   std::vector<int32_t> row_ptr(n_f + 1, 0), col(nnzb), src(nnzb);
   for (int s = 0; s < nnzb; ++s) {

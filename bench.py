@@ -34,6 +34,7 @@ WORKLOADS = {
     "ba_100k_5k": (100000, 5000, 8, 3),
     "ba_1k_200": (1000, 200, 8, 2),
     "ba_20k_2k": (20000, 2000, 8, 5),
+    "loc_1m_5k": (1000000, 5000, 8, 4),   # batched localisation (kernel 5), a step = one full batch
 }
 ITERS_PER_SOLVE = 5  # LM iterations per solve call; the solve restarts from the same initial state
 
@@ -157,6 +158,71 @@ def cpu_baseline(args, steps, warmup, threads=None):
                       % (sc, st, nc, args.workload, its, threads)}, dt, its
 
 
+def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
+    """BASELINE config 4: captures are sharded evenly, no communication at all."""
+    n_loc, n_tag, tpc, cfg_id = WORKLOADS[args.workload]
+    m = synth.make_localization_batch(n_loc, n_tag, tpc, seed=0xA55A0000 + cfg_id)
+    lo, hi = n_loc * rank // world, n_loc * (rank + 1) // world
+    b0, b1 = m.blk_offsets[lo], m.blk_offsets[hi]
+    offs = (m.blk_offsets[lo:hi + 1] - b0).astype(np.int32)
+    tag_idx, obs, seed = m.tag_idx[b0:b1], m.obs[b0:b1], m.seed_block[lo:hi]
+    s = ar.Solver(device=local_rank)
+    stream = torch.cuda.Stream()
+    s.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(1, args.warmup)):
+        pose, its, cost, term = s.localize_batch(offs, tag_idx, obs, seed, m.cam_true, m.tag_true)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    s.set_profiling(True)
+    kms = []
+    for _ in range(args.steps):
+        pose, its, cost, term = s.localize_batch(offs, tag_idx, obs, seed, m.cam_true, m.tag_true)
+        kms.append([k for k in s.kernel_times() if k["name"] == "localize"][0]["total_ms"])
+    barrier()
+    dt = time.perf_counter() - t0
+    ms_kernel = float(np.sum(kms))
+    if dist is not None:
+        t = torch.tensor([dt, ms_kernel], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, ms_kernel = float(t[0]), float(t[1])
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        nc = 4 * len(m.tag_idx)
+        peak, how = read_peaks()
+        err = np.abs(pose - m.cap_true[lo:hi])
+        alg = 17.0 * 4 * len(tag_idx) + 116.0 * (hi - lo)
+        line = {"metric": "observation_corners_per_sec", "value": nc * args.steps / (ms_kernel * 1e-3), "unit": "corners/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "captures_per_sec": n_loc * args.steps / (ms_kernel * 1e-3),
+                "config": {"workload": args.workload, "captures": n_loc, "tags": n_tag, "tags_per_capture": tpc,
+                           "corners": nc, "mean_lm_iterations": float(its.mean()),
+                           "median_abs_pose_error": float(np.median(err)), "l2_policy": "inputs larger than L2"},
+                "clocks": clk, "gpu_launches": 2 * args.steps,
+                "e2e": {"value": nc * args.steps / dt, "unit": "corners/s", "captures_per_sec": n_loc * args.steps / dt,
+                        "h2d_bytes_per_step": int(obs.nbytes + tag_idx.nbytes + offs.nbytes + seed.nbytes),
+                        "d2h_bytes_per_step": int(pose.nbytes + its.nbytes + cost.nbytes + term.nbytes),
+                        "what": "arslam_localize_batch from host arrays (H2D, kernel, D2H), wall clock"},
+                "roofline": {"bound": "hbm", "kernel": "localize", "achieved": alg * args.steps / (ms_kernel * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": alg * args.steps / (ms_kernel * 1e-3) / 1e9 / peak,
+                             "traffic": None, "peak_source": how,
+                             "note": "whole LM solve per capture in registers: FP64-latency bound, not HBM bound"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,6 +268,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.workload.startswith("loc_"):
+        return bench_localization(args, ar, synth, torch, dist, rank, world, local_rank)
     if args.scaling == "weak":
         n_cap *= world
     m = synth.make_map(n_cap, n_tag, tpc, seed=0xA55A0000 + cfg_id)

@@ -1,0 +1,56 @@
+"""Multi-GPU correctness check (run under torchrun on N GPUs): the sharded solve (captures
+split over ranks, one NCCL allreduce per linearisation) must walk the same LM trajectory
+as the single-GPU solve of the whole problem."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ar_slam_b200 as ar  # noqa: E402
+import bench  # noqa: E402
+from ar_slam_b200 import synth  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def fresh_uid():
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(ar.Solver.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    return bytes(uid.cpu().numpy().tobytes())
+
+
+ok = True
+for name, ls, (nc, nt) in (("dense", ar.LINSOLVE_DENSE, (3000, 400)), ("pcg", ar.LINSOLVE_PCG, (20000, 1500))):
+    m = synth.make_map(nc, nt, seed=31)
+    opts = ar.default_options(linear_solver=ls, pcg_tolerance=1e-10, pcg_max_iterations=3000)
+    s = ar.Solver(device=local, options=opts)
+    s.comm_init(rank, world, fresh_uid())
+    ci, ti, ob = bench.shard(m, rank, world)
+    s.set_problem(m.n_cap, m.n_tag, ci, ti, ob)
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    summ, log = s.solve()
+    cam, cap, tag = s.get_params()
+    s.close()
+    if rank == 0:
+        s1 = ar.Solver(device=local, options=opts)
+        s1.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s1.set_params(m.cam0, m.cap0, m.tag0)
+        summ1, log1 = s1.solve()
+        cam1, cap1, tag1 = s1.get_params()
+        s1.close()
+        same_it = summ["iterations"] == summ1["iterations"]
+        dcost = float(np.abs(log[:, 0] - log1[:len(log), 0]).max() / log1[0, 0]) if same_it else float("nan")
+        dp = max(np.abs(cap - cap1).max(), np.abs(tag - tag1).max(), abs(cam[0] - cam1[0]) / cam1[0])
+        good = same_it and dcost < 1e-9 and dp < 1e-6 and abs(summ["final_cost"] - summ1["final_cost"]) < 1e-8 * summ1["final_cost"]
+        ok = ok and good
+        print("%s: world %d  iterations %d vs %d  final cost %.9g vs %.9g  max trajectory diff %.2e  max param diff %.2e  %s"
+              % (name, world, summ["iterations"], summ1["iterations"], summ["final_cost"], summ1["final_cost"], dcost, dp,
+                 "OK" if good else "MISMATCH"), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
