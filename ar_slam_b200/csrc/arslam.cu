@@ -584,6 +584,8 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   return ARSLAM_OK;
 }
 
+static inline bool use_smem_flag(const PcgWorkspace& w) { return w.smem_ok && !getenv("ARSLAM_PCG_NO_SMEM"); }
+
 int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, const double* sc, const double* cam_minus,
                      double radius, double* x_out) {
   PcgWorkspace& w = s->pcg;
@@ -606,10 +608,17 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   a.row_ptr = w.row_ptr; a.col_idx = w.col_idx; a.S = w.Sfin; a.Minv = w.Minv;
   a.border = f.border; a.rhs = f.rhs;
   a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
-  a.partial = w.partial; a.scal = w.scal;
+  a.partial = w.partial; a.scal = w.scal; a.trace = nullptr;
+  static unsigned long long* d_trace = nullptr;
+  if (getenv("ARSLAM_PCG_TRACE")) {
+    if (!d_trace) cudaMalloc(&d_trace, sizeof(unsigned long long) * 64 * 1024 * 8);
+    cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 64 * 1024 * 8, s->stream);
+    a.trace = d_trace;
+  }
   sa.cta_row = w.cta_row; sa.halo_ptr = w.halo_ptr; sa.halo_col = w.halo_col; sa.lcol = w.lcol;
-  sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots;
-  const bool use_smem = w.smem_ok && !getenv("ARSLAM_PCG_NO_SMEM");
+  sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots; sa.max_rows = w.max_rows;
+  if (use_smem_flag(w)) CU(cudaMemsetAsync(w.partial, 0, 3 * 8 * sizeof(double), s->stream));
+  const bool use_smem = use_smem_flag(w);
   void* args_g[] = {(void*)&a};
   void* args_s[] = {(void*)&sa};
   Profiler::Rec r{0, nullptr, nullptr};
@@ -624,6 +633,25 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   if (s->prof.on) {
     cudaEventRecord(r.b, s->stream);
     s->prof.recs.push_back(r);
+  }
+  if (a.trace) {
+    std::vector<unsigned long long> h((size_t)64 * 1024 * 8);
+    cudaStreamSynchronize(s->stream);
+    cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+    const int G = use_smem ? w.smem_grid : w.grid;
+    for (int it = 0; it < 6; ++it) {
+      unsigned long long t0 = ~0ull, mx[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mn[8];
+      for (int k = 0; k < 8; ++k) mn[k] = ~0ull;
+      for (int c = 0; c < G; ++c) if (h[((size_t)it * G + c) * 8]) t0 = std::min(t0, h[((size_t)it * G + c) * 8]);
+      if (t0 == ~0ull) break;
+      for (int c = 0; c < G; ++c)
+        for (int k = 0; k < 8; ++k) {
+          const unsigned long long v = h[((size_t)it * G + c) * 8 + k];
+          if (v) { mx[k] = std::max(mx[k], v - t0); mn[k] = std::min(mn[k], v - t0); }
+        }
+      std::fprintf(stderr, "pcg trace it %d (ns): startA %llu..%llu | gathered %llu..%llu | row0 done %llu..%llu | endA %llu..%llu | sums1 %llu..%llu | endB %llu..%llu | sums2 %llu..%llu\n",
+                   it, mn[0], mx[0], mn[5], mx[5], mn[6], mx[6], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3], mn[4], mx[4]);
+    }
   }
   ++s->launches;
   LAUNCH("pcg_publish", 32.0, pcg_publish_kernel<<<1, 1, 0, s->stream>>>(w.scal, const_cast<double*>(sc)));

@@ -9,6 +9,7 @@
 // memory staging) instead of with global atomics.
 #pragma once
 #include <cstdint>
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 #include "model.cuh"
@@ -142,9 +143,15 @@ struct AccumArgs {
 };
 
 template <int SIDE, bool WITH_W>
-__global__ void __launch_bounds__(kAccumThreads, 2) accum_kernel(const AccumArgs a) {
-  __shared__ double stage[kAccumWarps][NV][33];
+__global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(const AccumArgs a) {
+  // one shared buffer, two lives: during the corner loop it holds the per-thread cp.async
+  // landing slots of the tag records (2 stages x 128 threads x 112 B, 16 B padding keeps the
+  // 128-bit reads conflict free); afterwards it is the [value][lane] staging of the reduction
+  __shared__ __align__(16) double raw[kAccumWarps * NV * 33];
+  double(*stage)[NV][33] = reinterpret_cast<double(*)[NV][33]>(raw);
   __shared__ int sseg[kAccumWarps][36];
+  constexpr int kSlot = 112;
+  unsigned char* tslot = reinterpret_cast<unsigned char*>(raw) + threadIdx.x * kSlot;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int pos = blockIdx.x * kAccumThreads + threadIdx.x;
   const int gwarp = pos >> 5;
@@ -182,17 +189,66 @@ __global__ void __launch_bounds__(kAccumThreads, 2) accum_kernel(const AccumArgs
       }
     }
     const double2* tsrc = reinterpret_cast<const double2*>(a.tag_pre + (size_t)kTagPre * tag);
+    // SIDE 0: the tag record is a random gather from L2 -> software pipeline with cp.async:
+    // corner i + 1's 96 bytes fly into shared memory while corner i is being computed.
+    if (SIDE == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) __pipeline_memcpy_async(tslot + 16 * k, tsrc + k, 16);
+      __pipeline_memcpy_async(tslot + 96, a.obs + pos, 8);
+      __pipeline_memcpy_async(tslot + 104, a.obs + (size_t)a.plane + pos, 8);
+      __pipeline_commit();
+    }
+    double tn[12];  // SIDE 1: next corner's (own, warp-broadcast) tag record, prefetched in registers
+    if (SIDE == 1) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double2 v = __ldg(tsrc + k);
+        tn[2 * k] = v.x;
+        tn[2 * k + 1] = v.y;
+      }
+    }
+    double oxn = 0.0, oyn = 0.0;
+    if (SIDE == 1) { oxn = a.obs[pos]; oyn = a.obs[(size_t)a.plane + pos]; }
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
       double tp[12];
+      double ox, oy;
+      if (SIDE == 0) {
+        if (i < 3) {
+          unsigned char* nxt = tslot + ((i + 1) & 1) * (kAccumThreads * kSlot);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double2 v = __ldg(tsrc + 6 * i + k);
-        tp[2 * k] = v.x;
-        tp[2 * k + 1] = v.y;
+          for (int k = 0; k < 6; ++k) __pipeline_memcpy_async(nxt + 16 * k, tsrc + 6 * (i + 1) + k, 16);
+          __pipeline_memcpy_async(nxt + 96, a.obs + (size_t)(2 * i + 2) * a.plane + pos, 8);
+          __pipeline_memcpy_async(nxt + 104, a.obs + (size_t)(2 * i + 3) * a.plane + pos, 8);
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(1);
+        const double2* cur = reinterpret_cast<const double2*>(tslot + (i & 1) * (kAccumThreads * kSlot));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const double2 v = cur[k];
+          tp[2 * k] = v.x;
+          tp[2 * k + 1] = v.y;
+        }
+        const double2 o2 = cur[6];
+        ox = o2.x;
+        oy = o2.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) tp[k] = tn[k];
+        ox = oxn;
+        oy = oyn;
+        if (i < 3) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const double2 v = __ldg(tsrc + 6 * (i + 1) + k);
+            tn[2 * k] = v.x;
+            tn[2 * k + 1] = v.y;
+          }
+          oxn = a.obs[(size_t)(2 * i + 2) * a.plane + pos];
+          oyn = a.obs[(size_t)(2 * i + 3) * a.plane + pos];
+        }
       }
-      const double ox = a.obs[(size_t)(2 * i) * a.plane + pos];
-      const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
       CornerJ j;
       corner_jacobian(cp, tp, f, ox, oy, j);
 #pragma unroll
@@ -252,6 +308,7 @@ __global__ void __launch_bounds__(kAccumThreads, 2) accum_kernel(const AccumArgs
       wc[0] = KK; wc[1] = Kr; wc[2] = rr; wc[3] = 0.0;
     }
   }
+  if (SIDE == 0) __syncthreads();  // every thread is done with its cp.async slots before the buffer is reused
   // stage the per-pose record, transposed: stage[v][lane]
   {
     double(*st)[33] = stage[wid];
@@ -274,25 +331,30 @@ __global__ void __launch_bounds__(kAccumThreads, 2) accum_kernel(const AccumArgs
   }
   __syncwarp();
   const int* sg = sseg[wid];
+  // run structure of this warp, identical for every lane: bit j of `ends` = lane j closes a run
+  const unsigned ends = __ballot_sync(0xffffffffu, sg[lane + 2] != own);
+  const bool head_open = sg[0] == sg[1];           // the first run started in the previous warp
+  const bool tail_open = !((ends >> 31) & 1u);     // the last run continues in the next warp
   for (int v = lane; v < NV; v += 32) {
     const double* col = stage[wid][v];
     double acc = 0.0;
-    int run_start = 0;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const int sj = sg[j + 1], sn = sg[j + 2];
-      acc += col[j];
-      if (sn != sj) {
-        if (sj >= 0) {
-          const bool starts_before = (run_start == 0) && (sg[0] == sj);
-          if (!starts_before) a.out_seg[(size_t)sj * NV + v] = acc;
-          else a.partial[((size_t)gwarp * 2 + 0) * NV + v] = acc;
-        }
-        acc = 0.0;
-        run_start = j + 1;
-      } else if (j == 31 && sj >= 0) {
-        a.partial[((size_t)gwarp * 2 + (run_start == 0 ? 0 : 1)) * NV + v] = acc;
+    unsigned m = ends;
+    int j0 = 0;
+    while (m) {
+      const int j1 = __ffs(m) - 1;  // run [j0, j1]
+      m &= m - 1;
+      for (int j = j0; j <= j1; ++j) acc += col[j];
+      const int sj = sg[j1 + 1];
+      if (sj >= 0) {
+        if (j0 == 0 && head_open) a.partial[((size_t)gwarp * 2 + 0) * NV + v] = acc;
+        else a.out_seg[(size_t)sj * NV + v] = acc;
       }
+      acc = 0.0;
+      j0 = j1 + 1;
+    }
+    if (tail_open && sg[32] >= 0) {
+      for (int j = j0; j < 32; ++j) acc += col[j];
+      a.partial[((size_t)gwarp * 2 + (j0 == 0 ? 0 : 1)) * NV + v] = acc;
     }
   }
 }

@@ -36,7 +36,7 @@ struct PcgWorkspace {
   double* scal = nullptr;       // [16]: S_kk, 1/S_kk, iterations, fail, ...
   // shared-memory resident variant: block rows are split into one contiguous range per CTA
   bool smem_ok = false;
-  int smem_grid = 0, cap_slots = 0, max_halo = 0, max_slots = 0;
+  int smem_grid = 0, cap_slots = 0, max_halo = 0, max_slots = 0, max_rows = 0;
   size_t smem_bytes = 0;
   int32_t* cta_row = nullptr;   // [smem_grid + 1]
   int32_t* halo_ptr = nullptr;  // [smem_grid + 1]
@@ -174,8 +174,10 @@ inline int pcg_symbolic(PcgWorkspace& ws, const std::vector<uint64_t>& keys, int
     ws.smem_grid = G;
     ws.max_halo = max_halo;
     ws.max_slots = max_slots;
+    ws.max_rows = max_rows;
     // dynamic shared memory: matrix slice | gathered halo vector | local column ids
-    const size_t fixed = (size_t)max_halo * 48 + (((size_t)max_slots * 2 + 15) / 16) * 16 + 2048;
+    const size_t fixed = (size_t)max_halo * 48 + (size_t)max_rows * (36 + 6) * 8 + ((size_t)max_halo + max_rows + 4) * 4 +
+                         (((size_t)max_slots * 2 + 15) / 16) * 16 + 2048;
     ws.smem_ok = max_halo < 65535 && max_rows <= 64 && smem_limit > fixed + 288 * 16;
     if (ws.smem_ok) {
       ws.cap_slots = (int)std::min<size_t>((smem_limit - fixed) / 288, (size_t)max_slots);
@@ -346,7 +348,15 @@ struct PcgArgs {
   double* q;
   double* partial;       // [grid][8]
   double* scal;          // [0] S_kk [1] 1/S_kk [2] iterations (out) [3] fail (in/out)
+  unsigned long long* trace;  // debug: [iteration][cta][5] globaltimer stamps, or null
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PCG_TRACE(slot) do { if (a.trace && threadIdx.x == 0 && it <= 64) a.trace[((size_t)(it - 1) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); } while (0)
 
 // deterministic grid-wide sums: every CTA adds the same numbers in the same order
 template <int NS>
@@ -554,58 +564,109 @@ struct PcgSmemArgs {
   const int32_t* halo_ptr;
   const int32_t* halo_col;
   const uint16_t* lcol;
-  int cap_slots, max_halo, max_slots;
+  int cap_slots, max_halo, max_slots, max_rows;
 };
+
+// grid-wide sum of NS doubles: CTA totals are added to a global accumulator with FP64 atomics
+// before the barrier and read back after it (three rotating accumulators, the next one is
+// cleared by CTA 0).  One L2 round trip after the barrier instead of a 148-slot read + reduce.
+template <int NS>
+__device__ __forceinline__ void grid_sums_atomic(cg::grid_group& grid, double (&v)[NS], double* accum /* [3][8] */,
+                                                 double* sm, int& round) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* cur = accum + 8 * (round % 3);
+  double* nxt = accum + 8 * ((round + 1) % 3);
+  ++round;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NS; ++i) sm[wid * NS + i] = v[i];
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      double acc = lane < kPcgWarps ? sm[lane * NS + i] : 0.0;
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(cur + i, acc);
+    }
+    if (blockIdx.x == 0 && lane < 8) nxt[lane] = 0.0;
+  }
+  grid.sync();
+  // ONE thread per CTA fetches the totals (every thread of every CTA loading the same line
+  // serialises at its L2 slice: ~10 us for 148 x 1024 threads), the rest get them from smem
+  if (threadIdx.x < NS) sm[72 + threadIdx.x] = __ldcg(cur + threadIdx.x);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NS; ++i) v[i] = sm[72 + i];
+}
 
 __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemArgs A) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ double sm[64 + 32 * 2 + 8];
+  __shared__ double sm[96];
   const PcgArgs& a = A.a;
+  // dynamic shared memory: matrix slice | halo vector | Minv | border | halo columns | row offsets | local column ids
   double* Ss = reinterpret_cast<double*>(dyn);                       // [cap_slots][36]
   double* xs = Ss + (size_t)A.cap_slots * 36;                        // [max_halo][6]
-  uint16_t* lc = reinterpret_cast<uint16_t*>(xs + (size_t)A.max_halo * 6);
+  double* Ms = xs + (size_t)A.max_halo * 6;                          // [max_rows][36]
+  double* bs = Ms + (size_t)A.max_rows * 36;                         // [max_rows][6]
+  int32_t* hc = reinterpret_cast<int32_t*>(bs + (size_t)A.max_rows * 6);  // [max_halo]
+  int32_t* rp = hc + A.max_halo;                                     // [max_rows + 1] local slot offsets
+  uint16_t* lc = reinterpret_cast<uint16_t*>(rp + A.max_rows + 2);   // [max_slots]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 3, rr_ = lane & 7;
   const bool act = rr_ < 6;
   const int n_f = a.n_f, camrow = 6 * n_f;
   const int r0 = A.cta_row[blockIdx.x], r1 = A.cta_row[blockIdx.x + 1];
+  const int nrow = r1 - r0;
   const int s_beg = a.row_ptr[r0], s_end = a.row_ptr[r1];
   const int nslot = s_end - s_beg, ncache = min(nslot, A.cap_slots);
   const int h0 = A.halo_ptr[blockIdx.x], nhalo = A.halo_ptr[blockIdx.x + 1] - h0;
-  const double skk = a.scal[0], iskk = a.scal[1];
+  if (tid == 0) { sm[81] = a.scal[0]; sm[82] = a.scal[1]; }
   const bool is_cam_owner = (blockIdx.x == 0 && tid == 0);
-  int parity = 0;
-  // matrix slice and local column ids -> shared memory (once)
+  int round = 0;
+  // everything that is constant over the iterations -> shared memory (once)
   {
-    const double2* src = reinterpret_cast<const double2*>(a.S + 36 * (size_t)s_beg);
-    double2* dst = reinterpret_cast<double2*>(Ss);
-    for (int i = tid; i < ncache * 18; i += kPcgThreads) dst[i] = src[i];
+    // blocks are stored TRANSPOSED in shared memory ([j][i]): lane (block, j) then reads one
+    // 48-byte column with three conflict-free 128-bit loads and feeds all six row sums
+    const double* src = a.S + 36 * (size_t)s_beg;
+    for (int i = tid; i < ncache * 36; i += kPcgThreads) {
+      const int sl = i / 36, k = i - sl * 36, r = k / 6, c = k - r * 6;
+      Ss[sl * 36 + c * 6 + r] = src[i];
+    }
     for (int i = tid; i < nslot; i += kPcgThreads) lc[i] = A.lcol[s_beg + i];
+    for (int i = tid; i < nhalo; i += kPcgThreads) hc[i] = A.halo_col[h0 + i];
+    for (int i = tid; i <= nrow; i += kPcgThreads) rp[i] = a.row_ptr[r0 + i] - s_beg;
+    for (int i = tid; i < nrow * 36; i += kPcgThreads) Ms[i] = a.Minv[36 * (size_t)r0 + i];
+    for (int i = tid; i < nrow * 6; i += kPcgThreads) bs[i] = a.border[6 * (size_t)r0 + i];
   }
-  // this warp's rows (at most two), state in registers of lanes 0..5
-  const int rowA = r0 + wid, rowB = r0 + wid + 32;
-  const bool hasA = rowA < r1, hasB = rowB < r1;
-  double xA = 0.0, xB = 0.0, rA = 0.0, rB = 0.0, qA = 0.0, qB = 0.0, pA = 0.0, pB = 0.0;
+  __syncthreads();
+  const double skk = sm[81], iskk = sm[82];
+  // this warp's rows (at most two); x, r, z, p, q of a row live in registers of lanes 0..5
+  const int lrA = wid, lrB = wid + 32;
+  const bool hasA = lrA < nrow, hasB = lrB < nrow;
+  const int rowA = r0 + lrA, rowB = r0 + lrB;
+  double xA = 0.0, xB = 0.0, rA = 0.0, rB = 0.0, qA = 0.0, qB = 0.0, pA = 0.0, pB = 0.0, zA = 0.0, zB = 0.0;
   double s2[2] = {0.0, 0.0};
-  auto precond = [&](int row, double rv) {
+  auto precond = [&](int lrow, double rv) {
     double zv = 0.0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       const double rc = __shfl_sync(0xffffffffu, rv, c);
-      if (lane < 6) zv += a.Minv[36 * (size_t)row + lane * 6 + c] * rc;
+      if (lane < 6) zv += Ms[36 * lrow + lane * 6 + c] * rc;
     }
     return zv;
   };
   if (hasA) {
     if (lane < 6) rA = a.rhs[6 * (size_t)rowA + lane];
-    const double zv = precond(rowA, rA);
-    if (lane < 6) { a.z[6 * (size_t)rowA + lane] = zv; a.p0[6 * (size_t)rowA + lane] = 0.0; s2[0] += rA * zv; s2[1] += rA * rA; }
+    zA = precond(lrA, rA);
+    if (lane < 6) { a.z[6 * (size_t)rowA + lane] = zA; a.p0[6 * (size_t)rowA + lane] = 0.0; s2[0] += rA * zA; s2[1] += rA * rA; }
   }
   if (hasB) {
     if (lane < 6) rB = a.rhs[6 * (size_t)rowB + lane];
-    const double zv = precond(rowB, rB);
-    if (lane < 6) { a.z[6 * (size_t)rowB + lane] = zv; a.p0[6 * (size_t)rowB + lane] = 0.0; s2[0] += rB * zv; s2[1] += rB * rB; }
+    zB = precond(lrB, rB);
+    if (lane < 6) { a.z[6 * (size_t)rowB + lane] = zB; a.p0[6 * (size_t)rowB + lane] = 0.0; s2[0] += rB * zB; s2[1] += rB * rB; }
   }
   double xk = 0.0, rk = 0.0;
   if (is_cam_owner) {
@@ -615,7 +676,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
     s2[0] += rk * zv;
     s2[1] += rk * rk;
   }
-  grid_sums<2>(grid, s2, a.partial, sm, parity);
+  grid_sums_atomic<2>(grid, s2, a.partial, sm, round);
   double rz = s2[0];
   const double bb = s2[1];
   const double thresh = a.tol * a.tol * bb;
@@ -627,42 +688,57 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
   if (!(bb == 0.0 || fail)) {
     while (it < a.max_iter) {
       ++it;
+      PCG_TRACE(0);
       // ---- phase A: gather p = z + beta p_old for the halo columns, q = S p from shared memory
-      const double pk = a.z[camrow] + beta * p_old[camrow];
+      if (tid == 0) sm[80] = __ldcg(a.z + camrow) + beta * __ldcg(p_old + camrow);
       for (int i = tid; i < nhalo * 6; i += kPcgThreads) {
-        const int c = A.halo_col[h0 + i / 6], k = i - (i / 6) * 6;
-        xs[i] = a.z[6 * (size_t)c + k] + beta * p_old[6 * (size_t)c + k];
+        const int h = i / 6, k = i - h * 6;
+        const size_t gi = 6 * (size_t)hc[h] + k;
+        xs[i] = __ldcg(a.z + gi) + beta * __ldcg(p_old + gi);
       }
       __syncthreads();
+      PCG_TRACE(5);
+      const double pk = sm[80];
       double sa[2] = {0.0, 0.0};
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
-        const int row = which == 0 ? rowA : rowB;
         if (!(which == 0 ? hasA : hasB)) continue;
-        double acc = 0.0;
-        const int s0 = a.row_ptr[row] - s_beg, s1 = a.row_ptr[row + 1] - s_beg;
-        double pf = 0.0;
-        for (int s = s0 + g; s < s1; s += 4) {
-          if (act) {
-            const double* B = (s < ncache ? Ss + 36 * (size_t)s : a.S + 36 * (size_t)(s_beg + s)) + rr_ * 6;
-            const double* xv = xs + 6 * (int)lc[s];
+        const int lrow = which == 0 ? lrA : lrB;
+        const int row = r0 + lrow;
+        const int s0 = rp[lrow], s1 = rp[lrow + 1];
+        // the block row as a dense 6 x 6(s1 - s0) matrix: lanes over its columns
+        double ac[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = lane; c < 6 * (s1 - s0); c += 32) {
+          const int sl = s0 + c / 6, j = c - (c / 6) * 6;
+          const double xv = xs[6 * (int)lc[sl] + j];
+          if (sl < ncache) {
+            const double2* col = reinterpret_cast<const double2*>(Ss + 36 * (size_t)sl + 6 * j);
+            const double2 c0 = col[0], c1 = col[1], c2 = col[2];
+            ac[0] += c0.x * xv; ac[1] += c0.y * xv; ac[2] += c1.x * xv;
+            ac[3] += c1.y * xv; ac[4] += c2.x * xv; ac[5] += c2.y * xv;
+          } else {  // the few slots that did not fit in shared memory: row-major in global memory
+            const double* Bg = a.S + 36 * (size_t)(s_beg + sl) + j;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) acc += B[j] * xv[j];
+            for (int i = 0; i < 6; ++i) ac[i] += __ldg(Bg + 6 * i) * xv;
           }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ac[i] = warp_sum(ac[i]);
+        const double acc = lane == 0 ? ac[0] : lane == 1 ? ac[1] : lane == 2 ? ac[2] : lane == 3 ? ac[3] : lane == 4 ? ac[4] : ac[5];
         if (lane < 6) {
-          pf = a.z[6 * (size_t)row + lane] + beta * p_old[6 * (size_t)row + lane];
-          const double bd = a.border[6 * (size_t)row + lane];
+          const double pf = (which == 0 ? zA : zB) + beta * (which == 0 ? pA : pB);
+          const double bd = bs[6 * lrow + lane];
           const double qf = acc + bd * pk;
-          p_new[6 * (size_t)row + lane] = pf;
+          p_new[6 * (size_t)row + lane] = pf;   // published for the neighbours' next gather
           sa[0] += pf * qf;
           sa[1] += bd * pf;
           if (which == 0) { pA = pf; qA = qf; } else { pB = pf; qB = qf; }
         }
+        if (which == 0) PCG_TRACE(6);
       }
-      grid_sums<2>(grid, sa, a.partial, sm, parity);
+      PCG_TRACE(1);
+      grid_sums_atomic<2>(grid, sa, a.partial, sm, round);
+      PCG_TRACE(2);
       const double qk = sa[1] + skk * pk;
       const double pq = sa[0] + pk * qk;
       if (!(pq > 0.0) || !isfinite(pq)) { fail = true; break; }
@@ -672,14 +748,14 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
       if (hasA) {
         xA += alpha * pA;
         rA -= alpha * qA;
-        const double zv = precond(rowA, rA);
-        if (lane < 6) { a.z[6 * (size_t)rowA + lane] = zv; sb[0] += rA * zv; sb[1] += rA * rA; }
+        zA = precond(lrA, rA);
+        if (lane < 6) { a.z[6 * (size_t)rowA + lane] = zA; sb[0] += rA * zA; sb[1] += rA * rA; }
       }
       if (hasB) {
         xB += alpha * pB;
         rB -= alpha * qB;
-        const double zv = precond(rowB, rB);
-        if (lane < 6) { a.z[6 * (size_t)rowB + lane] = zv; sb[0] += rB * zv; sb[1] += rB * rB; }
+        zB = precond(lrB, rB);
+        if (lane < 6) { a.z[6 * (size_t)rowB + lane] = zB; sb[0] += rB * zB; sb[1] += rB * rB; }
       }
       if (is_cam_owner) {
         p_new[camrow] = pk;
@@ -690,7 +766,9 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
         sb[0] += rk * zv;
         sb[1] += rk * rk;
       }
-      grid_sums<2>(grid, sb, a.partial, sm, parity);
+      PCG_TRACE(3);
+      grid_sums_atomic<2>(grid, sb, a.partial, sm, round);
+      PCG_TRACE(4);
       beta = sb[0] / rz;
       rz = sb[0];
       double* t = p_old; p_old = p_new; p_new = t;
