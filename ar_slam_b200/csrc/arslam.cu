@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/ar_slam_b200.h"
 #include "cholesky.cuh"
 #include "kernels.cuh"
@@ -118,6 +120,49 @@ struct Profiler {
 
 }  // namespace
 
+// ---- device-side construction of the two sorted SoA copies (set_problem) ------------
+__global__ void make_sort_keys_kernel(int n, const int32_t* __restrict__ own, const int32_t* __restrict__ oth,
+                                      unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  keys[b] = ((unsigned long long)(unsigned)own[b] << 32) | (unsigned)oth[b];
+  vals[b] = b;
+}
+// sorted position p takes block perm[p]: indices and the 8 observation planes
+__global__ void gather_sorted_kernel(int n, int plane, const int32_t* __restrict__ perm,
+                                     const unsigned long long* __restrict__ keys, const double* __restrict__ rect8,
+                                     int32_t* __restrict__ s_own, int32_t* __restrict__ s_oth, double* __restrict__ s_obs) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= plane) return;
+  if (p < n) {
+    const int b = perm[p];
+    const unsigned long long k = keys[p];
+    s_own[p] = (int32_t)(k >> 32);
+    s_oth[p] = (int32_t)(k & 0xffffffffu);
+    const double2* src = reinterpret_cast<const double2*>(rect8 + 8 * (size_t)b);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2 v = src[q];
+      s_obs[(size_t)(2 * q) * plane + p] = v.x;
+      s_obs[(size_t)(2 * q + 1) * plane + p] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s_obs[(size_t)q * plane + p] = 0.0;
+  }
+}
+// seg_off[i] = first sorted position whose own index is >= i  (i = 0 .. n_own)
+__global__ void segment_offsets_kernel(int n, int n_own, const int32_t* __restrict__ s_own, int32_t* __restrict__ off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_own) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_own[mid] < i) lo = mid + 1; else hi = mid;
+  }
+  off[i] = lo;
+}
+
 struct arslam_solver {
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -143,6 +188,9 @@ struct arslam_solver {
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part;
+  DevBuf<unsigned long long> sort_keys[2];
+  DevBuf<int32_t> sort_vals[2];
+  DevBuf<unsigned char> sort_tmp;
   double* h_sc = nullptr;  // pinned
   long long ld = 0;
   int n_pad = 0;
@@ -302,18 +350,6 @@ int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap) 
   return n;
 }
 
-// Stable counting sort of block ids by key.
-static void counting_sort(const std::vector<int32_t>& in_order, const int32_t* key, int n_key,
-                          std::vector<int32_t>& out_order, std::vector<int32_t>* offsets) {
-  std::vector<int32_t> cnt(n_key + 1, 0);
-  for (int32_t b : in_order) cnt[key[b] + 1]++;
-  for (int i = 0; i < n_key; ++i) cnt[i + 1] += cnt[i];
-  if (offsets) *offsets = cnt;
-  std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
-  out_order.resize(in_order.size());
-  for (int32_t b : in_order) out_order[pos[key[b]]++] = b;
-}
-
 int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk, const int32_t* cap_idx,
                        const int32_t* tag_idx, const double* rect8) {
   if (!s) return ARSLAM_ERR_INVALID;
@@ -334,37 +370,38 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   CU(cudaMemcpyAsync(s->o_cap.p, cap_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
-  std::vector<int32_t> ident(nb), tmp, order;
-  for (int b = 0; b < nb; ++b) ident[b] = b;
-  std::vector<int32_t> own(plane), oth(plane);
-  std::vector<double> obs((size_t)8 * plane);
+  // both sorted copies are built on the GPU from the one upload above: stable radix sort of
+  // (own << 32 | other) keys, then one gather kernel writes the index arrays and the 8 planes
+  CU(s->sort_keys[0].ensure(nb)); CU(s->sort_keys[1].ensure(nb)); CU(s->sort_vals[0].ensure(nb)); CU(s->sort_vals[1].ensure(nb));
   for (int side = 0; side < 2; ++side) {
-    const int32_t* k_own = side == 0 ? cap_idx : tag_idx;
-    const int32_t* k_oth = side == 0 ? tag_idx : cap_idx;
-    const int n_own = side == 0 ? s->n_cap : s->n_tag, n_oth = side == 0 ? s->n_tag : s->n_cap;
-    counting_sort(ident, k_oth, n_oth, tmp, nullptr);
-    counting_sort(tmp, k_own, n_own, order, &s->h_off[side]);
-    std::fill(obs.begin(), obs.end(), 0.0);
-    for (int p = 0; p < nb; ++p) {
-      const int b = order[p];
-      own[p] = k_own[b];
-      oth[p] = k_oth[b];
-      for (int k = 0; k < 8; ++k) obs[(size_t)k * plane + p] = rect8[8 * (size_t)b + k];
-    }
+    const int32_t* d_own = side == 0 ? s->o_cap.p : s->o_tag.p;
+    const int32_t* d_oth = side == 0 ? s->o_tag.p : s->o_cap.p;
+    const int n_own = side == 0 ? s->n_cap : s->n_tag;
     CU(s->s_own[side].ensure(plane)); CU(s->s_oth[side].ensure(plane)); CU(s->s_off[side].ensure(n_own + 1));
     CU(s->s_obs[side].ensure((size_t)8 * plane));
-    s->h_oth[side].assign(oth.begin(), oth.begin() + nb);
-    CU(cudaMemcpyAsync(s->s_own[side].p, own.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->s_oth[side].p, oth.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->s_off[side].p, s->h_off[side].data(), sizeof(int32_t) * (n_own + 1), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->s_obs[side].p, obs.data(), sizeof(double) * 8 * plane, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaStreamSynchronize(s->stream));  // host staging buffers are reused
+    make_sort_keys_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, d_own, d_oth, s->sort_keys[0].p, s->sort_vals[0].p);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s->sort_keys[0].p, s->sort_keys[1].p, s->sort_vals[0].p,
+                                       s->sort_vals[1].p, nb, 0, 64, s->stream));
+    CU(s->sort_tmp.ensure(tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(s->sort_tmp.p, tmp_bytes, s->sort_keys[0].p, s->sort_keys[1].p, s->sort_vals[0].p,
+                                       s->sort_vals[1].p, nb, 0, 64, s->stream));
+    gather_sorted_kernel<<<cdiv(plane, 256), 256, 0, s->stream>>>(nb, plane, s->sort_vals[1].p, s->sort_keys[1].p, s->o_obs.p,
+                                                                 s->s_own[side].p, s->s_oth[side].p, s->s_obs[side].p);
+    segment_offsets_kernel<<<cdiv(n_own + 1, 256), 256, 0, s->stream>>>(nb, n_own, s->s_own[side].p, s->s_off[side].p);
+    // the host keeps the segment structure for the symbolic phase of the sparse reduced system
+    s->h_off[side].resize(n_own + 1);
+    s->h_oth[side].resize(nb);
+    CU(cudaMemcpyAsync(s->h_off[side].data(), s->s_off[side].p, sizeof(int32_t) * (n_own + 1), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_oth[side].data(), s->s_oth[side].p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s->stream));
     CU(s->H[side].ensure((size_t)n_own * NV));
     CU(s->partial[side].ensure((size_t)s->n_warp * 2 * NV));
     CU(s->d_pose[side].ensure((size_t)6 * n_own));
     CU(s->warp_norm[side].ensure((size_t)12 * cdiv(n_own, 128) + 12));
     CU(s->warp_gmax[side].ensure((size_t)4 * cdiv(n_own, 128) + 4));
   }
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
   for (int k = 0; k < 2; ++k) {
     CU(s->cam[k].ensure(4)); CU(s->cap[k].ensure((size_t)6 * s->n_cap)); CU(s->tag[k].ensure((size_t)6 * s->n_tag));
     CU(s->cap_pre[k].ensure((size_t)kCapPre * s->n_cap)); CU(s->tag_pre[k].ensure((size_t)kTagPre * s->n_tag));
@@ -547,7 +584,8 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
   std::string err;
   std::vector<uint64_t> keys;
-  pcg_collect_keys(n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), keys);
+  pcg_collect_keys(n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), s->h_off[1 - side_e].data(),
+                   s->h_oth[1 - side_e].data(), keys);
   int urc = union_keys_across_ranks(s, keys);
   if (urc) return urc;
   const int rc = pcg_symbolic(s->pcg, keys, n_e, n_f, s->h_off[side_e].data(), s->stream, err,

@@ -63,16 +63,28 @@ struct PcgWorkspace {
 // ---- symbolic phase (host): block pattern of sum_e W_e^T W_e over the E segments
 // keys = (row << 32 | col) of every block of the reduced system this rank contributes to
 inline void pcg_collect_keys(int n_e, int n_f, const int32_t* e_off, const int32_t* f_of_blk,
-                             std::vector<uint64_t>& keys) {
+                             const int32_t* f_off, const int32_t* e_of_blk, std::vector<uint64_t>& keys) {
+  // row r of the reduced system couples F pose r with every F pose seen by an E pose that sees r.
+  // Walk r's blocks (F-sorted copy) -> their E poses -> those poses' blocks (E-sorted copy);
+  // a marker array removes duplicates, so the cost is the number of (block, partner) pairs.
   keys.clear();
-  keys.reserve((size_t)e_off[n_e] * 8 + n_f);
-  for (int e = 0; e < n_e; ++e)
-    for (int i = e_off[e]; i < e_off[e + 1]; ++i)
-      for (int j = e_off[e]; j < e_off[e + 1]; ++j)
-        keys.push_back((uint64_t)(uint32_t)f_of_blk[i] << 32 | (uint32_t)f_of_blk[j]);
-  for (int f = 0; f < n_f; ++f) keys.push_back((uint64_t)(uint32_t)f << 32 | (uint32_t)f);  // every diagonal block exists
-  std::sort(keys.begin(), keys.end());
-  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  keys.reserve((size_t)n_f * 24);
+  std::vector<int32_t> mark(n_f, -1), cols;
+  for (int r = 0; r < n_f; ++r) {
+    cols.clear();
+    mark[r] = r;
+    cols.push_back(r);  // every diagonal block exists
+    for (int b = f_off[r]; b < f_off[r + 1]; ++b) {
+      const int e = e_of_blk[b];
+      for (int q = e_off[e]; q < e_off[e + 1]; ++q) {
+        const int c = f_of_blk[q];
+        if (mark[c] != r) { mark[c] = r; cols.push_back(c); }
+      }
+    }
+    std::sort(cols.begin(), cols.end());
+    for (int c : cols) keys.push_back((uint64_t)(uint32_t)r << 32 | (uint32_t)c);
+  }
+  (void)n_e;
 }
 
 inline int pcg_symbolic(PcgWorkspace& ws, const std::vector<uint64_t>& keys, int n_e, int n_f, const int32_t* e_off,
@@ -615,8 +627,6 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
   int32_t* rp = hc + A.max_halo;                                     // [max_rows + 1] local slot offsets
   uint16_t* lc = reinterpret_cast<uint16_t*>(rp + A.max_rows + 2);   // [max_slots]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int g = lane >> 3, rr_ = lane & 7;
-  const bool act = rr_ < 6;
   const int n_f = a.n_f, camrow = 6 * n_f;
   const int r0 = A.cta_row[blockIdx.x], r1 = A.cta_row[blockIdx.x + 1];
   const int nrow = r1 - r0;

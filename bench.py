@@ -333,8 +333,8 @@ def main():
             dt = float(t.item())
         n_solves = len(e2e_sum)
         param_bytes = 8 * (3 + 6 * m.n_cap + 6 * m.n_tag)
-        h2d = (obs.nbytes + cap_idx.nbytes + tag_idx.nbytes) * 3 + n_solves * param_bytes
-        d2h = n_solves * param_bytes + 128 * args.steps
+        h2d = (obs.nbytes + cap_idx.nbytes + tag_idx.nbytes) + n_solves * param_bytes
+        d2h = n_solves * param_bytes + 192 * args.steps + 2 * (4 * len(cap_idx) + 4 * (m.n_cap + m.n_tag))
         e2e = {"value": n_corner_total * args.steps / dt, "unit": "corners/s",
                "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                "lm_iters_per_sec": args.steps / dt,
