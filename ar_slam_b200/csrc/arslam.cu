@@ -191,6 +191,9 @@ struct arslam_solver {
   DevBuf<unsigned long long> sort_keys[2];
   DevBuf<int32_t> sort_vals[2];
   DevBuf<unsigned char> sort_tmp;
+  // localisation batch buffers (kept between calls)
+  DevBuf<int32_t> l_off, l_tag, l_seed, l_it, l_term;
+  DevBuf<double> l_obs, l_tagpose, l_tagpre, l_pose, l_cost;
   double* h_sc = nullptr;  // pinned
   long long ld = 0;
   int n_pad = 0;
@@ -1097,8 +1100,8 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   CU(cudaSetDevice(s->device));
   s->prof.clear();
   s->launches = 0;
-  DevBuf<int32_t> d_off, d_tag, d_seed, d_it, d_term;
-  DevBuf<double> d_obs, d_tagpose, d_tagpre, d_pose, d_cost;
+  DevBuf<int32_t>&d_off = s->l_off, &d_tag = s->l_tag, &d_seed = s->l_seed, &d_it = s->l_it, &d_term = s->l_term;
+  DevBuf<double>&d_obs = s->l_obs, &d_tagpose = s->l_tagpose, &d_tagpre = s->l_tagpre, &d_pose = s->l_pose, &d_cost = s->l_cost;
   CU(d_off.ensure(n_loc + 1)); CU(d_tag.ensure(nb)); CU(d_seed.ensure(n_loc)); CU(d_it.ensure(n_loc)); CU(d_term.ensure(n_loc));
   CU(d_obs.ensure((size_t)8 * nb)); CU(d_tagpose.ensure((size_t)6 * n_tag)); CU(d_tagpre.ensure((size_t)kTagPre * n_tag));
   CU(d_pose.ensure((size_t)6 * n_loc)); CU(d_cost.ensure(n_loc));

@@ -166,3 +166,47 @@ def test_pcg_default_tolerance_converges_like_dense(gpu_solver_cls):
     # default pcg_tolerance 0.1 (inexact Newton, Ceres' eta): a couple more LM iterations, same minimum
     assert 0 <= out["pcg"]["iterations"] - out["dense"]["iterations"] <= 3
     assert abs(out["pcg"]["final_cost"] - out["dense"]["final_cost"]) <= 1e-5 * out["dense"]["final_cost"]
+
+
+@pytest.mark.parametrize("elim,ls", [(2, 1), (1, 1), (2, 2)])
+def test_ragged_visibility_matches_oracle(gpu_solver_cls, oracle, elim, ls):
+    """Captures seeing 1..12 tags, tags seen by 1..~150 captures: pose segments of every length,
+    straddling warps and CTAs in both sorted copies; unused tags and captures; a tag seen twice by
+    one capture.  Same LM trajectory as the oracle with either side eliminated and with PCG."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(700, 90, tags_per_capture=12, seed=17)
+    rng = np.random.default_rng(5)
+    keep = rng.random(len(m.cap_idx)) < rng.uniform(0.15, 1.0, m.n_cap)[m.cap_idx]
+    keep[np.unique(m.cap_idx, return_index=True)[1]] = True          # at least one block per capture ...
+    keep[m.cap_idx == 5] = False                                     # ... except capture 5: no blocks at all
+    ci, ti, ob = m.cap_idx[keep], m.tag_idx[keep], m.obs[keep]
+    ci = np.concatenate([ci, [7]]).astype(np.int32)                  # capture 7 sees its first tag twice
+    ti = np.concatenate([ti, [ti[np.nonzero(ci == 7)[0][0]]]]).astype(np.int32)
+    ob = np.concatenate([ob, ob[np.nonzero(ci == 7)[0][0]][None] + 0.5])
+    perm = rng.permutation(len(ci))                                  # blocks arrive in arbitrary order
+    ci, ti, ob = ci[perm], ti[perm], ob[perm]
+    opts = oracle.default_options(num_threads=4, elimination=elim)
+    cam_o, cap_o, tag_o, so, log_o = oracle.solve(m.n_cap, m.n_tag, ci, ti, ob, m.cam0, m.cap0, m.tag0, options=opts)
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(elimination=elim, linear_solver=ls, pcg_tolerance=1e-13,
+                                                             pcg_max_iterations=5000))
+    s.set_problem(m.n_cap, m.n_tag, ci, ti, ob)
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    sg, log_g = s.solve()
+    cam_g, cap_g, tag_g = s.get_params()
+    cost_g = s.evaluate(jacobians=False)[0] if False else None
+    s.close()
+    assert sg["eliminated_side"] == elim and sg["linear_solver"] == ls
+    assert sg["iterations"] == so["iterations"] and sg["reason"] == so["reason"]
+    n = so["iterations"] + 1
+    assert np.allclose(log_g[:n, 0], log_o[:n, 0], rtol=1e-7)
+    assert np.allclose(log_g[:n, 5], log_o[:n, 5], rtol=1e-4)
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-8 * so["final_cost"]
+    assert abs(cam_g[0] - cam_o[0]) <= 1e-6 * cam_o[0]
+    assert np.array_equal(cap_g[5], m.cap0[5])                       # the capture without blocks is untouched
+    used_t = np.unique(ti)
+    unused_t = np.setdiff1d(np.arange(m.n_tag), used_t)
+    assert np.array_equal(tag_g[unused_t], m.tag0[unused_t])
+    assert np.abs(tag_g[used_t] - tag_o[used_t]).max() < 1e-5
+    used_c = np.unique(ci)
+    assert np.abs(cap_g[used_c] - cap_o[used_c]).max() < 1e-5
