@@ -1125,7 +1125,7 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   a.o.parameter_tolerance = o.parameter_tolerance; a.o.tag_size = o.tag_size;
   a.pose = d_pose.p; a.iterations = d_it.p; a.final_cost = d_cost.p; a.termination = d_term.p;
   LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc,
-         localize_kernel<<<cdiv(n_loc * 32, 128), 128, 0, s->stream>>>(a));
+         localize_kernel<<<cdiv(n_loc * kLocGroup, 128), 128, 0, s->stream>>>(a));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(cap_pose6, d_pose.p, sizeof(double) * 6 * n_loc, cudaMemcpyDeviceToHost, s->stream));
   if (iterations) CU(cudaMemcpyAsync(iterations, d_it.p, sizeof(int32_t) * n_loc, cudaMemcpyDeviceToHost, s->stream));

@@ -1,13 +1,13 @@
 // localize.cuh -- kernel (5): batched independent per-capture localisation
-// against a fixed map.  One warp per capture runs the whole pipeline of
+// against a fixed map.  Eight lanes per capture (four captures per warp) run the whole pipeline of
 // ArSlamSolver::localizeOne (reference ar_slam/src/ar_slam_util.cpp:903-979)
 // on the device: seed from one tag (initCapturePose, :91-108), then the
 // trust-region LM that ceres::Solve would run on a problem whose tags and
 // camera are constant (:965, :972) -- a single free 6-vector, so the "Schur
 // complement" is one damped 6x6 Cholesky solve held in registers.
-// Lanes own observation corners (coalesced 16 B loads of the capture's
-// contiguous rect array); J^T J / J^T r are reduced with warp shuffles; every
-// lane then runs the same scalar LM control code.  No communication between
+// Lanes own residual blocks (64 B of the capture's contiguous rect array each);
+// J^T J / J^T r are reduced with shuffles inside the 8-lane group; every lane of
+// the group then runs the same scalar LM control code.  No communication between
 // captures, hence none between GPUs.
 #pragma once
 #include "kernels.cuh"
@@ -37,25 +37,40 @@ struct LocArgs {
   int32_t* termination;       // optional
 };
 
-// sum r^2 at pose x over the capture's corners (all lanes get the result)
-__device__ __forceinline__ double loc_cost(const LocArgs& a, int b0, int ncorner, const double x[6], int lane) {
+// Eight lanes per capture (one lane per residual block, its four corners in sequence), four
+// captures per warp: the scalar LM control code, the pose prep (sincos) and the 6x6 Cholesky
+// are shared by 8 lanes instead of 32, and the Gram reductions are 3 shuffle levels inside the
+// group (shuffles name only the group's lanes, so groups may diverge freely).
+constexpr int kLocGroup = 8;
+__device__ __forceinline__ double loc_group_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = kLocGroup / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+// sum r^2 at pose x over the capture's corners (all lanes of the group get the result)
+__device__ __forceinline__ double loc_cost(const LocArgs& a, int b0, int nb, const double x[6], int gl, unsigned mask) {
   double cp[kCapPre];
   prep_capture(x, cp);
   double s = 0.0;
-  for (int c = lane; c < ncorner; c += 32) {
-    const int blk = b0 + (c >> 2);
-    const double2 o = a.obs[4 * (size_t)b0 + c];
-    const double* tp = a.tag_pre + (size_t)kTagPre * a.tag_idx[blk] + 12 * (c & 3);
-    double r[2];
-    corner_residual(cp, tp, a.focal, o.x, o.y, r);
-    s += r[0] * r[0] + r[1] * r[1];
+  for (int j = gl; j < nb; j += kLocGroup) {
+    const int blk = b0 + j;
+    const double2* ob = a.obs + 4 * (size_t)blk;
+    const double* tp = a.tag_pre + (size_t)kTagPre * a.tag_idx[blk];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 o = ob[i];
+      double r[2];
+      corner_residual(cp, tp + 12 * i, a.focal, o.x, o.y, r);
+      s += r[0] * r[0] + r[1] * r[1];
+    }
   }
-  return warp_sum(s);
+  return loc_group_sum(s, mask);
 }
 
 // J^T J (upper packed 21), J^T r (6) and sum r^2 at pose x
-__device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int ncorner, const double x[6],
-                                              int lane, double H[21], double g[6], double& rr) {
+__device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int nb, const double x[6], int gl,
+                                              unsigned mask, double H[21], double g[6], double& rr) {
   double cp[kCapPre];
   prep_capture(x, cp);
 #pragma unroll
@@ -63,46 +78,51 @@ __device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int ncor
 #pragma unroll
   for (int i = 0; i < 6; ++i) g[i] = 0.0;
   rr = 0.0;
-  for (int c = lane; c < ncorner; c += 32) {
-    const int blk = b0 + (c >> 2);
-    const double2 o = a.obs[4 * (size_t)b0 + c];
-    const double* tp = a.tag_pre + (size_t)kTagPre * a.tag_idx[blk] + 12 * (c & 3);
-    CornerJ j;
-    corner_jacobian(cp, tp, a.focal, o.x, o.y, j);
+  for (int j = gl; j < nb; j += kLocGroup) {
+    const int blk = b0 + j;
+    const double2* ob = a.obs + 4 * (size_t)blk;
+    const double* tp = a.tag_pre + (size_t)kTagPre * a.tag_idx[blk];
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const double2 o = ob[i];
+      CornerJ cj;
+      corner_jacobian(cp, tp + 12 * i, a.focal, o.x, o.y, cj);
 #pragma unroll
-    for (int row = 0; row < 2; ++row) {
-      const double J[6] = {j.A[row][0], j.A[row][1], j.A[row][2], j.B[row][0], j.B[row][1], j.B[row][2]};
+      for (int row = 0; row < 2; ++row) {
+        const double J[6] = {cj.A[row][0], cj.A[row][1], cj.A[row][2], cj.B[row][0], cj.B[row][1], cj.B[row][2]};
 #pragma unroll
-      for (int p = 0; p < 6; ++p) {
+        for (int p = 0; p < 6; ++p) {
 #pragma unroll
-        for (int q = p; q < 6; ++q) H[tri6(p, q)] += J[p] * J[q];
-        g[p] += J[p] * j.r[row];
+          for (int q = p; q < 6; ++q) H[tri6(p, q)] += J[p] * J[q];
+          g[p] += J[p] * cj.r[row];
+        }
+        rr += cj.r[row] * cj.r[row];
       }
-      rr += j.r[row] * j.r[row];
     }
   }
 #pragma unroll
-  for (int i = 0; i < 21; ++i) H[i] = warp_sum(H[i]);
+  for (int i = 0; i < 21; ++i) H[i] = loc_group_sum(H[i], mask);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) g[i] = warp_sum(g[i]);
-  rr = warp_sum(rr);
+  for (int i = 0; i < 6; ++i) g[i] = loc_group_sum(g[i], mask);
+  rr = loc_group_sum(rr, mask);
 }
 
 __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
-  const int cap = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cap = gid / kLocGroup;
+  const int lane = threadIdx.x & 31, gl = lane & (kLocGroup - 1);
+  const unsigned mask = ((1u << kLocGroup) - 1u) << (lane & ~(kLocGroup - 1));
   if (cap >= a.n_loc) return;
   const int b0 = a.blk_off[cap], nb = a.blk_off[cap + 1] - b0;
   const int seed = a.seed_block[cap];
   if (seed < 0 || nb <= 0) {
-    if (lane == 0) {
+    if (gl == 0) {
       if (a.iterations) a.iterations[cap] = -1;
       if (a.final_cost) a.final_cost[cap] = 0.0;
       if (a.termination) a.termination[cap] = -1;
     }
     return;
   }
-  const int ncorner = 4 * nb;
   const LocOptions& o = a.o;
   double x[6];
   {
@@ -123,7 +143,7 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
 
   double H[21], g[6], rr;
   double scale[6], diag[6];
-  loc_normal_eq(a, b0, ncorner, x, lane, H, g, rr);
+  loc_normal_eq(a, b0, nb, x, gl, mask, H, g, rr);
   double x_cost = 0.5 * rr;
 #pragma unroll
   for (int i = 0; i < 6; ++i) scale[i] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(H[tri6(i, i)])) : 1.0;
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
     double xc[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) xc[i] = x[i] + delta[i];
-    double cand_cost = 0.5 * loc_cost(a, b0, ncorner, xc, lane);
+    double cand_cost = 0.5 * loc_cost(a, b0, nb, xc, gl, mask);
     if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
     double sn = 0.0;
 #pragma unroll
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) x_norm += x[i] * x[i];
       x_norm = sqrt(x_norm);
-      loc_normal_eq(a, b0, ncorner, x, lane, H, g, rr);
+      loc_normal_eq(a, b0, nb, x, gl, mask, H, g, rr);
       x_cost = 0.5 * rr;
       grad_max = 0.0;
 #pragma unroll
@@ -223,8 +243,9 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
       decrease_factor *= 2.0;
     }
   }
-  if (lane < 6) a.pose[6 * (size_t)cap + lane] = x[lane];
-  if (lane == 0) {
+  if (gl == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.pose[6 * (size_t)cap + i] = x[i];
     if (a.iterations) a.iterations[cap] = iteration;
     if (a.final_cost) a.final_cost[cap] = x_cost;
     if (a.termination) a.termination[cap] = termination;

@@ -198,6 +198,18 @@ def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
         nc = 4 * len(m.tag_idx)
         peak, how = read_peaks()
         err = np.abs(pose - m.cap_true[lo:hi])
+        cb = None
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import pyoracle as po
+            ns = min(n_loc, 50000)
+            threads = po.max_threads()
+            t1 = time.perf_counter()
+            po.localize_batch(m.blk_offsets[:ns + 1], m.tag_idx[:m.blk_offsets[ns]], m.obs[:m.blk_offsets[ns]],
+                              m.seed_block[:ns], m.cam_true, m.tag_true, num_threads=threads)
+            dtc = time.perf_counter() - t1
+            cb = {"value": 4 * int(m.blk_offsets[ns]) / dtc, "unit": "corners/s", "cores": threads, "kind": "port",
+                  "captures_per_sec": ns / dtc,
+                  "sample": "first %d captures of the same batch, restated localizeOne (not Ceres), OpenMP x%d" % (ns, threads)}
         alg = 17.0 * 4 * len(tag_idx) + 116.0 * (hi - lo)
         line = {"metric": "observation_corners_per_sec", "value": nc * args.steps / (ms_kernel * 1e-3), "unit": "corners/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel / args.steps,
@@ -215,7 +227,7 @@ def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
                              "peak": peak, "unit": "GB/s", "frac": alg * args.steps / (ms_kernel * 1e-3) / 1e9 / peak,
                              "traffic": None, "peak_source": how,
                              "note": "whole LM solve per capture in registers: FP64-latency bound, not HBM bound"},
-                "cpu_baseline": None}
+                "cpu_baseline": cb}
         print(json.dumps(line))
     s.close()
     if dist is not None:
