@@ -296,6 +296,8 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
   if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&s->h_sc, 128 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
+      cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(schur_eliminate_kernel<DenseTarget>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
       pcg_init() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -526,8 +528,17 @@ __global__ void axpy_kernel(int n, const double* a, const double* b, double sign
 }
 
 int nccl_sum(arslam_solver* s, double* buf, size_t count) {
+  Profiler::Rec r{0, nullptr, nullptr};
+  if (s->prof.on) {
+    r = Profiler::Rec{s->prof.id_of(count > 4096 ? "nccl_allreduce_large" : "nccl_allreduce_small", 8.0 * count), s->prof.ev(), s->prof.ev()};
+    cudaEventRecord(r.a, s->stream);
+  }
   const int rc = g_nccl.AllReduce(buf, buf, count, kNcclDouble, kNcclSum, s->comm, s->stream);
   if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  if (s->prof.on) {
+    cudaEventRecord(r.b, s->stream);
+    s->prof.recs.push_back(r);
+  }
   return ARSLAM_OK;
 }
 
@@ -621,7 +632,7 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
   LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
-         schur_eliminate_kernel<SparseTarget><<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(a2, t, s->n_blk, e_idx));
+         schur_eliminate_kernel<SparseTarget><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a2, t, s->n_blk, e_idx));
   return ARSLAM_OK;
 }
 
@@ -866,7 +877,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
         LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
-               schur_eliminate_kernel<DenseTarget><<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
+               schur_eliminate_kernel<DenseTarget><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
       } else {
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;

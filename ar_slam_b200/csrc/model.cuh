@@ -364,7 +364,11 @@ ARS_HD bool chol6(double H[36]) {
 #pragma unroll
     for (int k = 0; k < j; ++k) d -= H[j * 6 + k] * H[j * 6 + k];
     ok = ok && (d > 0.0);
+#if defined(__CUDA_ARCH__)
+    const double il = rsqrt(d);
+#else
     const double il = 1.0 / sqrt(d);
+#endif
     H[j * 6 + j] = il;
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {

@@ -112,8 +112,10 @@ inline int pcg_symbolic(PcgWorkspace& ws, const std::vector<uint64_t>& keys, int
   std::vector<int32_t> pair_off(std::max(e_off[n_e], 1));
   {
     long long acc = 0;
-    for (int e = 0; e < n_e; ++e)
-      for (int b = e_off[e]; b < e_off[e + 1]; ++b) { pair_off[b] = (int32_t)acc; acc += b - e_off[e] + 1; }
+    for (int e = 0; e < n_e; ++e) {
+      const int k = e_off[e + 1] - e_off[e];
+      for (int b = e_off[e]; b < e_off[e + 1]; ++b) { pair_off[b] = (int32_t)acc; acc += schur_pairs_of(b - e_off[e], k); }
+    }
     ws.n_pairs = acc;
   }
   const size_t nvec = (size_t)6 * n_f + 2;
@@ -241,15 +243,23 @@ struct SparseTarget {
   __device__ __forceinline__ double* elem(double* blk, int e) const { return blk + e; }
 };
 
-// fills pair_slot once per problem: thread per E-sorted block, loop over its partners
+// fills pair_slot once per problem: thread per E-sorted block, same partner enumeration as
+// schur_eliminate_kernel
 __global__ void pair_slot_kernel(int n_blk, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
                                  const int32_t* __restrict__ f_idx, const int32_t* __restrict__ pair_off,
                                  SparseTarget t, int32_t* __restrict__ out) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n_blk) return;
-  const int beg = e_off[e_idx[pos]];
+  const int e = e_idx[pos];
+  const int beg = e_off[e], k = e_off[e + 1] - beg, j = pos - beg;
   const int fj = f_idx[pos];
-  for (int i = 0; i <= pos - beg; ++i) out[(size_t)pair_off[pos] + i] = t.find(f_idx[beg + i], fj);
+  const int np = schur_pairs_of(j, k);
+  for (int d = 0; d < np; ++d) {
+    int i2 = j + d;
+    if (i2 >= k) i2 -= k;
+    const int fp = f_idx[beg + i2];
+    out[(size_t)pair_off[pos] + d] = t.find(min(fj, fp), max(fj, fp));
+  }
 }
 
 // ---- finalize: scale by sigma_F, add the F-pose diagonal blocks and damping,

@@ -75,34 +75,75 @@ struct DenseTarget {
   __device__ __forceinline__ double* elem(double* blk, int e) const { return blk + (size_t)(e / 6) * ld + (e % 6); }
 };
 
-// One thread per residual block (E-sorted order).  Thread j of a segment
-//   * rebuilds the segment's damped 6x6 block and factors it in registers
-//     (batched 6x6 Cholesky; the 8-fold redundancy inside a segment is cheaper
-//     than a shuffle broadcast of 21 + 12 doubles),
-//   * computes Y_j = Ht_ee^-1 (sig_e W_j) with coalesced plane loads/stores,
-//   * then walks its partners i <= j of the same segment (W_i is a warp-wide
-//     broadcast load) and adds W~_i^T Y_j to the reduced system.
+// number of (block, partner) products thread j of a k-block segment owns: partners are
+// (j + d) mod k for d = 0 .. k/2, the d = k/2 ring of an even k being split between the halves
+__host__ __device__ inline int schur_pairs_of(int j, int k) {
+  return (k & 1) ? (k + 1) / 2 : k / 2 + (j < k / 2 ? 1 : 0);
+}
+
+// forward substitution with the reciprocal-pivot factor: v = L^-1 v
+__device__ __forceinline__ void chol6_forward(const double L[36], double b[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
+    b[i] = s * L[i * 6 + i];
+  }
+}
+__device__ __forceinline__ void chol6_backward(const double L[36], double b[6]) {
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
+    b[i] = s * L[i * 6 + i];
+  }
+}
+
+constexpr int kSchurThreads = 128;
+constexpr size_t kSchurSmem = (size_t)(kSchurThreads * 37 + 4 * 32 * 37) * sizeof(double);
+
+// One thread per residual block (E-sorted order).  With Ht_ee = L L^T the Schur term of a
+// segment is sum_ij V_i^T V_j, V_j = L^-1 (sig_e W_j).  Thread j
+//   * rebuilds the segment's damped 6x6 block and factors it in registers (batched 6x6
+//     Cholesky; the redundancy inside a segment is cheaper than broadcasting 21 + 12 doubles),
+//   * computes V_j with coalesced plane loads and publishes it in shared memory,
+//   * forms its share of the k (k + 1) / 2 products V_a^T V_b -- partners (j + d) mod k, so
+//     every lane of the segment carries the same load -- stages each 6x6 result in shared
+//     memory, and the warp adds it to the reduced system with one FP64 atomic per lane on
+//     consecutive addresses (coalesced reductions at L2).
 template <typename Target>
-__global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk,
-                                                              const int32_t* __restrict__ e_idx) {
-  __shared__ double stage[4][32][37];
+__global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk,
+                                                                        const int32_t* __restrict__ e_idx) {
+  extern __shared__ __align__(16) double schur_sm[];
+  double(*Vs)[37] = reinterpret_cast<double(*)[37]>(schur_sm);                       // [128][37]
+  double(*stage)[32][37] = reinterpret_cast<double(*)[32][37]>(schur_sm + kSchurThreads * 37);  // [4][32][37]
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cta0 = blockIdx.x * blockDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool valid = pos < n_blk;
   const int e = valid ? e_idx[pos] : 0;
   const int beg = valid ? a.e_off[e] : 0;
-  const int j = valid ? pos - beg : -1;
-  double Y[36], s[6];
+  const int k = valid ? a.e_off[e + 1] - beg : 0;
+  const int j = valid ? pos - beg : 0;
+  double L[36], V[36], s[6];
   int fj = 0;
+  const size_t ps = a.plane;
   if (valid) {
-    double L[36], z[6], yb[6], hk[6];
-    load_scaled_E(a, e, L, z, hk, s);
+    double zl[6], ybl[6], hk[6];
+    load_scaled_E(a, e, L, zl, hk, s);
     const bool ok = chol6(L);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) yb[i] = hk[i];
-    chol6_solve(L, z);
-    chol6_solve(L, yb);
+    for (int i = 0; i < 6; ++i) ybl[i] = hk[i];
+    chol6_forward(L, zl);
+    chol6_forward(L, ybl);
     if (j == 0) {
+      double z[6], yb[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { z[i] = zl[i]; yb[i] = ybl[i]; }
+      chol6_backward(L, z);
+      chol6_backward(L, yb);
       double* zo = a.Z + 8 * (size_t)e;
       double c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -117,60 +158,81 @@ __global__ void __launch_bounds__(128) schur_eliminate_kernel(const SchurArgs a,
       double* sg = a.seg_cam + 4 * (size_t)e;
       sg[0] = c0; sg[1] = c1; sg[2] = ok ? 0.0 : 1.0; sg[3] = 0.0;
     }
-    const size_t ps = a.plane;
     fj = a.f_idx[pos];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       double col[6];
-      double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
+      chol6_forward(L, col);
+      double b0 = 0.0, b1 = 0.0;  // (sig_e W)^T Ht^-1 h = V^T (L^-1 h)
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
-        b0 += col[i] * yb[i];
-        b1 += col[i] * z[i];
+        V[i * 6 + c] = col[i];
+        Vs[threadIdx.x][i * 6 + c] = col[i];
+        b0 += col[i] * ybl[i];
+        b1 += col[i] * zl[i];
       }
-      chol6_solve(L, col);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) Y[i * 6 + c] = col[i];
       t.add_border(fj, c, b0, b1);
     }
   }
-  // pair products W~_i^T Y_j for partners i <= j of the same segment.  Every lane stages its
-  // 6x6 product in shared memory; the warp then adds it to the reduced system with one
-  // atomic per lane on consecutive addresses (coalesced reductions at L2).
-  int tmax = j;
+  __syncthreads();
+  const int my_pairs = valid ? schur_pairs_of(j, k) : 0;
+  int dmax = my_pairs;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-  const size_t ps = a.plane;
-  for (int i = 0; i <= tmax; ++i) {
-    const bool active = i <= j;
+  for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  for (int d = 0; d < dmax; ++d) {
+    const bool active = d < my_pairs;
     double* blk = nullptr;
     if (active) {
-      const int bi = beg + i;
-      const int fi = a.f_idx[bi];  // fi <= fj: blocks are sorted by F pose inside a segment
-      double Wi[36];
+      int i2 = j + d;
+      if (i2 >= k) i2 -= k;
+      const int ppos = beg + i2;
+      const int fp = a.f_idx[ppos];
+      double P[36];  // the partner's V
+      if (ppos >= cta0 && ppos < cta0 + kSchurThreads) {
 #pragma unroll
-      for (int m = 0; m < 6; ++m)
+        for (int q = 0; q < 36; ++q) P[q] = Vs[ppos - cta0][q];
+      } else {  // the segment continues in a neighbouring CTA: rebuild the partner's V (same L)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) Wi[m * 6 + c] = a.W[(size_t)(m * 6 + c) * ps + bi] * s[m];
-      blk = t.block(fi, fj, (a.pair_off ? (long long)a.pair_off[pos] : 0) + i);
-      const bool diag = fi == fj, twice = diag && (i != j);
+        for (int c = 0; c < 6; ++c) {
+          double col[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) col[i] = a.W[(size_t)(i * 6 + c) * ps + ppos] * s[i];
+          chol6_forward(L, col);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) P[i * 6 + c] = col[i];
+        }
+      }
+      // order the pair so that the block lands in the lower triangle: row = larger F pose
+      const bool own_first = fj <= fp;
+      const int fa = own_first ? fj : fp, fb = own_first ? fp : fj;
+      const bool diag = fa == fb, twice = diag && d != 0;
+      blk = t.block(fa, fb, (a.pair_off ? (long long)a.pair_off[pos] : 0) + d);
       double* st = stage[wid][lane];
+      // m1 = V^T P.  The product wanted is M = V_a^T V_b (element (6 fa + r, 6 fb + c)), stored
+      // transposed in the lower block (fb, fa): with the own block first that is m1^T, with the
+      // partner first it is m1 itself; on the diagonal (same F pose) m1 is stored as is.
+      const bool transpose = own_first && !diag;
 #pragma unroll
       for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          double acc = 0.0;  // M[r][c] = element (6 fi + r, 6 fj + c)
-          double acct = 0.0;
+          double m1 = 0.0;
 #pragma unroll
-          for (int m = 0; m < 6; ++m) {
-            acc += Wi[m * 6 + r] * Y[m * 6 + c];
-            if (twice) acct += Wi[m * 6 + c] * Y[m * 6 + r];
-          }
-          // lower-triangular storage: off-diagonal products land transposed in block (fj, fi)
-          if (!diag) st[c * 6 + r] = acc;
-          else st[r * 6 + c] = twice ? acc + acct : acc;
+          for (int m = 0; m < 6; ++m) m1 += V[m * 6 + r] * P[m * 6 + c];
+          st[transpose ? c * 6 + r : r * 6 + c] = m1;
         }
+      if (twice) {  // a tag seen twice by one capture: the two cross products M + M^T share a diagonal block
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = r; c < 6; ++c) {
+            const double v = r == c ? 2.0 * st[r * 6 + c] : st[r * 6 + c] + st[c * 6 + r];
+            st[r * 6 + c] = v;
+            st[c * 6 + r] = v;
+          }
+      }
     }
     __syncwarp();
     const unsigned m = __ballot_sync(0xffffffffu, active);

@@ -137,7 +137,8 @@ def cpu_baseline(args, steps, warmup, threads=None):
     scale = max(1, n_cap // args.cpu_sample_captures)
     sc, st = max(50, n_cap // scale), max(10, n_tag // scale)
     m = synth.make_map(sc, st, tpc, seed=0xA55A0000 + 100)
-    threads = threads or po.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1: ask the OS for the cores this process may use instead
+    threads = threads or len(os.sched_getaffinity(0))
     o = po.default_options(num_threads=threads, max_num_iterations=1, function_tolerance=0.0,
                            parameter_tolerance=0.0, gradient_tolerance=0.0)
     nc = 4 * len(m.cap_idx)
@@ -202,7 +203,7 @@ def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
         if not args.no_cpu_baseline and world == 1:
             from oracle import pyoracle as po
             ns = min(n_loc, 50000)
-            threads = po.max_threads()
+            threads = len(os.sched_getaffinity(0))
             t1 = time.perf_counter()
             po.localize_batch(m.blk_offsets[:ns + 1], m.tag_idx[:m.blk_offsets[ns]], m.obs[:m.blk_offsets[ns]],
                               m.seed_block[:ns], m.cam_true, m.tag_true, num_threads=threads)
