@@ -787,8 +787,20 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   sd.n_f = sd.f == 0 ? s->n_cap : s->n_tag;
   const int n = 6 * sd.n_f + 1;  // reduced dimension (F poses + focal)
   const int cam_row = n - 1, rhs_row = n;
+  // AUTO: the dense DMMA Cholesky where the reduced matrix is actually dense (>= 25 % of its
+  // 6x6 blocks are structurally non-zero, or it is tiny), block-sparse PCG otherwise
   int lin = o.linear_solver;
-  if (lin == ARSLAM_LINSOLVE_AUTO) lin = (n <= o.dense_max_dim) ? ARSLAM_LINSOLVE_DENSE : ARSLAM_LINSOLVE_PCG;
+  if (lin == ARSLAM_LINSOLVE_AUTO) {
+    lin = ARSLAM_LINSOLVE_PCG;
+    if (n <= 128) {
+      lin = ARSLAM_LINSOLVE_DENSE;
+    } else if (n <= o.dense_max_dim) {
+      int prc = pcg_prepare(s, sd.e, sd.n_e, sd.n_f);
+      if (prc) return prc;
+      const double fill = (double)s->pcg.nnzb / ((double)sd.n_f * (double)sd.n_f);
+      if (fill >= 0.25) lin = ARSLAM_LINSOLVE_DENSE;
+    }
+  }
   summary->eliminated_side = elim;
   summary->linear_solver = lin;
   summary->reduced_dim = n;

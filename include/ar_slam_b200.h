@@ -60,7 +60,8 @@ typedef struct arslam_options {
   int32_t jacobi_scaling;                    /* 1   */
   int32_t elimination;                       /* ARSLAM_ELIM_*; AUTO eliminates the larger pose set */
   int32_t linear_solver;                     /* ARSLAM_LINSOLVE_*; AUTO: dense Cholesky when the
-                                                reduced system is small/dense, PCG otherwise   */
+                                                reduced system is tiny or structurally dense
+                                                (>= 25 % block fill), block-sparse PCG otherwise */
   int32_t pcg_max_iterations;                /* 500 */
   int32_t num_intrinsics;                    /* 1: focal only (the reference's live model,
                                                 ar_slam_util.cpp:160-162); 3 reserved for the
@@ -78,8 +79,8 @@ typedef struct arslam_options {
   double parameter_tolerance;                /* 1e-8  */
   double pcg_tolerance;                      /* 0.1: relative residual ||S y - b|| / ||b|| at which PCG stops (inexact Newton; Ceres' eta) */
   double tag_size;                           /* 0.0635 m (ar_slam_util.hpp:319)                */
-  int64_t dense_max_dim;                     /* AUTO picks dense Cholesky up to this reduced
-                                                dimension (default 16384)                      */
+  int64_t dense_max_dim;                     /* AUTO never picks the dense Cholesky above this
+                                                reduced dimension (default 16384)              */
 } arslam_options;
 
 /* What ceres::Solver::Summary would have told the reference had it looked

@@ -66,7 +66,7 @@ def test_synthetic_1k_200_trajectory(gpu_solver_cls, oracle):
     m = synth.make_map(1000, 200)
     cam_o, cap_o, tag_o, so, log_o = oracle.solve(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs, m.cam0, m.cap0,
                                                   m.tag0, options=oracle.default_options(num_threads=4))
-    s = gpu_solver_cls(options=ar_slam_b200.default_options())
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ar_slam_b200.LINSOLVE_DENSE))
     s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
     s.set_params(m.cam0, m.cap0, m.tag0)
     sg, log_g = s.solve()
@@ -94,7 +94,7 @@ def test_elimination_sides_agree(gpu_solver_cls):
     m = synth.make_map(300, 80, seed=7)
     out = []
     for elim in (ar_slam_b200.ELIM_TAGS, ar_slam_b200.ELIM_CAPTURES):
-        s = gpu_solver_cls(options=ar_slam_b200.default_options(elimination=elim))
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(elimination=elim, linear_solver=ar_slam_b200.LINSOLVE_DENSE))
         s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
         s.set_params(m.cam0, m.cap0, m.tag0)
         summ, log = s.solve()
@@ -210,3 +210,19 @@ def test_ragged_visibility_matches_oracle(gpu_solver_cls, oracle, elim, ls):
     assert np.abs(tag_g[used_t] - tag_o[used_t]).max() < 1e-5
     used_c = np.unique(ci)
     assert np.abs(cap_g[used_c] - cap_o[used_c]).max() < 1e-5
+
+
+def test_auto_picks_dense_only_where_the_reduced_matrix_is_dense(gpu_solver_cls):
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    picks = {}
+    for name, (nc, nt, tpc) in {"sparse": (1000, 200, 8), "dense": (400, 24, 8)}.items():
+        m = synth.make_map(nc, nt, tpc, seed=23)
+        s = gpu_solver_cls()
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        picks[name], _ = s.solve()
+        s.close()
+        assert picks[name]["termination"] == 0
+    assert picks["sparse"]["linear_solver"] == ar_slam_b200.LINSOLVE_PCG
+    assert picks["dense"]["linear_solver"] == ar_slam_b200.LINSOLVE_DENSE
