@@ -187,7 +187,7 @@ struct arslam_solver {
   // normal equations
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
-  DevBuf<double> eval_out, small, colsum_part;
+  DevBuf<double> eval_out, small, colsum_part, linv;
   DevBuf<unsigned long long> sort_keys[2];
   DevBuf<int32_t> sort_vals[2];
   DevBuf<unsigned char> sort_tmp;
@@ -413,7 +413,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   }
   CU(s->W.ensure((size_t)36 * plane));
   CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp + 8));
-  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(4)); CU(s->colsum_part.ensure(4 * kColsumChunks));
+  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(4)); CU(s->colsum_part.ensure(4 * kColsumChunks)); CU(s->linv.ensure(CB * CB));
   s->have_problem = true;
   ++s->problem_version;
   return ARSLAM_OK;
@@ -927,12 +927,12 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (s->prof.on) {
         Profiler::Rec r{s->prof.id_of("dense_cholesky", 0.0), s->prof.ev(), s->prof.ev()};
         cudaEventRecord(r.a, s->stream);
-        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, sc + 12, s->stream);
+        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream);
         s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
         cudaEventRecord(r.b, s->stream);
         s->prof.recs.push_back(r);
       } else {
-        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, sc + 12, s->stream);
+        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream);
         s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
       }
     } else {

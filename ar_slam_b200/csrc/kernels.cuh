@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(co
   const unsigned ends = __ballot_sync(0xffffffffu, sg[lane + 2] != own);
   const bool head_open = sg[0] == sg[1];           // the first run started in the previous warp
   const bool tail_open = !((ends >> 31) & 1u);     // the last run continues in the next warp
-  for (int v = lane; v < NV; v += 32) {
+  {  // values 0..31: lane v walks the 32 columns of its value and flushes at every run end
+    const int v = lane;
     const double* col = stage[wid][v];
     double acc = 0.0;
     unsigned m = ends;
@@ -355,6 +356,23 @@ __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(co
     if (tail_open && sg[32] >= 0) {
       for (int j = j0; j < 32; ++j) acc += col[j];
       a.partial[((size_t)gwarp * 2 + (j0 == 0 ? 0 : 1)) * NV + v] = acc;
+    }
+  }
+  static_assert(NV == 33, "the last value is reduced by a segmented warp scan");
+  {  // value 32: a second walk would keep 31 lanes idle -> segmented inclusive scan over the lanes
+    double x = stage[wid][32][lane];
+    const int start = lane == 0 ? 0 : 32 - __clz(ends & ((1u << lane) - 1u));  // first lane of this lane's run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane - o >= start) x += y;
+    }
+    const bool run_end = (ends >> lane) & 1u;
+    if (run_end && own >= 0) {
+      if (start == 0 && head_open) a.partial[((size_t)gwarp * 2 + 0) * NV + 32] = x;
+      else a.out_seg[(size_t)own * NV + 32] = x;
+    } else if (lane == 31 && tail_open && own >= 0) {
+      a.partial[((size_t)gwarp * 2 + (start == 0 ? 0 : 1)) * NV + 32] = x;
     }
   }
 }

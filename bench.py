@@ -372,9 +372,16 @@ def main():
             top = max(cand, key=lambda k: k["total_ms"])
             sec = top["total_ms"] / top["launches"] * 1e-3
             ach = top["algorithmic_bytes"] / sec / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
+                with open(tp) as f:
+                    traffic = json.load(f).get(args.workload, {}).get(top["name"])
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": how,
-                        "us_per_launch": sec * 1e6}
+                        "frac": ach / peak, "traffic": traffic, "peak_source": how,
+                        "us_per_launch": sec * 1e6, "algorithmic_bytes": top["algorithmic_bytes"],
+                        "note": "fused evaluation+accumulation, J never in HBM: 18 B/corner in + 72 B/corner W out + "
+                                "264 B/pose; the kernel is also FP64-pipe bound (880 DFMA per block)"}
 
     if rank == 0:
         cb = None
