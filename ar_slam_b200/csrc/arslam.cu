@@ -188,6 +188,7 @@ struct arslam_solver {
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
+  DevBuf<double> Hx[2], partialx[2], warp_cam8;  // radial model: l1, l2 borders per pose side
   DevBuf<unsigned long long> sort_keys[2];
   DevBuf<int32_t> sort_vals[2];
   DevBuf<unsigned char> sort_tmp;
@@ -295,9 +296,10 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
   s->n_sm = n_sm;
   if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(&s->h_sc, 128 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
-      cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(schur_eliminate_kernel<DenseTarget>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
+      cudaMallocHost(&s->h_sc, 256 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
+      cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(schur_eliminate_kernel<DenseTarget, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(schur_eliminate_kernel<DenseTarget, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
       pcg_init() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -322,8 +324,8 @@ void arslam_destroy(arslam_solver* s) {
 
 int arslam_set_options(arslam_solver* s, const arslam_options* opt) {
   if (!s || !opt) return ARSLAM_ERR_INVALID;
-  if (opt->num_intrinsics != 1)
-    return s->fail(ARSLAM_ERR_UNSUPPORTED, "num_intrinsics=%d: only the reference's focal-only model is built", opt->num_intrinsics);
+  if (opt->num_intrinsics != 1 && opt->num_intrinsics != 3)
+    return s->fail(ARSLAM_ERR_INVALID, "num_intrinsics=%d: 1 (focal only, the reference's live model) or 3 (focal + radial l1, l2)", opt->num_intrinsics);
   s->opt = *opt;
   return ARSLAM_OK;
 }
@@ -413,7 +415,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   }
   CU(s->W.ensure((size_t)36 * plane));
   CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp + 8));
-  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(4)); CU(s->colsum_part.ensure(4 * kColsumChunks)); CU(s->linv.ensure(CB * CB));
+  CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(12)); CU(s->colsum_part.ensure(12 * kColsumChunks)); CU(s->linv.ensure(CB * CB));
   s->have_problem = true;
   ++s->problem_version;
   return ARSLAM_OK;
@@ -475,11 +477,19 @@ int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* j
   double* d_wc = d_ja + (size_t)48 * nb;
   double* d_cost = d_wc + nwarp;
   const bool want_j = jac_cam || jac_cap || jac_tag;
-  LAUNCH("eval_jacobian", (want_j ? 274.0 : 34.0) * nc,
-         eval_jacobian_kernel<<<cdiv(nc, 256), 256, 0, s->stream>>>(
-             nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
-             s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
-             want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
+  const bool dist = s->opt.num_intrinsics == 3;
+  if (dist)
+    LAUNCH("eval_jacobian", (want_j ? 274.0 : 34.0) * nc,
+           eval_jacobian_kernel<1><<<cdiv(nc, 256), 256, 0, s->stream>>>(
+               nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
+               s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
+               want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
+  else
+    LAUNCH("eval_jacobian", (want_j ? 274.0 : 34.0) * nc,
+           eval_jacobian_kernel<0><<<cdiv(nc, 256), 256, 0, s->stream>>>(
+               nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
+               s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
+               want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
   launch_colsum(s, nwarp, 1, d_wc, d_cost);
   CU(cudaGetLastError());
   double h_cost = 0.0;
@@ -503,7 +513,7 @@ int launch_colsum(arslam_solver* s, int n, int m, const double* in, double* out)
     LAUNCH("colsum", 8.0 * n * m, colsum_kernel<<<1, 1024, 0, s->stream>>>(n, m, in, out));
   } else {
     LAUNCH("colsum", 8.0 * n * m, colsum_stage1_kernel<<<kColsumChunks, 256, 0, s->stream>>>(n, m, in, s->colsum_part.p));
-    LAUNCH("colsum2", 4096.0, colsum_stage2_kernel<<<1, 128, 0, s->stream>>>(kColsumChunks, m, s->colsum_part.p, out));
+    LAUNCH("colsum2", 4096.0, colsum_stage2_kernel<<<1, 384, 0, s->stream>>>(kColsumChunks, m, s->colsum_part.p, out));
   }
   return ARSLAM_OK;
 }
@@ -632,7 +642,7 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
   LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
-         schur_eliminate_kernel<SparseTarget><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a2, t, s->n_blk, e_idx));
+         schur_eliminate_kernel<SparseTarget, 1><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a2, t, s->n_blk, e_idx));
   return ARSLAM_OK;
 }
 
@@ -715,8 +725,11 @@ struct Sides {
   int n_e, n_f;
 };
 
-int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, double* sc) {
+// HF / HFx: F-side records (inside the cross-rank reduction buffer); head: 12 doubles
+// [H_ff, g_f, sum r^2, 0 | f.l1, f.l2, l1.l1, l1.l2, l2.l2, g_l1, g_l2, 0]
+int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, double* HFx, double* head) {
   const int nb = s->n_blk, plane = s->plane, grid = cdiv(plane, kAccumThreads);
+  const bool dist = s->opt.num_intrinsics == 3;
   for (int pass = 0; pass < 2; ++pass) {
     const int side = pass == 0 ? sd.e : sd.f;
     const int n_own = side == 0 ? s->n_cap : s->n_tag;
@@ -729,31 +742,62 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
     a.W = s->W.p; a.warp_cam = s->warp_cam.p;
     const double bytes_e = (4.0 * 18.0 + 288.0) * nb + 264.0 * n_own;
     const double bytes_f = (4.0 * 18.0) * nb + 264.0 * n_own;
+#define ARS_ACC(SIDE_, W_, NAME_, BYTES_)                                                                      \
+    do {                                                                                                        \
+      if (dist) LAUNCH(NAME_, BYTES_, accum_kernel<SIDE_, W_, 1><<<grid, kAccumThreads, 0, s->stream>>>(a));    \
+      else LAUNCH(NAME_, BYTES_, accum_kernel<SIDE_, W_, 0><<<grid, kAccumThreads, 0, s->stream>>>(a));         \
+    } while (0)
     if (pass == 0) {
-      if (side == 0) LAUNCH("accum_E", bytes_e, accum_kernel<0, true><<<grid, kAccumThreads, 0, s->stream>>>(a));
-      else LAUNCH("accum_E", bytes_e, accum_kernel<1, true><<<grid, kAccumThreads, 0, s->stream>>>(a));
+      if (side == 0) ARS_ACC(0, true, "accum_E", bytes_e); else ARS_ACC(1, true, "accum_E", bytes_e);
     } else {
-      if (side == 0) LAUNCH("accum_F", bytes_f, accum_kernel<0, false><<<grid, kAccumThreads, 0, s->stream>>>(a));
-      else LAUNCH("accum_F", bytes_f, accum_kernel<1, false><<<grid, kAccumThreads, 0, s->stream>>>(a));
+      if (side == 0) ARS_ACC(0, false, "accum_F", bytes_f); else ARS_ACC(1, false, "accum_F", bytes_f);
     }
+#undef ARS_ACC
     LAUNCH("seg_fixup", 8.0 * NV * n_own,
-           seg_fixup_kernel<<<cdiv((long long)n_own * NV, 256), 256, 0, s->stream>>>(n_own, s->s_off[side].p, s->partial[side].p, a.out_seg));
+           seg_fixup_kernel<<<cdiv((long long)n_own * NV, 256), 256, 0, s->stream>>>(n_own, NV, s->s_off[side].p, s->partial[side].p, a.out_seg));
+    if (dist) {  // the l1, l2 columns
+      AccumCamArgs c;
+      c.n_blk = nb; c.plane = plane;
+      c.own_idx = a.own_idx; c.oth_idx = a.oth_idx; c.obs = a.obs;
+      c.cap_pre = a.cap_pre; c.tag_pre = a.tag_pre; c.cam = a.cam;
+      c.out_seg = pass == 0 ? s->Hx[side].p : HFx;
+      c.partial = s->partialx[side].p;
+      c.warp_cam = s->warp_cam8.p;
+      const double bytes_c = 72.0 * nb + 96.0 * n_own;
+      if (pass == 0) {
+        if (side == 0) LAUNCH("accum_cam_E", bytes_c, accum_cam_kernel<0, true><<<grid, kAccumThreads, 0, s->stream>>>(c));
+        else LAUNCH("accum_cam_E", bytes_c, accum_cam_kernel<1, true><<<grid, kAccumThreads, 0, s->stream>>>(c));
+      } else {
+        if (side == 0) LAUNCH("accum_cam_F", bytes_c, accum_cam_kernel<0, false><<<grid, kAccumThreads, 0, s->stream>>>(c));
+        else LAUNCH("accum_cam_F", bytes_c, accum_cam_kernel<1, false><<<grid, kAccumThreads, 0, s->stream>>>(c));
+      }
+      LAUNCH("seg_fixup", 8.0 * NVX * n_own,
+             seg_fixup_kernel<<<cdiv((long long)n_own * NVX, 256), 256, 0, s->stream>>>(n_own, NVX, s->s_off[side].p, s->partialx[side].p, c.out_seg));
+    }
   }
-  launch_colsum(s, s->n_warp, 4, s->warp_cam.p, sc);
+  launch_colsum(s, s->n_warp, 4, s->warp_cam.p, head);
+  if (dist) launch_colsum(s, s->n_warp, 8, s->warp_cam8.p, head + 4);
   return ARSLAM_OK;
 }
 
-__global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled) {
-  const double sg = enabled ? 1.0 / (1.0 + sqrt(sc[0])) : 1.0;
-  sc[14] = sg;
-  *sigF_cam = sg;
+__global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled, int nk) {
+  const double h[3] = {sc[0], sc[26], sc[28]};  // H_ff, H_l1l1, H_l2l2
+  const int slot[3] = {14, 34, 35};
+  for (int q = 0; q < nk; ++q) {
+    const double sg = enabled ? 1.0 / (1.0 + sqrt(h[q])) : 1.0;
+    sc[slot[q]] = sg;
+    sigF_cam[q] = sg;
+  }
 }
-__global__ void cam_step_kernel(const double* uF_cam, const double* cam, double* cam_c, double* d_cam, double* sc) {
-  const double d = -uF_cam[0];
-  d_cam[0] = d; d_cam[1] = 0.0; d_cam[2] = 0.0;
-  cam_c[0] = cam[0] + d; cam_c[1] = cam[1]; cam_c[2] = cam[2];
-  sc[13] = cam[0] - (cam[0] + d);
-  sc[15] = cam[0];
+__global__ void cam_step_kernel(const double* uF_cam, const double* cam, double* cam_c, double* d_cam, double* sc, int nk) {
+  const int dslot[3] = {13, 32, 33}, xslot[3] = {15, 36, 37};
+  for (int q = 0; q < 3; ++q) {
+    const double d = q < nk ? -uF_cam[q] : 0.0;
+    d_cam[q] = d;
+    cam_c[q] = cam[q] + d;
+    sc[dslot[q]] = cam[q] - (cam[q] + d);
+    sc[xslot[q]] = cam[q];
+  }
 }
 __global__ void collect_fail_kernel(int n_e, const double* Z, double* sc) {
   // any E pose whose damped 6x6 block was not positive definite
@@ -785,11 +829,16 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   sd.f = 1 - sd.e;
   sd.n_e = sd.e == 0 ? s->n_cap : s->n_tag;
   sd.n_f = sd.f == 0 ? s->n_cap : s->n_tag;
-  const int n = 6 * sd.n_f + 1;  // reduced dimension (F poses + focal)
-  const int cam_row = n - 1, rhs_row = n;
+  const int nk = o.num_intrinsics == 3 ? 3 : 1;  // live intrinsics: focal (+ l1, l2 of the radial model)
+  const bool dist = nk == 3;
+  const int n = 6 * sd.n_f + nk;  // reduced dimension (F poses + intrinsics)
+  const int cam_row = 6 * sd.n_f, rhs_row = n;
   // AUTO: the dense DMMA Cholesky where the reduced matrix is actually dense (>= 25 % of its
   // 6x6 blocks are structurally non-zero, or it is tiny), block-sparse PCG otherwise
   int lin = o.linear_solver;
+  if (dist && lin == ARSLAM_LINSOLVE_PCG)
+    return s->fail(ARSLAM_ERR_UNSUPPORTED, "the radial model (num_intrinsics = 3) is solved with the dense Cholesky only");
+  if (dist) lin = ARSLAM_LINSOLVE_DENSE;
   if (lin == ARSLAM_LINSOLVE_AUTO) {
     lin = ARSLAM_LINSOLVE_PCG;
     if (n <= 128) {
@@ -806,7 +855,12 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   summary->reduced_dim = n;
 
   // ---- buffers that depend on the roles
-  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * sd.n_e)); CU(s->seg_cam.ensure((size_t)4 * sd.n_e));
+  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * nk * sd.n_e)); CU(s->seg_cam.ensure((size_t)12 * sd.n_e));
+  if (dist) {
+    CU(s->Hx[sd.e].ensure((size_t)NVX * sd.n_e));
+    for (int side = 0; side < 2; ++side) CU(s->partialx[side].ensure((size_t)s->n_warp * 2 * NVX));
+    CU(s->warp_cam8.ensure((size_t)8 * s->n_warp));
+  }
   CU(s->seg_cross.ensure((size_t)sd.n_e));
   CU(s->sigE.ensure((size_t)6 * sd.n_e)); CU(s->sigF.ensure((size_t)n + 1)); CU(s->uF.ensure((size_t)n + 1));
   size_t s_elems = 0;
@@ -821,13 +875,15 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     s_elems = s->pcg.value_count();  // block values + border + rhs
     CU(s->yF.ensure((size_t)n + 1));
   }
-  // reduction buffer: [S or sparse values | cam_minus (4) | HF (n_f NV) | scalar head (4)]
-  const size_t red_tail = 4 + (size_t)sd.n_f * NV + 4;
+  // reduction buffer: [S or sparse values | cam_minus (12) | HF (n_f NV) | HFx (n_f NVX, radial model) | head (12)]
+  const size_t red_tail = 12 + (size_t)sd.n_f * NV + (dist ? (size_t)sd.n_f * NVX : 0) + 12;
   CU(s->red.ensure(s_elems + red_tail));
   double* S = s->red.p;
   double* cam_minus = S + s_elems;
-  double* HF = cam_minus + 4;
-  double* sc_head = HF + (size_t)sd.n_f * NV;  // cam_H, cam_g, sum_r2, 0 : summed across ranks
+  double* HF = cam_minus + 12;
+  double* HFx = dist ? HF + (size_t)sd.n_f * NV : nullptr;
+  double* sc_head = HF + (size_t)sd.n_f * NV + (dist ? (size_t)sd.n_f * NVX : 0);  // summed across ranks
+  CU(cudaMemsetAsync(sc_head, 0, 12 * sizeof(double), s->stream));
   double* sc = s->sc.p;
   CU(cudaMemsetAsync(sc, 0, kNumScalars * sizeof(double), s->stream));
 
@@ -835,7 +891,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   if (rc) return rc;
   s->cur = 0;
   launch_prep(s, 0);
-  launch_accumulate(s, sd, 0, HF, sc_head);
+  launch_accumulate(s, sd, 0, HF, HFx, sc_head);
 
   double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
   bool have_sigma = false, last_successful = true, fresh_linearisation = true, pending_acc = false;
@@ -878,33 +934,38 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       SchurArgs a;
       a.n_e = sd.n_e; a.plane = s->plane;
       a.e_off = s->s_off[sd.e].p; a.f_idx = s->s_oth[sd.e].p;
-      a.HE = s->H[sd.e].p; a.W = s->W.p; a.sig_e = s->sigE.p;
+      a.HE = s->H[sd.e].p; a.HEx = dist ? s->Hx[sd.e].p : nullptr; a.W = s->W.p; a.sig_e = s->sigE.p;
       a.radius = radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
       a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr;
       schur_args = a;
       CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
       CU(cudaMemsetAsync(sc + 12, 0, sizeof(double), s->stream));
-      LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(sd.n_e, 256), 256, 0, s->stream>>>(a));
+      LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(sd.n_e, 256), 256, 0, s->stream>>>(a, nk));
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
-        LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
-               schur_eliminate_kernel<DenseTarget><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
+        if (dist)
+          LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
+                 schur_eliminate_kernel<DenseTarget, 3><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
+        else
+          LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
+                 schur_eliminate_kernel<DenseTarget, 1><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
       } else {
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;
       }
-      launch_colsum(s, sd.n_e, 4, s->seg_cam.p, cam_minus);
+      launch_colsum(s, sd.n_e, 12, s->seg_cam.p, cam_minus);
     }
     if (s->world > 1) {
       // one allreduce per linearisation: partial Schur terms (+ on a fresh
       // linearisation the partial tag blocks, focal terms and cost)
-      const size_t cnt = fresh_linearisation ? s_elems + red_tail : s_elems + 4;
+      const size_t cnt = fresh_linearisation ? s_elems + red_tail : s_elems + 12;
       rc = nccl_sum(s, S, cnt);
       if (rc) return rc;
     }
     if (fresh_linearisation) {
       CU(cudaMemcpyAsync(sc, sc_head, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+      if (dist) CU(cudaMemcpyAsync(sc + 24, sc_head + 4, 8 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
       LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p));
       LAUNCH("colmax", 8.0 * ne_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, s->warp_gmax[sd.e].p, sc + 16));
       LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p));
@@ -913,17 +974,17 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
              sigma_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, o.jacobi_scaling, s->sigF.p));
-      LAUNCH("cam_sigma", 16.0, cam_sigma_kernel<<<1, 1, 0, s->stream>>>(sc, s->sigF.p + cam_row, o.jacobi_scaling));
+      LAUNCH("cam_sigma", 16.0, cam_sigma_kernel<<<1, 1, 0, s->stream>>>(sc, s->sigF.p + cam_row, o.jacobi_scaling, nk));
       have_sigma = true;
     }
     if (lin == ARSLAM_LINSOLVE_DENSE) {
       dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n + 1, 8));
       LAUNCH("dense_scale", 8.0 * n * n, dense_scale_kernel<<<grd, blk, 0, s->stream>>>(S, s->ld, rhs_row, s->sigF.p));
       LAUNCH("dense_add_pose", 8.0 * NV * sd.n_f,
-             dense_add_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, s->sigF.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row));
+             dense_add_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, HFx, s->sigF.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row));
       LAUNCH("dense_add_camera", 64.0,
              dense_add_camera_kernel<<<cdiv(std::max(1, s->n_pad - rhs_row - 1), 128), 128, 0, s->stream>>>(
-                 reinterpret_cast<LmScalars*>(sc), cam_minus, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row, s->n_pad));
+                 reinterpret_cast<LmScalars*>(sc), cam_minus, nk, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row, s->n_pad));
       if (s->prof.on) {
         Profiler::Rec r{s->prof.id_of("dense_cholesky", 0.0), s->prof.ev(), s->prof.ev()};
         cudaEventRecord(r.a, s->stream);
@@ -942,7 +1003,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
     {
       BacksubArgs b;
-      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row;
+      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk;
       b.d_e = s->d_pose[sd.e].p; b.seg_cross = s->seg_cross.p;
       LAUNCH("backsub", 292.0 * s->n_blk + 400.0 * sd.n_e,
              backsub_kernel<<<cdiv((long long)sd.n_e * kBsGroup, 128), 128, 0, s->stream>>>(b));
@@ -956,17 +1017,17 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       ApplyArgs ap;
       ap.uF_cam = s->uF.p + cam_row;
       ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
-      ap.rec = s->H[sd.e].p;
+      ap.rec = s->H[sd.e].p; ap.recx = dist ? s->Hx[sd.e].p : nullptr;
       ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
       LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
       launch_colsum(s, cdiv(sd.n_e, 128) * 4, 3, s->warp_norm[sd.e].p, sc + 6);
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
-      ap.rec = HF;
+      ap.rec = HF; ap.recx = HFx;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
       ap.count_norms = (s->rank == 0) ? 1 : 0;
       LAUNCH("apply_step", 144.0 * sd.n_f + 8.0 * NV * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
       launch_colsum(s, cdiv(sd.n_f, 128) * 4, 3, s->warp_norm[sd.f].p, sc + 9);
-      LAUNCH("cam_step", 64.0, cam_step_kernel<<<1, 1, 0, s->stream>>>(s->uF.p + cam_row, s->cam[k].p, s->cam[kc].p, s->d_cam.p, sc));
+      LAUNCH("cam_step", 64.0, cam_step_kernel<<<1, 1, 0, s->stream>>>(s->uF.p + cam_row, s->cam[k].p, s->cam[kc].p, s->d_cam.p, sc, nk));
     }
     cudaEventRecord(s->ev[1], s->stream);
     // ---------------- candidate point: cost at x + delta (residuals only)
@@ -978,8 +1039,13 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       c.cap_pre_c = s->cap_pre[kc].p; c.tag_pre_c = s->tag_pre[kc].p; c.cam_c = s->cam[kc].p;
       c.warp_out = s->warp_cand.p;
       const int grid = cdiv(s->plane, 256);
-      if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0><<<grid, 256, 0, s->stream>>>(c));
-      else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1><<<grid, 256, 0, s->stream>>>(c));
+      if (dist) {
+        if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0, 1><<<grid, 256, 0, s->stream>>>(c));
+        else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1, 1><<<grid, 256, 0, s->stream>>>(c));
+      } else {
+        if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0, 0><<<grid, 256, 0, s->stream>>>(c));
+        else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1, 0><<<grid, 256, 0, s->stream>>>(c));
+      }
       launch_colsum(s, grid * 8, 1, s->warp_cand.p, sc + 5);
     }
     if (s->world > 1) {
@@ -1003,6 +1069,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (fresh_linearisation) {
       x_cost = 0.5 * h[2];
       grad_max = std::max(std::max(h[16], h[17]), std::fabs(h[1]));
+      if (dist) grad_max = std::max(grad_max, std::max(std::fabs(h[29]), std::fabs(h[30])));
       if (iteration == 0) { summary->initial_cost = x_cost; log_iter(0, x_cost, 0.0, 0.0, 0.0, 1, 1); }
     }
     fresh_linearisation = false;
@@ -1013,11 +1080,17 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     ++iteration;
     last_successful = false;
     const double f_cur = h[15];
-    x_norm = std::sqrt(h[7] + h[10] + f_cur * f_cur + s->h_cam[1] * s->h_cam[1] + s->h_cam[2] * s->h_cam[2]);
-    const double step_norm = std::sqrt(h[6] + h[9] + h[13] * h[13]);
+    const double l1_cur = dist ? h[36] : s->h_cam[1], l2_cur = dist ? h[37] : s->h_cam[2];
+    x_norm = std::sqrt(h[7] + h[10] + f_cur * f_cur + l1_cur * l1_cur + l2_cur * l2_cur);
+    const double step_norm = std::sqrt(h[6] + h[9] + h[13] * h[13] + (dist ? h[32] * h[32] + h[33] * h[33] : 0.0));
     // model_cost_change = -(J d).(r + J d / 2) = -(g.d + d^T H d / 2), assembled from the block pieces
     const double d_focal = -h[13];
-    const double model_sum = h[4] + h[8] + h[11] + h[1] * d_focal + 0.5 * h[0] * d_focal * d_focal;
+    double model_sum = h[4] + h[8] + h[11] + h[1] * d_focal + 0.5 * h[0] * d_focal * d_focal;
+    if (dist) {  // intrinsics block of the radial model
+      const double d1 = -h[32], d2 = -h[33];
+      model_sum += h[29] * d1 + h[30] * d2 + h[24] * d_focal * d1 + h[25] * d_focal * d2 +
+                   0.5 * h[26] * d1 * d1 + h[27] * d1 * d2 + 0.5 * h[28] * d2 * d2;
+    }
     const double model_cost_change = -model_sum;
     const double cand_cost_raw = 0.5 * h[5];
     const bool lin_ok = (h[12] == 0.0) && std::isfinite(step_norm) && std::isfinite(model_sum);
@@ -1053,7 +1126,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         float a_ms = 0; cudaEventElapsedTime(&a_ms, s->ev[3], s->ev[4]); eval_ms += a_ms;
       }
       cudaEventRecord(s->ev[3], s->stream);
-      launch_accumulate(s, sd, kc, HF, sc_head);
+      launch_accumulate(s, sd, kc, HF, HFx, sc_head);
       cudaEventRecord(s->ev[4], s->stream);
       pending_acc = true;
       summary->num_jacobian_evals++;
@@ -1076,7 +1149,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   {
     const int k = s->cur;
     CU(cudaMemcpyAsync(s->h_sc + 32, s->cam[k].p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(s->h_sc + 40, sc_head, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_sc + 48, sc_head, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (s->world > 1) {
       rc = gather_captures(s, k);
       if (rc) return rc;
@@ -1086,9 +1159,10 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     s->h_cam[0] = s->h_sc[32];
+    if (dist) { s->h_cam[1] = s->h_sc[33]; s->h_cam[2] = s->h_sc[34]; }
     if (pending_acc) { float a_ms = 0; cudaEventElapsedTime(&a_ms, s->ev[3], s->ev[4]); eval_ms += a_ms; }
     // a successful last step was re-linearised but not read back yet: exact cost of the final point
-    if (fresh_linearisation && iteration > 0 && s->world == 1) x_cost = 0.5 * s->h_sc[42];
+    if (fresh_linearisation && iteration > 0 && s->world == 1) x_cost = 0.5 * s->h_sc[50];
   }
   s->prof.resolve();
   summary->iterations = iteration;
@@ -1138,7 +1212,8 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
          prep_tags_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>((int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p));
   LocArgs a;
   a.n_loc = (int)n_loc; a.blk_off = d_off.p; a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
-  a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p; a.focal = camera3[0];
+  a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p;
+  a.cam[0] = camera3[0]; a.cam[1] = camera3[1]; a.cam[2] = camera3[2];
   const arslam_options& o = s->opt;
   a.o.max_num_iterations = o.max_num_iterations; a.o.max_invalid = o.max_num_consecutive_invalid_steps;
   a.o.jacobi_scaling = o.jacobi_scaling; a.o.initial_radius = o.initial_trust_region_radius;
@@ -1147,8 +1222,10 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   a.o.function_tolerance = o.function_tolerance; a.o.gradient_tolerance = o.gradient_tolerance;
   a.o.parameter_tolerance = o.parameter_tolerance; a.o.tag_size = o.tag_size;
   a.pose = d_pose.p; a.iterations = d_it.p; a.final_cost = d_cost.p; a.termination = d_term.p;
-  LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc,
-         localize_kernel<<<cdiv(n_loc * kLocGroup, 128), 128, 0, s->stream>>>(a));
+  if (s->opt.num_intrinsics == 3)
+    LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc, localize_kernel<1><<<cdiv(n_loc * kLocGroup, 128), 128, 0, s->stream>>>(a));
+  else
+    LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc, localize_kernel<0><<<cdiv(n_loc * kLocGroup, 128), 128, 0, s->stream>>>(a));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(cap_pose6, d_pose.p, sizeof(double) * 6 * n_loc, cudaMemcpyDeviceToHost, s->stream));
   if (iterations) CU(cudaMemcpyAsync(iterations, d_it.p, sizeof(int32_t) * n_loc, cudaMemcpyDeviceToHost, s->stream));

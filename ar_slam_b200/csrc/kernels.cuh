@@ -63,6 +63,7 @@ __global__ void prep_tags_kernel(int n, const double* __restrict__ pose, double 
 // 16 B of residuals, 48 B of jac_cam, 96 B of jac_cap and of jac_tag, all
 // contiguous across consecutive threads (coalesced 128-bit stores).
 // Algorithmic bytes per corner: 16 obs + 2 idx + 16 r + 240 J = 274.
+template <int MODEL>
 __global__ void __launch_bounds__(256)
 eval_jacobian_kernel(int n_corner, const int32_t* __restrict__ cap_idx, const int32_t* __restrict__ tag_idx,
                      const double2* __restrict__ obs /* [n_corner] (x,y) */,
@@ -74,19 +75,20 @@ eval_jacobian_kernel(int n_corner, const int32_t* __restrict__ cap_idx, const in
   double rr = 0.0;
   if (t < n_corner) {
     const int b = t >> 2, i = t & 3;
-    const double f = cam[0];
+    const double cm[3] = {cam[0], cam[1], cam[2]};
     const double2 o = obs[t];
     const double* cp = cap_pre + (size_t)kCapPre * cap_idx[b];
     const double* tp = tag_pre + (size_t)kTagPre * tag_idx[b] + 12 * i;
     CornerJ j;
-    corner_jacobian(cp, tp, f, o.x, o.y, j);
+    double Kl[2][2];
+    corner_jacobian_m<MODEL>(cp, tp, cm, o.x, o.y, j, Kl);
     rr = j.r[0] * j.r[0] + j.r[1] * j.r[1];
     if (res) res[t] = make_double2(j.r[0], j.r[1]);
     if (jac_cam) {
       double2* d = jac_cam + 3 * (size_t)t;
-      d[0] = make_double2(j.K[0], 0.0);
-      d[1] = make_double2(0.0, j.K[1]);
-      d[2] = make_double2(0.0, 0.0);
+      d[0] = make_double2(j.K[0], Kl[0][0]);
+      d[1] = make_double2(Kl[0][1], j.K[1]);
+      d[2] = make_double2(Kl[1][0], Kl[1][1]);
     }
     if (jac_cap) {
       double2* d = jac_cap + 6 * (size_t)t;
@@ -109,6 +111,60 @@ eval_jacobian_kernel(int n_corner, const int32_t* __restrict__ cap_idx, const in
   }
   rr = warp_sum(rr);
   if ((threadIdx.x & 31) == 0) warp_cost[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = rr;
+}
+
+// Reduces the staged per-lane values ([value][lane], padded) over the runs of lanes that share
+// a pose and writes one record per run: runs inside the warp go straight to out_seg, pieces
+// that continue in a neighbouring warp go to `partial` (slot 0: the run started before this
+// warp or fills it, slot 1: it starts inside and continues) for seg_fixup_kernel.
+// sg[0] = pose of the lane before the warp, sg[1..32] = the lanes' poses, sg[33] = the next one.
+template <int NVT>
+__device__ __forceinline__ void segment_flush(const double (*st)[33], const int* sg, int own, int lane, int gwarp,
+                                              double* __restrict__ out_seg, double* __restrict__ partial) {
+  // run structure of this warp, identical for every lane: bit j of `ends` = lane j closes a run
+  const unsigned ends = __ballot_sync(0xffffffffu, sg[lane + 2] != own);
+  const bool head_open = sg[0] == sg[1];           // the first run started in the previous warp
+  const bool tail_open = !((ends >> 31) & 1u);     // the last run continues in the next warp
+  if (lane < NVT) {  // values 0..31: lane v walks the 32 columns of its value and flushes at every run end
+    const int v = lane;
+    const double* col = st[v];
+    double acc = 0.0;
+    unsigned m = ends;
+    int j0 = 0;
+    while (m) {
+      const int j1 = __ffs(m) - 1;  // run [j0, j1]
+      m &= m - 1;
+      for (int j = j0; j <= j1; ++j) acc += col[j];
+      const int sj = sg[j1 + 1];
+      if (sj >= 0) {
+        if (j0 == 0 && head_open) partial[((size_t)gwarp * 2 + 0) * NVT + v] = acc;
+        else out_seg[(size_t)sj * NVT + v] = acc;
+      }
+      acc = 0.0;
+      j0 = j1 + 1;
+    }
+    if (tail_open && sg[32] >= 0) {
+      for (int j = j0; j < 32; ++j) acc += col[j];
+      partial[((size_t)gwarp * 2 + (j0 == 0 ? 0 : 1)) * NVT + v] = acc;
+    }
+  }
+  static_assert(NVT <= 33, "at most one value beyond the 32 lanes");
+  if (NVT == 33) {  // value 32: a second walk would keep 31 lanes idle -> segmented inclusive scan over the lanes
+    double x = st[NVT - 1][lane];
+    const int start = lane == 0 ? 0 : 32 - __clz(ends & ((1u << lane) - 1u));  // first lane of this lane's run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane - o >= start) x += y;
+    }
+    const bool run_end = (ends >> lane) & 1u;
+    if (run_end && own >= 0) {
+      if (start == 0 && head_open) partial[((size_t)gwarp * 2 + 0) * NVT + 32] = x;
+      else out_seg[(size_t)own * NVT + 32] = x;
+    } else if (lane == 31 && tail_open && own >= 0) {
+      partial[((size_t)gwarp * 2 + (start == 0 ? 0 : 1)) * NVT + 32] = x;
+    }
+  }
 }
 
 // -------------------------------------- kernels (1)+(2) fused: accumulate --
@@ -142,7 +198,7 @@ struct AccumArgs {
   double* warp_cam;          // [n_warp][4]: sum K^2, sum K r, sum r^2, 0 (WITH_W)
 };
 
-template <int SIDE, bool WITH_W>
+template <int SIDE, bool WITH_W, int MODEL>
 __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(const AccumArgs a) {
   // one shared buffer, two lives: during the corner loop it holds the per-thread cp.async
   // landing slots of the tag records (2 stages x 128 threads x 112 B, 16 B padding keeps the
@@ -177,7 +233,7 @@ __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(co
   if (valid) {
     const int cap = SIDE == 0 ? own : oth;
     const int tag = SIDE == 0 ? oth : own;
-    const double f = a.cam[0];
+    const double cm[3] = {a.cam[0], MODEL ? a.cam[1] : 0.0, MODEL ? a.cam[2] : 0.0};
     double cp[kCapPre];
     {
       const double2* src = reinterpret_cast<const double2*>(a.cap_pre + (size_t)kCapPre * cap);
@@ -250,7 +306,12 @@ __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(co
         }
       }
       CornerJ j;
-      corner_jacobian(cp, tp, f, ox, oy, j);
+      if (MODEL == 0) {
+        corner_jacobian(cp, tp, cm[0], ox, oy, j);
+      } else {
+        double Kl[2][2];
+        corner_jacobian_m<1>(cp, tp, cm, ox, oy, j, Kl);  // the l1, l2 columns belong to accum_cam_kernel
+      }
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         const double* A = j.A[row];
@@ -330,60 +391,109 @@ __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(co
     }
   }
   __syncwarp();
-  const int* sg = sseg[wid];
-  // run structure of this warp, identical for every lane: bit j of `ends` = lane j closes a run
-  const unsigned ends = __ballot_sync(0xffffffffu, sg[lane + 2] != own);
-  const bool head_open = sg[0] == sg[1];           // the first run started in the previous warp
-  const bool tail_open = !((ends >> 31) & 1u);     // the last run continues in the next warp
-  {  // values 0..31: lane v walks the 32 columns of its value and flushes at every run end
-    const int v = lane;
-    const double* col = stage[wid][v];
-    double acc = 0.0;
-    unsigned m = ends;
-    int j0 = 0;
-    while (m) {
-      const int j1 = __ffs(m) - 1;  // run [j0, j1]
-      m &= m - 1;
-      for (int j = j0; j <= j1; ++j) acc += col[j];
-      const int sj = sg[j1 + 1];
-      if (sj >= 0) {
-        if (j0 == 0 && head_open) a.partial[((size_t)gwarp * 2 + 0) * NV + v] = acc;
-        else a.out_seg[(size_t)sj * NV + v] = acc;
-      }
-      acc = 0.0;
-      j0 = j1 + 1;
-    }
-    if (tail_open && sg[32] >= 0) {
-      for (int j = j0; j < 32; ++j) acc += col[j];
-      a.partial[((size_t)gwarp * 2 + (j0 == 0 ? 0 : 1)) * NV + v] = acc;
-    }
+  segment_flush<NV>(stage[wid], sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
+}
+
+// ---- radial model only: the l1, l2 columns of the normal equations ---------------------------
+// accum_kernel keeps its register budget for the pose blocks and the focal column; with the
+// radial model this second pass (same thread -> block mapping, Jacobians recomputed) adds
+//   * per pose: H_pose,l1 | H_pose,l2 (12 doubles, reduced with the same staged flush),
+//   * WITH_CAM (the E pass): per warp the intrinsics block entries that involve l1, l2:
+//     [f.l1, f.l2, l1.l1, l1.l2, l2.l2, l1.r, l2.r, 0].
+constexpr int NVX = 12;
+struct AccumCamArgs {
+  int n_blk, plane;
+  const int32_t* own_idx;
+  const int32_t* oth_idx;
+  const double* obs;
+  const double* cap_pre;
+  const double* tag_pre;
+  const double* cam;
+  double* out_seg;   // [n_pose][NVX]
+  double* partial;   // [n_warp][2][NVX]
+  double* warp_cam;  // [n_warp][8] (WITH_CAM)
+};
+template <int SIDE, bool WITH_CAM>
+__global__ void __launch_bounds__(kAccumThreads) accum_cam_kernel(const AccumCamArgs a) {
+  __shared__ double stage[kAccumWarps][NVX][33];
+  __shared__ int sseg[kAccumWarps][36];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int pos = blockIdx.x * kAccumThreads + threadIdx.x;
+  const int gwarp = pos >> 5;
+  const bool valid = pos < a.n_blk;
+  const int own = valid ? a.own_idx[pos] : -1;
+  const int oth = valid ? a.oth_idx[pos] : 0;
+  sseg[wid][lane + 1] = own;
+  if (lane == 0) {
+    const int w0 = gwarp << 5;
+    sseg[wid][0] = (w0 > 0 && w0 - 1 < a.n_blk) ? a.own_idx[w0 - 1] : -2;
+    sseg[wid][33] = (w0 + 32 < a.n_blk) ? a.own_idx[w0 + 32] : -1;
   }
-  static_assert(NV == 33, "the last value is reduced by a segmented warp scan");
-  {  // value 32: a second walk would keep 31 lanes idle -> segmented inclusive scan over the lanes
-    double x = stage[wid][32][lane];
-    const int start = lane == 0 ? 0 : 32 - __clz(ends & ((1u << lane) - 1u));  // first lane of this lane's run
+  double AL[3][2] = {{0, 0}, {0, 0}, {0, 0}}, OL[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  double cw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (valid) {
+    const int cap = SIDE == 0 ? own : oth, tag = SIDE == 0 ? oth : own;
+    const double cm[3] = {a.cam[0], a.cam[1], a.cam[2]};
+    const double* cp = a.cap_pre + (size_t)kCapPre * cap;
+    const double* tpb = a.tag_pre + (size_t)kTagPre * tag;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const double ox = a.obs[(size_t)(2 * i) * a.plane + pos];
+      const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
+      CornerJ j;
+      double Kl[2][2];
+      corner_jacobian_m<1>(cp, tpb + 12 * i, cm, ox, oy, j, Kl);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane - o >= start) x += y;
-    }
-    const bool run_end = (ends >> lane) & 1u;
-    if (run_end && own >= 0) {
-      if (start == 0 && head_open) a.partial[((size_t)gwarp * 2 + 0) * NV + 32] = x;
-      else a.out_seg[(size_t)own * NV + 32] = x;
-    } else if (lane == 31 && tail_open && own >= 0) {
-      a.partial[((size_t)gwarp * 2 + (start == 0 ? 0 : 1)) * NV + 32] = x;
+      for (int row = 0; row < 2; ++row) {
+        const double* O = SIDE == 0 ? j.B[row] : j.C[row];
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            AL[p][q] += j.A[row][p] * Kl[row][q];
+            OL[p][q] += O[p] * Kl[row][q];
+          }
+        if (WITH_CAM) {
+          cw[0] += j.K[row] * Kl[row][0];
+          cw[1] += j.K[row] * Kl[row][1];
+          cw[2] += Kl[row][0] * Kl[row][0];
+          cw[3] += Kl[row][0] * Kl[row][1];
+          cw[4] += Kl[row][1] * Kl[row][1];
+          cw[5] += Kl[row][0] * j.r[row];
+          cw[6] += Kl[row][1] * j.r[row];
+        }
+      }
     }
   }
+  if (WITH_CAM) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) cw[i] = warp_sum(cw[i]);
+    if (lane == 0) {
+      double* wc = a.warp_cam + 8 * (size_t)gwarp;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wc[i] = cw[i];
+    }
+  }
+  // record: [pose dof p (A: 0..2, O: 3..5)][l1] at p, [..][l2] at 6 + p
+  double(*st)[33] = stage[wid];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    st[p][lane] = AL[p][0];
+    st[3 + p][lane] = OL[p][0];
+    st[6 + p][lane] = AL[p][1];
+    st[9 + p][lane] = OL[p][1];
+  }
+  __syncwarp();
+  segment_flush<NVX>(stage[wid], sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
 }
 
 // Sums the pieces of poses whose blocks straddle warps (fixed order), and
 // zero-fills poses without blocks.  One thread per (pose, value).
-__global__ void seg_fixup_kernel(int n_pose, const int32_t* __restrict__ seg_off,
+__global__ void seg_fixup_kernel(int n_pose, int nv, const int32_t* __restrict__ seg_off,
                                  const double* __restrict__ partial, double* __restrict__ out_seg) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_pose * NV) return;
-  const int s = t / NV, v = t - s * NV;
+  if (t >= n_pose * nv) return;
+  const int s = t / nv, v = t - s * nv;
   const int b0 = seg_off[s], b1 = seg_off[s + 1];
   if (b1 == b0) { out_seg[t] = 0.0; return; }
   const int w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
@@ -391,38 +501,41 @@ __global__ void seg_fixup_kernel(int n_pose, const int32_t* __restrict__ seg_off
   double acc = 0.0;
   for (int w = w0; w <= w1; ++w) {
     const int slot = (w == w0 && (b0 & 31) != 0) ? 1 : 0;
-    acc += partial[((size_t)w * 2 + slot) * NV + v];
+    acc += partial[((size_t)w * 2 + slot) * nv + v];
   }
   out_seg[t] = acc;
 }
 
-// Deterministic column sums of a [n][m] array (m <= 4) into out[m]: every CTA
+// Deterministic column sums of a [n][m] array (m <= 12) into out[m]: every CTA
 // reduces one contiguous chunk in a fixed order (stage 1), one CTA adds the
 // chunk sums (stage 2).  Same result on every run, no atomics.
 constexpr int kColsumChunks = 128;
 __global__ void __launch_bounds__(256) colsum_stage1_kernel(int n, int m, const double* __restrict__ in,
-                                                            double* __restrict__ part /* [chunks][4] */) {
-  __shared__ double sm[8][4];
+                                                            double* __restrict__ part /* [chunks][12] */) {
+  __shared__ double sm[8][12];
   const int chunk = (n + gridDim.x - 1) / gridDim.x;
   const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
-  double acc[4] = {0, 0, 0, 0};
+  double acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = lo + threadIdx.x; i < hi; i += 256)
-    for (int c = 0; c < m; ++c) acc[c] += in[(size_t)i * m + c];
-  for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+#pragma unroll
+    for (int c = 0; c < 12; ++c) if (c < m) acc[c] += in[(size_t)i * m + c];
+#pragma unroll
+  for (int c = 0; c < 12; ++c) acc[c] = warp_sum(acc[c]);
   if ((threadIdx.x & 31) == 0)
-    for (int c = 0; c < 4; ++c) sm[threadIdx.x >> 5][c] = acc[c];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) sm[threadIdx.x >> 5][c] = acc[c];
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < 12) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
-    part[blockIdx.x * 4 + threadIdx.x] = t;
+    part[blockIdx.x * 12 + threadIdx.x] = t;
   }
 }
 __global__ void colsum_stage2_kernel(int chunks, int m, const double* __restrict__ part, double* __restrict__ out) {
   const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;  // one warp per column
   if (c >= m) return;
   double t = 0.0;
-  for (int i = lane; i < chunks; i += 32) t += part[i * 4 + c];
+  for (int i = lane; i < chunks; i += 32) t += part[i * 12 + c];
   t = warp_sum(t);
   if (lane == 0) out[c] = t;
 }
@@ -457,14 +570,14 @@ struct CandArgs {
   const double* cam_c;
   double* warp_out;        // [n_warp]: candidate sum r^2
 };
-template <int SIDE>
+template <int SIDE, int MODEL>
 __global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   double c2 = 0.0;
   if (pos < a.n_blk) {
     const int own = a.own_idx[pos], oth = a.oth_idx[pos];
     const int cap = SIDE == 0 ? own : oth, tag = SIDE == 0 ? oth : own;
-    const double fc = a.cam_c[0];
+    const double cm[3] = {a.cam_c[0], MODEL ? a.cam_c[1] : 0.0, MODEL ? a.cam_c[2] : 0.0};
     double cp[kCapPre];
     {
       const double2* src = reinterpret_cast<const double2*>(a.cap_pre_c + (size_t)kCapPre * cap);
@@ -482,7 +595,7 @@ __global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
       const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
       double tp3[3] = {__ldg(tpc + 12 * i), __ldg(tpc + 12 * i + 1), __ldg(tpc + 12 * i + 2)};
       double rc[2];
-      corner_residual(cp, tp3, fc, ox, oy, rc);
+      corner_residual_m<MODEL>(cp, tp3, cm, ox, oy, rc);
       c2 += rc[0] * rc[0] + rc[1] * rc[1];
     }
   }
@@ -526,8 +639,16 @@ struct LmScalars {
   double gmax_e;     // [16] max |g_i|, E poses
   double gmax_f;     // [17]
   double pcg_iters;  // [18]
-  double pad[5];
+  double pad[5];     // [19..23]
+  // radial model (num_intrinsics = 3) only
+  double H_f_l1, H_f_l2, H_l1_l1, H_l1_l2, H_l2_l2;  // [24..28] intrinsics block entries with l1, l2
+  double g_l1, g_l2;                                  // [29], [30]
+  double unused2;                                     // [31]
+  double d_l1, d_l2;                                  // [32], [33] steps
+  double sigma_l1, sigma_l2;                          // [34], [35] Jacobi scales
+  double l1, l2;                                      // [36], [37] current values
+  double pad2[2];
 };
-constexpr int kNumScalars = 24;
+constexpr int kNumScalars = 40;
 
 }  // namespace ars

@@ -29,7 +29,7 @@ struct LocArgs {
   const int32_t* seed_block;  // [n_loc] index within the capture, < 0: skip
   const double* tag_pose;     // [n_tag][6]
   const double* tag_pre;      // [n_tag][kTagPre] (world corners used)
-  double focal;
+  double cam[3];              // f, l1, l2
   LocOptions o;
   double* pose;               // [n_loc][6] out
   int32_t* iterations;        // optional
@@ -49,6 +49,7 @@ __device__ __forceinline__ double loc_group_sum(double v, unsigned mask) {
 }
 
 // sum r^2 at pose x over the capture's corners (all lanes of the group get the result)
+template <int MODEL>
 __device__ __forceinline__ double loc_cost(const LocArgs& a, int b0, int nb, const double x[6], int gl, unsigned mask) {
   double cp[kCapPre];
   prep_capture(x, cp);
@@ -61,7 +62,7 @@ __device__ __forceinline__ double loc_cost(const LocArgs& a, int b0, int nb, con
     for (int i = 0; i < 4; ++i) {
       const double2 o = ob[i];
       double r[2];
-      corner_residual(cp, tp + 12 * i, a.focal, o.x, o.y, r);
+      corner_residual_m<MODEL>(cp, tp + 12 * i, a.cam, o.x, o.y, r);
       s += r[0] * r[0] + r[1] * r[1];
     }
   }
@@ -69,6 +70,7 @@ __device__ __forceinline__ double loc_cost(const LocArgs& a, int b0, int nb, con
 }
 
 // J^T J (upper packed 21), J^T r (6) and sum r^2 at pose x
+template <int MODEL>
 __device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int nb, const double x[6], int gl,
                                               unsigned mask, double H[21], double g[6], double& rr) {
   double cp[kCapPre];
@@ -86,7 +88,8 @@ __device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int nb, 
     for (int i = 0; i < 4; ++i) {
       const double2 o = ob[i];
       CornerJ cj;
-      corner_jacobian(cp, tp + 12 * i, a.focal, o.x, o.y, cj);
+      double Kl[2][2];
+      corner_jacobian_m<MODEL>(cp, tp + 12 * i, a.cam, o.x, o.y, cj, Kl);
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         const double J[6] = {cj.A[row][0], cj.A[row][1], cj.A[row][2], cj.B[row][0], cj.B[row][1], cj.B[row][2]};
@@ -107,6 +110,7 @@ __device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int nb, 
   rr = loc_group_sum(rr, mask);
 }
 
+template <int MODEL>
 __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int cap = gid / kLocGroup;
@@ -138,12 +142,12 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
     const double* tp = a.tag_pose + 6 * (size_t)a.tag_idx[b0 + seed];
 #pragma unroll
     for (int i = 0; i < 6; ++i) tpose[i] = tp[i];
-    seed_capture_pose(rect, a.focal, tpose, o.tag_size, x);
+    seed_capture_pose(rect, a.cam[0], tpose, o.tag_size, x);
   }
 
   double H[21], g[6], rr;
   double scale[6], diag[6];
-  loc_normal_eq(a, b0, nb, x, gl, mask, H, g, rr);
+  loc_normal_eq<MODEL>(a, b0, nb, x, gl, mask, H, g, rr);
   double x_cost = 0.5 * rr;
 #pragma unroll
   for (int i = 0; i < 6; ++i) scale[i] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(H[tri6(i, i)])) : 1.0;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
     double xc[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) xc[i] = x[i] + delta[i];
-    double cand_cost = 0.5 * loc_cost(a, b0, nb, xc, gl, mask);
+    double cand_cost = 0.5 * loc_cost<MODEL>(a, b0, nb, xc, gl, mask);
     if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
     double sn = 0.0;
 #pragma unroll
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) x_norm += x[i] * x[i];
       x_norm = sqrt(x_norm);
-      loc_normal_eq(a, b0, nb, x, gl, mask, H, g, rr);
+      loc_normal_eq<MODEL>(a, b0, nb, x, gl, mask, H, g, rr);
       x_cost = 0.5 * rr;
       grad_max = 0.0;
 #pragma unroll

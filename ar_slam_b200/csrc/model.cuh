@@ -217,6 +217,80 @@ ARS_HD void corner_jacobian(const double* __restrict__ cp, const double* __restr
   }
 }
 
+// ---- radial model of the TODO at ar_slam_util.cpp:164-171 (BASELINE config 5) -------------
+//   r2 = xp^2 + yp^2,  d = 1 + r2 (l1 + l2 r2),  (u, v) = f d (xp, yp),  camera = [f, l1, l2]
+// All three intrinsics are live.  MODEL 0 is the reference's live focal-only model above.
+template <int MODEL>
+ARS_HD void corner_residual_m(const double* __restrict__ cp, const double* __restrict__ tp,
+                              const double cam[3], double ox, double oy, double r[2]) {
+  if (MODEL == 0) { corner_residual(cp, tp, cam[0], ox, oy, r); return; }
+  const double q0 = tp[0] + cp[18], q1 = tp[1] + cp[19], q2 = tp[2] + cp[20];
+  const double px = cp[0] * q0 + cp[1] * q1 + cp[2] * q2;
+  const double py = cp[3] * q0 + cp[4] * q1 + cp[5] * q2;
+  const double pz = cp[6] * q0 + cp[7] * q1 + cp[8] * q2;
+  const double iz = 1.0 / pz;
+  const double xp = px * iz, yp = py * iz;
+  const double r2 = xp * xp + yp * yp;
+  const double d = r2 * (cam[1] + cam[2] * r2) + 1.0;
+  r[0] = cam[0] * d * xp - ox;
+  r[1] = cam[0] * d * yp - oy;
+}
+
+// Kl[row][0..1] = d r / d l1, d r / d l2 (MODEL 1 only); o.K is d r / d f
+template <int MODEL>
+ARS_HD void corner_jacobian_m(const double* __restrict__ cp, const double* __restrict__ tp,
+                              const double cam[3], double ox, double oy, CornerJ& o, double Kl[2][2]) {
+  if (MODEL == 0) {
+    corner_jacobian(cp, tp, cam[0], ox, oy, o);
+    Kl[0][0] = Kl[0][1] = Kl[1][0] = Kl[1][1] = 0.0;
+    return;
+  }
+  const double f = cam[0], l1 = cam[1], l2 = cam[2];
+  const double q[3] = {tp[0] + cp[18], tp[1] + cp[19], tp[2] + cp[20]};
+  const double px = cp[0] * q[0] + cp[1] * q[1] + cp[2] * q[2];
+  const double py = cp[3] * q[0] + cp[4] * q[1] + cp[5] * q[2];
+  const double pz = cp[6] * q[0] + cp[7] * q[1] + cp[8] * q[2];
+  const double iz = 1.0 / pz;
+  const double xp = px * iz, yp = py * iz;
+  const double r2 = xp * xp + yp * yp;
+  const double d = r2 * (l1 + l2 * r2) + 1.0;
+  const double g2 = 2.0 * (l1 + 2.0 * l2 * r2);  // d(d)/d(xp) = g2 xp
+  o.r[0] = f * d * xp - ox;
+  o.r[1] = f * d * yp - oy;
+  o.K[0] = d * xp;
+  o.K[1] = d * yp;
+  Kl[0][0] = f * r2 * xp; Kl[0][1] = f * r2 * r2 * xp;
+  Kl[1][0] = f * r2 * yp; Kl[1][1] = f * r2 * r2 * yp;
+  // P = d(u, v)/d(xp, yp)
+  const double Pxy = f * g2 * xp * yp;
+  const double P[2][2] = {{f * (d + g2 * xp * xp), Pxy}, {Pxy, f * (d + g2 * yp * yp)}};
+  const bool small = cp[21] != 0.0;
+#pragma unroll
+  for (int row = 0; row < 2; ++row) {
+    // dp = d(u|v)/dp = P[row] . [[iz, 0, -xp iz], [0, iz, -yp iz]]
+    const double dp[3] = {P[row][0] * iz, P[row][1] * iz, -(P[row][0] * xp + P[row][1] * yp) * iz};
+    double a[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[j] = dp[0] * cp[j] + dp[1] * cp[3 + j] + dp[2] * cp[6 + j];
+    o.A[row][0] = a[0];
+    o.A[row][1] = a[1];
+    o.A[row][2] = a[2];
+    if (!small) {
+      const double c0 = q[1] * a[2] - q[2] * a[1];
+      const double c1 = q[2] * a[0] - q[0] * a[2];
+      const double c2 = q[0] * a[1] - q[1] * a[0];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o.B[row][k] = c0 * cp[9 + k] + c1 * cp[12 + k] + c2 * cp[15 + k];
+    } else {
+      o.B[row][0] = q[1] * dp[2] - q[2] * dp[1];
+      o.B[row][1] = q[2] * dp[0] - q[0] * dp[2];
+      o.B[row][2] = q[0] * dp[1] - q[1] * dp[0];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.C[row][k] = a[0] * tp[3 + k] + a[1] * tp[6 + k] + a[2] * tp[9 + k];
+  }
+}
+
 // ---- seeds (calcInitValues / initCapturePose, ar_slam_util.cpp:52-108),
 // needed on the device by the batched localisation kernel.
 ARS_HD double normalize_angle(double a) {

@@ -227,6 +227,7 @@ struct SparseTarget {
     atomicAdd(borderm + 6 * (size_t)f + c, b0);
     atomicAdd(rhsm + 6 * (size_t)f + c, b1);
   }
+  __device__ __forceinline__ void add_border_x(int, int, double, double) const {}  // radial model: dense solver only
   const int32_t* pair_slot;  // [n_pairs] precomputed slot of every (partner, block) pair, or null
   // lower block (row fj, col fi): precomputed slot, else bisection in the row's sorted column list
   __device__ __forceinline__ int find(int fi, int fj) const {
@@ -311,8 +312,8 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __re
     const double skk = sf * sf * (a.sc->cam_H - a.cam_minus[0]) + d;
     a.scal[0] = skk;
     a.scal[1] = 1.0 / skk;
-    a.rhs[6 * (size_t)a.n_f] = sf * (a.sc->cam_g - a.cam_minus[1]);
-    if (!(skk > 0.0) || a.cam_minus[2] != 0.0) a.scal[3] = 1.0;
+    a.rhs[6 * (size_t)a.n_f] = sf * (a.sc->cam_g - a.cam_minus[6]);
+    if (!(skk > 0.0) || a.cam_minus[9] != 0.0) a.scal[3] = 1.0;
   }
   if (row >= a.n_f) return;
   double sr[6];

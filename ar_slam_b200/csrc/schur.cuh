@@ -22,12 +22,13 @@ struct SchurArgs {
   const int32_t* f_idx;   // [n_blk]   F pose per E-sorted block
   const int32_t* pair_off; // [n_blk]  number of (partner, block) pairs before each block (sparse target)
   const double* HE;       // [n_e][NV]
+  const double* HEx;      // [n_e][NVX] l1, l2 borders (radial model), else null
   const double* W;        // 36 planes
   const double* sig_e;    // [6 n_e]
   double radius, min_diag, max_diag;
   double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
-  double* YB;             // [n_e][6]: Ht_ee^-1 sig_e H_e,f
-  double* seg_cam;        // [n_e][4]: (sig_e H_e,f).yb , (sig_e H_e,f).z , factorisation failed, 0
+  double* YB;             // [n_e][6 NK]: Ht_ee^-1 sig_e H_e,intrinsic_q
+  double* seg_cam;        // [n_e][12]: M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | 0 0
 };
 
 // decode p -> (i <= j) with p = j (j + 1) / 2 + i
@@ -36,6 +37,16 @@ __device__ __forceinline__ void tri_decode(int p, int& i, int& j) {
   while ((j + 1) * (j + 2) / 2 <= p) ++j;
   while (j * (j + 1) / 2 > p) --j;
   i = p - j * (j + 1) / 2;
+}
+
+// scaled borders of the l1, l2 columns of an E pose (radial model)
+__device__ __forceinline__ void load_scaled_Ex(const SchurArgs& a, int e, const double s[6], double hk1[6], double hk2[6]) {
+  const double* rx = a.HEx + (size_t)e * NVX;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    hk1[i] = rx[i] * s[i];
+    hk2[i] = rx[6 + i] * s[i];
+  }
 }
 
 __device__ __forceinline__ void load_scaled_E(const SchurArgs& a, int e, double L[36], double g[6],
@@ -68,6 +79,10 @@ struct DenseTarget {
   __device__ __forceinline__ void add_border(int f, int c, double b0, double b1) const {
     atomicAdd(S + (size_t)cam_row * ld + 6 * f + c, b0);
     atomicAdd(S + (size_t)rhs_row * ld + 6 * f + c, b1);
+  }
+  __device__ __forceinline__ void add_border_x(int f, int c, double bl1, double bl2) const {
+    atomicAdd(S + (size_t)(cam_row + 1) * ld + 6 * f + c, bl1);
+    atomicAdd(S + (size_t)(cam_row + 2) * ld + 6 * f + c, bl2);
   }
   // M[r][c] = element (6 fi + r, 6 fj + c), fi <= fj, of sum W~^T Y; stored in the lower triangle
   __device__ __forceinline__ double* block(int fi, int fj, long long /*pair*/) const { return S + (size_t)(6 * fj) * ld + 6 * fi; }
@@ -113,7 +128,7 @@ constexpr size_t kSchurSmem = (size_t)(kSchurThreads * 37 + 4 * 32 * 37) * sizeo
 //     every lane of the segment carries the same load -- stages each 6x6 result in shared
 //     memory, and the warp adds it to the reduced system with one FP64 atomic per lane on
 //     consecutive addresses (coalesced reductions at L2).
-template <typename Target>
+template <typename Target, int NK>
 __global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk,
                                                                         const int32_t* __restrict__ e_idx) {
   extern __shared__ __align__(16) double schur_sm[];
@@ -132,12 +147,20 @@ __global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const Sc
   const size_t ps = a.plane;
   if (valid) {
     double zl[6], ybl[6], hk[6];
+    double hk1[6], hk2[6], ybl1[6], ybl2[6];  // radial model: l1, l2 borders
     load_scaled_E(a, e, L, zl, hk, s);
     const bool ok = chol6(L);
 #pragma unroll
     for (int i = 0; i < 6; ++i) ybl[i] = hk[i];
     chol6_forward(L, zl);
     chol6_forward(L, ybl);
+    if (NK == 3) {
+      load_scaled_Ex(a, e, s, hk1, hk2);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { ybl1[i] = hk1[i]; ybl2[i] = hk2[i]; }
+      chol6_forward(L, ybl1);
+      chol6_forward(L, ybl2);
+    }
     if (j == 0) {
       double z[6], yb[6];
 #pragma unroll
@@ -145,18 +168,37 @@ __global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const Sc
       chol6_backward(L, z);
       chol6_backward(L, yb);
       double* zo = a.Z + 8 * (size_t)e;
-      double c0 = 0.0, c1 = 0.0;
+      double* sg = a.seg_cam + 12 * (size_t)e;
+      double m00 = 0.0, v0 = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         zo[i] = z[i];
-        a.YB[6 * (size_t)e + i] = yb[i];
-        c0 += hk[i] * yb[i];
-        c1 += hk[i] * z[i];
+        a.YB[6 * NK * (size_t)e + i] = yb[i];
+        m00 += hk[i] * yb[i];
+        v0 += hk[i] * z[i];
       }
       zo[6] = ok ? 0.0 : 1.0;
       zo[7] = 0.0;
-      double* sg = a.seg_cam + 4 * (size_t)e;
-      sg[0] = c0; sg[1] = c1; sg[2] = ok ? 0.0 : 1.0; sg[3] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) sg[i] = 0.0;
+      sg[0] = m00; sg[6] = v0; sg[9] = ok ? 0.0 : 1.0;
+      if (NK == 3) {
+        double yb1[6], yb2[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { yb1[i] = ybl1[i]; yb2[i] = ybl2[i]; }
+        chol6_backward(L, yb1);
+        chol6_backward(L, yb2);
+        double m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          a.YB[18 * (size_t)e + 6 + i] = yb1[i];
+          a.YB[18 * (size_t)e + 12 + i] = yb2[i];
+          m01 += hk[i] * yb1[i]; m02 += hk[i] * yb2[i];
+          m11 += hk1[i] * yb1[i]; m12 += hk1[i] * yb2[i]; m22 += hk2[i] * yb2[i];
+          v1 += hk1[i] * z[i]; v2 += hk2[i] * z[i];
+        }
+        sg[1] = m01; sg[2] = m02; sg[3] = m11; sg[4] = m12; sg[5] = m22; sg[7] = v1; sg[8] = v2;
+      }
     }
     fj = a.f_idx[pos];
 #pragma unroll
@@ -165,15 +207,17 @@ __global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const Sc
 #pragma unroll
       for (int i = 0; i < 6; ++i) col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
       chol6_forward(L, col);
-      double b0 = 0.0, b1 = 0.0;  // (sig_e W)^T Ht^-1 h = V^T (L^-1 h)
+      double b0 = 0.0, b1 = 0.0, bl1 = 0.0, bl2 = 0.0;  // (sig_e W)^T Ht^-1 h = V^T (L^-1 h)
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         V[i * 6 + c] = col[i];
         Vs[threadIdx.x][i * 6 + c] = col[i];
         b0 += col[i] * ybl[i];
         b1 += col[i] * zl[i];
+        if (NK == 3) { bl1 += col[i] * ybl1[i]; bl2 += col[i] * ybl2[i]; }
       }
       t.add_border(fj, c, b0, b1);
+      if (NK == 3) t.add_border_x(fj, c, bl1, bl2);
     }
   }
   __syncthreads();
@@ -255,12 +299,12 @@ __global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const Sc
 }
 
 // E poses without blocks never reach schur_eliminate_kernel: clear their records.
-__global__ void schur_empty_kernel(const SchurArgs a) {
+__global__ void schur_empty_kernel(const SchurArgs a, int nk) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n_e || a.e_off[e + 1] > a.e_off[e]) return;
   for (int i = 0; i < 8; ++i) a.Z[8 * (size_t)e + i] = 0.0;
-  for (int i = 0; i < 6; ++i) a.YB[6 * (size_t)e + i] = 0.0;
-  for (int i = 0; i < 4; ++i) a.seg_cam[4 * (size_t)e + i] = 0.0;
+  for (int i = 0; i < 6 * nk; ++i) a.YB[6 * nk * (size_t)e + i] = 0.0;
+  for (int i = 0; i < 12; ++i) a.seg_cam[12 * (size_t)e + i] = 0.0;
 }
 
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
@@ -275,8 +319,8 @@ __global__ void dense_scale_kernel(double* __restrict__ S, long long ld, int n /
 
 // Adds the F-pose diagonal blocks sig H_ff sig + D^2, the camera border and
 // the gradient to the dense system.  One thread per F pose.
-__global__ void dense_add_pose_kernel(int n_f, const double* __restrict__ HF, const double* __restrict__ sigF,
-                                      double radius, double min_diag, double max_diag,
+__global__ void dense_add_pose_kernel(int n_f, const double* __restrict__ HF, const double* __restrict__ HFx,
+                                      const double* __restrict__ sigF, double radius, double min_diag, double max_diag,
                                       double* __restrict__ S, long long ld, int cam_row, int rhs_row) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n_f) return;
@@ -295,21 +339,32 @@ __global__ void dense_add_pose_kernel(int n_f, const double* __restrict__ HF, co
     }
     S[(size_t)cam_row * ld + 6 * f + i] += rec[27 + i] * s[i] * sc_cam;
     S[(size_t)rhs_row * ld + 6 * f + i] += rec[21 + i] * s[i];
+    if (HFx) {  // radial model: rows of l1, l2
+      S[(size_t)(cam_row + 1) * ld + 6 * f + i] += HFx[(size_t)f * NVX + i] * s[i] * sigF[cam_row + 1];
+      S[(size_t)(cam_row + 2) * ld + 6 * f + i] += HFx[(size_t)f * NVX + 6 + i] * s[i] * sigF[cam_row + 2];
+    }
   }
 }
 
-// Camera row / rhs tail / identity padding.  cam_minus = column sums of seg_cam.
-__global__ void dense_add_camera_kernel(LmScalars* __restrict__ sc, const double* __restrict__ cam_minus,
+// Intrinsics block / rhs tail / identity padding.  cam_minus = column sums of seg_cam (12 values).
+__global__ void dense_add_camera_kernel(LmScalars* __restrict__ sc, const double* __restrict__ cam_minus, int nk,
                                         double radius, double min_diag, double max_diag, double* __restrict__ S,
                                         long long ld, int cam_row, int rhs_row, int n_pad) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double sf = sc->sigma_f;
-    const double h = sc->cam_H * sf * sf;
-    const double d = fmin(fmax(h, min_diag), max_diag) / radius;
-    S[(size_t)cam_row * ld + cam_row] = sf * sf * (sc->cam_H - cam_minus[0]) + d;
-    S[(size_t)rhs_row * ld + cam_row] = sf * (sc->cam_g - cam_minus[1]);
+    const double H[6] = {sc->cam_H, sc->H_f_l1, sc->H_f_l2, sc->H_l1_l1, sc->H_l1_l2, sc->H_l2_l2};  // 00 01 02 11 12 22
+    const double g[3] = {sc->cam_g, sc->g_l1, sc->g_l2};
+    const double sg[3] = {sc->sigma_f, sc->sigma_l1, sc->sigma_l2};
+    const int idx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int q = 0; q < nk; ++q) {
+      for (int p = 0; p <= q; ++p) {
+        double v = sg[q] * sg[p] * (H[idx[q][p]] - cam_minus[idx[q][p]]);
+        if (p == q) v += fmin(fmax(sg[q] * sg[q] * H[idx[q][q]], min_diag), max_diag) / radius;
+        S[(size_t)(cam_row + q) * ld + cam_row + p] = v;
+      }
+      S[(size_t)rhs_row * ld + cam_row + q] = sg[q] * (g[q] - cam_minus[6 + q]);
+    }
     S[(size_t)rhs_row * ld + rhs_row] = 1e300;
-    if (cam_minus[2] != 0.0) sc->chol_fail = 1.0;  // some E pose's damped 6x6 block was not positive definite
+    if (cam_minus[9] != 0.0) sc->chol_fail = 1.0;  // some E pose's damped 6x6 block was not positive definite
   }
   const int i = rhs_row + 1 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) S[(size_t)i * ld + i] = 1.0;
@@ -331,8 +386,8 @@ __global__ void scale_uF_kernel(int n, const double* __restrict__ y, const doubl
 // Bytes per corner: 72 (W) + 1 (index).
 struct BacksubArgs {
   SchurArgs sa;       // HE, W, sig_e, radius, e_off, f_idx, Z, YB
-  const double* uF;   // [6 n_f + 1]
-  int cam_row;
+  const double* uF;   // [6 n_f + nk]
+  int cam_row, nk;
   double* d_e;        // [6 n_e] step of the E poses
   double* seg_cross;  // [n_e]
 };
@@ -372,10 +427,12 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) t[i] *= s[i];
     chol6_solve(L, t);
-    const double uc = a.uF[a.cam_row];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-      de[i] = -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - a.sa.YB[6 * (size_t)e + i] * uc);
+    for (int i = 0; i < 6; ++i) {
+      double ybu = 0.0;
+      for (int q = 0; q < a.nk; ++q) ybu += a.sa.YB[6 * a.nk * (size_t)e + 6 * q + i] * a.uF[a.cam_row + q];
+      de[i] = -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - ybu);
+    }
   }
   double cross = 0.0;
   for (int j = gl; j < k; j += kBsGroup) {
@@ -406,7 +463,8 @@ struct ApplyArgs {
   const double* step;       // [6 n_pose]: d_e (already the step) or uF (to be negated)
   int negate;
   const double* rec;        // [n_pose][NV] normal-equation records of this side (unscaled)
-  const double* uF_cam;     // -> uF[cam_row]; the focal step is its negative
+  const double* recx;       // [n_pose][NVX] l1, l2 borders (radial model) or null
+  const double* uF_cam;     // -> uF[cam_row .. cam_row + nk); the intrinsics step is its negative
   double* delta;            // [6 n_pose] out (unscaled step)
   double* x_cand;           // [6 n_pose] out
   double* warp_out;         // [n_warp][3]: sum delta^2, sum x^2, sum (g.d + d^T H d / 2 + d_cam H_pose,f.d)
@@ -436,13 +494,16 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
     if (active && a.count_norms) {
       const double* rec = a.rec + (size_t)i * NV;
       const double dcam = -a.uF_cam[0];
+      const double dl1 = a.recx ? -a.uF_cam[1] : 0.0, dl2 = a.recx ? -a.uF_cam[2] : 0.0;
       double q = 0.0;
 #pragma unroll
       for (int p = 0; p < 6; ++p) {
         double hd = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) hd += rec[p <= c ? tri6(p, c) : tri6(c, p)] * d[c];
-        q += d[p] * (rec[21 + p] + 0.5 * hd + dcam * rec[27 + p]);
+        double border = dcam * rec[27 + p];
+        if (a.recx) border += dl1 * a.recx[(size_t)i * NVX + p] + dl2 * a.recx[(size_t)i * NVX + 6 + p];
+        q += d[p] * (rec[21 + p] + 0.5 * hd + border);
       }
       mq = q;
     }

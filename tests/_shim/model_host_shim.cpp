@@ -30,6 +30,31 @@ void shim_eval_block(const double* cam, const double* cap, const double* tag, do
     }
   }
 }
+// same with the radial model (camera = f, l1, l2)
+void shim_eval_block_dist(const double* cam, const double* cap, const double* tag, double tag_size,
+                          const double* rect8, double* res, double* jc, double* jp, double* ja) {
+  double cp[ars::kCapPre], tp[ars::kTagPre];
+  ars::prep_capture(cap, cp);
+  ars::prep_tag(tag, tag_size, tp);
+  for (int i = 0; i < 4; ++i) {
+    ars::CornerJ o;
+    double Kl[2][2], r2[2];
+    ars::corner_jacobian_m<1>(cp, tp + 12 * i, cam, rect8[2 * i], rect8[2 * i + 1], o, Kl);
+    ars::corner_residual_m<1>(cp, tp + 12 * i, cam, rect8[2 * i], rect8[2 * i + 1], r2);
+    for (int row = 0; row < 2; ++row) {
+      const int k = 2 * i + row;
+      res[k] = o.r[row];
+      if (r2[row] != o.r[row]) res[k] = 1e300;
+      jc[k * 3 + 0] = o.K[row]; jc[k * 3 + 1] = Kl[row][0]; jc[k * 3 + 2] = Kl[row][1];
+      for (int j = 0; j < 3; ++j) {
+        jp[k * 6 + j] = o.A[row][j];
+        jp[k * 6 + 3 + j] = o.B[row][j];
+        ja[k * 6 + j] = o.A[row][j];
+        ja[k * 6 + 3 + j] = o.C[row][j];
+      }
+    }
+  }
+}
 void shim_seed_capture_pose(const double* rect8, double focal, const double* tag_pose, double tag_size,
                             double* out6) {
   ars::seed_capture_pose(rect8, focal, tag_pose, tag_size, out6);

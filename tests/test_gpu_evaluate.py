@@ -98,3 +98,42 @@ def test_errors_are_reported(gpu_solver_cls):
     with pytest.raises(ar_slam_b200.ArslamError):
         s.evaluate()                                            # no problem set
     s.close()
+
+
+def test_radial_model_matches_oracle(gpu_solver_cls, oracle):
+    """num_intrinsics = 3: the radial model of the TODO at ar_slam_util.cpp:164-171."""
+    import ar_slam_b200
+    rng = np.random.default_rng(7)
+    cam, cap, tag, ci, ti, obs = random_blocks(rng, 64, 40, 50000)
+    cam = np.array([cam[0], 0.11, -0.07])
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3))
+    s.set_problem(len(cap), len(tag), ci, ti, obs)
+    s.set_params(cam, cap, tag)
+    gc, gr, gjc, gjp, gja = s.evaluate()
+    s.close()
+    oc, orr, ojc, ojp, oja = oracle.evaluate(ci, ti, obs, cam, cap, tag, model=1, num_threads=4)
+    assert np.abs(gr - orr).max() <= 1e-9 * max(1.0, np.abs(orr).max())
+    assert abs(gc - oc) <= 1e-12 * oc
+    assert np.abs(ojc[:, :, 1:]).max() > 0.0
+    assert jac_rel_err(gjc, ojc) <= 1e-9
+    assert jac_rel_err(gjp, ojp) <= 1e-9
+    assert jac_rel_err(gja, oja) <= 1e-9
+
+
+def test_radial_known_answer_vectors(gpu_solver_cls):
+    import ar_slam_b200
+    with open(os.path.join(GOLD, "kat_projection.json")) as f:
+        kat = json.load(f)
+    n = 0
+    for c in kat["cases"]:
+        if c["model"] != 1:
+            continue
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3))
+        s.set_problem(1, 1, [0], [0], np.zeros((1, 8)))
+        s.set_params(c["camera"], [c["capture"]], [c["tag"]])
+        _, r, _, _, _ = s.evaluate(jacobians=False)
+        s.close()
+        uv = np.array([float(x) for x in c["uv"]])
+        assert np.abs(r.reshape(-1) - uv).max() <= 1e-9 * max(1.0, np.abs(uv).max())
+        n += 1
+    assert n == 2

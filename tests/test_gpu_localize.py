@@ -55,3 +55,28 @@ def test_batch_matches_oracle(gpu_solver_cls, oracle):
     # and the answer is right: close to the ground-truth pose
     err = np.abs(pose[ok] - m.cap_true[ok])
     assert np.median(err[:, :3]) < 5e-3 and np.median(err[:, 3:]) < 5e-3
+
+
+def test_batch_radial_model(gpu_solver_cls, oracle):
+    """Localisation against a map whose camera carries radial distortion (num_intrinsics = 3)."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_localization_batch(4000, 300, seed=9)
+    cam = np.array([m.cam_true[0], 0.08, -0.03])
+    n_blk = len(m.tag_idx)
+    cap_idx = np.repeat(np.arange(len(m.blk_offsets) - 1), np.diff(m.blk_offsets)).astype(np.int32)
+    _, uv, _, _, _ = oracle.evaluate(cap_idx, m.tag_idx, np.zeros((n_blk, 8)), cam, m.cap_true, m.tag_true,
+                                     model=1, jacobians=False)
+    obs = (uv + np.random.default_rng(9).normal(0, 0.3, uv.shape)).astype(np.float32).astype(np.float64)
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3))
+    pose, its, cost, term = s.localize_batch(m.blk_offsets, m.tag_idx, obs, m.seed_block, cam, m.tag_true)
+    s.close()
+    po, io, co, to = oracle.localize_batch(m.blk_offsets, m.tag_idx, obs, m.seed_block, cam, m.tag_true,
+                                           model=1, num_threads=4)
+    same = its == io
+    assert same.mean() > 0.995
+    assert np.array_equal(term[same], to[same])
+    assert np.allclose(cost[same], co[same], rtol=1e-9)
+    assert np.abs(pose[same] - po[same]).max() < 1e-8
+    err = np.abs(pose - m.cap_true)
+    assert np.median(err[:, :3]) < 5e-3 and np.median(err[:, 3:]) < 5e-3

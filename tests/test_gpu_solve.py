@@ -226,3 +226,59 @@ def test_auto_picks_dense_only_where_the_reduced_matrix_is_dense(gpu_solver_cls)
         assert picks[name]["termination"] == 0
     assert picks["sparse"]["linear_solver"] == ar_slam_b200.LINSOLVE_PCG
     assert picks["dense"]["linear_solver"] == ar_slam_b200.LINSOLVE_DENSE
+
+
+def _radial_map(oracle, n_cap, n_tag, seed, l1=0.08, l2=-0.03):
+    """Synthetic map re-rendered through the radial model (camera = f, l1, l2)."""
+    from ar_slam_b200 import synth
+    m = synth.make_map(n_cap, n_tag, seed=seed)
+    m.cam_true = np.array([m.cam_true[0], l1, l2])
+    _, uv, _, _, _ = oracle.evaluate(m.cap_idx, m.tag_idx, np.zeros_like(m.obs), m.cam_true, m.cap_true, m.tag_true,
+                                     model=1, jacobians=False)
+    rng = np.random.default_rng(seed)
+    m.obs = (uv + rng.normal(0, 0.3, uv.shape)).astype(np.float32).astype(np.float64)
+    return m
+
+
+@pytest.mark.parametrize("elim", [1, 2])
+def test_radial_model_trajectory(gpu_solver_cls, oracle, elim):
+    """num_intrinsics = 3 (f, l1, l2 all free; ar_slam_util.cpp:164-171 TODO, BASELINE config 5)."""
+    import ar_slam_b200
+    m = _radial_map(oracle, 400, 100, seed=21)
+    cam_o, cap_o, tag_o, so, log_o = oracle.solve(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs, m.cam0, m.cap0,
+                                                  m.tag0, options=oracle.default_options(num_threads=4), model=1)
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, elimination=elim))
+    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    sg, log_g = s.solve()
+    cam_g, cap_g, tag_g = s.get_params()
+    s.close()
+    assert sg["linear_solver"] == ar_slam_b200.LINSOLVE_DENSE and sg["eliminated_side"] == elim
+    assert sg["iterations"] == so["iterations"] and sg["termination"] == so["termination"] == 0
+    n = so["iterations"] + 1
+    assert np.allclose(log_g[:n, 0], log_o[:n, 0], rtol=1e-7, atol=0)
+    assert np.allclose(log_g[1:n, 3], log_o[1:n, 3], rtol=1e-5)
+    assert np.allclose(log_g[:n, 5], log_o[:n, 5], rtol=1e-5)
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-8 * so["final_cost"]
+    assert np.abs(cam_g - cam_o).max() <= 1e-6 * max(1.0, np.abs(cam_o).max())
+    # and the distortion is actually recovered
+    assert abs(cam_g[1] - 0.08) < 0.02 and abs(cam_g[0] - m.cam_true[0]) < 2.0
+    # the focal-only model cannot explain these observations
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(elimination=elim))
+    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    s1, _ = s.solve()
+    s.close()
+    assert s1["final_cost"] > 1.5 * sg["final_cost"]
+
+
+def test_radial_model_rejects_pcg(gpu_solver_cls):
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(100, 40, seed=3)
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, linear_solver=ar_slam_b200.LINSOLVE_PCG))
+    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    with pytest.raises(ar_slam_b200.ArslamError):
+        s.solve()
+    s.close()

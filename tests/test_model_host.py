@@ -90,3 +90,25 @@ def test_register_cholesky(shim):
     H = np.eye(6)
     H[3, 3] = -1.0
     assert shim.shim_chol6_solve(_p(H), _p(b), _p(x)) == 0   # Eigen::LLT-style failure
+
+
+def test_radial_model_matches_jets(shim, oracle):
+    """The TODO model of ar_slam_util.cpp:164-171 (config 5): closed form vs the oracle's Jets."""
+    rng = np.random.default_rng(8)
+    worst = 0.0
+    for t in range(1500):
+        cam = np.array([rng.uniform(300, 3000), rng.normal(0, 0.08), rng.normal(0, 0.03)])
+        cap = np.concatenate([rng.normal(0, 0.5, 3), rng.normal(0, 0.8, 3)])
+        tag = np.concatenate([rng.normal(0, 0.5, 3) + [0, 0, 2.0], rng.normal(0, 0.8, 3)])
+        if t % 5 == 0:
+            cap[3:] = 0
+        rect = rng.normal(0, 200, 8)
+        _, r0, c0, p0, a0 = oracle.evaluate([0], [0], rect[None], cam, cap[None], tag[None], model=1)
+        res, jc, jp, ja = np.zeros(8), np.zeros((8, 3)), np.zeros((8, 6)), np.zeros((8, 6))
+        shim.shim_eval_block_dist(_p(cam), _p(cap), _p(tag), C.c_double(0.0635), _p(rect), _p(res), _p(jc), _p(jp),
+                                  _p(ja))
+        J0 = np.concatenate([c0[0], p0[0], a0[0]], 1)
+        J = np.concatenate([jc, jp, ja], 1)
+        worst = max(worst, (np.abs(J - J0).max(axis=1) / np.linalg.norm(J0, axis=1)).max(),
+                    (np.abs(res - r0[0]) / np.maximum(1, np.abs(r0[0]))).max())
+    assert worst <= 1e-9
