@@ -187,14 +187,20 @@ class Solver:
         self._check(self._lib.arslam_solve(self._h, C.byref(s), _p(lg), C.c_int32(rows if log else 0)))
         return s.as_dict(), (lg[: s.iterations + 1] if log else None)
 
-    def localize_batch(self, blk_offsets, tag_idx, rect8, seed_block, cam, tag_pose):
+    def localize_batch(self, blk_offsets, tag_idx, rect8, seed_block, cam, tag_pose, out=None):
         blk_offsets, tag_idx, seed_block = _i32(blk_offsets), _i32(tag_idx), _i32(seed_block)
         rect8, cam, tag_pose = _f64(rect8).reshape(-1), _f64(cam), _f64(tag_pose).reshape(-1)
         n = len(blk_offsets) - 1
-        pose = np.zeros((n, 6))
-        its = np.zeros(n, dtype=np.int32)
-        cost = np.zeros(n)
-        term = np.zeros(n, dtype=np.int32)
+        if out is not None:  # caller-owned result arrays (e.g. pinned memory)
+            pose, its, cost, term = out
+            if pose.shape != (n, 6) or pose.dtype != np.float64 or its.dtype != np.int32 or cost.dtype != np.float64 \
+                    or term.dtype != np.int32 or len(its) != n or len(cost) != n or len(term) != n:
+                raise ValueError("out = (pose [n,6] f64, iterations [n] i32, final_cost [n] f64, termination [n] i32)")
+        else:
+            pose = np.zeros((n, 6))
+            its = np.zeros(n, dtype=np.int32)
+            cost = np.zeros(n)
+            term = np.zeros(n, dtype=np.int32)
         self._check(self._lib.arslam_localize_batch(
             self._h, C.c_int64(n), _p(blk_offsets, C.c_int32), _p(tag_idx, C.c_int32), _p(rect8),
             _p(seed_block, C.c_int32), C.c_int64(tag_pose.size // 6), _p(cam), _p(tag_pose), _p(pose),

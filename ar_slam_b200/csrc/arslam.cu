@@ -178,7 +178,6 @@ struct arslam_solver {
   // sorted copies: side 0 capture-sorted, side 1 tag-sorted
   DevBuf<int32_t> s_own[2], s_oth[2], s_off[2];
   DevBuf<double> s_obs[2];
-  std::vector<int32_t> h_off[2], h_oth[2];
   long long problem_version = 0, pcg_version = -1;
   int pcg_side = -1, n_sm = 0;
   // parameters: two sets (current / candidate)
@@ -396,11 +395,6 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
     gather_sorted_kernel<<<cdiv(plane, 256), 256, 0, s->stream>>>(nb, plane, s->sort_vals[1].p, s->sort_keys[1].p, s->o_obs.p,
                                                                  s->s_own[side].p, s->s_oth[side].p, s->s_obs[side].p);
     segment_offsets_kernel<<<cdiv(n_own + 1, 256), 256, 0, s->stream>>>(nb, n_own, s->s_own[side].p, s->s_off[side].p);
-    // the host keeps the segment structure for the symbolic phase of the sparse reduced system
-    s->h_off[side].resize(n_own + 1);
-    s->h_oth[side].resize(nb);
-    CU(cudaMemcpyAsync(s->h_off[side].data(), s->s_off[side].p, sizeof(int32_t) * (n_own + 1), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(s->h_oth[side].data(), s->s_oth[side].p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s->stream));
     CU(s->H[side].ensure((size_t)n_own * NV));
     CU(s->partial[side].ensure((size_t)s->n_warp * 2 * NV));
     CU(s->d_pose[side].ensure((size_t)6 * n_own));
@@ -578,42 +572,53 @@ int gather_captures(arslam_solver* s, int k) {
 // ---- PCG hooks ---------------------------------------------------------------
 // Multi-GPU: every rank must use the same block pattern of the reduced system (the partial
 // values are summed element-wise), so the ranks' pair-key lists are all-gathered and united.
-int union_keys_across_ranks(arslam_solver* s, std::vector<uint64_t>& keys) {
+__global__ void pad_keys_kernel(unsigned long long* keys, long long from, long long to, unsigned long long sentinel) {
+  const long long i = from + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < to) keys[i] = sentinel;
+}
+int union_keys_across_ranks(arslam_solver* s) {
   if (s->world <= 1) return ARSLAM_OK;
-  DevBuf<long long> cnt, sendb, recvb;
+  PcgWorkspace& w = s->pcg;
+  const unsigned long long sentinel = (unsigned long long)w.n_f * (unsigned long long)w.n_f;  // above every key
+  DevBuf<long long> cnt;
   CU(cnt.ensure(1));
-  long long n_local = (long long)keys.size(), n_max = 0;
+  long long n_local = w.nnzb, n_max = 0;
   CU(cudaMemcpyAsync(cnt.p, &n_local, sizeof(long long), cudaMemcpyHostToDevice, s->stream));
   int rc = g_nccl.AllReduce(cnt.p, cnt.p, 1, kNcclInt64, kNcclMax, s->comm, s->stream);
   if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllReduce(max): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   CU(cudaMemcpyAsync(&n_max, cnt.p, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
-  std::vector<uint64_t> padded(keys);
-  padded.resize((size_t)n_max, ~0ull);
-  CU(sendb.ensure((size_t)n_max)); CU(recvb.ensure((size_t)n_max * s->world));
-  CU(cudaMemcpyAsync(sendb.p, padded.data(), sizeof(uint64_t) * n_max, cudaMemcpyHostToDevice, s->stream));
-  rc = g_nccl.AllGather(sendb.p, recvb.p, (size_t)n_max, kNcclInt64, s->comm, s->stream);
+  const long long n_all = n_max * s->world;
+  if (n_all >= (1LL << 31)) return s->fail(ARSLAM_ERR_UNSUPPORTED, "pcg symbolic: more than 2^31 block pairs across ranks");
+  // padded local list -> keys[1][0 .. n_max), gathered into keys[0][0 .. n_max * world)
+  CU(w.keys[1].ensure((size_t)n_all));
+  CU(cudaMemcpyAsync(w.keys[1].p, w.keys[0].p, sizeof(unsigned long long) * n_local, cudaMemcpyDeviceToDevice, s->stream));
+  if (n_max > n_local)
+    pad_keys_kernel<<<cdiv(n_max - n_local, 256), 256, 0, s->stream>>>(w.keys[1].p, n_local, n_max, sentinel);
+  CU(w.keys[0].ensure((size_t)n_all));
+  rc = g_nccl.AllGather(w.keys[1].p, w.keys[0].p, (size_t)n_max, kNcclInt64, s->comm, s->stream);
   if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-  std::vector<uint64_t> all((size_t)n_max * s->world);
-  CU(cudaMemcpyAsync(all.data(), recvb.p, sizeof(uint64_t) * all.size(), cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
-  std::sort(all.begin(), all.end());
-  all.erase(std::unique(all.begin(), all.end()), all.end());
-  if (!all.empty() && all.back() == ~0ull) all.pop_back();
-  keys.swap(all);
+  int nn = 0;
+  CU(pcg_sort_unique(w, (int)n_all, sym_key_bits(w.n_f), s->stream, &nn));
+  // the sentinel, if any rank padded, sorts last
+  if (nn > 0) {
+    unsigned long long last = 0;
+    CU(cudaMemcpyAsync(&last, w.keys[0].p + (nn - 1), sizeof(last), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (last == sentinel) --nn;
+  }
+  w.nnzb = nn;
   return ARSLAM_OK;
 }
 
 int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
   std::string err;
-  std::vector<uint64_t> keys;
-  pcg_collect_keys(n_e, n_f, s->h_off[side_e].data(), s->h_oth[side_e].data(), s->h_off[1 - side_e].data(),
-                   s->h_oth[1 - side_e].data(), keys);
-  int urc = union_keys_across_ranks(s, keys);
+  int rc = pcg_symbolic_keys(s->pcg, n_e, n_f, s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->s_oth[side_e].p, s->stream, err);
+  if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
+  const int urc = union_keys_across_ranks(s);
   if (urc) return urc;
-  const int rc = pcg_symbolic(s->pcg, keys, n_e, n_f, s->h_off[side_e].data(), s->stream, err,
-                              s->n_sm, (size_t)227 * 1024 - 2048);
+  rc = pcg_symbolic_build(s->pcg, s->stream, err, s->n_sm, (size_t)227 * 1024 - 2048);
   if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel, kPcgThreads, 0));

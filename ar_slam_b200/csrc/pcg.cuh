@@ -10,6 +10,9 @@
 #pragma once
 #include <algorithm>
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -21,6 +24,25 @@ namespace cg = cooperative_groups;
 
 constexpr int kPcgThreads = 1024;  // one CTA per SM, ~one block row per warp
 constexpr int kPcgWarps = kPcgThreads / 32;
+
+template <class T>
+struct PcgBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = n + n / 8 + 64;
+    const cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  PcgBuf() = default;
+  PcgBuf(const PcgBuf&) = delete;
+  PcgBuf& operator=(const PcgBuf&) = delete;
+  ~PcgBuf() { cudaFree(p); }
+};
 
 struct PcgWorkspace {
   int n_f = 0, nnzb = 0, grid = 0;
@@ -48,167 +70,264 @@ struct PcgWorkspace {
   int32_t* pair_slot = nullptr; // [n_pairs]
   long long n_pairs = 0;
   size_t value_count() const { return (size_t)36 * nnzb + (size_t)12 * n_f; }
-  void release() {
-    cudaFree(row_ptr); cudaFree(col_idx); cudaFree(src_slot); cudaFree(Sfin); cudaFree(Minv);
-    cudaFree(vec); cudaFree(partial); cudaFree(scal);
-    cudaFree(cta_row); cudaFree(halo_ptr); cudaFree(halo_col); cudaFree(lcol); cudaFree(diag_slot); cudaFree(slot_row); cudaFree(pair_off); cudaFree(pair_slot);
-    pair_off = pair_slot = nullptr;
-    cta_row = halo_ptr = halo_col = diag_slot = slot_row = nullptr; lcol = nullptr; smem_ok = false;
-    row_ptr = col_idx = src_slot = nullptr; Sfin = Minv = vec = partial = scal = nullptr;
-    valid = false;
-  }
-  ~PcgWorkspace() { release(); }
+  // storage (grow-only, so a new problem of similar size allocates nothing); the pointers above alias it
+  PcgBuf<int32_t> b_row_ptr, b_col_idx, b_src_slot, b_cta_row, b_halo_ptr, b_halo_col, b_diag_slot, b_slot_row, b_pair_off, b_pair_slot;
+  PcgBuf<uint16_t> b_lcol;
+  PcgBuf<double> b_Sfin, b_Minv, b_vec, b_partial, b_scal;
+  // symbolic phase scratch
+  PcgBuf<unsigned long long> keys[2], hkeys[2];
+  PcgBuf<long long> cnt_keys, cnt_pairs, off_keys, off_pairs;
+  PcgBuf<int> counts;
+  PcgBuf<unsigned char> tmp;
+  int* h_counts = nullptr;  // pinned
+  ~PcgWorkspace() { if (h_counts) cudaFreeHost(h_counts); }
 };
 
-// ---- symbolic phase (host): block pattern of sum_e W_e^T W_e over the E segments
-// keys = (row << 32 | col) of every block of the reduced system this rank contributes to
-inline void pcg_collect_keys(int n_e, int n_f, const int32_t* e_off, const int32_t* f_of_blk,
-                             const int32_t* f_off, const int32_t* e_of_blk, std::vector<uint64_t>& keys) {
-  // row r of the reduced system couples F pose r with every F pose seen by an E pose that sees r.
-  // Walk r's blocks (F-sorted copy) -> their E poses -> those poses' blocks (E-sorted copy);
-  // a marker array removes duplicates, so the cost is the number of (block, partner) pairs.
-  keys.clear();
-  keys.reserve((size_t)n_f * 24);
-  std::vector<int32_t> mark(n_f, -1), cols;
-  for (int r = 0; r < n_f; ++r) {
-    cols.clear();
-    mark[r] = r;
-    cols.push_back(r);  // every diagonal block exists
-    for (int b = f_off[r]; b < f_off[r + 1]; ++b) {
-      const int e = e_of_blk[b];
-      for (int q = e_off[e]; q < e_off[e + 1]; ++q) {
-        const int c = f_of_blk[q];
-        if (mark[c] != r) { mark[c] = r; cols.push_back(c); }
-      }
-    }
-    std::sort(cols.begin(), cols.end());
-    for (int c : cols) keys.push_back((uint64_t)(uint32_t)r << 32 | (uint32_t)c);
+// ---- symbolic phase (device): block pattern of sum_e W_e^T W_e over the E segments.
+// Every E-sorted block (e, f) emits the keys (f, f') of all blocks (e, f') of its segment; the
+// keys row * n_f + col are radix-sorted and de-duplicated, which is the BSR pattern in row-major
+// order.  Everything below (row pointers, transpose partners, the per-SM row ranges of the
+// shared-memory solver and their halo lists) is derived from the sorted keys by bisection, so
+// the host only ever sees a handful of counts.
+__global__ void sym_counts_kernel(int n_blk, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
+                                  long long* __restrict__ n_keys, long long* __restrict__ n_pairs) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos > n_blk) return;
+  if (pos == n_blk) { n_keys[pos] = 0; n_pairs[pos] = 0; return; }  // the scans' totals land here
+  const int e = e_idx[pos];
+  const int beg = e_off[e], k = e_off[e + 1] - beg;
+  n_keys[pos] = k;
+  n_pairs[pos] = schur_pairs_of(pos - beg, k);
+}
+__global__ void sym_emit_keys_kernel(int n_blk, int n_f, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
+                                     const int32_t* __restrict__ f_idx, const long long* __restrict__ key_off,
+                                     unsigned long long* __restrict__ keys) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos < n_f) keys[key_off[n_blk] + pos] = (unsigned long long)pos * n_f + pos;  // every diagonal block exists
+  if (pos >= n_blk) return;
+  const int e = e_idx[pos];
+  const int beg = e_off[e], k = e_off[e + 1] - beg;
+  const unsigned long long row = (unsigned long long)f_idx[pos] * n_f;
+  unsigned long long* out = keys + key_off[pos];
+  for (int q = 0; q < k; ++q) out[q] = row + f_idx[beg + q];
+}
+__global__ void sym_narrow_kernel(int n, const long long* __restrict__ in, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)in[i];
+}
+__device__ __forceinline__ int sym_lower_bound(const unsigned long long* __restrict__ a, int n, unsigned long long v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
   }
-  (void)n_e;
+  return lo;
+}
+__global__ void sym_rows_kernel(int n_f, int nnzb, const unsigned long long* __restrict__ keys, int32_t* __restrict__ row_ptr) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= n_f) row_ptr[r] = sym_lower_bound(keys, nnzb, (unsigned long long)r * n_f);
+}
+__global__ void sym_slots_kernel(int n_f, int nnzb, const unsigned long long* __restrict__ keys, int32_t* __restrict__ col,
+                                 int32_t* __restrict__ slot_row, int32_t* __restrict__ src, int32_t* __restrict__ diag_slot) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl >= nnzb) return;
+  const unsigned long long key = keys[sl];
+  const int r = (int)(key / n_f), c = (int)(key % n_f);
+  col[sl] = c;
+  slot_row[sl] = r;
+  if (c == r) diag_slot[r] = sl;
+  // an upper block takes its values from the transpose partner, the slot of (c, r)
+  src[sl] = c <= r ? sl : sym_lower_bound(keys, nnzb, (unsigned long long)c * n_f + r);
+}
+// one contiguous block-row range per CTA, balanced by block count
+__global__ void sym_cta_rows_kernel(int G, int n_f, int nnzb, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ cta_row) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > G) return;
+  if (c == 0) { cta_row[0] = 0; return; }
+  if (c == G) { cta_row[G] = n_f; return; }
+  const long long target = (long long)nnzb * c / G;
+  int lo = 0, hi = n_f;  // number of rows r with row_ptr[r + 1] <= target
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (row_ptr[mid + 1] <= target) lo = mid + 1; else hi = mid;
+  }
+  cta_row[c] = lo;
+}
+__device__ __forceinline__ int sym_cta_of_row(const int32_t* __restrict__ cta_row, int G, int r) {
+  int lo = 0, hi = G;  // last c with cta_row[c] <= r
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (cta_row[mid] <= r) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void sym_halo_keys_kernel(int nnzb, int n_f, int G, const int32_t* __restrict__ cta_row, const int32_t* __restrict__ slot_row,
+                                     const int32_t* __restrict__ col, unsigned long long* __restrict__ hkeys) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl >= nnzb) return;
+  hkeys[sl] = (unsigned long long)sym_cta_of_row(cta_row, G, slot_row[sl]) * n_f + col[sl];
+}
+__global__ void sym_halo_kernel(int n_halo, int n_f, int G, const unsigned long long* __restrict__ hkeys, int32_t* __restrict__ halo_col,
+                                int32_t* __restrict__ halo_ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_halo) halo_col[i] = (int32_t)(hkeys[i] % n_f);
+  if (i <= G) halo_ptr[i] = sym_lower_bound(hkeys, n_halo, (unsigned long long)i * n_f);
+}
+__global__ void sym_lcol_kernel(int nnzb, int n_halo, int n_f, int G, const int32_t* __restrict__ cta_row, const int32_t* __restrict__ slot_row,
+                                const int32_t* __restrict__ col, const unsigned long long* __restrict__ hkeys,
+                                const int32_t* __restrict__ halo_ptr, uint16_t* __restrict__ lcol) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl >= nnzb) return;
+  const int c = sym_cta_of_row(cta_row, G, slot_row[sl]);
+  lcol[sl] = (uint16_t)(sym_lower_bound(hkeys, n_halo, (unsigned long long)c * n_f + col[sl]) - halo_ptr[c]);
+}
+// out: max halo size, max slots, max rows over the CTAs (single CTA)
+__global__ void sym_maxima_kernel(int G, const int32_t* __restrict__ cta_row, const int32_t* __restrict__ halo_ptr,
+                                  const int32_t* __restrict__ row_ptr, int32_t* __restrict__ out) {
+  __shared__ int m[3];
+  if (threadIdx.x < 3) m[threadIdx.x] = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < G; c += blockDim.x) {
+    atomicMax(&m[0], halo_ptr[c + 1] - halo_ptr[c]);
+    atomicMax(&m[1], row_ptr[cta_row[c + 1]] - row_ptr[cta_row[c]]);
+    atomicMax(&m[2], cta_row[c + 1] - cta_row[c]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) out[threadIdx.x] = m[threadIdx.x];
 }
 
-inline int pcg_symbolic(PcgWorkspace& ws, const std::vector<uint64_t>& keys, int n_e, int n_f, const int32_t* e_off,
-                        cudaStream_t st, std::string& err, int n_sm, size_t smem_limit) {
-  ws.release();
-  const int nnzb = (int)keys.size();
-  std::vector<int32_t> row_ptr(n_f + 1, 0), col(nnzb), src(nnzb);
-  for (int s = 0; s < nnzb; ++s) {
-    row_ptr[(keys[s] >> 32) + 1]++;
-    col[s] = (int32_t)(keys[s] & 0xffffffffu);
-  }
-  for (int f = 0; f < n_f; ++f) row_ptr[f + 1] += row_ptr[f];
-  for (int r = 0; r < n_f; ++r)
-    for (int s = row_ptr[r]; s < row_ptr[r + 1]; ++s) {
-      const int c = col[s];
-      if (c <= r) { src[s] = s; continue; }
-      // transpose partner: slot of (c, r)
-      const int32_t* b = col.data() + row_ptr[c];
-      const int32_t* e = col.data() + row_ptr[c + 1];
-      const int32_t* it = std::lower_bound(b, e, r);
-      src[s] = (int32_t)(it - col.data());
-    }
-  ws.n_f = n_f;
-  ws.nnzb = nnzb;
-  std::vector<int32_t> pair_off(std::max(e_off[n_e], 1));
-  {
-    long long acc = 0;
-    for (int e = 0; e < n_e; ++e) {
-      const int k = e_off[e + 1] - e_off[e];
-      for (int b = e_off[e]; b < e_off[e + 1]; ++b) { pair_off[b] = (int32_t)acc; acc += schur_pairs_of(b - e_off[e], k); }
-    }
-    ws.n_pairs = acc;
-  }
-  const size_t nvec = (size_t)6 * n_f + 2;
+inline int sym_key_bits(int n_f) {
+  unsigned long long top = (unsigned long long)n_f * (unsigned long long)n_f;  // also the padding sentinel
+  int bits = 1;
+  while (bits < 64 && (top >> bits)) ++bits;
+  return bits;
+}
+// sorts keys[0..n) (ws.keys[0] -> de-duplicated into ws.keys[0] again); returns the count in *n_out
+inline cudaError_t pcg_sort_unique(PcgWorkspace& ws, int n, int bits, cudaStream_t st, int* n_out) {
+  cudaError_t ce;
+  size_t t1 = 0, t2 = 0;
+  if ((ce = cub::DeviceRadixSort::SortKeys(nullptr, t1, ws.keys[0].p, ws.keys[1].p, n, 0, bits, st)) != cudaSuccess) return ce;
+  if ((ce = cub::DeviceSelect::Unique(nullptr, t2, ws.keys[1].p, ws.keys[0].p, ws.counts.p, n, st)) != cudaSuccess) return ce;
+  if ((ce = ws.tmp.ensure(std::max(t1, t2))) != cudaSuccess) return ce;
+  t1 = t2 = ws.tmp.cap;
+  if ((ce = cub::DeviceRadixSort::SortKeys(ws.tmp.p, t1, ws.keys[0].p, ws.keys[1].p, n, 0, bits, st)) != cudaSuccess) return ce;
+  if ((ce = cub::DeviceSelect::Unique(ws.tmp.p, t2, ws.keys[1].p, ws.keys[0].p, ws.counts.p, n, st)) != cudaSuccess) return ce;
+  if ((ce = cudaMemcpyAsync(ws.h_counts, ws.counts.p, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return ce;
+  if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return ce;
+  *n_out = ws.h_counts[0];
+  return cudaSuccess;
+}
+
+// phase 1: the sorted unique keys of this rank's blocks -> ws.keys[0][0 .. ws.nnzb), and pair_off
+inline int pcg_symbolic_keys(PcgWorkspace& ws, int n_e, int n_f, int n_blk, const int32_t* e_idx, const int32_t* e_off,
+                             const int32_t* f_idx, cudaStream_t st, std::string& err) {
+  (void)n_e;
+  ws.valid = false;
   cudaError_t ce = cudaSuccess;
-  auto A = [&](void** p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, bytes); };
-  A((void**)&ws.row_ptr, sizeof(int32_t) * (n_f + 1));
-  A((void**)&ws.col_idx, sizeof(int32_t) * nnzb);
-  A((void**)&ws.src_slot, sizeof(int32_t) * nnzb);
-  A((void**)&ws.Sfin, sizeof(double) * 36 * nnzb);
-  A((void**)&ws.Minv, sizeof(double) * 36 * n_f);
-  A((void**)&ws.vec, sizeof(double) * 8 * nvec);
-  A((void**)&ws.partial, sizeof(double) * 8 * 4096);
-  A((void**)&ws.scal, sizeof(double) * 16);
+#define PCG_TRY(x) do { if (ce == cudaSuccess) ce = (x); } while (0)
+  if (!ws.h_counts) PCG_TRY(cudaMallocHost((void**)&ws.h_counts, 8 * sizeof(long long)));
+  PCG_TRY(ws.cnt_keys.ensure((size_t)n_blk + 1)); PCG_TRY(ws.cnt_pairs.ensure((size_t)n_blk + 1));
+  PCG_TRY(ws.off_keys.ensure((size_t)n_blk + 1)); PCG_TRY(ws.off_pairs.ensure((size_t)n_blk + 1));
+  PCG_TRY(ws.counts.ensure(8));
+  if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+  sym_counts_kernel<<<(n_blk + 256) / 256, 256, 0, st>>>(n_blk, e_idx, e_off, ws.cnt_keys.p, ws.cnt_pairs.p);
+  size_t t1 = 0;
+  PCG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t1, ws.cnt_keys.p, ws.off_keys.p, n_blk + 1, st));
+  PCG_TRY(ws.tmp.ensure(t1));
+  t1 = ws.tmp.cap;
+  PCG_TRY(cub::DeviceScan::ExclusiveSum(ws.tmp.p, t1, ws.cnt_keys.p, ws.off_keys.p, n_blk + 1, st));
+  t1 = ws.tmp.cap;
+  PCG_TRY(cub::DeviceScan::ExclusiveSum(ws.tmp.p, t1, ws.cnt_pairs.p, ws.off_pairs.p, n_blk + 1, st));
+  long long* hc = reinterpret_cast<long long*>(ws.h_counts);
+  PCG_TRY(cudaMemcpyAsync(hc, ws.off_keys.p + n_blk, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  PCG_TRY(cudaMemcpyAsync(hc + 1, ws.off_pairs.p + n_blk, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  PCG_TRY(cudaStreamSynchronize(st));
+  if (ce != cudaSuccess) { err = std::string("pcg symbolic (counts): ") + cudaGetErrorString(ce); return -2; }
+  const long long n_keys = hc[0] + n_f;
+  ws.n_pairs = hc[1];
+  if (n_keys >= (1LL << 31)) { err = "pcg symbolic: more than 2^31 block pairs"; return -2; }
+  PCG_TRY(ws.keys[0].ensure((size_t)n_keys)); PCG_TRY(ws.keys[1].ensure((size_t)n_keys));
   if (ws.n_pairs < (1LL << 31)) {
-    A((void**)&ws.pair_off, sizeof(int32_t) * pair_off.size());
-    A((void**)&ws.pair_slot, sizeof(int32_t) * std::max<long long>(ws.n_pairs, 1));
+    PCG_TRY(ws.b_pair_off.ensure((size_t)n_blk + 1)); PCG_TRY(ws.b_pair_slot.ensure((size_t)std::max<long long>(ws.n_pairs, 1)));
+    if (ce == cudaSuccess) sym_narrow_kernel<<<(n_blk + 255) / 256, 256, 0, st>>>(n_blk, ws.off_pairs.p, ws.b_pair_off.p);
+    ws.pair_off = ws.b_pair_off.p; ws.pair_slot = ws.b_pair_slot.p;
+  } else {
+    ws.pair_off = nullptr; ws.pair_slot = nullptr;
   }
   if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
-  cudaMemcpyAsync(ws.row_ptr, row_ptr.data(), sizeof(int32_t) * (n_f + 1), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(ws.col_idx, col.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(ws.src_slot, src.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice, st);
-  if (ws.pair_off) cudaMemcpyAsync(ws.pair_off, pair_off.data(), sizeof(int32_t) * pair_off.size(), cudaMemcpyHostToDevice, st);
-  ce = cudaStreamSynchronize(st);
-  if (ce != cudaSuccess) { err = std::string("pcg symbolic upload: ") + cudaGetErrorString(ce); return -2; }
-  // ---- one contiguous block-row range per SM, balanced by block count; the CTA keeps its
-  // slice of the matrix in shared memory for the whole solve (33 MB of SMEM across 148 SMs)
+  sym_emit_keys_kernel<<<(std::max(n_blk, n_f) + 255) / 256, 256, 0, st>>>(n_blk, n_f, e_idx, e_off, f_idx, ws.off_keys.p, ws.keys[0].p);
+  int nn = 0;
+  PCG_TRY(pcg_sort_unique(ws, (int)n_keys, sym_key_bits(n_f), st, &nn));
+  if (ce != cudaSuccess) { err = std::string("pcg symbolic (sort): ") + cudaGetErrorString(ce); return -2; }
+  ws.n_f = n_f;
+  ws.nnzb = nn;
+  return 0;
+}
+
+// phase 2: everything derived from the sorted keys ws.keys[0][0 .. ws.nnzb)
+inline int pcg_symbolic_build(PcgWorkspace& ws, cudaStream_t st, std::string& err, int n_sm, size_t smem_limit) {
+  const int n_f = ws.n_f, nnzb = ws.nnzb, G = n_sm;
+  const size_t nvec = (size_t)6 * n_f + 2;
+  cudaError_t ce = cudaSuccess;
+  PCG_TRY(ws.b_row_ptr.ensure((size_t)n_f + 1)); PCG_TRY(ws.b_col_idx.ensure(nnzb)); PCG_TRY(ws.b_src_slot.ensure(nnzb));
+  PCG_TRY(ws.b_Sfin.ensure((size_t)36 * nnzb)); PCG_TRY(ws.b_Minv.ensure((size_t)36 * n_f)); PCG_TRY(ws.b_vec.ensure(8 * nvec));
+  PCG_TRY(ws.b_partial.ensure(8 * 4096)); PCG_TRY(ws.b_scal.ensure(16));
+  PCG_TRY(ws.b_diag_slot.ensure(std::max(n_f, 1))); PCG_TRY(ws.b_slot_row.ensure(std::max(nnzb, 1)));
+  PCG_TRY(ws.b_cta_row.ensure((size_t)G + 1)); PCG_TRY(ws.b_halo_ptr.ensure((size_t)G + 1)); PCG_TRY(ws.b_lcol.ensure(std::max(nnzb, 1)));
+  if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+  ws.row_ptr = ws.b_row_ptr.p; ws.col_idx = ws.b_col_idx.p; ws.src_slot = ws.b_src_slot.p; ws.Sfin = ws.b_Sfin.p;
+  ws.Minv = ws.b_Minv.p; ws.vec = ws.b_vec.p; ws.partial = ws.b_partial.p; ws.scal = ws.b_scal.p;
+  ws.diag_slot = ws.b_diag_slot.p; ws.slot_row = ws.b_slot_row.p; ws.cta_row = ws.b_cta_row.p; ws.halo_ptr = ws.b_halo_ptr.p;
+  ws.lcol = ws.b_lcol.p;
+  const unsigned long long* keys = ws.keys[0].p;
+  sym_rows_kernel<<<(n_f + 256) / 256, 256, 0, st>>>(n_f, nnzb, keys, ws.row_ptr);
+  sym_slots_kernel<<<(nnzb + 255) / 256, 256, 0, st>>>(n_f, nnzb, keys, ws.col_idx, ws.slot_row, ws.src_slot, ws.diag_slot);
+  sym_cta_rows_kernel<<<(G + 256) / 256, 256, 0, st>>>(G, n_f, nnzb, ws.row_ptr, ws.cta_row);
+  // halo lists: distinct (CTA, column) pairs.  keys[0] still holds the pattern, so sort from a copy in keys[1]
+  // through the spare halves: hkeys live in ws.hkeys[0/1]
+  PCG_TRY(ws.hkeys[0].ensure(std::max(nnzb, 1))); PCG_TRY(ws.hkeys[1].ensure(std::max(nnzb, 1)));
+  if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+  sym_halo_keys_kernel<<<(nnzb + 255) / 256, 256, 0, st>>>(nnzb, n_f, G, ws.cta_row, ws.slot_row, ws.col_idx, ws.hkeys[0].p);
+  int n_halo = 0;
   {
-    const int G = n_sm;
-    std::vector<int32_t> cta_row(G + 1, n_f), halo_ptr(G + 1, 0), halo_col, diag(n_f, 0);
-    std::vector<uint16_t> lcol(nnzb, 0);
-    cta_row[0] = 0;
-    {
-      int r = 0;
-      for (int c = 0; c < G; ++c) {
-        const long long target = (long long)nnzb * (c + 1) / G;
-        while (r < n_f && row_ptr[r + 1] <= target) ++r;
-        if (c == G - 1) r = n_f;
-        cta_row[c + 1] = r;
-      }
-    }
-    int max_halo = 0, max_slots = 0, max_rows = 0;
-    std::vector<int32_t> tmp;
-    for (int c = 0; c < G; ++c) {
-      const int s0 = row_ptr[cta_row[c]], s1 = row_ptr[cta_row[c + 1]];
-      tmp.assign(col.begin() + s0, col.begin() + s1);
-      std::sort(tmp.begin(), tmp.end());
-      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      for (int sl = s0; sl < s1; ++sl)
-        lcol[sl] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), col[sl]) - tmp.begin());
-      halo_ptr[c + 1] = halo_ptr[c] + (int)tmp.size();
-      halo_col.insert(halo_col.end(), tmp.begin(), tmp.end());
-      max_halo = std::max(max_halo, (int)tmp.size());
-      max_slots = std::max(max_slots, s1 - s0);
-      max_rows = std::max(max_rows, cta_row[c + 1] - cta_row[c]);
-    }
-    for (int r = 0; r < n_f; ++r)
-      diag[r] = (int32_t)(std::lower_bound(col.begin() + row_ptr[r], col.begin() + row_ptr[r + 1], r) - col.begin());
-    {
-      std::vector<int32_t> srow(nnzb);
-      for (int r = 0; r < n_f; ++r)
-        for (int sl = row_ptr[r]; sl < row_ptr[r + 1]; ++sl) srow[sl] = r;
-      if (ce == cudaSuccess) ce = cudaMalloc((void**)&ws.diag_slot, sizeof(int32_t) * std::max(n_f, 1));
-      if (ce == cudaSuccess) ce = cudaMalloc((void**)&ws.slot_row, sizeof(int32_t) * std::max(nnzb, 1));
-      if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
-      cudaMemcpyAsync(ws.diag_slot, diag.data(), sizeof(int32_t) * n_f, cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(ws.slot_row, srow.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice, st);
-      ce = cudaStreamSynchronize(st);
-      if (ce != cudaSuccess) { err = std::string("pcg symbolic upload: ") + cudaGetErrorString(ce); return -2; }
-    }
-    ws.smem_grid = G;
-    ws.max_halo = max_halo;
-    ws.max_slots = max_slots;
-    ws.max_rows = max_rows;
-    // dynamic shared memory: matrix slice | gathered halo vector | local column ids
-    const size_t fixed = (size_t)max_halo * 48 + (size_t)max_rows * (36 + 6) * 8 + ((size_t)max_halo + max_rows + 4) * 4 +
-                         (((size_t)max_slots * 2 + 15) / 16) * 16 + 2048;
-    ws.smem_ok = max_halo < 65535 && max_rows <= 64 && smem_limit > fixed + 288 * 16;
-    if (ws.smem_ok) {
-      ws.cap_slots = (int)std::min<size_t>((smem_limit - fixed) / 288, (size_t)max_slots);
-      ws.smem_bytes = (size_t)ws.cap_slots * 288 + fixed - 2048;
-      auto A2 = [&](void** p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
-      A2((void**)&ws.cta_row, sizeof(int32_t) * (G + 1));
-      A2((void**)&ws.halo_ptr, sizeof(int32_t) * (G + 1));
-      A2((void**)&ws.halo_col, sizeof(int32_t) * halo_col.size());
-      A2((void**)&ws.lcol, sizeof(uint16_t) * nnzb);
-      if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
-      cudaMemcpyAsync(ws.cta_row, cta_row.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(ws.halo_ptr, halo_ptr.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(ws.halo_col, halo_col.data(), sizeof(int32_t) * halo_col.size(), cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(ws.lcol, lcol.data(), sizeof(uint16_t) * nnzb, cudaMemcpyHostToDevice, st);
-      ce = cudaStreamSynchronize(st);
-      if (ce != cudaSuccess) { err = std::string("pcg symbolic upload: ") + cudaGetErrorString(ce); return -2; }
-    }
+    unsigned long long top = (unsigned long long)(G + 1) * (unsigned long long)n_f;
+    int bits = 1;
+    while (bits < 64 && (top >> bits)) ++bits;
+    size_t t1 = 0, t2 = 0;
+    PCG_TRY(cub::DeviceRadixSort::SortKeys(nullptr, t1, ws.hkeys[0].p, ws.hkeys[1].p, nnzb, 0, bits, st));
+    PCG_TRY(cub::DeviceSelect::Unique(nullptr, t2, ws.hkeys[1].p, ws.hkeys[0].p, ws.counts.p, nnzb, st));
+    PCG_TRY(ws.tmp.ensure(std::max(t1, t2)));
+    t1 = t2 = ws.tmp.cap;
+    PCG_TRY(cub::DeviceRadixSort::SortKeys(ws.tmp.p, t1, ws.hkeys[0].p, ws.hkeys[1].p, nnzb, 0, bits, st));
+    PCG_TRY(cub::DeviceSelect::Unique(ws.tmp.p, t2, ws.hkeys[1].p, ws.hkeys[0].p, ws.counts.p, nnzb, st));
+    PCG_TRY(cudaMemcpyAsync(ws.h_counts, ws.counts.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCG_TRY(cudaStreamSynchronize(st));
+    if (ce != cudaSuccess) { err = std::string("pcg symbolic (halo): ") + cudaGetErrorString(ce); return -2; }
+    n_halo = ws.h_counts[0];
+  }
+  PCG_TRY(ws.b_halo_col.ensure(std::max(n_halo, 1)));
+  if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+  ws.halo_col = ws.b_halo_col.p;
+  sym_halo_kernel<<<(std::max(n_halo, G + 1) + 255) / 256, 256, 0, st>>>(n_halo, n_f, G, ws.hkeys[0].p, ws.halo_col, ws.halo_ptr);
+  sym_lcol_kernel<<<(nnzb + 255) / 256, 256, 0, st>>>(nnzb, n_halo, n_f, G, ws.cta_row, ws.slot_row, ws.col_idx, ws.hkeys[0].p,
+                                                      ws.halo_ptr, ws.lcol);
+  sym_maxima_kernel<<<1, 256, 0, st>>>(G, ws.cta_row, ws.halo_ptr, ws.row_ptr, ws.counts.p + 1);
+  PCG_TRY(cudaMemcpyAsync(ws.h_counts + 1, ws.counts.p + 1, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  PCG_TRY(cudaStreamSynchronize(st));
+  if (ce != cudaSuccess) { err = std::string("pcg symbolic (layout): ") + cudaGetErrorString(ce); return -2; }
+#undef PCG_TRY
+  const int max_halo = ws.h_counts[1], max_slots = ws.h_counts[2], max_rows = ws.h_counts[3];
+  ws.smem_grid = G;
+  ws.max_halo = max_halo;
+  ws.max_slots = max_slots;
+  ws.max_rows = max_rows;
+  // dynamic shared memory: matrix slice | gathered halo vector | local column ids
+  const size_t fixed = (size_t)max_halo * 48 + (size_t)max_rows * (36 + 6) * 8 + ((size_t)max_halo + max_rows + 4) * 4 +
+                       (((size_t)max_slots * 2 + 15) / 16) * 16 + 2048;
+  ws.smem_ok = max_halo < 65535 && max_rows <= 64 && smem_limit > fixed + 288 * 16;
+  if (ws.smem_ok) {
+    ws.cap_slots = (int)std::min<size_t>((smem_limit - fixed) / 288, (size_t)max_slots);
+    ws.smem_bytes = (size_t)ws.cap_slots * 288 + fixed - 2048;
   }
   ws.valid = true;
   return 0;

@@ -429,8 +429,9 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
     chol6_solve(L, t);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      double ybu = 0.0;
-      for (int q = 0; q < a.nk; ++q) ybu += a.sa.YB[6 * a.nk * (size_t)e + 6 * q + i] * a.uF[a.cam_row + q];
+      double ybu = a.sa.YB[6 * a.nk * (size_t)e + i] * a.uF[a.cam_row];
+      if (a.nk == 3)
+        ybu += a.sa.YB[18 * (size_t)e + 6 + i] * a.uF[a.cam_row + 1] + a.sa.YB[18 * (size_t)e + 12 + i] * a.uF[a.cam_row + 2];
       de[i] = -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - ybu);
     }
   }
