@@ -165,8 +165,14 @@ class Solver:
             raise ValueError("parameter array sizes do not match the problem")
         self._check(self._lib.arslam_set_params(self._h, _p(cam), _p(cap), _p(tag)))
 
-    def get_params(self):
-        cam, cap, tag = np.zeros(3), np.zeros((self.n_cap, 6)), np.zeros((self.n_tag, 6))
+    def get_params(self, out=None):
+        """(camera3, cap_pose [n_cap, 6], tag_pose [n_tag, 6]); out = caller-owned (cap, tag) arrays, e.g. pinned.
+        In a multi-GPU solve only the rank's own capture range of cap_pose is written."""
+        cam = np.zeros(3)
+        cap, tag = out if out is not None else (np.zeros((self.n_cap, 6)), np.zeros((self.n_tag, 6)))
+        if cap.shape != (self.n_cap, 6) or tag.shape != (self.n_tag, 6) or cap.dtype != np.float64 or tag.dtype != np.float64 \
+                or not cap.flags.c_contiguous or not tag.flags.c_contiguous:
+            raise ValueError("out = (cap [n_cap, 6] f64, tag [n_tag, 6] f64), C-contiguous")
         self._check(self._lib.arslam_get_params(self._h, _p(cam), _p(cap), _p(tag)))
         return cam, cap, tag
 

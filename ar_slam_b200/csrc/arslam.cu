@@ -128,6 +128,10 @@ __global__ void make_sort_keys_kernel(int n, const int32_t* __restrict__ own, co
   keys[b] = ((unsigned long long)(unsigned)own[b] << 32) | (unsigned)oth[b];
   vals[b] = b;
 }
+__global__ void shift_index_kernel(int n, int32_t* idx, int32_t by) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n) idx[b] += by;
+}
 // sorted position p takes block perm[p]: indices and the 8 observation planes
 __global__ void gather_sorted_kernel(int n, int plane, const int32_t* __restrict__ perm,
                                      const unsigned long long* __restrict__ keys, const double* __restrict__ rect8,
@@ -171,7 +175,9 @@ struct arslam_solver {
   // problem
   int n_cap = 0, n_tag = 0, n_blk = 0, plane = 0, n_warp = 0;
   bool have_problem = false, have_params = false;
-  std::vector<double> h_cam, h_cap, h_tag;  // host mirror of the parameters
+  std::vector<double> h_cam;  // host mirror of the camera (poses stay on the device between calls)
+  // multi-GPU: captures are re-indexed to the rank's own range [cap_lo, cap_lo + n_cap) of the n_cap_global captures
+  int cap_lo = 0, n_cap_global = 0;
   // original order (evaluate API)
   DevBuf<int32_t> o_cap, o_tag;
   DevBuf<double> o_obs;
@@ -368,6 +374,16 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
       return s->fail(ARSLAM_ERR_INVALID, "set_problem: block %lld has an index out of range", (long long)b);
   CU(cudaSetDevice(s->device));
   s->have_problem = false;
+  s->have_params = false;
+  s->cap_lo = 0;
+  s->n_cap_global = (int)n_cap;
+  if (s->world > 1) {
+    // a rank only ever touches the captures of its own blocks: work on that index range alone
+    int32_t lo = cap_idx[0], hi = cap_idx[0];
+    for (int64_t b = 1; b < n_blk; ++b) { lo = std::min(lo, cap_idx[b]); hi = std::max(hi, cap_idx[b]); }
+    s->cap_lo = lo;
+    n_cap = (int64_t)hi - lo + 1;
+  }
   s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk = (int)n_blk;
   s->plane = ((int)n_blk + 31) / 32 * 32;
   s->n_warp = s->plane / 32;
@@ -376,6 +392,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   CU(cudaMemcpyAsync(s->o_cap.p, cap_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
+  if (s->cap_lo) shift_index_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, s->o_cap.p, -s->cap_lo);
   // both sorted copies are built on the GPU from the one upload above: stable radix sort of
   // (own << 32 | other) keys, then one gather kernel writes the index arrays and the 8 planes
   CU(s->sort_keys[0].ensure(nb)); CU(s->sort_keys[1].ensure(nb)); CU(s->sort_vals[0].ensure(nb)); CU(s->sort_vals[1].ensure(nb));
@@ -418,9 +435,17 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
 int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6, const double* tag_pose6) {
   if (!s || !camera3 || !cap_pose6 || !tag_pose6) return ARSLAM_ERR_INVALID;
   if (!s->have_problem) return s->fail(ARSLAM_ERR_INVALID, "set_params before set_problem");
+  CU(cudaSetDevice(s->device));
   s->h_cam.assign(camera3, camera3 + 3);
-  s->h_cap.assign(cap_pose6, cap_pose6 + (size_t)6 * s->n_cap);
-  s->h_tag.assign(tag_pose6, tag_pose6 + (size_t)6 * s->n_tag);
+  // straight from the caller's arrays into parameter set 0 (DMA when they are pinned); in a
+  // multi-GPU solve only the rank's own capture range is moved
+  double* cam4 = s->h_sc + 200;  // pinned staging
+  cam4[0] = camera3[0]; cam4[1] = camera3[1]; cam4[2] = camera3[2]; cam4[3] = 0.0;
+  CU(cudaMemcpyAsync(s->cam[0].p, cam4, 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->cap[0].p, cap_pose6 + (size_t)6 * s->cap_lo, sizeof(double) * 6 * s->n_cap, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->tag[0].p, tag_pose6, sizeof(double) * 6 * s->n_tag, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));  // the caller may reuse its arrays
+  s->cur = 0;
   s->have_params = true;
   return ARSLAM_OK;
 }
@@ -428,18 +453,13 @@ int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap
 int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, double* tag_pose6) {
   if (!s) return ARSLAM_ERR_INVALID;
   if (!s->have_params) return s->fail(ARSLAM_ERR_INVALID, "get_params before set_params");
+  CU(cudaSetDevice(s->device));
+  const int k = s->cur;
   if (camera3) std::memcpy(camera3, s->h_cam.data(), 3 * sizeof(double));
-  if (cap_pose6) std::memcpy(cap_pose6, s->h_cap.data(), sizeof(double) * 6 * s->n_cap);
-  if (tag_pose6) std::memcpy(tag_pose6, s->h_tag.data(), sizeof(double) * 6 * s->n_tag);
-  return ARSLAM_OK;
-}
-
-static int upload_params(arslam_solver* s, int k) {
-  double cam4[4] = {s->h_cam[0], s->h_cam[1], s->h_cam[2], 0.0};
-  CU(cudaMemcpyAsync(s->cam[k].p, cam4, sizeof(cam4), cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(s->cap[k].p, s->h_cap.data(), sizeof(double) * 6 * s->n_cap, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(s->tag[k].p, s->h_tag.data(), sizeof(double) * 6 * s->n_tag, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaStreamSynchronize(s->stream));  // cam4 is on the stack
+  if (cap_pose6)
+    CU(cudaMemcpyAsync(cap_pose6 + (size_t)6 * s->cap_lo, s->cap[k].p, sizeof(double) * 6 * s->n_cap, cudaMemcpyDeviceToHost, s->stream));
+  if (tag_pose6) CU(cudaMemcpyAsync(tag_pose6, s->tag[k].p, sizeof(double) * 6 * s->n_tag, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
   return ARSLAM_OK;
 }
 
@@ -458,9 +478,8 @@ int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* j
   s->prof.clear();
   const int nb = s->n_blk, nc = 4 * nb;
   const int nwarp = cdiv(nc, 256) * 8;
-  int rc = upload_params(s, 0);
-  if (rc) return rc;
-  launch_prep(s, 0);
+  const int kp = s->cur;
+  launch_prep(s, kp);
   // outputs live in one scratch allocation: res 8 | jc 24 | jp 48 | ja 48 per block, then warp costs
   const size_t per_blk = 8 + 24 + 48 + 48;
   CU(s->eval_out.ensure(per_blk * nb + nwarp + 8));
@@ -475,14 +494,14 @@ int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* j
   if (dist)
     LAUNCH("eval_jacobian", (want_j ? 274.0 : 34.0) * nc,
            eval_jacobian_kernel<1><<<cdiv(nc, 256), 256, 0, s->stream>>>(
-               nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
-               s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
+               nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[kp].p, s->tag_pre[kp].p,
+               s->cam[kp].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
                want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
   else
     LAUNCH("eval_jacobian", (want_j ? 274.0 : 34.0) * nc,
            eval_jacobian_kernel<0><<<cdiv(nc, 256), 256, 0, s->stream>>>(
-               nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[0].p, s->tag_pre[0].p,
-               s->cam[0].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
+               nc, s->o_cap.p, s->o_tag.p, reinterpret_cast<const double2*>(s->o_obs.p), s->cap_pre[kp].p, s->tag_pre[kp].p,
+               s->cam[kp].p, reinterpret_cast<double2*>(d_res), want_j ? reinterpret_cast<double2*>(d_jc) : nullptr,
                want_j ? reinterpret_cast<double2*>(d_jp) : nullptr, want_j ? reinterpret_cast<double2*>(d_ja) : nullptr, d_wc));
   launch_colsum(s, nwarp, 1, d_wc, d_cost);
   CU(cudaGetLastError());
@@ -526,10 +545,6 @@ __global__ void small_unpack_kernel(double* sc, const double* buf, int world) {
     sc[16] = m;
   }
 }
-__global__ void axpy_kernel(int n, const double* a, const double* b, double sign, double* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = a[i] + sign * b[i];
-}
 
 int nccl_sum(arslam_solver* s, double* buf, size_t count) {
   Profiler::Rec r{0, nullptr, nullptr};
@@ -553,19 +568,6 @@ int small_allreduce(arslam_solver* s, double* sc) {
   int rc = nccl_sum(s, s->small.p, 8 + s->world);
   if (rc) return rc;
   LAUNCH("small_unpack", 128.0, small_unpack_kernel<<<1, 32, 0, s->stream>>>(sc, s->small.p, s->world));
-  return ARSLAM_OK;
-}
-
-// every capture is moved by exactly one rank: pose = initial + sum over ranks (pose_r - initial)
-int gather_captures(arslam_solver* s, int k) {
-  const int n = 6 * s->n_cap;
-  double* init = s->d_pose[0].p;
-  double* diff = s->cap[1 - k].p;
-  CU(cudaMemcpyAsync(init, s->h_cap.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-  LAUNCH("axpy", 24.0 * n, axpy_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->cap[k].p, init, -1.0, diff));
-  int rc = nccl_sum(s, diff, n);
-  if (rc) return rc;
-  LAUNCH("axpy", 24.0 * n, axpy_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, init, diff, 1.0, s->cap[k].p));
   return ARSLAM_OK;
 }
 
@@ -892,11 +894,9 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   double* sc = s->sc.p;
   CU(cudaMemsetAsync(sc, 0, kNumScalars * sizeof(double), s->stream));
 
-  int rc = upload_params(s, 0);
-  if (rc) return rc;
-  s->cur = 0;
-  launch_prep(s, 0);
-  launch_accumulate(s, sd, 0, HF, HFx, sc_head);
+  int rc = ARSLAM_OK;
+  launch_prep(s, s->cur);
+  launch_accumulate(s, sd, s->cur, HF, HFx, sc_head);
 
   double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
   bool have_sigma = false, last_successful = true, fresh_linearisation = true, pending_acc = false;
@@ -1155,12 +1155,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     const int k = s->cur;
     CU(cudaMemcpyAsync(s->h_sc + 32, s->cam[k].p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemcpyAsync(s->h_sc + 48, sc_head, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (s->world > 1) {
-      rc = gather_captures(s, k);
-      if (rc) return rc;
-    }
-    CU(cudaMemcpyAsync(s->h_cap.data(), s->cap[k].p, sizeof(double) * 6 * s->n_cap, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(s->h_tag.data(), s->tag[k].p, sizeof(double) * 6 * s->n_tag, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     s->h_cam[0] = s->h_sc[32];
@@ -1266,6 +1260,8 @@ int arslam_comm_init(arslam_solver* s, int rank, int world_size, const void* id1
   int rc = init(&s->comm, world_size, id, rank);
   if (rc != 0) return s->fail(ARSLAM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   s->rank = rank;
+  s->have_problem = false;  // blocks must be (re)declared after the communicator exists: ranks re-index their captures
+  s->have_params = false;
   s->world = world_size;
   return ARSLAM_OK;
 }

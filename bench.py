@@ -258,7 +258,8 @@ def main():
     ap.add_argument("--cpu-sample-captures", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
+                    help="weak: every GPU gets the workload's captures (the map, i.e. the tags, is shared); strong: the workload is split")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -134,7 +134,14 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
 
 /* Parameter blocks live in the caller's Capture::inv_pose / Aruco::pose /
  * camera_.params (ar_slam_util.hpp:72,208,237); Ceres updated them in place
- * through raw pointers, here they are copied in before and out after. */
+ * through raw pointers, here they are copied in before and out after, straight
+ * between the caller's arrays and HBM (DMA when the arrays are pinned; both
+ * calls return after the copy has completed).  All arrays are indexed by the
+ * global capture / tag index.  Under arslam_comm_init a rank reads and writes
+ * only the captures of its own blocks -- the index range [min, max] of its
+ * cap_idx; the rest of cap_pose6 is neither read nor written -- so ranks that
+ * own disjoint capture ranges can share one output array or gather the
+ * ranges themselves.  Camera and tag poses are replicated on every rank. */
 int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6,
                       const double* tag_pose6);
 int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, double* tag_pose6);
@@ -172,7 +179,8 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
 /* Multi-GPU (new; the reference is single-threaded): one process per GPU.
  * Rank 0 calls arslam_comm_unique_id, ships the 128 bytes to the other ranks
  * by any means (torch.distributed, MPI, a file), then every rank calls
- * arslam_comm_init.  Afterwards arslam_solve sums the per-rank partial normal
+ * arslam_comm_init (before arslam_set_problem: it invalidates a problem
+ * declared earlier).  Afterwards arslam_solve sums the per-rank partial normal
  * equations with one ncclAllReduce per linearisation over NVLink. */
 int arslam_comm_unique_id(void* id128);
 int arslam_comm_init(arslam_solver* s, int rank, int world_size, const void* id128);

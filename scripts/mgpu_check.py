@@ -34,8 +34,11 @@ for name, ls, (nc, nt) in (("dense", ar.LINSOLVE_DENSE, (3000, 400)), ("pcg", ar
     s.set_problem(m.n_cap, m.n_tag, ci, ti, ob)
     s.set_params(m.cam0, m.cap0, m.tag0)
     summ, log = s.solve()
-    cam, cap, tag = s.get_params()
+    cam, cap, tag = s.get_params()   # cap: only this rank's capture range is filled, zeros elsewhere
     s.close()
+    cap_all = torch.from_numpy(cap).cuda()
+    dist.all_reduce(cap_all)           # disjoint ranges: the sum is the union
+    cap = cap_all.cpu().numpy()
     if rank == 0:
         s1 = ar.Solver(device=local, options=opts)
         s1.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
