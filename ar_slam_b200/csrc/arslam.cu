@@ -940,7 +940,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       a.n_e = sd.n_e; a.plane = s->plane;
       a.e_off = s->s_off[sd.e].p; a.f_idx = s->s_oth[sd.e].p;
       a.HE = s->H[sd.e].p; a.HEx = dist ? s->Hx[sd.e].p : nullptr; a.W = s->W.p; a.sig_e = s->sigE.p;
-      a.radius = radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
+      a.radius = radius; a.inv_radius = 1.0 / radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
       a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr;
       schur_args = a;
       CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));

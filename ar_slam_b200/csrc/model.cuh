@@ -430,13 +430,16 @@ ARS_HD void seed_capture_pose(const double rect[8], double focal, const double t
 // overwrites the lower triangle of the same array, with the RECIPROCALS of the
 // pivots on the diagonal (the solves then need no division).  Returns false on
 // a non-positive pivot (Eigen::LLT's failure condition).
+// (All loops below have constant trip counts and compile-time predicates: loops whose bounds
+// depend on an outer index are not reliably unrolled, and then the 6x6 array lands in local memory.)
 ARS_HD bool chol6(double H[36]) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = H[j * 6 + j];
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= H[j * 6 + k] * H[j * 6 + k];
+    for (int k = 0; k < 6; ++k)
+      if (k < j) d -= H[j * 6 + k] * H[j * 6 + k];
     ok = ok && (d > 0.0);
 #if defined(__CUDA_ARCH__)
     const double il = rsqrt(d);
@@ -445,11 +448,14 @@ ARS_HD bool chol6(double H[36]) {
 #endif
     H[j * 6 + j] = il;
 #pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double s = H[i * 6 + j];
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double s = H[i * 6 + j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= H[i * 6 + k] * H[j * 6 + k];
-      H[i * 6 + j] = s * il;
+        for (int k = 0; k < 6; ++k)
+          if (k < j) s -= H[i * 6 + k] * H[j * 6 + k];
+        H[i * 6 + j] = s * il;
+      }
     }
   }
   return ok;
@@ -459,14 +465,17 @@ ARS_HD void chol6_solve(const double L[36], double b[6]) {
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
+    for (int k = 0; k < 6; ++k)
+      if (k < i) s -= L[i * 6 + k] * b[k];
     b[i] = s * L[i * 6 + i];
   }
 #pragma unroll
-  for (int i = 5; i >= 0; --i) {
+  for (int ii = 0; ii < 6; ++ii) {
+    const int i = 5 - ii;
     double s = b[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
+    for (int k = 0; k < 6; ++k)
+      if (k > i) s -= L[k * 6 + i] * b[k];
     b[i] = s * L[i * 6 + i];
   }
 }

@@ -25,7 +25,7 @@ struct SchurArgs {
   const double* HEx;      // [n_e][NVX] l1, l2 borders (radial model), else null
   const double* W;        // 36 planes
   const double* sig_e;    // [6 n_e]
-  double radius, min_diag, max_diag;
+  double radius, inv_radius, min_diag, max_diag;  // inv_radius = 1 / radius (host)
   double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
   double* YB;             // [n_e][6 NK]: Ht_ee^-1 sig_e H_e,intrinsic_q
   double* seg_cam;        // [n_e][12]: M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | 0 0
@@ -52,7 +52,7 @@ __device__ __forceinline__ void load_scaled_Ex(const SchurArgs& a, int e, const 
 __device__ __forceinline__ void load_scaled_E(const SchurArgs& a, int e, double L[36], double g[6],
                                               double hk[6], double s[6]) {
   const double* rec = a.HE + (size_t)e * NV;
-  const double radius = a.radius;
+  const double inv_radius = a.inv_radius;
 #pragma unroll
   for (int i = 0; i < 6; ++i) s[i] = a.sig_e[6 * (size_t)e + i];
 #pragma unroll
@@ -64,7 +64,7 @@ __device__ __forceinline__ void load_scaled_E(const SchurArgs& a, int e, double 
       L[j * 6 + i] = h;
     }
     const double d = fmin(fmax(L[i * 6 + i], a.min_diag), a.max_diag);
-    L[i * 6 + i] += d / radius;
+    L[i * 6 + i] += d * inv_radius;
     g[i] = rec[21 + i] * s[i];
     hk[i] = rec[27 + i] * s[i];
   }
@@ -102,16 +102,19 @@ __device__ __forceinline__ void chol6_forward(const double L[36], double b[6]) {
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
+    for (int k = 0; k < 6; ++k)
+      if (k < i) s -= L[i * 6 + k] * b[k];
     b[i] = s * L[i * 6 + i];
   }
 }
 __device__ __forceinline__ void chol6_backward(const double L[36], double b[6]) {
 #pragma unroll
-  for (int i = 5; i >= 0; --i) {
+  for (int ii = 0; ii < 6; ++ii) {
+    const int i = 5 - ii;
     double s = b[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
+    for (int k = 0; k < 6; ++k)
+      if (k > i) s -= L[k * 6 + i] * b[k];
     b[i] = s * L[i * 6 + i];
   }
 }
@@ -423,9 +426,11 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) t[i] = group_sum(t[i]);
   double de[6] = {0, 0, 0, 0, 0, 0};
+  double cross = 0.0;
   if (k > 0) {
+    double tr[6];  // sum_j W_j u_j, unscaled
 #pragma unroll
-    for (int i = 0; i < 6; ++i) t[i] *= s[i];
+    for (int i = 0; i < 6; ++i) { tr[i] = t[i]; t[i] *= s[i]; }
     chol6_solve(L, t);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -433,21 +438,10 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
       if (a.nk == 3)
         ybu += a.sa.YB[18 * (size_t)e + 6 + i] * a.uF[a.cam_row + 1] + a.sa.YB[18 * (size_t)e + 12 + i] * a.uF[a.cam_row + 2];
       de[i] = -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - ybu);
+      // cross term of the model cost change, -sum_j d_e^T W_j u_j = -d_e . (sum_j W_j u_j)
+      cross -= de[i] * tr[i];
     }
   }
-  double cross = 0.0;
-  for (int j = gl; j < k; j += kBsGroup) {
-    const int blk = beg + j;
-    const int f = a.sa.f_idx[blk];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      double w = 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) w += de[i] * a.sa.W[(size_t)(i * 6 + c) * ps + blk];
-      cross -= w * a.uF[6 * (size_t)f + c];
-    }
-  }
-  cross = group_sum(cross);
   if (valid && gl == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) a.d_e[6 * (size_t)e + i] = de[i];
