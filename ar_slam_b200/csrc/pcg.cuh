@@ -343,8 +343,8 @@ struct SparseTarget {
   double* borderm;  // [6 n_f]  sum W~^T yb
   double* rhsm;     // [6 n_f]  sum W~^T z
   __device__ __forceinline__ void add_border(int f, int c, double b0, double b1) const {
-    atomicAdd(borderm + 6 * (size_t)f + c, b0);
-    atomicAdd(rhsm + 6 * (size_t)f + c, b1);
+    red_add_f64(borderm + 6 * (size_t)f + c, b0);
+    red_add_f64(rhsm + 6 * (size_t)f + c, b1);
   }
   __device__ __forceinline__ void add_border_x(int, int, double, double) const {}  // radial model: dense solver only
   const int32_t* pair_slot;  // [n_pairs] precomputed slot of every (partner, block) pair, or null

@@ -31,6 +31,13 @@ struct SchurArgs {
   double* seg_cam;        // [n_e][12]: M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | 0 0
 };
 
+// FP64 add to global memory without a return value.  atomicAdd through a pointer whose address
+// space the compiler cannot prove (e.g. one that went through a shuffle) becomes a generic ATOM
+// that returns the old value; consecutive ones then serialise on the destination register.
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+
 // decode p -> (i <= j) with p = j (j + 1) / 2 + i
 __device__ __forceinline__ void tri_decode(int p, int& i, int& j) {
   j = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -77,12 +84,12 @@ struct DenseTarget {
   long long ld;
   int cam_row, rhs_row;
   __device__ __forceinline__ void add_border(int f, int c, double b0, double b1) const {
-    atomicAdd(S + (size_t)cam_row * ld + 6 * f + c, b0);
-    atomicAdd(S + (size_t)rhs_row * ld + 6 * f + c, b1);
+    red_add_f64(S + (size_t)cam_row * ld + 6 * f + c, b0);
+    red_add_f64(S + (size_t)rhs_row * ld + 6 * f + c, b1);
   }
   __device__ __forceinline__ void add_border_x(int f, int c, double bl1, double bl2) const {
-    atomicAdd(S + (size_t)(cam_row + 1) * ld + 6 * f + c, bl1);
-    atomicAdd(S + (size_t)(cam_row + 2) * ld + 6 * f + c, bl2);
+    red_add_f64(S + (size_t)(cam_row + 1) * ld + 6 * f + c, bl1);
+    red_add_f64(S + (size_t)(cam_row + 2) * ld + 6 * f + c, bl2);
   }
   // M[r][c] = element (6 fi + r, 6 fj + c), fi <= fj, of sum W~^T Y; stored in the lower triangle
   __device__ __forceinline__ double* block(int fi, int fj, long long /*pair*/) const { return S + (size_t)(6 * fj) * ld + 6 * fi; }
@@ -291,11 +298,11 @@ __global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const Sc
       for (int q = 0; q < 8; ++q) {
         const int src = base + q;
         double* dst = reinterpret_cast<double*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(blk), src));
-        if ((m >> src) & 1u) atomicAdd(t.elem(dst, lane), stage[wid][src][lane]);
+        if ((m >> src) & 1u) red_add_f64(t.elem(dst, lane), stage[wid][src][lane]);
       }
       const int src = base + (lane >> 2);
       double* dst = reinterpret_cast<double*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(blk), src));
-      if ((m >> src) & 1u) atomicAdd(t.elem(dst, 32 + (lane & 3)), stage[wid][src][32 + (lane & 3)]);
+      if ((m >> src) & 1u) red_add_f64(t.elem(dst, 32 + (lane & 3)), stage[wid][src][32 + (lane & 3)]);
     }
     __syncwarp();
   }
