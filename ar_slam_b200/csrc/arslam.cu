@@ -245,6 +245,24 @@ struct arslam_solver {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// main launch + the launch for the products whose partner sits in another CTA (schur.cuh)
+template <typename Target, int NK>
+void launch_schur(arslam_solver* s, const SchurArgs& a, const Target& t, const int32_t* e_idx, double bytes) {
+  const int grid = cdiv(s->n_blk, kSchurThreads);
+  LAUNCH("schur_eliminate", bytes, schur_eliminate_kernel<Target, NK, false><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+  LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+}
+template <typename Target, int NK>
+cudaError_t schur_kernel_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
+  // three CTAs of 75 KB per SM need the full shared-memory carve-out
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return e;
+}
+
+
+
 extern "C" {
 
 namespace { int launch_colsum(arslam_solver* s, int n, int m, const double* in, double* out); }
@@ -302,9 +320,8 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
   if (opt) s->opt = *opt; else arslam_default_options(&s->opt);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(&s->h_sc, 256 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
-      cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(schur_eliminate_kernel<DenseTarget, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(schur_eliminate_kernel<DenseTarget, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem) != cudaSuccess ||
+      schur_kernel_attributes<SparseTarget, 1>() != cudaSuccess || schur_kernel_attributes<DenseTarget, 1>() != cudaSuccess ||
+      schur_kernel_attributes<DenseTarget, 3>() != cudaSuccess ||
       pcg_init() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -648,8 +665,7 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   t.pair_slot = s->pcg.pair_slot;
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
-  LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb,
-         schur_eliminate_kernel<SparseTarget, 1><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a2, t, s->n_blk, e_idx));
+  launch_schur<SparseTarget, 1>(s, a2, t, e_idx, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb);
   return ARSLAM_OK;
 }
 
@@ -949,12 +965,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
-        if (dist)
-          LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
-                 schur_eliminate_kernel<DenseTarget, 3><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
-        else
-          LAUNCH("schur_eliminate", (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e,
-                 schur_eliminate_kernel<DenseTarget, 1><<<cdiv(s->n_blk, kSchurThreads), kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, s->s_own[sd.e].p));
+        if (dist) launch_schur<DenseTarget, 3>(s, a, t, s->s_own[sd.e].p, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e);
+        else launch_schur<DenseTarget, 1>(s, a, t, s->s_own[sd.e].p, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e);
       } else {
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;

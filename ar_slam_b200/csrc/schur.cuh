@@ -133,165 +133,180 @@ constexpr size_t kSchurSmem = (size_t)(kSchurThreads * 37 + 4 * 32 * 37) * sizeo
 // segment is sum_ij V_i^T V_j, V_j = L^-1 (sig_e W_j).  Thread j
 //   * rebuilds the segment's damped 6x6 block and factors it in registers (batched 6x6
 //     Cholesky; the redundancy inside a segment is cheaper than broadcasting 21 + 12 doubles),
-//   * computes V_j with coalesced plane loads and publishes it in shared memory,
+//   * computes V_j (its 36 W loads are issued before the factorisation) and publishes it in
+//     shared memory,
 //   * forms its share of the k (k + 1) / 2 products V_a^T V_b -- partners (j + d) mod k, so
-//     every lane of the segment carries the same load -- stages each 6x6 result in shared
-//     memory, and the warp adds it to the reduced system with one FP64 atomic per lane on
-//     consecutive addresses (coalesced reductions at L2).
-template <typename Target, int NK>
-__global__ void __launch_bounds__(kSchurThreads) schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk,
-                                                                        const int32_t* __restrict__ e_idx) {
+//     every lane of the segment carries the same load -- reading the partner's V from shared
+//     memory, stages each 6x6 result in shared memory, and the warp adds it to the reduced
+//     system with one FP64 reduction per lane on consecutive addresses (coalesced at L2).
+// A partner that sits in a neighbouring CTA (a segment cut by a CTA boundary, or longer than a
+// CTA) is not in shared memory.  Those products are left to a second launch of the same kernel
+// with STRADDLE = true, which rebuilds the partner's V column by column from W (same L); the
+// main launch then does not need L after V and fits three CTAs per SM.
+template <typename Target, int NK, bool STRADDLE>
+__global__ void __launch_bounds__(kSchurThreads, STRADDLE ? 1 : 3)
+schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32_t* __restrict__ e_idx) {
   extern __shared__ __align__(16) double schur_sm[];
   double(*Vs)[37] = reinterpret_cast<double(*)[37]>(schur_sm);                       // [128][37]
   double(*stage)[32][37] = reinterpret_cast<double(*)[32][37]>(schur_sm + kSchurThreads * 37);  // [4][32][37]
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   const int cta0 = blockIdx.x * blockDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const bool valid = pos < n_blk;
+  bool valid = pos < n_blk;
   const int e = valid ? e_idx[pos] : 0;
   const int beg = valid ? a.e_off[e] : 0;
   const int k = valid ? a.e_off[e + 1] - beg : 0;
   const int j = valid ? pos - beg : 0;
+  // the second launch only concerns segments that leave their CTA
+  if (STRADDLE) valid = valid && (beg < cta0 || beg + k > cta0 + kSchurThreads);
   double L[36], V[36], s[6];
   int fj = 0;
   const size_t ps = a.plane;
   if (valid) {
+#pragma unroll
+    for (int q = 0; q < 36; ++q) V[q] = a.W[(size_t)q * ps + pos];  // in flight during the factorisation
     double zl[6], ybl[6], hk[6];
     double hk1[6], hk2[6], ybl1[6], ybl2[6];  // radial model: l1, l2 borders
     load_scaled_E(a, e, L, zl, hk, s);
     const bool ok = chol6(L);
+    fj = a.f_idx[pos];
+    if (!STRADDLE) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) ybl[i] = hk[i];
-    chol6_forward(L, zl);
-    chol6_forward(L, ybl);
-    if (NK == 3) {
-      load_scaled_Ex(a, e, s, hk1, hk2);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { ybl1[i] = hk1[i]; ybl2[i] = hk2[i]; }
-      chol6_forward(L, ybl1);
-      chol6_forward(L, ybl2);
-    }
-    if (j == 0) {
-      double z[6], yb[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { z[i] = zl[i]; yb[i] = ybl[i]; }
-      chol6_backward(L, z);
-      chol6_backward(L, yb);
-      double* zo = a.Z + 8 * (size_t)e;
-      double* sg = a.seg_cam + 12 * (size_t)e;
-      double m00 = 0.0, v0 = 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        zo[i] = z[i];
-        a.YB[6 * NK * (size_t)e + i] = yb[i];
-        m00 += hk[i] * yb[i];
-        v0 += hk[i] * z[i];
-      }
-      zo[6] = ok ? 0.0 : 1.0;
-      zo[7] = 0.0;
-#pragma unroll
-      for (int i = 0; i < 12; ++i) sg[i] = 0.0;
-      sg[0] = m00; sg[6] = v0; sg[9] = ok ? 0.0 : 1.0;
+      for (int i = 0; i < 6; ++i) ybl[i] = hk[i];
+      chol6_forward(L, zl);
+      chol6_forward(L, ybl);
       if (NK == 3) {
-        double yb1[6], yb2[6];
+        load_scaled_Ex(a, e, s, hk1, hk2);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { yb1[i] = ybl1[i]; yb2[i] = ybl2[i]; }
-        chol6_backward(L, yb1);
-        chol6_backward(L, yb2);
-        double m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, v1 = 0, v2 = 0;
+        for (int i = 0; i < 6; ++i) { ybl1[i] = hk1[i]; ybl2[i] = hk2[i]; }
+        chol6_forward(L, ybl1);
+        chol6_forward(L, ybl2);
+      }
+      if (j == 0) {
+        double z[6], yb[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { z[i] = zl[i]; yb[i] = ybl[i]; }
+        chol6_backward(L, z);
+        chol6_backward(L, yb);
+        double* zo = a.Z + 8 * (size_t)e;
+        double* sg = a.seg_cam + 12 * (size_t)e;
+        double m00 = 0.0, v0 = 0.0;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          a.YB[18 * (size_t)e + 6 + i] = yb1[i];
-          a.YB[18 * (size_t)e + 12 + i] = yb2[i];
-          m01 += hk[i] * yb1[i]; m02 += hk[i] * yb2[i];
-          m11 += hk1[i] * yb1[i]; m12 += hk1[i] * yb2[i]; m22 += hk2[i] * yb2[i];
-          v1 += hk1[i] * z[i]; v2 += hk2[i] * z[i];
+          zo[i] = z[i];
+          a.YB[6 * NK * (size_t)e + i] = yb[i];
+          m00 += hk[i] * yb[i];
+          v0 += hk[i] * z[i];
         }
-        sg[1] = m01; sg[2] = m02; sg[3] = m11; sg[4] = m12; sg[5] = m22; sg[7] = v1; sg[8] = v2;
+        zo[6] = ok ? 0.0 : 1.0;
+        zo[7] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sg[i] = 0.0;
+        sg[0] = m00; sg[6] = v0; sg[9] = ok ? 0.0 : 1.0;
+        if (NK == 3) {
+          double yb1[6], yb2[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { yb1[i] = ybl1[i]; yb2[i] = ybl2[i]; }
+          chol6_backward(L, yb1);
+          chol6_backward(L, yb2);
+          double m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            a.YB[18 * (size_t)e + 6 + i] = yb1[i];
+            a.YB[18 * (size_t)e + 12 + i] = yb2[i];
+            m01 += hk[i] * yb1[i]; m02 += hk[i] * yb2[i];
+            m11 += hk1[i] * yb1[i]; m12 += hk1[i] * yb2[i]; m22 += hk2[i] * yb2[i];
+            v1 += hk1[i] * z[i]; v2 += hk2[i] * z[i];
+          }
+          sg[1] = m01; sg[2] = m02; sg[3] = m11; sg[4] = m12; sg[5] = m22; sg[7] = v1; sg[8] = v2;
+        }
       }
     }
-    fj = a.f_idx[pos];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       double col[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) col[i] = a.W[(size_t)(i * 6 + c) * ps + pos] * s[i];
+      for (int i = 0; i < 6; ++i) col[i] = V[i * 6 + c] * s[i];
       chol6_forward(L, col);
-      double b0 = 0.0, b1 = 0.0, bl1 = 0.0, bl2 = 0.0;  // (sig_e W)^T Ht^-1 h = V^T (L^-1 h)
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        V[i * 6 + c] = col[i];
-        Vs[threadIdx.x][i * 6 + c] = col[i];
-        b0 += col[i] * ybl[i];
-        b1 += col[i] * zl[i];
-        if (NK == 3) { bl1 += col[i] * ybl1[i]; bl2 += col[i] * ybl2[i]; }
+      for (int i = 0; i < 6; ++i) V[i * 6 + c] = col[i];
+      if (!STRADDLE) {
+        double b0 = 0.0, b1 = 0.0, bl1 = 0.0, bl2 = 0.0;  // (sig_e W)^T Ht^-1 h = V^T (L^-1 h)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          Vs[threadIdx.x][i * 6 + c] = col[i];
+          b0 += col[i] * ybl[i];
+          b1 += col[i] * zl[i];
+          if (NK == 3) { bl1 += col[i] * ybl1[i]; bl2 += col[i] * ybl2[i]; }
+        }
+        t.add_border(fj, c, b0, b1);
+        if (NK == 3) t.add_border_x(fj, c, bl1, bl2);
       }
-      t.add_border(fj, c, b0, b1);
-      if (NK == 3) t.add_border_x(fj, c, bl1, bl2);
     }
   }
-  __syncthreads();
+  if (!STRADDLE) __syncthreads();
   const int my_pairs = valid ? schur_pairs_of(j, k) : 0;
   int dmax = my_pairs;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
   for (int d = 0; d < dmax; ++d) {
-    const bool active = d < my_pairs;
+    bool active = d < my_pairs;
     double* blk = nullptr;
     if (active) {
       int i2 = j + d;
       if (i2 >= k) i2 -= k;
       const int ppos = beg + i2;
-      const int fp = a.f_idx[ppos];
-      double P[36];  // the partner's V
-      if (ppos >= cta0 && ppos < cta0 + kSchurThreads) {
-#pragma unroll
-        for (int q = 0; q < 36; ++q) P[q] = Vs[ppos - cta0][q];
-      } else {  // the segment continues in a neighbouring CTA: rebuild the partner's V (same L)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double col[6];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) col[i] = a.W[(size_t)(i * 6 + c) * ps + ppos] * s[i];
-          chol6_forward(L, col);
-#pragma unroll
-          for (int i = 0; i < 6; ++i) P[i * 6 + c] = col[i];
-        }
-      }
-      // order the pair so that the block lands in the lower triangle: row = larger F pose
-      const bool own_first = fj <= fp;
-      const int fa = own_first ? fj : fp, fb = own_first ? fp : fj;
-      const bool diag = fa == fb, twice = diag && d != 0;
-      blk = t.block(fa, fb, (a.pair_off ? (long long)a.pair_off[pos] : 0) + d);
-      double* st = stage[wid][lane];
-      // m1 = V^T P.  The product wanted is M = V_a^T V_b (element (6 fa + r, 6 fb + c)), stored
-      // transposed in the lower block (fb, fa): with the own block first that is m1^T, with the
-      // partner first it is m1 itself; on the diagonal (same F pose) m1 is stored as is.
-      const bool transpose = own_first && !diag;
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
+      const bool in_cta = ppos >= cta0 && ppos < cta0 + kSchurThreads;
+      active = STRADDLE ? !in_cta : in_cta;
+      if (active) {
+        const int fp = a.f_idx[ppos];
+        // order the pair so that the block lands in the lower triangle: row = larger F pose
+        const bool own_first = fj <= fp;
+        const int fa = own_first ? fj : fp, fb = own_first ? fp : fj;
+        const bool diag = fa == fb, twice = diag && d != 0;
+        blk = t.block(fa, fb, (a.pair_off ? (long long)a.pair_off[pos] : 0) + d);
+        double* st = stage[wid][lane];
+        // m1 = V^T P, P the partner's V.  The product wanted is M = V_a^T V_b (element
+        // (6 fa + r, 6 fb + c)), stored transposed in the lower block (fb, fa): with the own block
+        // first that is m1^T, with the partner first it is m1 itself; on the diagonal (same F
+        // pose) m1 is stored as is.
+        const bool transpose = own_first && !diag;
+        const double* Pp = Vs[STRADDLE ? 0 : ppos - cta0];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          double m1 = 0.0;
+          double pc[6];  // column c of P
+          if (STRADDLE) {
 #pragma unroll
-          for (int m = 0; m < 6; ++m) m1 += V[m * 6 + r] * P[m * 6 + c];
-          st[transpose ? c * 6 + r : r * 6 + c] = m1;
-        }
-      if (twice) {  // a tag seen twice by one capture: the two cross products M + M^T share a diagonal block
+            for (int i = 0; i < 6; ++i) pc[i] = a.W[(size_t)(i * 6 + c) * ps + ppos] * s[i];
+            chol6_forward(L, pc);
+          } else {
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int c = r; c < 6; ++c) {
-            const double v = r == c ? 2.0 * st[r * 6 + c] : st[r * 6 + c] + st[c * 6 + r];
-            st[r * 6 + c] = v;
-            st[c * 6 + r] = v;
+            for (int m = 0; m < 6; ++m) pc[m] = Pp[m * 6 + c];
           }
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            double m1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) m1 += V[m * 6 + r] * pc[m];
+            st[transpose ? c * 6 + r : r * 6 + c] = m1;
+          }
+        }
+        if (twice) {  // a tag seen twice by one capture: the two cross products M + M^T share a diagonal block
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) {
+              const double v = r == c ? 2.0 * st[r * 6 + c] : st[r * 6 + c] + st[c * 6 + r];
+              st[r * 6 + c] = v;
+              st[c * 6 + r] = v;
+            }
+        }
       }
     }
     __syncwarp();
     const unsigned m = __ballot_sync(0xffffffffu, active);
     // lanes 0..31 of the warp add elements 0..31 of every staged block; the 4-element tails
-    // (elements 32..35) of eight blocks at a time share one more warp-wide atomic
+    // (elements 32..35) of eight blocks at a time share one more warp-wide reduction
     for (int base = 0; base < 32; base += 8) {
       if (!((m >> base) & 0xffu)) continue;
 #pragma unroll
