@@ -193,6 +193,7 @@ struct arslam_solver {
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
+  DevBuf<unsigned> tickets;  // one ticket per in-kernel grid reduction (kernels.cuh), zero between launches
   DevBuf<double> Hx[2], partialx[2], warp_cam8;  // radial model: l1, l2 borders per pose side
   DevBuf<unsigned long long> sort_keys[2];
   DevBuf<int32_t> sort_vals[2];
@@ -443,6 +444,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   }
   CU(s->W.ensure((size_t)36 * plane));
   CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp + 8));
+  if (!s->tickets.p) { CU(s->tickets.ensure(16)); CU(cudaMemsetAsync(s->tickets.p, 0, 16 * sizeof(unsigned), s->stream)); }
   CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(12)); CU(s->colsum_part.ensure(12 * kColsumChunks)); CU(s->linv.ensure(CB * CB));
   s->have_problem = true;
   ++s->problem_version;
@@ -798,7 +800,7 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
              seg_fixup_kernel<<<cdiv((long long)n_own * NVX, 256), 256, 0, s->stream>>>(n_own, NVX, s->s_off[side].p, s->partialx[side].p, c.out_seg));
     }
   }
-  launch_colsum(s, s->n_warp, 4, s->warp_cam.p, head);
+  LAUNCH("reduce_partials", 32.0 * grid, reduce_partials_kernel<4, false><<<1, 1024, 0, s->stream>>>(s->warp_cam.p, grid, head));
   if (dist) launch_colsum(s, s->n_warp, 8, s->warp_cam8.p, head + 4);
   return ARSLAM_OK;
 }
@@ -878,13 +880,13 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   summary->reduced_dim = n;
 
   // ---- buffers that depend on the roles
-  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * nk * sd.n_e)); CU(s->seg_cam.ensure((size_t)12 * sd.n_e));
+  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * nk * sd.n_e)); CU(s->seg_cam.ensure((size_t)12 * cdiv(s->n_blk, kSchurThreads)));
   if (dist) {
     CU(s->Hx[sd.e].ensure((size_t)NVX * sd.n_e));
     for (int side = 0; side < 2; ++side) CU(s->partialx[side].ensure((size_t)s->n_warp * 2 * NVX));
     CU(s->warp_cam8.ensure((size_t)8 * s->n_warp));
   }
-  CU(s->seg_cross.ensure((size_t)sd.n_e));
+  CU(s->seg_cross.ensure((size_t)cdiv((long long)sd.n_e * kBsGroup, 128) + 1));
   CU(s->sigE.ensure((size_t)6 * sd.n_e)); CU(s->sigF.ensure((size_t)n + 1)); CU(s->uF.ensure((size_t)n + 1));
   size_t s_elems = 0;
   if (lin == ARSLAM_LINSOLVE_DENSE) {
@@ -922,7 +924,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   double eval_ms = 0.0, lin_ms = 0.0;
   summary->num_jacobian_evals = 1;
   summary->num_successful_steps = 1;
-  const int ne_warps = cdiv(sd.n_e, 32), nf_warps = cdiv(sd.n_f, 32);
 
   auto log_iter = [&](int it, double cost, double cost_change, double step_norm, double rho, int valid, int ok) {
     if (iter_log && it < log_rows) {
@@ -971,7 +972,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;
       }
-      launch_colsum(s, sd.n_e, 12, s->seg_cam.p, cam_minus);
+      LAUNCH("reduce_partials", 96.0 * cdiv(s->n_blk, kSchurThreads),
+             reduce_partials_kernel<12, false><<<1, 1024, 0, s->stream>>>(s->seg_cam.p, cdiv(s->n_blk, kSchurThreads), cam_minus));
     }
     if (s->world > 1) {
       // one allreduce per linearisation: partial Schur terms (+ on a fresh
@@ -983,10 +985,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (fresh_linearisation) {
       CU(cudaMemcpyAsync(sc, sc_head, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
       if (dist) CU(cudaMemcpyAsync(sc + 24, sc_head + 4, 8 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p));
-      LAUNCH("colmax", 8.0 * ne_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_e, 128) * 4, s->warp_gmax[sd.e].p, sc + 16));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p));
-      LAUNCH("colmax", 8.0 * nf_warps, colmax_kernel<<<1, 1024, 0, s->stream>>>(cdiv(sd.n_f, 128) * 4, s->warp_gmax[sd.f].p, sc + 17));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
@@ -1021,10 +1021,9 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     {
       BacksubArgs b;
       b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk;
-      b.d_e = s->d_pose[sd.e].p; b.seg_cross = s->seg_cross.p;
+      b.d_e = s->d_pose[sd.e].p; b.seg_cross = s->seg_cross.p; b.ticket = s->tickets.p + 4; b.out_cross = sc + 4;
       LAUNCH("backsub", 292.0 * s->n_blk + 400.0 * sd.n_e,
              backsub_kernel<<<cdiv((long long)sd.n_e * kBsGroup, 128), 128, 0, s->stream>>>(b));
-      launch_colsum(s, sd.n_e, 1, s->seg_cross.p, sc + 4);
     }
     double* x_e = sd.e == 0 ? s->cap[k].p : s->tag[k].p;
     double* x_f = sd.f == 0 ? s->cap[k].p : s->tag[k].p;
@@ -1036,14 +1035,14 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
       ap.rec = s->H[sd.e].p; ap.recx = dist ? s->Hx[sd.e].p : nullptr;
       ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
+      ap.ticket = s->tickets.p + 5; ap.out = sc + 6;
       LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
-      launch_colsum(s, cdiv(sd.n_e, 128) * 4, 3, s->warp_norm[sd.e].p, sc + 6);
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
       ap.rec = HF; ap.recx = HFx;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
+      ap.ticket = s->tickets.p + 6; ap.out = sc + 9;
       ap.count_norms = (s->rank == 0) ? 1 : 0;
       LAUNCH("apply_step", 144.0 * sd.n_f + 8.0 * NV * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
-      launch_colsum(s, cdiv(sd.n_f, 128) * 4, 3, s->warp_norm[sd.f].p, sc + 9);
       LAUNCH("cam_step", 64.0, cam_step_kernel<<<1, 1, 0, s->stream>>>(s->uF.p + cam_row, s->cam[k].p, s->cam[kc].p, s->d_cam.p, sc, nk));
     }
     cudaEventRecord(s->ev[1], s->stream);
@@ -1054,7 +1053,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       c.n_blk = s->n_blk; c.plane = s->plane;
       c.own_idx = s->s_own[sd.e].p; c.oth_idx = s->s_oth[sd.e].p; c.obs = s->s_obs[sd.e].p;
       c.cap_pre_c = s->cap_pre[kc].p; c.tag_pre_c = s->tag_pre[kc].p; c.cam_c = s->cam[kc].p;
-      c.warp_out = s->warp_cand.p;
+      c.warp_out = s->warp_cand.p; c.ticket = s->tickets.p + 7; c.out = sc + 5;
       const int grid = cdiv(s->plane, 256);
       if (dist) {
         if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0, 1><<<grid, 256, 0, s->stream>>>(c));
@@ -1063,7 +1062,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         if (sd.e == 0) LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<0, 0><<<grid, 256, 0, s->stream>>>(c));
         else LAUNCH("candidate", 72.0 * s->n_blk, candidate_kernel<1, 0><<<grid, 256, 0, s->stream>>>(c));
       }
-      launch_colsum(s, grid * 8, 1, s->warp_cand.p, sc + 5);
     }
     if (s->world > 1) {
       // small allreduce: sums [model, cand_r2, step2_e, xnorm2_e, step2_f, xnorm2_f] and

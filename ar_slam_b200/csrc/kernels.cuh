@@ -31,6 +31,81 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// Grid-wide, bit-reproducible reductions folded into the producing kernel.  v[] holds
+// warp-reduced values (valid in lane 0 of every warp); every thread of the CTA must call.
+//   cta_partial:           the CTA's totals -> part[blockIdx.x][M]
+//   reduce_partials:       one CTA adds n partial rows in a fixed order -> out[0..M)
+//   grid_reduce_last_cta:  both; the CTA that arrives last (atomic ticket, which wraps back to
+//                          zero for the next launch) runs reduce_partials.  The ticket costs every
+//                          CTA a fence + an atomic round trip, so it is used by the light kernels
+//                          only; the heavy ones write partials and leave the sum to
+//                          reduce_partials_kernel.
+__host__ __device__ constexpr int grid_reduce_scratch_doubles(int M, int WARPS) { return (WARPS + (WARPS * 32) / M) * M + 2; }
+template <int M, bool MAX, int WARPS>
+__device__ __forceinline__ bool cta_partial(const double (&v)[M], double* __restrict__ part, double* scratch) {
+  double(*gr_sm)[M] = reinterpret_cast<double(*)[M]>(scratch);  // [WARPS][M]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < M; ++c) gr_sm[wid][c] = v[c];
+  __syncthreads();
+  if (threadIdx.x < M) {
+    double t = gr_sm[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) t = MAX ? fmax(t, gr_sm[w][threadIdx.x]) : t + gr_sm[w][threadIdx.x];
+    __stcg(part + (size_t)blockIdx.x * M + threadIdx.x, t);
+    return true;
+  }
+  return false;
+}
+template <int M, bool MAX, int THREADS>
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int n, double* __restrict__ out,
+                                                double* scratch /* [THREADS / M][M] */) {
+  // thread (g, c): partial rows g, g + G, ... of column c; then the G groups in order
+  constexpr int G = THREADS / M;
+  double(*gr_fin)[M] = reinterpret_cast<double(*)[M]>(scratch);
+  const int c = threadIdx.x % M, g = threadIdx.x / M;
+  if (g < G) {
+    double t = 0.0;
+    for (int i = g; i < n; i += G) {
+      const double x = __ldcg(part + (size_t)i * M + c);
+      t = MAX ? fmax(t, x) : t + x;
+    }
+    gr_fin[g][c] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < M) {
+    double r = gr_fin[0][threadIdx.x];
+    for (int q = 1; q < G; ++q) r = MAX ? fmax(r, gr_fin[q][threadIdx.x]) : r + gr_fin[q][threadIdx.x];
+    out[threadIdx.x] = r;
+  }
+}
+template <int M, bool MAX>
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double scratch[(1024 / M) * M];
+  reduce_partials<M, MAX, 1024>(part, n, out, scratch);
+}
+template <int M, bool MAX, int WARPS>
+__device__ __forceinline__ void grid_reduce_last_cta(const double (&v)[M], double* __restrict__ part,
+                                                     unsigned* __restrict__ ticket, double* __restrict__ out,
+                                                     double* scratch /* shared, grid_reduce_scratch_doubles(M, WARPS) */) {
+  constexpr int G = (WARPS * 32) / M;
+  int* gr_last = reinterpret_cast<int*>(scratch + (WARPS + G) * M);
+  if (cta_partial<M, MAX, WARPS>(v, part, scratch)) __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *gr_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!*gr_last) return;
+  __threadfence();
+  reduce_partials<M, MAX, WARPS * 32>(part, (int)gridDim.x, out, scratch + WARPS * M);
+}
+template <int M, bool MAX, int WARPS>
+__device__ __forceinline__ void grid_reduce_last_cta(const double (&v)[M], double* __restrict__ part,
+                                                     unsigned* __restrict__ ticket, double* __restrict__ out) {
+  __shared__ double gr_scratch[grid_reduce_scratch_doubles(M, WARPS)];
+  grid_reduce_last_cta<M, MAX, WARPS>(v, part, ticket, out, gr_scratch);
+}
+
 // ---------------------------------------------------------------- prep -----
 __global__ void prep_captures_kernel(int n, const double* __restrict__ pose, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,7 +270,7 @@ struct AccumArgs {
   double* out_seg;           // [n_pose][NV]
   double* partial;           // [n_warp][2][NV]
   double* W;                 // 36 planes [e][plane] (WITH_W)
-  double* warp_cam;          // [n_warp][4]: sum K^2, sum K r, sum r^2, 0 (WITH_W)
+  double* warp_cam;          // [grid][4] CTA partials of sum K^2, sum K r, sum r^2, 0 (WITH_W)
 };
 
 template <int SIDE, bool WITH_W, int MODEL>
@@ -361,13 +436,9 @@ __global__ void __launch_bounds__(kAccumThreads, WITH_W ? 2 : 3) accum_kernel(co
     }
   }
   if (WITH_W) {
-    KK = warp_sum(KK);
-    Kr = warp_sum(Kr);
-    rr = warp_sum(rr);
-    if (lane == 0) {
-      double* wc = a.warp_cam + 4 * (size_t)gwarp;
-      wc[0] = KK; wc[1] = Kr; wc[2] = rr; wc[3] = 0.0;
-    }
+    const double v[4] = {warp_sum(KK), warp_sum(Kr), warp_sum(rr), 0.0};
+    __shared__ double cam_scratch[kAccumWarps * 4];
+    cta_partial<4, false, kAccumWarps>(v, a.warp_cam, cam_scratch);
   }
   if (SIDE == 0) __syncthreads();  // every thread is done with its cp.async slots before the buffer is reused
   // stage the per-pose record, transposed: stage[v][lane]
@@ -568,7 +639,9 @@ struct CandArgs {
   const double* cap_pre_c; // prep records at x + delta
   const double* tag_pre_c;
   const double* cam_c;
-  double* warp_out;        // [n_warp]: candidate sum r^2
+  double* warp_out;        // [grid] CTA partials of the candidate's sum r^2
+  unsigned* ticket;
+  double* out;             // [1]
 };
 template <int SIDE, int MODEL>
 __global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
@@ -599,8 +672,8 @@ __global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
       c2 += rc[0] * rc[0] + rc[1] * rc[1];
     }
   }
-  c2 = warp_sum(c2);
-  if ((threadIdx.x & 31) == 0) a.warp_out[pos >> 5] = c2;
+  const double v[1] = {warp_sum(c2)};
+  grid_reduce_last_cta<1, false, 8>(v, a.warp_out, a.ticket, a.out);
 }
 
 // ------------------------------------------------------------ LM vectors ---

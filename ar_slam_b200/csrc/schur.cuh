@@ -28,7 +28,7 @@ struct SchurArgs {
   double radius, inv_radius, min_diag, max_diag;  // inv_radius = 1 / radius (host)
   double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
   double* YB;             // [n_e][6 NK]: Ht_ee^-1 sig_e H_e,intrinsic_q
-  double* seg_cam;        // [n_e][12]: M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | 0 0
+  double* seg_cam;        // [grid][12] CTA partials of M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | 0 0
 };
 
 // FP64 add to global memory without a return value.  atomicAdd through a pointer whose address
@@ -162,6 +162,13 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
   double L[36], V[36], s[6];
   int fj = 0;
   const size_t ps = a.plane;
+  // camera terms of the segments (written by their first thread), parked in the staging area
+  // until the CTA reduces them below
+  double(*cs)[12] = reinterpret_cast<double(*)[12]>(schur_sm + kSchurThreads * 37);
+  if (!STRADDLE && !(valid && j == 0)) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cs[threadIdx.x][i] = 0.0;
+  }
   if (valid) {
 #pragma unroll
     for (int q = 0; q < 36; ++q) V[q] = a.W[(size_t)q * ps + pos];  // in flight during the factorisation
@@ -189,7 +196,7 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
         chol6_backward(L, z);
         chol6_backward(L, yb);
         double* zo = a.Z + 8 * (size_t)e;
-        double* sg = a.seg_cam + 12 * (size_t)e;
+        double* sg = cs[threadIdx.x];
         double m00 = 0.0, v0 = 0.0;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -244,7 +251,14 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
       }
     }
   }
-  if (!STRADDLE) __syncthreads();
+  if (!STRADDLE) {
+    __syncthreads();
+    double cm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cm[i] = (NK == 3 || i == 0 || i == 6 || i == 9) ? warp_sum(cs[threadIdx.x][i]) : 0.0;
+    cta_partial<12, false, kSchurThreads / 32>(cm, a.seg_cam, schur_sm + kSchurThreads * 37 + kSchurThreads * 12);
+    __syncthreads();  // the staging area is reused by the products
+  }
   const int my_pairs = valid ? schur_pairs_of(j, k) : 0;
   int dmax = my_pairs;
 #pragma unroll
@@ -329,7 +343,6 @@ __global__ void schur_empty_kernel(const SchurArgs a, int nk) {
   if (e >= a.n_e || a.e_off[e + 1] > a.e_off[e]) return;
   for (int i = 0; i < 8; ++i) a.Z[8 * (size_t)e + i] = 0.0;
   for (int i = 0; i < 6 * nk; ++i) a.YB[6 * nk * (size_t)e + i] = 0.0;
-  for (int i = 0; i < 12; ++i) a.seg_cam[12 * (size_t)e + i] = 0.0;
 }
 
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
@@ -414,7 +427,9 @@ struct BacksubArgs {
   const double* uF;   // [6 n_f + nk]
   int cam_row, nk;
   double* d_e;        // [6 n_e] step of the E poses
-  double* seg_cross;  // [n_e]
+  double* seg_cross;  // [grid] CTA partials of the cross term -sum_j d_e^T W_j u_j
+  unsigned* ticket;
+  double* out_cross;  // [1]
 };
 constexpr int kBsGroup = 8;  // lanes per E pose: four poses per warp (8 blocks per capture is the common case)
 __device__ __forceinline__ double group_sum(double v) {
@@ -467,8 +482,9 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   if (valid && gl == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) a.d_e[6 * (size_t)e + i] = de[i];
-    a.seg_cross[e] = cross;
   }
+  const double v[1] = {warp_sum(valid && gl == 0 ? cross : 0.0)};
+  grid_reduce_last_cta<1, false, 4>(v, a.seg_cross, a.ticket, a.out_cross);
 }
 
 // delta_F = -uF ; candidate = x + delta on both pose sides and the camera;
@@ -484,7 +500,9 @@ struct ApplyArgs {
   const double* uF_cam;     // -> uF[cam_row .. cam_row + nk); the intrinsics step is its negative
   double* delta;            // [6 n_pose] out (unscaled step)
   double* x_cand;           // [6 n_pose] out
-  double* warp_out;         // [n_warp][3]: sum delta^2, sum x^2, sum (g.d + d^T H d / 2 + d_cam H_pose,f.d)
+  double* warp_out;         // [grid][3] CTA partials of sum delta^2, sum x^2, sum (g.d + d^T H d / 2 + d_cam H_pose,f.d)
+  unsigned* ticket;
+  double* out;              // [3]
   int count_norms;          // 0: this rank does not own the sums of this side (multi-GPU)
 };
 __global__ void apply_step_kernel(const ApplyArgs a) {
@@ -525,28 +543,21 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
       mq = q;
     }
   }
-  d2 = warp_sum(d2);
-  x2 = warp_sum(x2);
-  mq = warp_sum(mq);
-  if ((threadIdx.x & 31) == 0) {
-    double* o = a.warp_out + 3 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    o[0] = d2;
-    o[1] = x2;
-    o[2] = mq;
-  }
+  const double v[3] = {warp_sum(d2), warp_sum(x2), warp_sum(mq)};
+  grid_reduce_last_cta<3, false, 4>(v, a.warp_out, a.ticket, a.out);
 }
 
-// max |g| over poses that own blocks -> per-warp maxima
-__global__ void gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
-                               double* __restrict__ warp_out) {
+// max |g| over poses that own blocks
+__global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
+                                                      double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double m = 0.0;
   if (i < n_pose && seg_off[i + 1] > seg_off[i]) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) m = fmax(m, fabs(rec[(size_t)i * NV + 21 + k]));
   }
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) warp_out[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = m;
+  const double v[1] = {warp_max(m)};
+  grid_reduce_last_cta<1, true, 4>(v, part, ticket, out);
 }
 __global__ void __launch_bounds__(1024) colmax_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
   __shared__ double sm[1024];
