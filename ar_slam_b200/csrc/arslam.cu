@@ -713,7 +713,12 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
     r = Profiler::Rec{s->prof.id_of("pcg_solve", 288.0 * w.nnzb), s->prof.ev(), s->prof.ev()};
     cudaEventRecord(r.a, s->stream);
   }
-  if (use_smem)
+  // one barrier per iteration for the inexact-Newton tolerances; the classic recurrence when the
+  // system is to be solved tightly (its attainable accuracy is higher)
+  const bool pipelined = use_smem && s->opt.pcg_tolerance >= 1e-6 && !getenv("ARSLAM_PCG_CLASSIC");
+  if (pipelined)
+    CU(cudaLaunchCooperativeKernel((void*)pcg_pipe_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
+  else if (use_smem)
     CU(cudaLaunchCooperativeKernel((void*)pcg_smem_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
   else
     CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args_g, 0, s->stream));

@@ -714,7 +714,7 @@ struct PcgSmemArgs {
 // cleared by CTA 0).  One L2 round trip after the barrier instead of a 148-slot read + reduce.
 template <int NS>
 __device__ __forceinline__ void grid_sums_atomic(cg::grid_group& grid, double (&v)[NS], double* accum /* [3][8] */,
-                                                 double* sm, int& round) {
+                                                 double* sm /* shared, (kPcgWarps + 1) * NS doubles */, int& round) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* cur = accum + 8 * (round % 3);
   double* nxt = accum + 8 * ((round + 1) % 3);
@@ -737,10 +737,10 @@ __device__ __forceinline__ void grid_sums_atomic(cg::grid_group& grid, double (&
   grid.sync();
   // ONE thread per CTA fetches the totals (every thread of every CTA loading the same line
   // serialises at its L2 slice: ~10 us for 148 x 1024 threads), the rest get them from smem
-  if (threadIdx.x < NS) sm[72 + threadIdx.x] = __ldcg(cur + threadIdx.x);
+  if (threadIdx.x < NS) sm[kPcgWarps * NS + threadIdx.x] = __ldcg(cur + threadIdx.x);
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NS; ++i) v[i] = sm[72 + i];
+  for (int i = 0; i < NS; ++i) v[i] = sm[kPcgWarps * NS + i];
 }
 
 __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemArgs A) {
@@ -925,8 +925,199 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
   }
 }
 
+// Six per-lane partial sums -> component c in lanes 4c .. 4c + 3 (recursive halving over the
+// lane bits 4, 3, 2, then a plain butterfly over bits 1, 0): 9 double shuffles instead of 30.
+__device__ __forceinline__ double reduce6_halving(const double (&ac)[6], int lane) {
+  const double a8[8] = {ac[0], ac[1], ac[2], ac[3], ac[4], ac[5], 0.0, 0.0};
+  double a4[4], a2[2];
+  bool hi = (lane & 16) != 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const double recv = __shfl_xor_sync(0xffffffffu, hi ? a8[t] : a8[t + 4], 16);
+    a4[t] = (hi ? a8[t + 4] : a8[t]) + recv;
+  }
+  hi = (lane & 8) != 0;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const double recv = __shfl_xor_sync(0xffffffffu, hi ? a4[t] : a4[t + 2], 8);
+    a2[t] = (hi ? a4[t + 2] : a4[t]) + recv;
+  }
+  hi = (lane & 4) != 0;
+  double a1 = (hi ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi ? a2[0] : a2[1], 4);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;
+}
+
+// ---- pipelined PCG (Ghysels & Vanroose): ONE grid barrier per iteration --------------------
+// The classic recurrence needs two grid-wide sums per iteration (p.q, then r.z) with the
+// matrix product between them.  The pipelined form carries w = A u, s = A p, z = A q along by
+// recurrences, so the sums of iteration i (r.u, w.u, r.r and the border dot b.m) are formed
+// BEFORE the product n = A m, m = M^-1 w, and the barrier that publishes m to the neighbours is
+// the same barrier that completes the sums.  Same shared-memory resident matrix slice as
+// pcg_smem_kernel.  A row's state (x r u w p s q z) lives in one register set per lane: lanes
+// 0..5 hold the warp's first row, lanes 8..13 its second, lane 16 of CTA 0 / warp 0 the camera
+// scalar.  Rounding differs from the classic recurrence and the attainable accuracy is lower,
+// so the host picks this kernel for inexact-Newton tolerances only (pcg_tolerance >= 1e-6).
+__global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ double sm[(kPcgWarps + 1) * 4 + 12];
+  constexpr int kVk = (kPcgWarps + 1) * 4 + 4;  // camera component of the gathered vector; S_kk, 1 / S_kk next to it
+  const PcgArgs& a = A.a;
+  double* Ss = reinterpret_cast<double*>(dyn);                       // [cap_slots][36]
+  double* xs = Ss + (size_t)A.cap_slots * 36;                        // [max_halo][6]
+  double* Ms = xs + (size_t)A.max_halo * 6;                          // [max_rows][36]
+  double* bs = Ms + (size_t)A.max_rows * 36;                         // [max_rows][6]
+  int32_t* hc = reinterpret_cast<int32_t*>(bs + (size_t)A.max_rows * 6);  // [max_halo]
+  int32_t* rp = hc + A.max_halo;                                     // [max_rows + 1] local slot offsets
+  uint16_t* lc = reinterpret_cast<uint16_t*>(rp + A.max_rows + 2);   // [max_slots]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_f = a.n_f, camrow = 6 * n_f;
+  const int r0 = A.cta_row[blockIdx.x], r1 = A.cta_row[blockIdx.x + 1];
+  const int nrow = r1 - r0;
+  const int s_beg = a.row_ptr[r0], s_end = a.row_ptr[r1];
+  const int nslot = s_end - s_beg, ncache = min(nslot, A.cap_slots);
+  const int h0 = A.halo_ptr[blockIdx.x], nhalo = A.halo_ptr[blockIdx.x + 1] - h0;
+  if (tid == 0) { sm[kVk + 1] = a.scal[0]; sm[kVk + 2] = a.scal[1]; }
+  int round = 0;
+  {
+    const double* src = a.S + 36 * (size_t)s_beg;
+    for (int i = tid; i < ncache * 36; i += kPcgThreads) {
+      const int sl = i / 36, k = i - sl * 36, r = k / 6, c = k - r * 6;
+      Ss[sl * 36 + c * 6 + r] = src[i];  // transposed blocks, see pcg_smem_kernel
+    }
+    for (int i = tid; i < nslot; i += kPcgThreads) lc[i] = A.lcol[s_beg + i];
+    for (int i = tid; i < nhalo; i += kPcgThreads) hc[i] = A.halo_col[h0 + i];
+    for (int i = tid; i <= nrow; i += kPcgThreads) rp[i] = a.row_ptr[r0 + i] - s_beg;
+    for (int i = tid; i < nrow * 36; i += kPcgThreads) Ms[i] = a.Minv[36 * (size_t)r0 + i];
+    for (int i = tid; i < nrow * 6; i += kPcgThreads) bs[i] = a.border[6 * (size_t)r0 + i];
+  }
+  __syncthreads();
+  const double skk = sm[kVk + 1], iskk = sm[kVk + 2];
+  const int lrA = wid, lrB = wid + 32;
+  const bool hasA = lrA < nrow, hasB = lrB < nrow;
+  const bool isA = hasA && lane < 6, isB = hasB && lane >= 8 && lane < 14;
+  const bool isK = blockIdx.x == 0 && wid == 0 && lane == 16;
+  const bool isRow = isA || isB, owner = isRow || isK;
+  const int comp = isB ? lane - 8 : (lane < 6 ? lane : 0);
+  const int lrow = isB ? lrB : lrA;
+  const size_t gi = isK ? (size_t)camrow : 6 * (size_t)(r0 + lrow) + comp;
+  const double bd = isRow ? bs[6 * lrow + comp] : 0.0;
+
+  auto precond = [&](double v) {  // M^-1 v: the row's inverse diagonal block, 1 / S_kk for the camera
+    double o = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double va = __shfl_sync(0xffffffffu, v, c), vb = __shfl_sync(0xffffffffu, v, 8 + c);
+      if (isA) o += Ms[36 * lrA + lane * 6 + c] * va;
+      else if (isB) o += Ms[36 * lrB + (lane - 8) * 6 + c] * vb;
+    }
+    if (isK) o = v * iskk;
+    return o;
+  };
+  // halo of `buf` -> xs, camera component -> sm[kVk]
+  auto gather = [&](const double* buf) {
+    if (tid == 0) sm[kVk] = __ldcg(buf + camrow);
+    for (int i = tid; i < nhalo * 6; i += kPcgThreads) {
+      const int h = i / 6, k = i - h * 6;
+      xs[i] = __ldcg(buf + 6 * (size_t)hc[h] + k);
+    }
+    __syncthreads();
+  };
+  // this lane's component of A v, v gathered in xs / sm[kVk]; bv = b . v over all rows
+  auto product = [&](double bv) {
+    const double vk = sm[kVk];
+    double res = 0.0;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      if (!(which == 0 ? hasA : hasB)) continue;
+      const int lr = which == 0 ? lrA : lrB;
+      const int s0 = rp[lr], s1 = rp[lr + 1];
+      double ac[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = lane; c < 6 * (s1 - s0); c += 32) {
+        const int sl = s0 + c / 6, j = c - (c / 6) * 6;
+        const double xv = xs[6 * (int)lc[sl] + j];
+        if (sl < ncache) {
+          const double2* col = reinterpret_cast<const double2*>(Ss + 36 * (size_t)sl + 6 * j);
+          const double2 c0 = col[0], c1 = col[1], c2 = col[2];
+          ac[0] += c0.x * xv; ac[1] += c0.y * xv; ac[2] += c1.x * xv;
+          ac[3] += c1.y * xv; ac[4] += c2.x * xv; ac[5] += c2.y * xv;
+        } else {
+          const double* Bg = a.S + 36 * (size_t)(s_beg + sl) + j;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ac[i] += __ldg(Bg + 6 * i) * xv;
+        }
+      }
+      const double tot = reduce6_halving(ac, lane);
+      const double mine = __shfl_sync(0xffffffffu, tot, (4 * (which == 0 ? lane : lane - 8)) & 31);
+      if (which == 0 ? isA : isB) res = mine + bd * vk;
+    }
+    if (isK) res = bv + skk * vk;
+    return res;
+  };
+
+  double x = 0.0, r = 0.0, u = 0.0, w = 0.0, p = 0.0, s_ = 0.0, q = 0.0, z = 0.0;
+  double* buf[2] = {a.p0, a.p1};
+  // r0 = rhs (x0 = 0), u0 = M^-1 r0, w0 = A u0
+  if (owner) r = a.rhs[gi];
+  u = precond(r);
+  if (owner) buf[0][gi] = u;
+  double s2[2] = {isRow ? bd * u : 0.0, owner ? r * r : 0.0};
+  grid_sums_atomic<2>(grid, s2, a.partial, sm, round);
+  const double bb = s2[1];
+  const double thresh = a.tol * a.tol * bb;
+  bool fail = !(bb >= 0.0) || !isfinite(bb);
+  int it = 0;
+  if (!(bb == 0.0 || fail)) {
+    gather(buf[0]);
+    w = product(s2[0]);
+    double gamma_prev = 1.0, alpha_prev = 1.0;
+    while (it < a.max_iter) {
+      const double m = precond(w);
+      double* mb = buf[(it + 1) & 1];
+      if (owner) mb[gi] = m;
+      double sv[4] = {owner ? r * u : 0.0, owner ? w * u : 0.0, owner ? r * r : 0.0, isRow ? bd * m : 0.0};
+      grid_sums_atomic<4>(grid, sv, a.partial, sm, round);
+      const double gamma = sv[0], delta = sv[1];
+      if (!isfinite(sv[2])) { fail = true; break; }
+      if (sv[2] <= thresh) break;
+      double beta = 0.0, alpha;
+      if (it == 0) {
+        if (!(delta > 0.0) || !isfinite(delta)) { fail = true; break; }
+        alpha = gamma / delta;
+      } else {
+        beta = gamma / gamma_prev;
+        const double den = delta - beta * gamma / alpha_prev;
+        if (!(den > 0.0) || !isfinite(den)) { fail = true; break; }
+        alpha = gamma / den;
+      }
+      gather(mb);
+      const double n = product(sv[3]);
+      z = n + beta * z;
+      q = m + beta * q;
+      s_ = w + beta * s_;
+      p = u + beta * p;
+      x += alpha * p;
+      r -= alpha * s_;
+      u -= alpha * q;
+      w -= alpha * z;
+      gamma_prev = gamma;
+      alpha_prev = alpha;
+      ++it;
+    }
+  }
+  if (owner) a.x[gi] = x;
+  if (isK) {
+    a.scal[2] = (double)it;
+    if (fail) a.scal[3] = 1.0;
+  }
+}
+
 inline cudaError_t pcg_init() {
-  return cudaFuncSetAttribute(pcg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  cudaError_t e = cudaFuncSetAttribute(pcg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pcg_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  return e;
 }
 
 }  // namespace ars

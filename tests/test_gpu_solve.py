@@ -151,6 +151,28 @@ def test_pcg_matches_dense(gpu_solver_cls, oracle):
     assert abs(sp["final_cost"] - so["final_cost"]) <= 1e-8 * so["final_cost"]
 
 
+def test_pipelined_pcg_matches_dense(gpu_solver_cls):
+    """pcg_tolerance >= 1e-6 selects the one-barrier (pipelined) recurrence: at 1e-6 the LM
+    trajectory still follows the dense Cholesky path closely."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(4000, 600, seed=33)
+    res = {}
+    for name, ls in (("dense", ar_slam_b200.LINSOLVE_DENSE), ("pcg", ar_slam_b200.LINSOLVE_PCG)):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ls, pcg_tolerance=1e-6, pcg_max_iterations=2000))
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        summ, log = s.solve()
+        res[name] = (summ, log, s.get_params())
+        s.close()
+    (sd, ld, pd), (sp, lp, pp) = res["dense"], res["pcg"]
+    assert sp["linear_solver_iterations"] > 0
+    assert sp["iterations"] == sd["iterations"] and sp["reason"] == sd["reason"]
+    assert np.allclose(lp[:, 0], ld[:, 0], rtol=1e-6)
+    assert abs(sp["final_cost"] - sd["final_cost"]) <= 1e-7 * sd["final_cost"]
+    assert abs(pp[0][0] - pd[0][0]) <= 1e-6 * pd[0][0]
+
+
 def test_pcg_default_tolerance_converges_like_dense(gpu_solver_cls):
     import ar_slam_b200
     from ar_slam_b200 import synth
