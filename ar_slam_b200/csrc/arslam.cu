@@ -387,18 +387,24 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
     return s->fail(ARSLAM_ERR_INVALID, "set_problem: empty problem or null pointer");
   if (n_blk > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
     return s->fail(ARSLAM_ERR_INVALID, "set_problem: problem too large for 32-bit block indices");
-  for (int64_t b = 0; b < n_blk; ++b)
-    if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
-      return s->fail(ARSLAM_ERR_INVALID, "set_problem: block %lld has an index out of range", (long long)b);
   CU(cudaSetDevice(s->device));
   s->have_problem = false;
   s->have_params = false;
+  // the observations (the bulk of the upload) start moving first; the index check below runs on
+  // the host while the DMA is in flight (when the caller's arrays are pinned)
+  CU(s->o_obs.ensure((size_t)n_blk * 8));
+  CU(cudaMemcpyAsync(s->o_obs.p, rect8, sizeof(double) * 8 * n_blk, cudaMemcpyHostToDevice, s->stream));
+  int32_t lo = cap_idx[0], hi = cap_idx[0];
+  for (int64_t b = 0; b < n_blk; ++b) {
+    if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
+      return s->fail(ARSLAM_ERR_INVALID, "set_problem: block %lld has an index out of range", (long long)b);
+    lo = std::min(lo, cap_idx[b]);
+    hi = std::max(hi, cap_idx[b]);
+  }
   s->cap_lo = 0;
   s->n_cap_global = (int)n_cap;
   if (s->world > 1) {
     // a rank only ever touches the captures of its own blocks: work on that index range alone
-    int32_t lo = cap_idx[0], hi = cap_idx[0];
-    for (int64_t b = 1; b < n_blk; ++b) { lo = std::min(lo, cap_idx[b]); hi = std::max(hi, cap_idx[b]); }
     s->cap_lo = lo;
     n_cap = (int64_t)hi - lo + 1;
   }
@@ -406,10 +412,9 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   s->plane = ((int)n_blk + 31) / 32 * 32;
   s->n_warp = s->plane / 32;
   const int nb = s->n_blk, plane = s->plane;
-  CU(s->o_cap.ensure(nb)); CU(s->o_tag.ensure(nb)); CU(s->o_obs.ensure((size_t)nb * 8));
+  CU(s->o_cap.ensure(nb)); CU(s->o_tag.ensure(nb));
   CU(cudaMemcpyAsync(s->o_cap.p, cap_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(s->o_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
   if (s->cap_lo) shift_index_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, s->o_cap.p, -s->cap_lo);
   // both sorted copies are built on the GPU from the one upload above: stable radix sort of
   // (own << 32 | other) keys, then one gather kernel writes the index arrays and the 8 planes
@@ -648,7 +653,7 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.pair_slot) {
     SparseTarget t;
     t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx; t.Sraw = nullptr; t.borderm = nullptr; t.rhsm = nullptr;
-    t.pair_slot = nullptr;
+    t.pair_slot = nullptr; t.lower_of = s->pcg.src_slot;
     LAUNCH("pair_slot", 4.0 * s->pcg.n_pairs,
            pair_slot_kernel<<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p,
                                                                       s->s_oth[side_e].p, s->pcg.pair_off, t, s->pcg.pair_slot));
@@ -662,9 +667,9 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   SparseTarget t;
   t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx;
   t.Sraw = Sraw;
-  t.borderm = Sraw + (size_t)36 * s->pcg.nnzb;
+  t.borderm = Sraw + (size_t)36 * s->pcg.nnz_lower;
   t.rhsm = t.borderm + (size_t)6 * s->pcg.n_f;
-  t.pair_slot = s->pcg.pair_slot;
+  t.pair_slot = s->pcg.pair_slot; t.lower_of = s->pcg.src_slot;
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
   launch_schur<SparseTarget, 1>(s, a2, t, e_idx, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb);
@@ -681,7 +686,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   CU(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), s->stream));
   PcgFinalizeArgs f;
   f.n_f = n_f; f.nnzb = w.nnzb; f.row_ptr = w.row_ptr; f.col_idx = w.col_idx; f.src_slot = w.src_slot;
-  f.Sraw = Sraw; f.borderm = Sraw + (size_t)36 * w.nnzb; f.rhsm = f.borderm + (size_t)6 * n_f;
+  f.Sraw = Sraw; f.borderm = Sraw + (size_t)36 * w.nnz_lower; f.rhsm = f.borderm + (size_t)6 * n_f;
   f.HF = HF; f.sigF = s->sigF.p; f.sc = reinterpret_cast<const LmScalars*>(sc); f.cam_minus = cam_minus;
   f.radius = radius; f.min_diag = s->opt.min_lm_diagonal; f.max_diag = s->opt.max_lm_diagonal;
   f.Sfin = w.Sfin; f.Minv = w.Minv; f.border = v + 6 * nvec; f.rhs = v + 7 * nvec; f.scal = w.scal;

@@ -45,12 +45,12 @@ struct PcgBuf {
 };
 
 struct PcgWorkspace {
-  int n_f = 0, nnzb = 0, grid = 0;
+  int n_f = 0, nnzb = 0, nnz_lower = 0, grid = 0;  // nnz_lower: blocks with col <= row, the ones that are formed
   bool valid = false;
   long long total_iterations = 0;
   int32_t* row_ptr = nullptr;   // [n_f + 1]
   int32_t* col_idx = nullptr;   // [nnzb]
-  int32_t* src_slot = nullptr;  // [nnzb]: slot holding the (lower) source block, transposed if col > row
+  int32_t* src_slot = nullptr;  // [nnzb]: index, in the compact array of lower blocks, of the source block (transposed if col > row)
   double* Sfin = nullptr;       // [nnzb][36] final scaled + damped blocks
   double* Minv = nullptr;       // [n_f][36]  inverse diagonal blocks (block-Jacobi)
   double* vec = nullptr;        // x | r | z | p0 | p1 | q | border | rhs : 8 x (6 n_f + 2)
@@ -69,9 +69,9 @@ struct PcgWorkspace {
   int32_t* pair_off = nullptr;  // [n_blk] (E-sorted) pairs before each block
   int32_t* pair_slot = nullptr; // [n_pairs]
   long long n_pairs = 0;
-  size_t value_count() const { return (size_t)36 * nnzb + (size_t)12 * n_f; }
+  size_t value_count() const { return (size_t)36 * nnz_lower + (size_t)12 * n_f; }  // lower blocks | border | rhs
   // storage (grow-only, so a new problem of similar size allocates nothing); the pointers above alias it
-  PcgBuf<int32_t> b_row_ptr, b_col_idx, b_src_slot, b_cta_row, b_halo_ptr, b_halo_col, b_diag_slot, b_slot_row, b_pair_off, b_pair_slot;
+  PcgBuf<int32_t> b_lowflag, b_lrank, b_row_ptr, b_col_idx, b_src_slot, b_cta_row, b_halo_ptr, b_halo_col, b_diag_slot, b_slot_row, b_pair_off, b_pair_slot;
   PcgBuf<uint16_t> b_lcol;
   PcgBuf<double> b_Sfin, b_Minv, b_vec, b_partial, b_scal;
   // symbolic phase scratch
@@ -138,6 +138,16 @@ __global__ void sym_slots_kernel(int n_f, int nnzb, const unsigned long long* __
   if (c == r) diag_slot[r] = sl;
   // an upper block takes its values from the transpose partner, the slot of (c, r)
   src[sl] = c <= r ? sl : sym_lower_bound(keys, nnzb, (unsigned long long)c * n_f + r);
+}
+// The elimination only forms the lower blocks (col <= row); they are stored compactly, so the
+// array that is zeroed, reduced across ranks and read by the finalisation is half the pattern.
+__global__ void sym_lower_flag_kernel(int nnzb, const int32_t* __restrict__ col, const int32_t* __restrict__ slot_row, int32_t* __restrict__ flag) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl <= nnzb) flag[sl] = (sl < nnzb && col[sl] <= slot_row[sl]) ? 1 : 0;
+}
+__global__ void sym_compact_src_kernel(int nnzb, const int32_t* __restrict__ lrank, int32_t* __restrict__ src) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl < nnzb) src[sl] = lrank[src[sl]];
 }
 // one contiguous block-row range per CTA, balanced by block count
 __global__ void sym_cta_rows_kernel(int G, int n_f, int nnzb, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ cta_row) {
@@ -282,6 +292,18 @@ inline int pcg_symbolic_build(PcgWorkspace& ws, cudaStream_t st, std::string& er
   const unsigned long long* keys = ws.keys[0].p;
   sym_rows_kernel<<<(n_f + 256) / 256, 256, 0, st>>>(n_f, nnzb, keys, ws.row_ptr);
   sym_slots_kernel<<<(nnzb + 255) / 256, 256, 0, st>>>(n_f, nnzb, keys, ws.col_idx, ws.slot_row, ws.src_slot, ws.diag_slot);
+  {
+    PCG_TRY(ws.b_lowflag.ensure((size_t)nnzb + 1)); PCG_TRY(ws.b_lrank.ensure((size_t)nnzb + 1));
+    if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
+    sym_lower_flag_kernel<<<(nnzb + 256) / 256, 256, 0, st>>>(nnzb, ws.col_idx, ws.slot_row, ws.b_lowflag.p);
+    size_t t1 = 0;
+    PCG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t1, ws.b_lowflag.p, ws.b_lrank.p, nnzb + 1, st));
+    PCG_TRY(ws.tmp.ensure(t1));
+    t1 = ws.tmp.cap;
+    PCG_TRY(cub::DeviceScan::ExclusiveSum(ws.tmp.p, t1, ws.b_lowflag.p, ws.b_lrank.p, nnzb + 1, st));
+    sym_compact_src_kernel<<<(nnzb + 255) / 256, 256, 0, st>>>(nnzb, ws.b_lrank.p, ws.src_slot);
+    PCG_TRY(cudaMemcpyAsync(ws.h_counts + 4, ws.b_lrank.p + nnzb, sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
   sym_cta_rows_kernel<<<(G + 256) / 256, 256, 0, st>>>(G, n_f, nnzb, ws.row_ptr, ws.cta_row);
   // halo lists: distinct (CTA, column) pairs.  keys[0] still holds the pattern, so sort from a copy in keys[1]
   // through the spare halves: hkeys live in ws.hkeys[0/1]
@@ -317,6 +339,7 @@ inline int pcg_symbolic_build(PcgWorkspace& ws, cudaStream_t st, std::string& er
   if (ce != cudaSuccess) { err = std::string("pcg symbolic (layout): ") + cudaGetErrorString(ce); return -2; }
 #undef PCG_TRY
   const int max_halo = ws.h_counts[1], max_slots = ws.h_counts[2], max_rows = ws.h_counts[3];
+  ws.nnz_lower = ws.h_counts[4];
   ws.smem_grid = G;
   ws.max_halo = max_halo;
   ws.max_slots = max_slots;
@@ -357,8 +380,9 @@ struct SparseTarget {
     }
     return lo;
   }
+  const int32_t* lower_of;  // [nnzb] compact index of a slot's lower source block (= PcgWorkspace::src_slot)
   __device__ __forceinline__ double* block(int fi, int fj, long long pair) const {
-    return Sraw + 36 * (size_t)(pair_slot ? pair_slot[pair] : find(fi, fj));
+    return Sraw + 36 * (size_t)(pair_slot ? pair_slot[pair] : lower_of[find(fi, fj)]);
   }
   __device__ __forceinline__ double* elem(double* blk, int e) const { return blk + e; }
 };
@@ -378,7 +402,7 @@ __global__ void pair_slot_kernel(int n_blk, const int32_t* __restrict__ e_idx, c
     int i2 = j + d;
     if (i2 >= k) i2 -= k;
     const int fp = f_idx[beg + i2];
-    out[(size_t)pair_off[pos] + d] = t.find(min(fj, fp), max(fj, fp));
+    out[(size_t)pair_off[pos] + d] = t.lower_of[t.find(min(fj, fp), max(fj, fp))];
   }
 }
 
@@ -446,7 +470,7 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __re
     a.rhs[6 * (size_t)row + i] = sr[i] * (rec[21 + i] - a.rhsm[6 * (size_t)row + i]);
   }
   const int s = diag_slot[row];
-  const double* src = a.Sraw + 36 * (size_t)s;
+  const double* src = a.Sraw + 36 * (size_t)a.src_slot[s];
   double* dst = a.Sfin + 36 * (size_t)s;
   double D[36];
 #pragma unroll

@@ -357,11 +357,15 @@ def main():
             s.options.max_num_iterations = ITERS_PER_SOLVE
             s.set_options(s.options)
 
+        keep_out = [torch.empty((m.n_cap, 6), dtype=torch.float64, pin_memory=True),
+                    torch.empty((m.n_tag, 6), dtype=torch.float64, pin_memory=True)]
+        out = tuple(t.numpy() for t in keep_out)
+
         def one_call():
             s.set_problem(m.n_cap, m.n_tag, p_cap_idx, p_tag_idx, p_obs)
             s.set_params(p_cam0, p_cap0, p_tag0)
             summ, _ = s.solve(log=False)
-            s.get_params()
+            s.get_params(out=out)
             return summ
         one_call()
         n_solves = max(1, -(-args.steps // ITERS_PER_SOLVE))

@@ -304,3 +304,37 @@ def test_radial_model_rejects_pcg(gpu_solver_cls):
     with pytest.raises(ar_slam_b200.ArslamError):
         s.solve()
     s.close()
+
+
+def test_parameter_round_trip_and_continued_solve(gpu_solver_cls):
+    """set_params / get_params move data straight between the caller's arrays and HBM: what was set
+    comes back bit-exactly, a solve updates it in place (as Ceres updates the caller's parameter
+    blocks, ar_slam_util.hpp:72,208,237), and a second solve continues from the result."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(500, 120, seed=5)
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(max_num_iterations=3))
+    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    with pytest.raises(ar_slam_b200.ArslamError):
+        s.get_params()                      # nothing set yet for this problem
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    cam, cap, tag = s.get_params()
+    assert np.array_equal(cam, m.cam0) and np.array_equal(cap, m.cap0) and np.array_equal(tag, m.tag0)
+    s1, _ = s.solve()
+    cam1, cap1, tag1 = s.get_params()
+    assert s1["iterations"] == 3 and s1["final_cost"] < s1["initial_cost"]
+    assert not np.array_equal(cap1, m.cap0)
+    c1, _, _, _, _ = s.evaluate(jacobians=False)
+    assert abs(c1 - s1["final_cost"]) <= 1e-12 * c1          # evaluate sees the solved state
+    s2, _ = s.solve()                                         # continues, does not restart
+    assert abs(s2["initial_cost"] - s1["final_cost"]) <= 1e-12 * s1["final_cost"]
+    assert s2["final_cost"] <= s1["final_cost"]
+    # caller-owned output arrays
+    out_cap, out_tag = np.zeros((m.n_cap, 6)), np.zeros((m.n_tag, 6))
+    cam2, cap2, tag2 = s.get_params(out=(out_cap, out_tag))
+    assert cap2 is out_cap and tag2 is out_tag and np.abs(out_cap).max() > 0
+    # a new problem invalidates the parameters
+    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    with pytest.raises(ar_slam_b200.ArslamError):
+        s.solve()
+    s.close()
