@@ -64,8 +64,10 @@ typedef struct arslam_options {
                                                 (>= 25 % block fill), block-sparse PCG otherwise */
   int32_t pcg_max_iterations;                /* 500 */
   int32_t num_intrinsics;                    /* 1: focal only (the reference's live model,
-                                                ar_slam_util.cpp:160-162); 3 reserved for the
-                                                radial TODO model (:164-171)                  */
+                                                ar_slam_util.cpp:160-162, l1 / l2 inert);
+                                                3: focal + l1 + l2 of the radial TODO model
+                                                (:164-171), evaluation, localisation and the
+                                                dense-Cholesky solve (PCG: ARSLAM_ERR_UNSUPPORTED) */
   int32_t verbose;                           /* 0; 1 prints the per-iteration table like
                                                 minimizer_progress_to_stdout (:1012)          */
   double initial_trust_region_radius;        /* 1e4   */
@@ -77,7 +79,10 @@ typedef struct arslam_options {
   double function_tolerance;                 /* 1e-6  */
   double gradient_tolerance;                 /* 1e-10 */
   double parameter_tolerance;                /* 1e-8  */
-  double pcg_tolerance;                      /* 0.1: relative residual ||S y - b|| / ||b|| at which PCG stops (inexact Newton; Ceres' eta) */
+  double pcg_tolerance;                      /* 0.1: relative residual ||S y - b|| / ||b|| at which
+                                                PCG stops (inexact Newton; Ceres' eta).  >= 1e-6
+                                                runs the one-barrier pipelined recurrence, tighter
+                                                values the classic one                          */
   double tag_size;                           /* 0.0635 m (ar_slam_util.hpp:319)                */
   int64_t dense_max_dim;                     /* AUTO never picks the dense Cholesky above this
                                                 reduced dimension (default 16384)              */
