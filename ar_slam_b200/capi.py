@@ -159,6 +159,17 @@ class Solver:
                                                  _p(tag_idx, C.c_int32), _p(rect8)))
         self.n_cap, self.n_tag, self.n_blk = int(n_cap), int(n_tag), len(cap_idx)
 
+    def append_blocks(self, n_cap, n_tag, cap_idx, tag_idx, rect8):
+        """Adds blocks to the problem on the device (n_cap / n_tag: new totals); set_params must follow."""
+        cap_idx, tag_idx, rect8 = _i32(cap_idx), _i32(tag_idx), _f64(rect8).reshape(-1)
+        if rect8.size != 8 * len(cap_idx) or len(tag_idx) != len(cap_idx):
+            raise ValueError("cap_idx, tag_idx and rect8 disagree on the number of blocks")
+        had = getattr(self, "n_blk", 0)
+        self._check(self._lib.arslam_append_blocks(self._h, C.c_int64(n_cap), C.c_int64(n_tag),
+                                                   C.c_int64(len(cap_idx)), _p(cap_idx, C.c_int32),
+                                                   _p(tag_idx, C.c_int32), _p(rect8)))
+        self.n_cap, self.n_tag, self.n_blk = int(n_cap), int(n_tag), had + len(cap_idx)
+
     def set_params(self, cam, cap, tag):
         cam, cap, tag = _f64(cam), _f64(cap).reshape(-1), _f64(tag).reshape(-1)
         if cam.size != 3 or cap.size != 6 * self.n_cap or tag.size != 6 * self.n_tag:

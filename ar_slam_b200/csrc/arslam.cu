@@ -84,6 +84,20 @@ struct DevBuf {
     if (e == cudaSuccess) n = count;
     return e;
   }
+  // capacity >= count with the first `keep` elements preserved (amortised growth)
+  cudaError_t grow_keep(size_t count, size_t keep, cudaStream_t st) {
+    if (count <= n && p) return cudaSuccess;
+    T* q = nullptr;
+    const size_t cap = count + count / 2 + 16;
+    cudaError_t e = cudaMalloc(&q, cap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (p) cudaFree(p);
+    p = q;
+    n = cap;
+    return e;
+  }
 };
 
 struct Profiler {
@@ -380,44 +394,37 @@ int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap) 
   return n;
 }
 
-int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk, const int32_t* cap_idx,
-                       const int32_t* tag_idx, const double* rect8) {
-  if (!s) return ARSLAM_ERR_INVALID;
-  if (n_cap <= 0 || n_tag <= 0 || n_blk <= 0 || !cap_idx || !tag_idx || !rect8)
-    return s->fail(ARSLAM_ERR_INVALID, "set_problem: empty problem or null pointer");
-  if (n_blk > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
-    return s->fail(ARSLAM_ERR_INVALID, "set_problem: problem too large for 32-bit block indices");
-  CU(cudaSetDevice(s->device));
-  s->have_problem = false;
-  s->have_params = false;
+namespace {
+
+// validates blocks [first, first + n_new) and moves them into the original-order arrays
+int store_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t first, int64_t n_new, const int32_t* cap_idx,
+                 const int32_t* tag_idx, const double* rect8, int32_t* lo_out, int32_t* hi_out) {
   // the observations (the bulk of the upload) start moving first; the index check below runs on
   // the host while the DMA is in flight (when the caller's arrays are pinned)
-  CU(s->o_obs.ensure((size_t)n_blk * 8));
-  CU(cudaMemcpyAsync(s->o_obs.p, rect8, sizeof(double) * 8 * n_blk, cudaMemcpyHostToDevice, s->stream));
+  CU(s->o_obs.grow_keep((size_t)(first + n_new) * 8, (size_t)first * 8, s->stream));
+  CU(cudaMemcpyAsync(s->o_obs.p + 8 * first, rect8, sizeof(double) * 8 * n_new, cudaMemcpyHostToDevice, s->stream));
   int32_t lo = cap_idx[0], hi = cap_idx[0];
-  for (int64_t b = 0; b < n_blk; ++b) {
+  for (int64_t b = 0; b < n_new; ++b) {
     if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
-      return s->fail(ARSLAM_ERR_INVALID, "set_problem: block %lld has an index out of range", (long long)b);
+      return s->fail(ARSLAM_ERR_INVALID, "block %lld has an index out of range", (long long)(first + b));
     lo = std::min(lo, cap_idx[b]);
     hi = std::max(hi, cap_idx[b]);
   }
-  s->cap_lo = 0;
-  s->n_cap_global = (int)n_cap;
-  if (s->world > 1) {
-    // a rank only ever touches the captures of its own blocks: work on that index range alone
-    s->cap_lo = lo;
-    n_cap = (int64_t)hi - lo + 1;
-  }
-  s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk = (int)n_blk;
-  s->plane = ((int)n_blk + 31) / 32 * 32;
+  CU(s->o_cap.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
+  CU(s->o_tag.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
+  CU(cudaMemcpyAsync(s->o_cap.p + first, cap_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->o_tag.p + first, tag_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
+  *lo_out = lo;
+  *hi_out = hi;
+  return ARSLAM_OK;
+}
+
+// both sorted copies are built on the GPU from the original-order arrays: stable radix sort of
+// (own << 32 | other) keys, then one gather kernel writes the index arrays and the 8 planes
+int rebuild_views(arslam_solver* s) {
+  s->plane = (s->n_blk + 31) / 32 * 32;
   s->n_warp = s->plane / 32;
   const int nb = s->n_blk, plane = s->plane;
-  CU(s->o_cap.ensure(nb)); CU(s->o_tag.ensure(nb));
-  CU(cudaMemcpyAsync(s->o_cap.p, cap_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(s->o_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
-  if (s->cap_lo) shift_index_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, s->o_cap.p, -s->cap_lo);
-  // both sorted copies are built on the GPU from the one upload above: stable radix sort of
-  // (own << 32 | other) keys, then one gather kernel writes the index arrays and the 8 planes
   CU(s->sort_keys[0].ensure(nb)); CU(s->sort_keys[1].ensure(nb)); CU(s->sort_vals[0].ensure(nb)); CU(s->sort_vals[1].ensure(nb));
   for (int side = 0; side < 2; ++side) {
     const int32_t* d_own = side == 0 ? s->o_cap.p : s->o_tag.p;
@@ -454,6 +461,56 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
   s->have_problem = true;
   ++s->problem_version;
   return ARSLAM_OK;
+}
+
+}  // namespace
+
+int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk, const int32_t* cap_idx,
+                       const int32_t* tag_idx, const double* rect8) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (n_cap <= 0 || n_tag <= 0 || n_blk <= 0 || !cap_idx || !tag_idx || !rect8)
+    return s->fail(ARSLAM_ERR_INVALID, "set_problem: empty problem or null pointer");
+  if (n_blk > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
+    return s->fail(ARSLAM_ERR_INVALID, "set_problem: problem too large for 32-bit block indices");
+  CU(cudaSetDevice(s->device));
+  s->have_problem = false;
+  s->have_params = false;
+  int32_t lo = 0, hi = 0;
+  const int rc = store_blocks(s, n_cap, n_tag, 0, n_blk, cap_idx, tag_idx, rect8, &lo, &hi);
+  if (rc) return rc;
+  s->cap_lo = 0;
+  s->n_cap_global = (int)n_cap;
+  if (s->world > 1) {
+    // a rank only ever touches the captures of its own blocks: work on that index range alone
+    s->cap_lo = lo;
+    n_cap = (int64_t)hi - lo + 1;
+    if (s->cap_lo) shift_index_kernel<<<cdiv(n_blk, 256), 256, 0, s->stream>>>((int)n_blk, s->o_cap.p, -s->cap_lo);
+  }
+  s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk = (int)n_blk;
+  return rebuild_views(s);
+}
+
+int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_new, const int32_t* cap_idx,
+                         const int32_t* tag_idx, const double* rect8) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem) return arslam_set_problem(s, n_cap, n_tag, n_new, cap_idx, tag_idx, rect8);
+  if (s->world > 1) return s->fail(ARSLAM_ERR_UNSUPPORTED, "append_blocks under arslam_comm_init: declare the rank's blocks with set_problem");
+  if (n_new <= 0 || !cap_idx || !tag_idx || !rect8) return s->fail(ARSLAM_ERR_INVALID, "append_blocks: no blocks or null pointer");
+  if (n_cap < s->n_cap || n_tag < s->n_tag) return s->fail(ARSLAM_ERR_INVALID, "append_blocks: pose counts cannot shrink");
+  if (s->n_blk + n_new > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
+    return s->fail(ARSLAM_ERR_INVALID, "append_blocks: problem too large for 32-bit block indices");
+  CU(cudaSetDevice(s->device));
+  s->have_problem = false;
+  s->have_params = false;
+  int32_t lo = 0, hi = 0;
+  const int rc = store_blocks(s, n_cap, n_tag, s->n_blk, n_new, cap_idx, tag_idx, rect8, &lo, &hi);
+  if (rc) {  // the earlier blocks are intact
+    s->have_problem = true;
+    return rc;
+  }
+  s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk += (int)n_new;
+  s->n_cap_global = (int)n_cap;
+  return rebuild_views(s);
 }
 
 int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6, const double* tag_pose6) {

@@ -259,6 +259,9 @@ void ArSlamSolver::compareProjections() const {
   for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(arucos_[i].data(), 6, tag.begin() + 6 * i);
   arslam_solver* g = self->handle();
   check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), added.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+  self->device_blocks_ = added;
+  self->device_captures_ = captures_.size();
+  self->device_arucos_ = arucos_.size();
   check(g, arslam_set_params(g, camera_.params.data(), cap.data(), tag.data()), "set_params");
   double cost = 0;
   check(g, arslam_evaluate(g, &cost, res.data(), nullptr, nullptr, nullptr), "evaluate");
@@ -439,14 +442,30 @@ void ArSlamSolver::localizeMany(unsigned first_loc_cap_idx) {
 // == ceres::Solve(options{max_num_iterations 50, DENSE_SCHUR}, &problem_, &summary)
 void ArSlamSolver::optimize(const Capture&) {
   if (problem_blocks_.empty()) return;
+  // The incremental schedules only ever append residual blocks between two resetProblem calls
+  // (reference :723, :832 add to the live ceres::Problem).  When the blocks already on the GPU
+  // are a prefix of the problem, only the new ones are uploaded (arslam_append_blocks); the
+  // sorted views are rebuilt on the device either way.
+  const bool is_extension = !device_blocks_.empty() && device_blocks_.size() < problem_blocks_.size() &&
+                            device_captures_ <= captures_.size() && device_arucos_ <= arucos_.size() &&
+                            std::equal(device_blocks_.begin(), device_blocks_.end(), problem_blocks_.begin(),
+                                       [](BlockHandle a, BlockHandle b) { return a.idx == b.idx; });
+  const bool is_same = device_blocks_.size() == problem_blocks_.size() && device_captures_ == captures_.size() &&
+                       device_arucos_ == arucos_.size() &&
+                       std::equal(device_blocks_.begin(), device_blocks_.end(), problem_blocks_.begin(),
+                                  [](BlockHandle a, BlockHandle b) { return a.idx == b.idx; });
+  const size_t first = is_extension ? device_blocks_.size() : 0;
   std::vector<int32_t> ci, ti;
   std::vector<double> rect;
-  ci.reserve(problem_blocks_.size()); ti.reserve(problem_blocks_.size()); rect.reserve(8 * problem_blocks_.size());
-  for (BlockHandle h : problem_blocks_) {
-    const Block& b = at(h);
-    ci.push_back(b.capture.idx);
-    ti.push_back(b.aruco.idx);
-    for (const Point& p : b.aruco_rect.corners) { rect.push_back(p.x); rect.push_back(p.y); }
+  if (!is_same) {
+    const size_t n_up = problem_blocks_.size() - first;
+    ci.reserve(n_up); ti.reserve(n_up); rect.reserve(8 * n_up);
+    for (size_t k = first; k < problem_blocks_.size(); ++k) {
+      const Block& b = at(problem_blocks_[k]);
+      ci.push_back(b.capture.idx);
+      ti.push_back(b.aruco.idx);
+      for (const Point& p : b.aruco_rect.corners) { rect.push_back(p.x); rect.push_back(p.y); }
+    }
   }
   std::vector<double> cap(6 * captures_.size()), tag(6 * arucos_.size());
   for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(captures_[i].data(), 6, cap.begin() + 6 * i);
@@ -454,7 +473,13 @@ void ArSlamSolver::optimize(const Capture&) {
   arslam_solver* g = handle();
   std::cout << "Starting solver..." << std::endl;
   check(g, arslam_set_options(g, &options_), "set_options");
-  check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), problem_blocks_.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+  if (is_extension)
+    check(g, arslam_append_blocks(g, captures_.size(), arucos_.size(), ci.size(), ci.data(), ti.data(), rect.data()), "append_blocks");
+  else if (!is_same)
+    check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), ci.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+  device_blocks_ = problem_blocks_;
+  device_captures_ = captures_.size();
+  device_arucos_ = arucos_.size();
   check(g, arslam_set_params(g, camera_.params.data(), cap.data(), tag.data()), "set_params");
   // like the reference, a solver that does not converge is not an error (summary discarded at :1013-1017);
   // API misuse and CUDA failures are

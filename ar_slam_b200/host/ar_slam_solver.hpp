@@ -149,6 +149,8 @@ protected:
   arslam_solver* gpu_ = nullptr;              // replaces `ceres::Problem problem_` (hpp:473)
   arslam_options options_;
   std::vector<BlockHandle> problem_blocks_;   // residual blocks in AddResidualBlock order
+  std::vector<BlockHandle> device_blocks_;    // the blocks resident on the GPU, in upload order (incremental uploads)
+  size_t device_captures_ = 0, device_arucos_ = 0;
   arslam_summary last_summary_{};
   std::vector<arslam_summary> summaries_;
 

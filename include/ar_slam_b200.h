@@ -137,6 +137,18 @@ int arslam_set_stream(arslam_solver* s, void* cuda_stream);
 int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk,
                        const int32_t* cap_idx, const int32_t* tag_idx, const double* rect8);
 
+/* The incremental schedules (solveIncremental :629-678, solve :744-866) add the
+ * blocks of one capture to the live ceres::Problem and solve again (:723, :832).
+ * arslam_append_blocks is that AddResidualBlock loop for a problem already on
+ * the device: only the n_new blocks cross the bus, the earlier observations
+ * stay in HBM and the sorted copies are rebuilt there.  n_cap / n_tag are the
+ * new totals (they may grow, never shrink).  Afterwards the result is the same,
+ * bit for bit, as arslam_set_problem with all blocks; parameters must be set
+ * again (arslam_set_params).  Without a current problem it is arslam_set_problem.
+ * Not available under arslam_comm_init (ARSLAM_ERR_UNSUPPORTED). */
+int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_new,
+                         const int32_t* cap_idx, const int32_t* tag_idx, const double* rect8);
+
 /* Parameter blocks live in the caller's Capture::inv_pose / Aruco::pose /
  * camera_.params (ar_slam_util.hpp:72,208,237); Ceres updated them in place
  * through raw pointers, here they are copied in before and out after, straight

@@ -338,3 +338,41 @@ def test_parameter_round_trip_and_continued_solve(gpu_solver_cls):
     with pytest.raises(ar_slam_b200.ArslamError):
         s.solve()
     s.close()
+
+
+def test_append_blocks_equals_full_problem(gpu_solver_cls):
+    """arslam_append_blocks (the AddResidualBlock loop of the incremental schedules,
+    ar_slam_util.cpp:723, :832) leaves the device in the state arslam_set_problem builds from
+    all blocks: evaluation is bit-identical, the solve agrees."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(600, 150, seed=17)
+    cut1 = int(np.searchsorted(m.cap_idx, 250))    # blocks of captures 0..249
+    cut2 = int(np.searchsorted(m.cap_idx, 251))    # one more capture, as solveIncremental adds them
+    opts = ar_slam_b200.default_options(max_num_iterations=4, linear_solver=ar_slam_b200.LINSOLVE_DENSE)
+    full = gpu_solver_cls(options=opts)
+    full.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    full.set_params(m.cam0, m.cap0, m.tag0)
+    inc = gpu_solver_cls(options=opts)
+    inc.append_blocks(250, m.n_tag, m.cap_idx[:cut1], m.tag_idx[:cut1], m.obs[:cut1])   # no problem yet: == set_problem
+    inc.append_blocks(251, m.n_tag, m.cap_idx[cut1:cut2], m.tag_idx[cut1:cut2], m.obs[cut1:cut2])
+    with pytest.raises(ar_slam_b200.ArslamError):
+        inc.solve()                                   # parameters must be set again
+    with pytest.raises(ar_slam_b200.ArslamError):
+        inc.append_blocks(100, m.n_tag, m.cap_idx[:1], m.tag_idx[:1], m.obs[:1])         # counts cannot shrink
+    with pytest.raises(ar_slam_b200.ArslamError):
+        inc.append_blocks(251, m.n_tag, [251], [0], np.zeros((1, 8)))                    # index out of range
+    inc.append_blocks(m.n_cap, m.n_tag, m.cap_idx[cut2:], m.tag_idx[cut2:], m.obs[cut2:])
+    assert inc.n_blk == full.n_blk == len(m.cap_idx)
+    inc.set_params(m.cam0, m.cap0, m.tag0)
+    cf, rf, jcf, jpf, jaf = full.evaluate()
+    ci, ri, jci, jpi, jai = inc.evaluate()
+    assert cf == ci and np.array_equal(rf, ri) and np.array_equal(jpf, jpi) and np.array_equal(jaf, jai)
+    sf, lf = full.solve()
+    si, li = inc.solve()
+    assert si["iterations"] == sf["iterations"] and si["initial_cost"] == sf["initial_cost"]
+    assert abs(si["final_cost"] - sf["final_cost"]) <= 1e-10 * sf["final_cost"]
+    pf, pi = full.get_params(), inc.get_params()
+    assert np.abs(pf[1] - pi[1]).max() < 1e-9 and np.abs(pf[2] - pi[2]).max() < 1e-9
+    full.close()
+    inc.close()
