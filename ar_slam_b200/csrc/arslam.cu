@@ -545,10 +545,10 @@ int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, doub
 }
 
 static int launch_prep(arslam_solver* s, int k) {
-  LAUNCH("prep_captures", 48.0 * s->n_cap + 8.0 * kCapPre * s->n_cap,
-         prep_captures_kernel<<<cdiv(s->n_cap, 128), 128, 0, s->stream>>>(s->n_cap, s->cap[k].p, s->cap_pre[k].p));
-  LAUNCH("prep_tags", 48.0 * s->n_tag + 8.0 * kTagPre * s->n_tag,
-         prep_tags_kernel<<<cdiv(s->n_tag, 128), 128, 0, s->stream>>>(s->n_tag, s->tag[k].p, s->opt.tag_size, s->tag_pre[k].p));
+  const int cap_ctas = cdiv(s->n_cap, 128);
+  LAUNCH("prep_poses", (48.0 + 8.0 * kCapPre) * s->n_cap + (48.0 + 8.0 * kTagPre) * s->n_tag,
+         prep_poses_kernel<<<cap_ctas + cdiv(s->n_tag, 128), 128, 0, s->stream>>>(s->n_cap, s->cap[k].p, s->cap_pre[k].p, s->n_tag, s->tag[k].p,
+                                                                               s->opt.tag_size, s->tag_pre[k].p, cap_ctas));
   return ARSLAM_OK;
 }
 
@@ -740,13 +740,12 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   PcgWorkspace& w = s->pcg;
   const size_t nvec = (size_t)6 * n_f + 2;
   double* v = w.vec;
-  CU(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), s->stream));
   PcgFinalizeArgs f;
   f.n_f = n_f; f.nnzb = w.nnzb; f.row_ptr = w.row_ptr; f.col_idx = w.col_idx; f.src_slot = w.src_slot;
   f.Sraw = Sraw; f.borderm = Sraw + (size_t)36 * w.nnz_lower; f.rhsm = f.borderm + (size_t)6 * n_f;
   f.HF = HF; f.sigF = s->sigF.p; f.sc = reinterpret_cast<const LmScalars*>(sc); f.cam_minus = cam_minus;
   f.radius = radius; f.min_diag = s->opt.min_lm_diagonal; f.max_diag = s->opt.max_lm_diagonal;
-  f.Sfin = w.Sfin; f.Minv = w.Minv; f.border = v + 6 * nvec; f.rhs = v + 7 * nvec; f.scal = w.scal;
+  f.Sfin = w.Sfin; f.Minv = w.Minv; f.border = v + 6 * nvec; f.rhs = v + 7 * nvec; f.scal = w.scal; f.partial = w.partial;
   LAUNCH("pcg_finalize_offdiag", 2.0 * 288.0 * w.nnzb,
          pcg_finalize_offdiag_kernel<<<cdiv((long long)w.nnzb * 6, 256), 256, 0, s->stream>>>(f, w.slot_row));
   LAUNCH("pcg_finalize", 8.0 * (NV + 36 + 36 + 36 + 24) * n_f,
@@ -758,6 +757,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   a.border = f.border; a.rhs = f.rhs;
   a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
   a.partial = w.partial; a.scal = w.scal; a.trace = nullptr;
+  a.sigF = s->sigF.p; a.uF = s->uF.p; a.sc = const_cast<double*>(sc);
   static unsigned long long* d_trace = nullptr;
   if (getenv("ARSLAM_PCG_TRACE")) {
     if (!d_trace) cudaMalloc(&d_trace, sizeof(unsigned long long) * 64 * 1024 * 8);
@@ -766,7 +766,6 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   }
   sa.cta_row = w.cta_row; sa.halo_ptr = w.halo_ptr; sa.halo_col = w.halo_col; sa.lcol = w.lcol;
   sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots; sa.max_rows = w.max_rows;
-  if (use_smem_flag(w)) CU(cudaMemsetAsync(w.partial, 0, 3 * 8 * sizeof(double), s->stream));
   const bool use_smem = use_smem_flag(w);
   void* args_g[] = {(void*)&a};
   void* args_s[] = {(void*)&sa};
@@ -808,7 +807,6 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
     }
   }
   ++s->launches;
-  LAUNCH("pcg_publish", 32.0, pcg_publish_kernel<<<1, 1, 0, s->stream>>>(w.scal, const_cast<double*>(sc)));
   return ARSLAM_OK;
 }
 
@@ -879,16 +877,6 @@ __global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled, int 
     const double sg = enabled ? 1.0 / (1.0 + sqrt(h[q])) : 1.0;
     sc[slot[q]] = sg;
     sigF_cam[q] = sg;
-  }
-}
-__global__ void cam_step_kernel(const double* uF_cam, const double* cam, double* cam_c, double* d_cam, double* sc, int nk) {
-  const int dslot[3] = {13, 32, 33}, xslot[3] = {15, 36, 37};
-  for (int q = 0; q < 3; ++q) {
-    const double d = q < nk ? -uF_cam[q] : 0.0;
-    d_cam[q] = d;
-    cam_c[q] = cam[q] + d;
-    sc[dslot[q]] = cam[q] - (cam[q] + d);
-    sc[xslot[q]] = cam[q];
   }
 }
 __global__ void collect_fail_kernel(int n_e, const double* Z, double* sc) {
@@ -1028,8 +1016,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr;
       schur_args = a;
       CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
-      CU(cudaMemsetAsync(sc + 12, 0, sizeof(double), s->stream));
-      LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(sd.n_e, 256), 256, 0, s->stream>>>(a, nk));
+      LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(std::max(sd.n_e, 1), 256), 256, 0, s->stream>>>(a, nk, sc + 12));
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
@@ -1050,10 +1037,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (rc) return rc;
     }
     if (fresh_linearisation) {
-      CU(cudaMemcpyAsync(sc, sc_head, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-      if (dist) CU(cudaMemcpyAsync(sc + 24, sc_head + 4, 8 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16, sc_head, sc, nk));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, nullptr, nullptr, nk));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
@@ -1084,7 +1069,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       rc = pcg_launch_solve(s, sd.n_f, S, HF, sc, cam_minus, radius, s->yF.p);
       if (rc) return rc;
     }
-    LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
+    if (lin == ARSLAM_LINSOLVE_DENSE)  // (the PCG kernels write uF themselves)
+      LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
     {
       BacksubArgs b;
       b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk;
@@ -1103,14 +1089,15 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       ap.rec = s->H[sd.e].p; ap.recx = dist ? s->Hx[sd.e].p : nullptr;
       ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
       ap.ticket = s->tickets.p + 5; ap.out = sc + 6;
+      ap.cam = nullptr; ap.cam_c = nullptr; ap.d_cam = nullptr; ap.sc = sc; ap.nk = nk;
       LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
       ap.rec = HF; ap.recx = HFx;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
       ap.ticket = s->tickets.p + 6; ap.out = sc + 9;
+      ap.cam = s->cam[k].p; ap.cam_c = s->cam[kc].p; ap.d_cam = s->d_cam.p;  // this launch also steps the intrinsics
       ap.count_norms = (s->rank == 0) ? 1 : 0;
       LAUNCH("apply_step", 144.0 * sd.n_f + 8.0 * NV * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
-      LAUNCH("cam_step", 64.0, cam_step_kernel<<<1, 1, 0, s->stream>>>(s->uF.p + cam_row, s->cam[k].p, s->cam[kc].p, s->d_cam.p, sc, nk));
     }
     cudaEventRecord(s->ev[1], s->stream);
     // ---------------- candidate point: cost at x + delta (residuals only)
@@ -1284,8 +1271,8 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   CU(cudaMemcpyAsync(d_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(d_tagpose.p, tag_pose6, sizeof(double) * 6 * n_tag, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(d_pose.p, cap_pose6, sizeof(double) * 6 * n_loc, cudaMemcpyHostToDevice, s->stream));
-  LAUNCH("prep_tags", 8.0 * (6 + kTagPre) * n_tag,
-         prep_tags_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>((int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p));
+  LAUNCH("prep_poses", 8.0 * (6 + kTagPre) * n_tag,
+         prep_poses_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>(0, nullptr, nullptr, (int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p, 0));
   LocArgs a;
   a.n_loc = (int)n_loc; a.blk_off = d_off.p; a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
   a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p;

@@ -107,28 +107,31 @@ __device__ __forceinline__ void grid_reduce_last_cta(const double (&v)[M], doubl
 }
 
 // ---------------------------------------------------------------- prep -----
-__global__ void prep_captures_kernel(int n, const double* __restrict__ pose, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double p[6], rec[kCapPre];
+// both pose sides in one launch: CTAs [0, cap_ctas) prepare captures, the rest tags
+__global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double* __restrict__ cap_pose, double* __restrict__ cap_out,
+                                                         int n_tag, const double* __restrict__ tag_pose, double tag_size,
+                                                         double* __restrict__ tag_out, int cap_ctas) {
+  if ((int)blockIdx.x < cap_ctas) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cap) return;
+    double p[6], rec[kCapPre];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) p[k] = pose[6 * (size_t)i + k];
-  prep_capture(p, rec);
-  double2* o = reinterpret_cast<double2*>(out + (size_t)kCapPre * i);
+    for (int k = 0; k < 6; ++k) p[k] = cap_pose[6 * (size_t)i + k];
+    prep_capture(p, rec);
+    double2* o = reinterpret_cast<double2*>(cap_out + (size_t)kCapPre * i);
 #pragma unroll
-  for (int k = 0; k < kCapPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
-}
-__global__ void prep_tags_kernel(int n, const double* __restrict__ pose, double tag_size,
-                                 double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double p[6], rec[kTagPre];
+    for (int k = 0; k < kCapPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+  } else {
+    const int i = (blockIdx.x - cap_ctas) * blockDim.x + threadIdx.x;
+    if (i >= n_tag) return;
+    double p[6], rec[kTagPre];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) p[k] = pose[6 * (size_t)i + k];
-  prep_tag(p, tag_size, rec);
-  double2* o = reinterpret_cast<double2*>(out + (size_t)kTagPre * i);
+    for (int k = 0; k < 6; ++k) p[k] = tag_pose[6 * (size_t)i + k];
+    prep_tag(p, tag_size, rec);
+    double2* o = reinterpret_cast<double2*>(tag_out + (size_t)kTagPre * i);
 #pragma unroll
-  for (int k = 0; k < kTagPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    for (int k = 0; k < kTagPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+  }
 }
 
 // ------------------------------------------------ kernel (1): evaluate -----

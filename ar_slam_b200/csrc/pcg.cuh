@@ -427,11 +427,14 @@ struct PcgFinalizeArgs {
   double* border;         // [6 n_f] final S_f,cam
   double* rhs;            // [6 n_f + 1] final right-hand side
   double* scal;           // [0] S_kk  [1] 1/S_kk  [3] fail
+  double* partial;        // PcgWorkspace::partial (cleared here)
 };
 
 // off-diagonal blocks: one thread per (slot, block row i) -- 6 consecutive doubles each
 __global__ void pcg_finalize_offdiag_kernel(const PcgFinalizeArgs a, const int32_t* __restrict__ slot_row) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 16) a.scal[t] = 0.0;          // (pcg_finalize_kernel, the next launch, fills [0], [1], [3])
+  if (t < 24) a.partial[t] = 0.0;       // the three rotating accumulators of grid_sums_atomic
   if (t >= a.nnzb * 6) return;
   const int s = t / 6, i = t - s * 6;
   const int row = slot_row[s], col = a.col_idx[s];
@@ -515,6 +518,11 @@ struct PcgArgs {
   double* partial;       // [grid][8]
   double* scal;          // [0] S_kk [1] 1/S_kk [2] iterations (out) [3] fail (in/out)
   unsigned long long* trace;  // debug: [iteration][cta][5] globaltimer stamps, or null
+  // results go straight to the LM loop: unscaled step uF = sigF . x, iteration count -> sc[18],
+  // failure -> sc[12]
+  const double* sigF;
+  double* uF;
+  double* sc;
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -568,10 +576,6 @@ __device__ __forceinline__ void grid_sums(cg::grid_group& grid, double (&v)[NS],
   __syncthreads();
 }
 
-__global__ void pcg_publish_kernel(const double* scal, double* sc) {
-  sc[18] = scal[2];                      // PCG iterations of this solve
-  if (scal[3] != 0.0) sc[12] = 1.0;      // failure -> invalid LM step
-}
 
 __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -711,9 +715,13 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
     if (sb[1] <= thresh) break;
     if (!isfinite(sb[1])) { fail = true; break; }
   }
+  // unscaled step for the LM loop (x is complete: the loop leaves through a grid-wide sum)
+  for (int i = blockIdx.x * kPcgThreads + threadIdx.x; i <= camrow; i += gridDim.x * kPcgThreads) a.uF[i] = a.sigF[i] * a.x[i];
   if (is_cam_owner) {
     a.scal[2] = (double)it;
     if (fail) a.scal[3] = 1.0;
+    a.sc[18] = (double)it;
+    if (fail || a.scal[3] != 0.0) a.sc[12] = 1.0;
   }
 }
 
@@ -940,12 +948,15 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_smem_kernel(const PcgSmemA
       if (!isfinite(sb[1])) { fail = true; break; }
     }
   }
-  if (hasA && lane < 6) a.x[6 * (size_t)rowA + lane] = xA;
-  if (hasB && lane < 6) a.x[6 * (size_t)rowB + lane] = xB;
+  if (hasA && lane < 6) { a.x[6 * (size_t)rowA + lane] = xA; a.uF[6 * (size_t)rowA + lane] = a.sigF[6 * (size_t)rowA + lane] * xA; }
+  if (hasB && lane < 6) { a.x[6 * (size_t)rowB + lane] = xB; a.uF[6 * (size_t)rowB + lane] = a.sigF[6 * (size_t)rowB + lane] * xB; }
   if (is_cam_owner) {
     a.x[camrow] = xk;
+    a.uF[camrow] = a.sigF[camrow] * xk;
     a.scal[2] = (double)it;
     if (fail) a.scal[3] = 1.0;
+    a.sc[18] = (double)it;
+    if (fail || a.scal[3] != 0.0) a.sc[12] = 1.0;
   }
 }
 
@@ -1131,10 +1142,12 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
       ++it;
     }
   }
-  if (owner) a.x[gi] = x;
+  if (owner) { a.x[gi] = x; a.uF[gi] = a.sigF[gi] * x; }
   if (isK) {
     a.scal[2] = (double)it;
     if (fail) a.scal[3] = 1.0;
+    a.sc[18] = (double)it;
+    if (fail || a.scal[3] != 0.0) a.sc[12] = 1.0;
   }
 }
 

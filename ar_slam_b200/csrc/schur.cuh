@@ -338,8 +338,9 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
 }
 
 // E poses without blocks never reach schur_eliminate_kernel: clear their records.
-__global__ void schur_empty_kernel(const SchurArgs a, int nk) {
+__global__ void schur_empty_kernel(const SchurArgs a, int nk, double* __restrict__ fail_flag) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) *fail_flag = 0.0;  // LmScalars::chol_fail of the linear solve that starts here
   if (e >= a.n_e || a.e_off[e + 1] > a.e_off[e]) return;
   for (int i = 0; i < 8; ++i) a.Z[8 * (size_t)e + i] = 0.0;
   for (int i = 0; i < 6 * nk; ++i) a.YB[6 * nk * (size_t)e + i] = 0.0;
@@ -504,9 +505,25 @@ struct ApplyArgs {
   unsigned* ticket;
   double* out;              // [3]
   int count_norms;          // 0: this rank does not own the sums of this side (multi-GPU)
+  // camera step (done by one thread of the launch that has cam != null)
+  const double* cam;        // [3] current intrinsics, or null
+  double* cam_c;            // [3] candidate intrinsics
+  double* d_cam;            // [3] step
+  double* sc;               // LmScalars
+  int nk;
 };
 __global__ void apply_step_kernel(const ApplyArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.cam && i == 0) {
+    const int dslot[3] = {13, 32, 33}, xslot[3] = {15, 36, 37};
+    for (int q = 0; q < 3; ++q) {
+      const double d = q < a.nk ? -a.uF_cam[q] : 0.0;
+      a.d_cam[q] = d;
+      a.cam_c[q] = a.cam[q] + d;
+      a.sc[dslot[q]] = a.cam[q] - (a.cam[q] + d);
+      a.sc[xslot[q]] = a.cam[q];
+    }
+  }
   double d2 = 0.0, x2 = 0.0, mq = 0.0;
   if (i < a.n_pose) {
     const bool active = a.seg_off[i + 1] > a.seg_off[i];
@@ -549,8 +566,12 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
 
 // max |g| over poses that own blocks
 __global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
-                                                      double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out) {
+                                                      double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out,
+                                                      const double* __restrict__ head, double* __restrict__ sc, int nk) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // the freshly summed camera scalars move next to the other LM scalars (head may be null)
+  if (head && i < 3) sc[i] = head[i];
+  if (head && nk == 3 && i >= 4 && i < 12) sc[24 + (i - 4)] = head[i];
   double m = 0.0;
   if (i < n_pose && seg_off[i + 1] > seg_off[i]) {
 #pragma unroll
