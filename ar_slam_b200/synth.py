@@ -51,14 +51,20 @@ def matrix_to_aa(R):
 
 
 def project(cam, cap_pose, tag_pose, tag_size=TAG_SIZE):
-    """Corner pixels [n,4,2] and depths [n,4] of n (capture, tag) pairs."""
+    """Corner pixels [n,4,2] and depths [n,4] of n (capture, tag) pairs.  cam = (f, l1, l2): with
+    l1 = l2 = 0 the reference's live focal-only model, otherwise the radial model of the TODO at
+    ar_slam_util.cpp:164-171, f (1 + l1 r^2 + l2 r^4) (x', y')."""
     Ra, Rc = rodrigues(tag_pose[:, 3:]), rodrigues(cap_pose[:, 3:])
     m = np.zeros((4, 3))
     m[:, :2] = 0.5 * tag_size * _DIRS
     pw = np.einsum("nij,kj->nki", Ra, m) + tag_pose[:, None, :3]
     q = pw + cap_pose[:, None, :3]
     p = np.einsum("nij,nkj->nki", Rc, q)
-    uv = cam[0] * p[..., :2] / p[..., 2:3]
+    xy = p[..., :2] / p[..., 2:3]
+    if len(cam) >= 3 and (cam[1] != 0.0 or cam[2] != 0.0):
+        r2 = (xy * xy).sum(-1, keepdims=True)
+        xy = xy * (r2 * (cam[1] + cam[2] * r2) + 1.0)
+    uv = cam[0] * xy
     return uv, p[..., 2]
 
 
@@ -67,7 +73,7 @@ class SynthMap:
 
 
 def make_map(n_cap, n_tag, tags_per_capture=8, seed=0xA55A0002, noise_px=0.3, pitch=0.3,
-             init_noise_t=0.02, init_noise_r_deg=2.0, f_init=800.0):
+             init_noise_t=0.02, init_noise_r_deg=2.0, f_init=800.0, distortion=(0.0, 0.0)):
     """Returns a SynthMap with ground truth, observations and a perturbed initial state."""
     rng = np.random.Generator(np.random.Philox(key=int(seed)))
     # ---- tags on a jittered grid
@@ -83,7 +89,7 @@ def make_map(n_cap, n_tag, tags_per_capture=8, seed=0xA55A0002, noise_px=0.3, pi
     tag_pose = np.concatenate([tag_t, tag_w], axis=1)
     extent = side * pitch
     tree = cKDTree(tag_t[:, :2])
-    cam_true = np.array([F_TRUE, 0.0, 0.0])
+    cam_true = np.array([F_TRUE, float(distortion[0]), float(distortion[1])])
 
     cap_pose = np.zeros((n_cap, 6))
     blk_cap, blk_tag, blk_obs = [], [], []

@@ -96,6 +96,9 @@ def bench_options(ar, iters, args):
     elif args.linear_solver == "pcg":
         o.linear_solver = ar.LINSOLVE_PCG
     o.pcg_tolerance = args.pcg_tolerance
+    o.num_intrinsics = args.num_intrinsics
+    if args.num_intrinsics == 3 and args.linear_solver == "auto":
+        o.dense_max_dim = 1 << 20   # the radial model is solved with the dense Cholesky
     return o
 
 
@@ -255,6 +258,8 @@ def main():
     ap.add_argument("--workload", default="ba_100k_5k", choices=sorted(WORKLOADS))
     ap.add_argument("--linear-solver", default="auto", choices=["auto", "dense", "pcg"])
     ap.add_argument("--pcg-tolerance", type=float, default=0.1)
+    ap.add_argument("--num-intrinsics", type=int, default=1, choices=[1, 3],
+                    help="3: BASELINE config 5's radial model (l1 = -0.05, l2 = 0.01 in the data, f, l1, l2 all free)")
     ap.add_argument("--cpu-sample-captures", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -296,7 +301,8 @@ def main():
         return bench_localization(args, ar, synth, torch, dist, rank, world, local_rank)
     if args.scaling == "weak":
         n_cap *= world
-    m = synth.make_map(n_cap, n_tag, tpc, seed=0xA55A0000 + cfg_id)
+    m = synth.make_map(n_cap, n_tag, tpc, seed=0xA55A0000 + cfg_id,
+                       distortion=(-0.05, 0.01) if args.num_intrinsics == 3 else (0.0, 0.0))
     cap_idx, tag_idx, obs = shard(m, rank, world)
     n_corner_total = 4 * len(m.cap_idx)
 
@@ -430,6 +436,7 @@ def main():
                 "config": {"workload": args.workload, "captures": m.n_cap, "tags": m.n_tag, "tags_per_capture": tpc,
                            "blocks": int(len(m.cap_idx)), "corners": int(n_corner_total),
                            "linear_solver": {1: "dense_cholesky_dmma", 2: "pcg"}[summaries[0]["linear_solver"]],
+                           "intrinsics": "f, l1, l2 (radial model)" if args.num_intrinsics == 3 else "f (focal only, the reference's live model)",
                            "eliminated": {1: "tags", 2: "captures"}[summaries[0]["eliminated_side"]],
                            "reduced_dim": summaries[0]["reduced_dim"], "iters_per_solve": ITERS_PER_SOLVE,
                            "l2_policy": "inputs larger than L2 (W + observations > 126 MB) for ba_100k_5k; "
