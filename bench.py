@@ -422,7 +422,27 @@ def main():
                         "frac": ach / peak, "traffic": traffic, "peak_source": how,
                         "us_per_launch": sec * 1e6, "algorithmic_bytes": top["algorithmic_bytes"],
                         "note": "fused evaluation+accumulation, J never in HBM: 18 B/corner in + 72 B/corner W out + "
-                                "264 B/pose; the kernel is also FP64-pipe bound (880 DFMA per block)"}
+                                "264 B/pose; the kernel is also FP64-pipe bound (800 FP64 instructions per block)"}
+            tot = sum(k["total_ms"] for k in kt)
+            roofline["share_of_step"] = top["total_ms"] / tot if tot else None
+            by_time = sorted(kt, key=lambda k: -k["total_ms"])[:3]
+            roofline["largest_kernels"] = [{"kernel": k["name"], "share_of_step": k["total_ms"] / tot} for k in by_time]
+        # dense path: the blocked Cholesky dominates; its roofline is the FP64 tensor (DMMA) pipe
+        chol = [k for k in kt if k["name"] == "dense_cholesky" and k["launches"] > 0]
+        if chol and cand and chol[0]["total_ms"] > max(k["total_ms"] for k in cand):
+            n = summaries[0]["reduced_dim"]
+            sec = chol[0]["total_ms"] / chol[0]["launches"] * 1e-3
+            flops = n ** 3 / 3.0 + 2.0 * n * n
+            dg_peak, dg_how = 35.5, "measured cuBLAS DGEMM on this pool's B200 (profiles/r1_fp64_peaks.json)"
+            fp = os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")
+            if os.path.exists(fp):
+                with open(fp) as f:
+                    dg_peak = max(json.load(f).values())
+            roofline = {"bound": "tensor", "kernel": "dense_cholesky", "achieved": flops / sec / 1e12, "peak": dg_peak,
+                        "unit": "TFLOP/s", "frac": flops / sec / 1e12 / dg_peak, "traffic": None, "peak_source": dg_how,
+                        "us_per_launch": sec * 1e6, "algorithmic_flops": flops,
+                        "note": "FP64 DMMA (mma.sync.m8n8k4.f64) blocked Cholesky + solve, n^3/3 + 2 n^2 flop, n = %d; "
+                                "the peak is FP64, not the bf16 figure of MEASURED_PEAKS.json" % n}
 
     if rank == 0:
         cb = None
