@@ -146,6 +146,10 @@ __global__ void shift_index_kernel(int n, int32_t* idx, int32_t by) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < n) idx[b] += by;
 }
+__global__ void segment_sizes_kernel(int n, const int32_t* __restrict__ off, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)(off[i + 1] - off[i]);
+}
 // sorted position p takes block perm[p]: indices and the 8 observation planes
 __global__ void gather_sorted_kernel(int n, int plane, const int32_t* __restrict__ perm,
                                      const unsigned long long* __restrict__ keys, const double* __restrict__ rect8,
@@ -207,6 +211,7 @@ struct arslam_solver {
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
+  DevBuf<double> f_blocks;   // multi-GPU: per F pose, number of blocks over all ranks
   DevBuf<unsigned> tickets;  // one ticket per in-kernel grid reduction (kernels.cuh), zero between launches
   DevBuf<double> Hx[2], partialx[2], warp_cam8;  // radial model: l1, l2 borders per pose side
   DevBuf<unsigned long long> sort_keys[2];
@@ -902,7 +907,10 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   // ---- which pose side is eliminated
   Sides sd;
   int elim = o.elimination;
-  if (elim == ARSLAM_ELIM_AUTO) elim = (s->n_cap >= s->n_tag) ? ARSLAM_ELIM_CAPTURES : ARSLAM_ELIM_TAGS;
+  // AUTO eliminates the larger pose set; under arslam_comm_init the captures are sharded (n_cap is this
+  // rank's range) and are the only side that can be eliminated locally
+  if (elim == ARSLAM_ELIM_AUTO)
+    elim = (s->world > 1 || s->n_cap >= s->n_tag) ? ARSLAM_ELIM_CAPTURES : ARSLAM_ELIM_TAGS;
   if (s->world > 1 && elim != ARSLAM_ELIM_CAPTURES)
     return s->fail(ARSLAM_ERR_UNSUPPORTED, "multi-GPU solve shards captures and must eliminate them");
   sd.e = elim == ARSLAM_ELIM_CAPTURES ? 0 : 1;
@@ -968,6 +976,16 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   CU(cudaMemsetAsync(sc, 0, kNumScalars * sizeof(double), s->stream));
 
   int rc = ARSLAM_OK;
+  // multi-GPU: an F pose (tag) is live when ANY rank holds a block of it; a rank that holds none must
+  // still move it, or the replicated tag poses drift apart
+  const double* f_blocks_all = nullptr;
+  if (s->world > 1) {
+    CU(s->f_blocks.ensure((size_t)sd.n_f));
+    segment_sizes_kernel<<<cdiv(sd.n_f, 256), 256, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, s->f_blocks.p);
+    int rcb = nccl_sum(s, s->f_blocks.p, (size_t)sd.n_f);
+    if (rcb) return rcb;
+    f_blocks_all = s->f_blocks.p;
+  }
   launch_prep(s, s->cur);
   launch_accumulate(s, sd, s->cur, HF, HFx, sc_head);
 
@@ -1037,8 +1055,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (rc) return rc;
     }
     if (fresh_linearisation) {
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16, sc_head, sc, nk));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, nullptr, nullptr, nk));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16, sc_head, sc, nk, nullptr));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, nullptr, nullptr, nk, f_blocks_all));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
@@ -1085,12 +1103,14 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     {
       ApplyArgs ap;
       ap.uF_cam = s->uF.p + cam_row;
+      ap.blocks_all = nullptr;
       ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
       ap.rec = s->H[sd.e].p; ap.recx = dist ? s->Hx[sd.e].p : nullptr;
       ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
       ap.ticket = s->tickets.p + 5; ap.out = sc + 6;
       ap.cam = nullptr; ap.cam_c = nullptr; ap.d_cam = nullptr; ap.sc = sc; ap.nk = nk;
       LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
+      ap.blocks_all = f_blocks_all;
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
       ap.rec = HF; ap.recx = HFx;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;

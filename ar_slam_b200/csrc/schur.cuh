@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
 struct ApplyArgs {
   int n_pose;
   const int32_t* seg_off;   // [n_pose + 1] (sorted by this side)
+  const double* blocks_all; // multi-GPU, F side: blocks of the pose summed over all ranks (a rank may hold none), else null
   const double* x;          // [6 n_pose]
   const double* step;       // [6 n_pose]: d_e (already the step) or uF (to be negated)
   int negate;
@@ -526,7 +527,7 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
   }
   double d2 = 0.0, x2 = 0.0, mq = 0.0;
   if (i < a.n_pose) {
-    const bool active = a.seg_off[i + 1] > a.seg_off[i];
+    const bool active = a.blocks_all ? a.blocks_all[i] > 0.0 : a.seg_off[i + 1] > a.seg_off[i];
     double d[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -567,13 +568,14 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
 // max |g| over poses that own blocks
 __global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
                                                       double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out,
-                                                      const double* __restrict__ head, double* __restrict__ sc, int nk) {
+                                                      const double* __restrict__ head, double* __restrict__ sc, int nk,
+                                                      const double* __restrict__ blocks_all) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   // the freshly summed camera scalars move next to the other LM scalars (head may be null)
   if (head && i < 3) sc[i] = head[i];
   if (head && nk == 3 && i >= 4 && i < 12) sc[24 + (i - 4)] = head[i];
   double m = 0.0;
-  if (i < n_pose && seg_off[i + 1] > seg_off[i]) {
+  if (i < n_pose && (blocks_all ? blocks_all[i] > 0.0 : seg_off[i + 1] > seg_off[i])) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) m = fmax(m, fabs(rec[(size_t)i * NV + 21 + k]));
   }

@@ -25,7 +25,9 @@ def fresh_uid():
 
 
 ok = True
-for name, ls, (nc, nt) in (("dense", ar.LINSOLVE_DENSE, (3000, 400)), ("pcg", ar.LINSOLVE_PCG, (20000, 1500))):
+# "few-captures": every rank misses some of the tags, which must move all the same
+for name, ls, (nc, nt) in (("dense", ar.LINSOLVE_DENSE, (3000, 400)), ("pcg", ar.LINSOLVE_PCG, (20000, 1500)),
+                           ("few-captures", ar.LINSOLVE_DENSE, (40 * world, 200))):
     m = synth.make_map(nc, nt, seed=31)
     opts = ar.default_options(linear_solver=ls, pcg_tolerance=1e-10, pcg_max_iterations=3000)
     s = ar.Solver(device=local, options=opts)
