@@ -211,6 +211,7 @@ struct arslam_solver {
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
+  DenseCholesky::LookAhead lookahead;  // second stream + events of the dense factorisation
   DevBuf<double> f_blocks;   // multi-GPU: per F pose, number of blocks over all ranks
   DevBuf<unsigned> tickets;  // one ticket per in-kernel grid reduction (kernels.cuh), zero between launches
   DevBuf<double> Hx[2], partialx[2], warp_cam8;  // radial model: l1, l2 borders per pose side
@@ -956,6 +957,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     s->n_pad = (n + 1 + CB - 1) / CB * CB;
     s->ld = s->n_pad;
     s_elems = (size_t)s->n_pad * s->ld;
+    CU(s->linv.ensure((size_t)(s->n_pad / CB) * CB * CB));
     CU(s->yF.ensure((size_t)s->n_pad));
   } else {
     int rc = pcg_prepare(s, sd.e, sd.n_e, sd.n_f);
@@ -1075,13 +1077,13 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (s->prof.on) {
         Profiler::Rec r{s->prof.id_of("dense_cholesky", 0.0), s->prof.ev(), s->prof.ev()};
         cudaEventRecord(r.a, s->stream);
-        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream);
-        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
+        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream, s->lookahead);
+        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, s->stream);
         cudaEventRecord(r.b, s->stream);
         s->prof.recs.push_back(r);
       } else {
-        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream);
-        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->stream);
+        s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream, s->lookahead);
+        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, s->stream);
       }
     } else {
       rc = pcg_launch_solve(s, sd.n_f, S, HF, sc, cam_minus, radius, s->yF.p);

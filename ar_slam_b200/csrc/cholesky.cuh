@@ -8,7 +8,16 @@
 // right-hand side rides along as one extra row, so the sweep also does the
 // forward substitution; dense_backsolve then solves L^T y = w.
 // Failure (non-positive pivot) raises *fail like Eigen's info() != Success.
+//
+// Two-level blocking.  A 64-wide right-looking sweep updates every trailing tile with K = 64,
+// i.e. 4 flop per byte of C traffic: HBM bound, not tensor bound.  So the 64-wide steps only
+// keep the columns of the current 256-wide OUTER panel up to date (syrk_dmma_kernel on that
+// strip), and the rest of the trailing matrix receives the whole outer panel at once from
+// syrk_big_dmma_kernel: 128 x 128 tiles of C, K = 256, operands streamed through a two-stage
+// cp.async pipeline -- ~15 flop per byte, which puts the update on the DMMA pipe.
 #pragma once
+#include <algorithm>
+#include <vector>
 #include <cuda_runtime.h>
 
 namespace ars {
@@ -76,19 +85,23 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
-// --- trailing update C(ti,tj) -= P(ti) P(tj)^T on 64x64 tiles, tj <= ti ----
+// m16n8k8 FP64 MMA (sm_90+): A 16x8 row (a0 (g,t) a1 (g+8,t) a2 (g,t+4) a3 (g+8,t+4)), B 8x8 col
+// (b0 (k=t,n=g) b1 (k=t+4,n=g)), C/D 16x8 (c0 (g,2t) c1 (g,2t+1) c2 (g+8,2t) c3 (g+8,2t+1)); g = lane / 4, t = lane % 4
+__device__ __forceinline__ void dmma1688(double (&d)[4], const double (&a)[4], const double (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+               : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
+// --- in-panel update C(ti,tj) -= P(ti) P(tj)^T on 64x64 tiles, tj <= ti, tj inside the outer panel ----
 // 4 warps per CTA, each a 32x32 quadrant = 4x4 DMMA tiles, K = 64.
 __global__ void __launch_bounds__(128) syrk_dmma_kernel(double* __restrict__ A, long long ld, int k0) {
   extern __shared__ double sm[];
   double(*Pi)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(sm);
   double(*Pj)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(sm + CB * CB_LD);
-  // decode linear tile id -> (ti >= tj)
-  const int p = blockIdx.x;
-  int tj, ti;
-  ti = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
-  while (ti * (ti + 1) / 2 > p) --ti;
-  tj = p - ti * (ti + 1) / 2;
+  // tile (ti >= tj) of the strip: grid (row tiles, column tiles of the outer panel)
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  if (ti < tj) return;
   const int r0 = k0 + CB + ti * CB, c0 = k0 + CB + tj * CB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (int e = tid; e < CB * CB; e += 128) {
@@ -125,6 +138,120 @@ __global__ void __launch_bounds__(128) syrk_dmma_kernel(double* __restrict__ A, 
       v.x -= acc[mi][ni][0];
       v.y -= acc[mi][ni][1];
       *c = v;
+    }
+}
+
+// --- trailing update with a whole outer panel: C(ti,tj) -= P(ti) P(tj)^T, 128x128 tiles, K = kw ----
+// P = A[:, K0 .. K0 + kw), the finished outer panel.  8 warps (2 x 4), warp tile 64 x 32 =
+// 8 x 4 DMMA tiles; k runs in chunks of 32 through a two-stage cp.async pipeline.
+constexpr int BT = 128;          // C tile
+constexpr int BK = 32;           // k chunk
+constexpr int BK_LD = BK + 4;    // shared-memory row stride: conflict-free DMMA fragment loads, 16-byte aligned rows
+constexpr int kBigThreads = 256;
+constexpr size_t kBigSmem = (size_t)2 /*stages*/ * 2 /*Pi, Pj*/ * BT * BK_LD * sizeof(double);
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+// Tiles: strip_cols > 0: grid (row tiles, strip_cols) = the tile columns [0, strip_cols) (the next outer
+// panel, updated first so that its factorisation can start); else a linear id over the triangle of the
+// tiles with ti >= tj >= tile_off (the rest, which runs beside that factorisation on a second stream).
+__global__ void __launch_bounds__(kBigThreads, 1) syrk_big_dmma_kernel(double* __restrict__ A, long long ld, int K0, int kw,
+                                                                       int n_pad, int tile_off, int strip_cols) {
+  extern __shared__ __align__(16) double sm[];
+  int ti, tj;
+  if (strip_cols > 0) {
+    ti = blockIdx.x;
+    tj = blockIdx.y;
+    if (ti < tj) return;
+  } else {
+    const int p = blockIdx.x;
+    ti = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+    while (ti * (ti + 1) / 2 > p) --ti;
+    tj = p - ti * (ti + 1) / 2;
+    ti += tile_off;
+    tj += tile_off;
+  }
+  const int base = K0 + kw;
+  const int r0 = base + ti * BT, c0 = base + tj * BT;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  auto stage_ptr = [&](int st, int which) { return sm + (size_t)(st * 2 + which) * BT * BK_LD; };
+  // one chunk = 2 x (128 rows x 32 doubles): 4096 16-byte pieces, 16 per thread
+  auto load_chunk = [&](int st, int kc) {
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int e = tid + it * kBigThreads;      // 0 .. 4095
+      const int which = e >> 11, q = e & 2047;   // 2048 pieces per operand
+      const int r = q >> 4, c2 = (q & 15) * 2;   // row, first double of the piece
+      const int gr = (which == 0 ? r0 : c0) + r;
+      double* dst = stage_ptr(st, which) + r * BK_LD + c2;
+      if (gr < n_pad) cp_async16(dst, A + (size_t)gr * ld + K0 + kc * BK + c2);
+      else { dst[0] = 0.0; dst[1] = 0.0; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int rb = (w >> 2) * 64, cb = (w & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][4];  // 4 x 4 MMA tiles of 16 x 8
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0;
+  const int nchunk = kw / BK;
+  load_chunk(0, 0);
+  for (int kc = 0; kc < nchunk; ++kc) {
+    if (kc + 1 < nchunk) {
+      load_chunk((kc + 1) & 1, kc + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double* Pi = stage_ptr(kc & 1, 0);
+    const double* Pj = stage_ptr(kc & 1, 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 8) {
+      double af[4][4], bf[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const double* r0p = Pi + (rb + mi * 16 + g) * BK_LD + kk + t;
+        af[mi][0] = r0p[0];
+        af[mi][1] = r0p[8 * BK_LD];
+        af[mi][2] = r0p[4];
+        af[mi][3] = r0p[8 * BK_LD + 4];
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const double* c0p = Pj + (cb + ni * 8 + g) * BK_LD + kk + t;
+        bf[ni][0] = c0p[0];
+        bf[ni][1] = c0p[4];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma1688(acc[mi][ni], af[mi], bf[ni]);
+    }
+    __syncthreads();  // the stage is overwritten by the load issued in the next iteration
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gr = r0 + rb + mi * 16 + g + 8 * h;
+      if (gr >= n_pad) continue;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int gc = c0 + cb + ni * 8 + 2 * t;
+        if (gc >= n_pad) continue;
+        double2* c = reinterpret_cast<double2*>(A + (size_t)gr * ld + gc);
+        double2 v = *c;
+        v.x -= acc[mi][ni][2 * h];
+        v.y -= acc[mi][ni][2 * h + 1];
+        *c = v;
+      }
     }
 }
 
@@ -171,34 +298,44 @@ __global__ void __launch_bounds__(128) trsm_dmma_kernel(double* __restrict__ A, 
 }
 
 // --- one 64-block step of L^T y = w (w = row rhs_row), from the bottom up ---
-// Every CTA solves the diagonal block redundantly in shared memory, CTA 0
-// publishes y_k, and CTA b folds y_k into w[256 b .. 256 b + 255] (< k0).
+// y_k = Linv_k^T w_k with the block inverse kept from the factorisation (no 64-step substitution
+// chain): every CTA forms y_k redundantly, CTA 0 publishes it, and CTA b folds y_k into
+// w[64 b .. 64 b + 63] (< k0).  Only the leading nv unknowns of the last block are real.
 __global__ void __launch_bounds__(256) backsolve_step_kernel(double* __restrict__ A, long long ld, int k0,
-                                                             int n, int rhs_row, double* __restrict__ y) {
-  __shared__ double L[CB][CB + 1];
-  __shared__ double wv[CB];
+                                                             int n, int rhs_row, double* __restrict__ y,
+                                                             const double* __restrict__ Linv) {
+  __shared__ double wv[CB], yv[CB];
   const int tid = threadIdx.x;
   const int nv = min(CB, n - k0);
-  for (int e = tid; e < CB * CB; e += 256) {
-    const int r = e / CB, c = e % CB;
-    L[r][c] = (c <= r && r < nv) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-  }
   if (tid < CB) wv[tid] = tid < nv ? A[(size_t)rhs_row * ld + k0 + tid] : 0.0;
   __syncthreads();
-  for (int c = nv - 1; c >= 0; --c) {
-    if (tid == 0) wv[c] = wv[c] / L[c][c];
-    __syncthreads();
-    if (tid < c) wv[tid] -= L[c][tid] * wv[c];
-    __syncthreads();
+  {
+    // y_r = sum_{c >= r} Linv[c][r] w_c: four lanes per r
+    const int r = tid >> 2, part = tid & 3;
+    double acc = 0.0;
+    for (int c = r + part; c < nv; c += 4) acc += Linv[c * CB + r] * wv[c];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) yv[r] = r < nv ? acc : 0.0;
   }
-  if (blockIdx.x == 0 && tid < nv) y[k0 + tid] = wv[tid];
-  const int j = blockIdx.x * 256 + tid;
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < nv) y[k0 + tid] = yv[tid];
+  // w[j] -= sum_r L[k0 + r][j] y_r for 64 columns j per CTA: four groups of 16 rows each, so that
+  // every thread has 16 independent loads in flight instead of a 64-long chain
+  __shared__ double part[4][CB];
+  const int jl = tid & 63, grp = tid >> 6;
+  const int j = blockIdx.x * CB + jl;
+  double s = 0.0;
   if (j < k0) {
-    double s = 0.0;
-#pragma unroll 8
-    for (int r = 0; r < nv; ++r) s += A[(size_t)(k0 + r) * ld + j] * wv[r];
-    A[(size_t)rhs_row * ld + j] -= s;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int r = grp * 16 + q;
+      if (r < nv) s += A[(size_t)(k0 + r) * ld + j] * yv[r];
+    }
   }
+  part[grp][jl] = s;
+  __syncthreads();
+  if (grp == 0 && j < k0) A[(size_t)rhs_row * ld + j] -= (part[0][jl] + part[1][jl]) + (part[2][jl] + part[3][jl]);
 }
 
 struct DenseCholesky {
@@ -206,29 +343,90 @@ struct DenseCholesky {
   static cudaError_t init() {
     cudaError_t e = cudaFuncSetAttribute(trsm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    e = cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(syrk_big_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
   }
-  // factor rows/cols [0, n_pad); linv = 64 x 64 scratch; returns number of launches
-  static int factor(double* A, long long ld, int n_pad, double* linv, double* fail, cudaStream_t st) {
+  static constexpr int NB = 256;  // outer panel width
+  // Second stream + events for the look-ahead: after outer panel P is factored, the update of the
+  // NEXT panel's columns (strip) stays on the caller's stream, followed by that panel's
+  // factorisation, while the update of everything beyond (rest) runs on `aux` (lower priority,
+  // so the latency-bound factorisation kernels get SM slots first).
+  struct LookAhead {
+    cudaStream_t aux = nullptr;
+    std::vector<cudaEvent_t> ev;  // [2 P]: panel P factored, [2 P + 1]: rest(P) done
+    cudaError_t ensure(int panels) {
+      if (!aux) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const cudaError_t e = cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, lo);
+        if (e != cudaSuccess) return e;
+      }
+      while ((int)ev.size() < 2 * panels) {
+        cudaEvent_t x;
+        const cudaError_t e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        ev.push_back(x);
+      }
+      return cudaSuccess;
+    }
+    ~LookAhead() {
+      for (cudaEvent_t x : ev) cudaEventDestroy(x);
+      if (aux) cudaStreamDestroy(aux);
+    }
+  };
+  // factor rows/cols [0, n_pad); linv = (n_pad / 64) x 64 x 64: the inverses of the diagonal blocks' factors;
+  // returns the number of launches
+  static int factor(double* A, long long ld, int n_pad, double* linv, double* fail, cudaStream_t st, LookAhead& la) {
     int launches = 0;
-    for (int k0 = 0; k0 < n_pad; k0 += CB) {
-      potrf_inv_kernel<<<1, CB, 0, st>>>(A, ld, k0, linv, fail);
+    const int panels = (n_pad + NB - 1) / NB;
+    if (la.ensure(panels) != cudaSuccess) return 0;
+    int last_rest = -1;  // last panel whose rest update was launched on aux
+    for (int P = 0; P < panels; ++P) {
+      const int K0 = P * NB;
+      const int kw = std::min(NB, n_pad - K0);
+      for (int k0 = K0; k0 < K0 + kw; k0 += CB) {
+        double* linv_k = linv + (size_t)(k0 / CB) * CB * CB;  // kept for the back-substitution
+        potrf_inv_kernel<<<1, CB, 0, st>>>(A, ld, k0, linv_k, fail);
+        ++launches;
+        const int rem = (n_pad - k0 - CB) / CB;          // row tiles below the diagonal block
+        if (rem > 0) {
+          trsm_dmma_kernel<<<rem, 128, kTileSmem, st>>>(A, ld, k0, linv_k);
+          ++launches;
+          const int ntj = (K0 + kw - k0 - CB) / CB;      // column tiles still inside the outer panel
+          if (ntj > 0) {
+            syrk_dmma_kernel<<<dim3(rem, ntj), 128, kTileSmem, st>>>(A, ld, k0);
+            ++launches;
+          }
+        }
+      }
+      const int left = n_pad - K0 - kw;                  // trailing rows / columns
+      if (left <= 0) break;
+      const int nt = (left + BT - 1) / BT;
+      const int strip = std::min(nt, NB / BT);           // tile columns of the next outer panel
+      cudaEventRecord(la.ev[2 * P], st);                 // panel P is factored
+      // the strip reads and writes columns that rest(P - 1) wrote
+      if (last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);
+      syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip);
       ++launches;
-      const int rem = (n_pad - k0 - CB) / CB;
-      if (rem > 0) {
-        trsm_dmma_kernel<<<rem, 128, kTileSmem, st>>>(A, ld, k0, linv);
-        syrk_dmma_kernel<<<rem * (rem + 1) / 2, 128, kTileSmem, st>>>(A, ld, k0);
-        launches += 2;
+      if (nt > strip) {
+        const int m = nt - strip;
+        cudaStreamWaitEvent(la.aux, la.ev[2 * P], 0);
+        syrk_big_dmma_kernel<<<m * (m + 1) / 2, kBigThreads, kBigSmem, la.aux>>>(A, ld, K0, kw, n_pad, strip, 0);
+        cudaEventRecord(la.ev[2 * P + 1], la.aux);
+        last_rest = P;
+        ++launches;
       }
     }
+    if (last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);  // (already implied by the last strip; harmless)
     return launches;
   }
   // solves L^T y = w for the leading n unknowns; w is row rhs_row (== n) and is destroyed
-  static int backsolve(double* A, long long ld, int n, int rhs_row, double* y, cudaStream_t st) {
+  static int backsolve(double* A, long long ld, int n, int rhs_row, double* y, const double* linv, cudaStream_t st) {
     int launches = 0;
     for (int k0 = ((n - 1) / CB) * CB; k0 >= 0; k0 -= CB) {
-      const int grid = k0 > 0 ? (k0 + 255) / 256 : 1;
-      backsolve_step_kernel<<<grid, 256, 0, st>>>(A, ld, k0, n, rhs_row, y);
+      const int grid = k0 > 0 ? (k0 + CB - 1) / CB : 1;
+      backsolve_step_kernel<<<grid, 256, 0, st>>>(A, ld, k0, n, rhs_row, y, linv + (size_t)(k0 / CB) * CB * CB);
       ++launches;
     }
     return launches;
