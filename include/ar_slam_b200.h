@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ARSLAM_ABI_VERSION 1
+#define ARSLAM_ABI_VERSION 2 /* 2: arslam_append_blocks, device-resident parameters */
 
 enum {
   ARSLAM_OK = 0,
