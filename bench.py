@@ -48,14 +48,30 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a
+    thread (the timed region is a few tens of ms, too short for nvidia-smi's 100 ms loop), with
+    nvidia-smi as the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index=0):
         self.samples, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        self.sm, self.mx, self.mask = [], None, 0
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -65,11 +81,27 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            reasons = [name for name, bit in self.BITS if self.mask & bit]
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -80,7 +112,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def bench_options(ar, iters, args):
@@ -252,8 +284,8 @@ def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ba_100k_5k", choices=sorted(WORKLOADS))
     ap.add_argument("--linear-solver", default="auto", choices=["auto", "dense", "pcg"])
