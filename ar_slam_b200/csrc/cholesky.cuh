@@ -25,60 +25,136 @@ namespace ars {
 constexpr int CB = 64;        // panel width / tile size
 constexpr int CB_LD = CB + 4; // shared-memory row stride (bank-conflict free for the DMMA fragments)
 
-// --- factor the CB x CB diagonal block and invert its factor (one CTA, one thread per row) --
-// Left-looking column Cholesky in shared memory, then every thread forward-substitutes one
-// column of the identity: Linv = L^-1 (lower triangular).  With Linv the panel solve below is
-// a GEMM and runs on the FP64 tensor pipe as well.
-__global__ void __launch_bounds__(CB) potrf_inv_kernel(double* __restrict__ A, long long ld, int k0,
-                                                       double* __restrict__ Linv, double* __restrict__ fail) {
-  // one array, two triangles: the lower one (with diagonal) holds L, the strictly upper one
-  // receives Linv^T (Linv is lower triangular, its diagonal is 1 / L[r][r])
-  __shared__ double T[CB][CB + 1];
-  __shared__ double dinv[CB];
-  __shared__ double piv;
-  const int i = threadIdx.x;
-  for (int c = 0; c < CB; ++c) T[i][c] = (c <= i) ? A[(size_t)(k0 + i) * ld + k0 + c] : 0.0;
-  __syncthreads();
-  for (int j = 0; j < CB; ++j) {
-    double s0 = 0.0, s1 = 0.0;
-    if (i >= j) {
-      int k = 0;
-      for (; k + 1 < j; k += 2) {
-        s0 += T[i][k] * T[j][k];
-        s1 += T[i][k + 1] * T[j][k + 1];
-      }
-      if (k < j) s0 += T[i][k] * T[j][k];
+// --- factor the CB x CB diagonal block and invert its factor (one CTA, 256 threads) --------
+// With Linv = L^-1 the panel solve below is a GEMM and runs on the FP64 tensor pipe as well, and
+// the back-substitution reuses it.  This kernel sits on the critical path of every 64-wide step
+// (188 times for n = 12 003), so it is built for latency (profiles/r1_microbench.txt: a
+// thread-per-row column Cholesky in shared memory takes 73 us, this one 30 us):
+// Blocked: the 64 x 64 block is a 4 x 4 grid of 16 x 16 sub-blocks.  The diagonal sub-blocks are
+// factored and inverted by ONE warp with the rows in registers and shuffles instead of shared-memory round
+// trips and CTA barriers; panel solves, trailing updates and the block inverse are 16 x 16 x 16 products by
+// all 256 threads (one output element each).
+constexpr int SB = 16;        // sub-block
+constexpr int TLD = CB + 1;   // shared-memory row stride
+constexpr size_t kPotrfSmem = (size_t)(2 * CB * TLD + 3 * SB * (SB + 1)) * sizeof(double);
+__device__ __forceinline__ void potrf16_warp(double* T /* block (kb,kb), row stride TLD */, double* X /* same position in the inverse */,
+                                             double* fail) {
+  const int lane = threadIdx.x & 31;
+  const int i = lane & 15;  // lanes 16..31 mirror lanes 0..15 (keeps the shuffles full-warp)
+  double a[SB], p[SB], x[SB];
+#pragma unroll
+  for (int c = 0; c < SB; ++c) a[c] = (c <= i) ? T[i * TLD + c] : 0.0;
+#pragma unroll
+  for (int j = 0; j < SB; ++j) {
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0) && lane == 0) *fail = 1.0;
+    p[j] = rsqrt(d);
+    a[j] *= p[j];  // lane j: d / sqrt(d) = sqrt(d); lanes i > j: l_ij
+#pragma unroll
+    for (int c = j + 1; c < SB; ++c) {
+      const double lc = __shfl_sync(0xffffffffu, a[j], c);
+      a[c] -= a[j] * lc;  // only c <= i is used later
     }
-    const double sres = (i >= j) ? T[i][j] - (s0 + s1) : 0.0;
-    if (i == j) {
-      if (!(sres > 0.0)) *fail = 1.0;
-      piv = 1.0 / sqrt(sres);
-    }
-    __syncthreads();
-    if (i >= j) T[i][j] = sres * piv;  // i == j: d / sqrt(d) = sqrt(d)
-    if (i == j) dinv[j] = piv;
-    __syncthreads();
   }
-  // column i of L^-1: x_r = (delta_ri - sum_{k=i}^{r-1} L[r][k] x_k) / L[r][r], x_r kept at T[i][r]
-  double xi = dinv[i];  // x_i
-  for (int r = i + 1; r < CB; ++r) {
-    double s0 = -T[r][i] * xi, s1 = 0.0;
-    int k = i + 1;
-    for (; k + 1 < r; k += 2) {
-      s0 -= T[r][k] * T[i][k];
-      s1 -= T[r][k + 1] * T[i][k + 1];
-    }
-    if (k < r) s0 -= T[r][k] * T[i][k];
-    T[i][r] = (s0 + s1) * dinv[r];
+  // inverse, lane c owns column c: x_r = p_r (delta_rc - sum_{k<r} L[r][k] x_k)
+#pragma unroll
+  for (int r = 0; r < SB; ++r) {
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) sum += __shfl_sync(0xffffffffu, a[k], r) * x[k];
+    x[r] = r < i ? 0.0 : (r == i ? p[r] : -p[r] * sum);
   }
-  __syncthreads();
-  for (int c = 0; c < CB; ++c) {
-    if (c <= i) A[(size_t)(k0 + i) * ld + k0 + c] = T[i][c];
-    // Linv[i][c] = x_i of column c = T[c][i] for c < i, dinv on the diagonal, 0 above
-    Linv[i * CB + c] = c < i ? T[c][i] : (c == i ? dinv[i] : 0.0);
+  if (lane < SB) {
+#pragma unroll
+    for (int c = 0; c < SB; ++c) {
+      if (c <= i) T[i * TLD + c] = a[c];
+      X[c * TLD + i] = c >= i ? x[c] : 0.0;  // X[r][col i] = x[r]
+    }
   }
 }
-
+__global__ void __launch_bounds__(256) potrf_inv_kernel(double* __restrict__ A, long long ld, int k0,
+                                                        double* __restrict__ Linv, double* __restrict__ fail) {
+  extern __shared__ double sm3[];
+  double* T = sm3;                 // [64][65] L
+  double* X = sm3 + CB * TLD;      // [64][65] L^-1 (lower)
+  double* S = X + CB * TLD;        // [3][16][17] temporaries
+  const int tid = threadIdx.x;
+  const int er = tid >> 4, ec = tid & 15;  // the output element this thread owns in a 16 x 16 product
+  A += (size_t)k0 * ld + k0;
+#pragma unroll
+  for (int q = 0; q < CB * CB / 256; ++q) {  // 16 independent loads per thread
+    const int e = tid + q * 256;
+    const int r = e >> 6, c = e & 63;
+    T[r * TLD + c] = (c <= r) ? A[(size_t)r * ld + c] : 0.0;
+    X[r * TLD + c] = 0.0;
+  }
+  __syncthreads();
+  for (int kb = 0; kb < 4; ++kb) {
+    if (tid < 32) potrf16_warp(T + (kb * SB) * TLD + kb * SB, X + (kb * SB) * TLD + kb * SB, fail);
+    __syncthreads();
+    // panel: L(ib,kb) = A(ib,kb) Xkk^T, element (r,c) = sum_{m<=c} A(r,m) Xkk(c,m)
+    double v[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ib = kb + 1 + q;
+      v[q] = 0.0;
+      if (ib < 4) {
+        const double* a = T + (ib * SB + er) * TLD + kb * SB;
+        const double* xk = X + (kb * SB + ec) * TLD + kb * SB;
+#pragma unroll
+        for (int m = 0; m < SB; ++m) v[q] += a[m] * xk[m];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ib = kb + 1 + q;
+      if (ib < 4) T[(ib * SB + er) * TLD + kb * SB + ec] = v[q];
+    }
+    __syncthreads();
+    // trailing update: T(ib,jb) -= L(ib,kb) L(jb,kb)^T, ib >= jb > kb
+    for (int ib = kb + 1; ib < 4; ++ib)
+      for (int jb = kb + 1; jb <= ib; ++jb) {
+        const double* a = T + (ib * SB + er) * TLD + kb * SB;
+        const double* b = T + (jb * SB + ec) * TLD + kb * SB;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < SB; ++m) s += a[m] * b[m];
+        T[(ib * SB + er) * TLD + jb * SB + ec] -= s;
+      }
+    __syncthreads();
+  }
+  // block inverse by anti-diagonals: X(i,j) = -Xii * sum_{k=j}^{i-1} L(i,k) X(k,j)
+  for (int d = 1; d < 4; ++d) {
+    const int nb = 4 - d;  // blocks (i, j) = (j + d, j), j = 0 .. nb - 1
+    for (int j = 0; j < nb; ++j) {
+      const int i = j + d;
+      double s = 0.0;
+      for (int k = j; k < i; ++k) {
+        const double* a = T + (i * SB + er) * TLD + k * SB;   // L(i,k) row er
+        const double* b = X + (k * SB) * TLD + j * SB + ec;   // X(k,j) column ec
+#pragma unroll
+        for (int m = 0; m < SB; ++m) s += a[m] * b[m * TLD];
+      }
+      S[(j * SB + er) * (SB + 1) + ec] = s;
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+      const int i = j + d;
+      const double* a = X + (i * SB + er) * TLD + i * SB;     // Xii row er (lower triangular)
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < SB; ++m) s += a[m] * S[(j * SB + m) * (SB + 1) + ec];
+      X[(i * SB + er) * TLD + j * SB + ec] = -s;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < CB * CB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (c <= r) A[(size_t)r * ld + c] = T[r * TLD + c];
+    Linv[e] = c <= r ? X[r * TLD + c] : 0.0;
+  }
+}
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
@@ -343,6 +419,8 @@ struct DenseCholesky {
   static cudaError_t init() {
     cudaError_t e = cudaFuncSetAttribute(trsm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(syrk_big_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
@@ -387,7 +465,7 @@ struct DenseCholesky {
       const int kw = std::min(NB, n_pad - K0);
       for (int k0 = K0; k0 < K0 + kw; k0 += CB) {
         double* linv_k = linv + (size_t)(k0 / CB) * CB * CB;  // kept for the back-substitution
-        potrf_inv_kernel<<<1, CB, 0, st>>>(A, ld, k0, linv_k, fail);
+        potrf_inv_kernel<<<1, 256, kPotrfSmem, st>>>(A, ld, k0, linv_k, fail);
         ++launches;
         const int rem = (n_pad - k0 - CB) / CB;          // row tiles below the diagonal block
         if (rem > 0) {
