@@ -885,13 +885,6 @@ __global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled, int 
     sigF_cam[q] = sg;
   }
 }
-__global__ void collect_fail_kernel(int n_e, const double* Z, double* sc) {
-  // any E pose whose damped 6x6 block was not positive definite
-  double f = 0.0;
-  for (int i = threadIdx.x; i < n_e; i += blockDim.x) f = fmax(f, Z[8 * (size_t)i + 6]);
-  f = warp_max(f);
-  if ((threadIdx.x & 31) == 0 && f != 0.0) sc[12] = 1.0;
-}
 
 }  // namespace
 
@@ -1236,7 +1229,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       log_iter(iteration, cand_cost, cost_change, step_norm, rho, 1, 0);
     }
   }
-  // ---- results: current parameter set back to the host mirror
+  // ---- results: the poses stay on the device (arslam_get_params); camera and final cost come back
   {
     const int k = s->cur;
     CU(cudaMemcpyAsync(s->h_sc + 32, s->cam[k].p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

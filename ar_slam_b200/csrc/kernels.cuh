@@ -693,8 +693,8 @@ __global__ void sigma_pose_kernel(int n_pose, const double* __restrict__ rec, in
   }
 }
 
-// Small device-resident scalar block shared by the LM kernels (24 doubles;
-// the colsum / colmax reductions write straight into its fields).
+// Small device-resident scalar block shared by the LM kernels (kNumScalars doubles; the
+// in-kernel grid reductions write straight into its fields).
 struct LmScalars {
   double cam_H;      // [0] sum K^2   (J^T J of the focal length)
   double cam_g;      // [1] sum K r

@@ -582,17 +582,5 @@ __global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t*
   const double v[1] = {warp_max(m)};
   grid_reduce_last_cta<1, true, 4>(v, part, ticket, out);
 }
-__global__ void __launch_bounds__(1024) colmax_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
-  __shared__ double sm[1024];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) acc = fmax(acc, in[i]);
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = 512; s > 0; s >>= 1) {
-    if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = sm[0];
-}
 
 }  // namespace ars
