@@ -17,6 +17,7 @@
 // cp.async pipeline -- ~15 flop per byte, which puts the update on the DMMA pipe.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -233,15 +234,17 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 // panel, updated first so that its factorisation can start); else a linear id over the triangle of the
 // tiles with ti >= tj >= tile_off (the rest, which runs beside that factorisation on a second stream).
 __global__ void __launch_bounds__(kBigThreads, 1) syrk_big_dmma_kernel(double* __restrict__ A, long long ld, int K0, int kw,
-                                                                       int n_pad, int tile_off, int strip_cols) {
+                                                                       int n_pad, int tile_off, int strip_cols, int n_tiles) {
   extern __shared__ __align__(16) double sm[];
+  // rest mode: a persistent grid smaller than the GPU walks the tiles, so that the SMs it leaves
+  // free take the latency-bound kernels of the next panel's factorisation (look-ahead)
+  for (int p = blockIdx.x; p < (strip_cols > 0 ? (int)gridDim.x : n_tiles); p += gridDim.x) {
   int ti, tj;
   if (strip_cols > 0) {
     ti = blockIdx.x;
     tj = blockIdx.y;
     if (ti < tj) return;
   } else {
-    const int p = blockIdx.x;
     ti = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
     while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
     while (ti * (ti + 1) / 2 > p) --ti;
@@ -329,6 +332,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) syrk_big_dmma_kernel(double* _
         *c = v;
       }
     }
+  __syncthreads();  // all warps are done with the stages before the next tile's loads
+  }
 }
 
 // --- panel solve as a GEMM: X = A_tile Linv^T on 64x64 tiles (in place), DMMA ----------------
@@ -432,9 +437,16 @@ struct DenseCholesky {
   // so the latency-bound factorisation kernels get SM slots first).
   struct LookAhead {
     cudaStream_t aux = nullptr;
+    int rest_ctas = 140;          // persistent CTAs of the rest update (one per SM): the other SMs serve the factorisation chain
     std::vector<cudaEvent_t> ev;  // [2 P]: panel P factored, [2 P + 1]: rest(P) done
     cudaError_t ensure(int panels) {
       if (!aux) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int free_sms = 8;   // measured best of 0 / 8 / 16 / 24 / 32 at n = 12 003 (34.0 / 36.8 ms with 8 / 0); ARSLAM_CHOL_FREE_SMS overrides
+        if (const char* e = getenv("ARSLAM_CHOL_FREE_SMS")) free_sms = atoi(e);
+        rest_ctas = std::max(1, sms - free_sms);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         const cudaError_t e = cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, lo);
@@ -485,12 +497,13 @@ struct DenseCholesky {
       cudaEventRecord(la.ev[2 * P], st);                 // panel P is factored
       // the strip reads and writes columns that rest(P - 1) wrote
       if (last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);
-      syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip);
+      syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip, 0);
       ++launches;
       if (nt > strip) {
         const int m = nt - strip;
         cudaStreamWaitEvent(la.aux, la.ev[2 * P], 0);
-        syrk_big_dmma_kernel<<<m * (m + 1) / 2, kBigThreads, kBigSmem, la.aux>>>(A, ld, K0, kw, n_pad, strip, 0);
+        const int tiles = m * (m + 1) / 2;
+        syrk_big_dmma_kernel<<<std::min(tiles, la.rest_ctas), kBigThreads, kBigSmem, la.aux>>>(A, ld, K0, kw, n_pad, strip, 0, tiles);
         cudaEventRecord(la.ev[2 * P + 1], la.aux);
         last_rest = P;
         ++launches;
