@@ -147,15 +147,17 @@ def shard(m, rank, world):
     return m.cap_idx[lo:hi], m.tag_idx[lo:hi], m.obs[lo:hi]
 
 
-def run_solves(s, m, total_iters):
-    """Runs solves of ITERS_PER_SOLVE iterations from the same start until total_iters are done."""
+def run_solves(s, m, total_iters, start=None):
+    """Runs solves of ITERS_PER_SOLVE iterations from the same start until total_iters are done.
+    start = (cam, cap, tag) arrays to restart from (pinned copies of the initial state)."""
+    cam0, cap0, tag0 = start if start is not None else (m.cam0, m.cap0, m.tag0)
     done, summaries = 0, []
     while done < total_iters:
         n = min(ITERS_PER_SOLVE, total_iters - done)
         if s.options.max_num_iterations != n:
             s.options.max_num_iterations = n
             s.set_options(s.options)
-        s.set_params(m.cam0, m.cap0, m.tag0)
+        s.set_params(cam0, cap0, tag0)
         summ, _ = s.solve(log=False)
         if summ["iterations"] != n:
             raise RuntimeError("solve stopped after %d of %d iterations (%s)" % (summ["iterations"], n, summ["reason_name"]))
@@ -355,9 +357,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # every solve restarts from the same initial state, re-sent from pinned host memory (the only
+    # host -> device traffic inside the timed region: 4.9 MB per 5 LM iterations)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.ascontiguousarray(a[:0])).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    keep_start = [pinned(a) for a in (m.cam0, m.cap0, m.tag0)]
+    start = tuple(t.numpy() for t in keep_start)
     # ---- warm-up
     if args.warmup > 0:
-        run_solves(s, m, args.warmup)
+        run_solves(s, m, args.warmup, start)
     # ---- timed region: exactly --steps LM iterations, CUDA events on the solver's stream
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -366,7 +376,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        summaries = run_solves(s, m, args.steps)
+        summaries = run_solves(s, m, args.steps, start)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -385,10 +395,6 @@ def main():
         # what ArSlamSolver::optimize does per call (ar_slam_util.cpp:1001-1018 with the blocks of
         # :720-727): the whole problem and the parameters go host -> device from pinned host memory,
         # ITERS_PER_SOLVE LM iterations run, the parameters come back.  One untimed call first.
-        def pinned(a):
-            t = torch.empty(a.shape, dtype=torch.from_numpy(np.ascontiguousarray(a[:0])).dtype, pin_memory=True)
-            t.numpy()[...] = a
-            return t
         keep = [pinned(a) for a in (cap_idx, tag_idx, obs, m.cam0, m.cap0, m.tag0)]
         p_cap_idx, p_tag_idx, p_obs, p_cam0, p_cap0, p_tag0 = [t.numpy() for t in keep]
         if s.options.max_num_iterations != ITERS_PER_SOLVE:
@@ -433,7 +439,7 @@ def main():
     if rank == 0:
         s.set_profiling(True)
     if True:
-        run_solves(s, m, ITERS_PER_SOLVE)
+        run_solves(s, m, ITERS_PER_SOLVE, start)
     if rank == 0:
         kt = s.kernel_times()
         s.set_profiling(False)
