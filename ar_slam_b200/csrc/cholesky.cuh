@@ -470,7 +470,10 @@ struct DenseCholesky {
   static int factor(double* A, long long ld, int n_pad, double* linv, double* fail, cudaStream_t st, LookAhead& la) {
     int launches = 0;
     const int panels = (n_pad + NB - 1) / NB;
-    if (la.ensure(panels) != cudaSuccess) return 0;
+    // without the second stream (creation failed) everything runs in order on the caller's stream
+    const bool two_streams = la.ensure(panels) == cudaSuccess;
+    if (!two_streams) cudaGetLastError();
+    cudaStream_t aux = two_streams ? la.aux : st;
     int last_rest = -1;  // last panel whose rest update was launched on aux
     for (int P = 0; P < panels; ++P) {
       const int K0 = P * NB;
@@ -494,22 +497,22 @@ struct DenseCholesky {
       if (left <= 0) break;
       const int nt = (left + BT - 1) / BT;
       const int strip = std::min(nt, NB / BT);           // tile columns of the next outer panel
-      cudaEventRecord(la.ev[2 * P], st);                 // panel P is factored
+      if (two_streams) cudaEventRecord(la.ev[2 * P], st);  // panel P is factored
       // the strip reads and writes columns that rest(P - 1) wrote
-      if (last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);
+      if (two_streams && last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);
       syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip, 0);
       ++launches;
       if (nt > strip) {
         const int m = nt - strip;
-        cudaStreamWaitEvent(la.aux, la.ev[2 * P], 0);
+        if (two_streams) cudaStreamWaitEvent(aux, la.ev[2 * P], 0);
         const int tiles = m * (m + 1) / 2;
-        syrk_big_dmma_kernel<<<std::min(tiles, la.rest_ctas), kBigThreads, kBigSmem, la.aux>>>(A, ld, K0, kw, n_pad, strip, 0, tiles);
-        cudaEventRecord(la.ev[2 * P + 1], la.aux);
+        syrk_big_dmma_kernel<<<std::min(tiles, la.rest_ctas), kBigThreads, kBigSmem, aux>>>(A, ld, K0, kw, n_pad, strip, 0, tiles);
+        if (two_streams) cudaEventRecord(la.ev[2 * P + 1], aux);
         last_rest = P;
         ++launches;
       }
     }
-    if (last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);  // (already implied by the last strip; harmless)
+    if (two_streams && last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);  // join
     return launches;
   }
   // solves L^T y = w for the leading n unknowns; w is row rhs_row (== n) and is destroyed
