@@ -205,7 +205,7 @@ struct arslam_solver {
   long long problem_version = 0, pcg_version = -1;
   int pcg_side = -1, n_sm = 0;
   // parameters: two sets (current / candidate)
-  DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2];
+  DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2], tag_cor[2];
   int cur = 0;
   // normal equations
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
@@ -459,6 +459,7 @@ int rebuild_views(arslam_solver* s) {
   for (int k = 0; k < 2; ++k) {
     CU(s->cam[k].ensure(4)); CU(s->cap[k].ensure((size_t)6 * s->n_cap)); CU(s->tag[k].ensure((size_t)6 * s->n_tag));
     CU(s->cap_pre[k].ensure((size_t)kCapPre * s->n_cap)); CU(s->tag_pre[k].ensure((size_t)kTagPre * s->n_tag));
+    CU(s->tag_cor[k].ensure((size_t)12 * s->n_tag));
   }
   CU(s->W.ensure((size_t)36 * plane));
   CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp + 8));
@@ -554,7 +555,7 @@ static int launch_prep(arslam_solver* s, int k) {
   const int cap_ctas = cdiv(s->n_cap, 128);
   LAUNCH("prep_poses", (48.0 + 8.0 * kCapPre) * s->n_cap + (48.0 + 8.0 * kTagPre) * s->n_tag,
          prep_poses_kernel<<<cap_ctas + cdiv(s->n_tag, 128), 128, 0, s->stream>>>(s->n_cap, s->cap[k].p, s->cap_pre[k].p, s->n_tag, s->tag[k].p,
-                                                                               s->opt.tag_size, s->tag_pre[k].p, cap_ctas));
+                                                                               s->opt.tag_size, s->tag_pre[k].p, cap_ctas, s->tag_cor[k].p));
   return ARSLAM_OK;
 }
 
@@ -1121,7 +1122,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       CandArgs c;
       c.n_blk = s->n_blk; c.plane = s->plane;
       c.own_idx = s->s_own[sd.e].p; c.oth_idx = s->s_oth[sd.e].p; c.obs = s->s_obs[sd.e].p;
-      c.cap_pre_c = s->cap_pre[kc].p; c.tag_pre_c = s->tag_pre[kc].p; c.cam_c = s->cam[kc].p;
+      c.cap_pre_c = s->cap_pre[kc].p; c.tag_cor_c = s->tag_cor[kc].p; c.cam_c = s->cam[kc].p;
       c.warp_out = s->warp_cand.p; c.ticket = s->tickets.p + 7; c.out = sc + 5;
       const int grid = cdiv(s->plane, 256);
       if (dist) {
@@ -1287,7 +1288,7 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   CU(cudaMemcpyAsync(d_tagpose.p, tag_pose6, sizeof(double) * 6 * n_tag, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(d_pose.p, cap_pose6, sizeof(double) * 6 * n_loc, cudaMemcpyHostToDevice, s->stream));
   LAUNCH("prep_poses", 8.0 * (6 + kTagPre) * n_tag,
-         prep_poses_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>(0, nullptr, nullptr, (int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p, 0));
+         prep_poses_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>(0, nullptr, nullptr, (int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p, 0, nullptr));
   LocArgs a;
   a.n_loc = (int)n_loc; a.blk_off = d_off.p; a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
   a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p;

@@ -108,9 +108,11 @@ __device__ __forceinline__ void grid_reduce_last_cta(const double (&v)[M], doubl
 
 // ---------------------------------------------------------------- prep -----
 // both pose sides in one launch: CTAs [0, cap_ctas) prepare captures, the rest tags
+// tag_cor (optional): the four world corners alone, 12 contiguous doubles per tag, for the residual-only
+// kernels (six 128-bit loads instead of twelve scalar ones spread over the 384-byte record)
 __global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double* __restrict__ cap_pose, double* __restrict__ cap_out,
                                                          int n_tag, const double* __restrict__ tag_pose, double tag_size,
-                                                         double* __restrict__ tag_out, int cap_ctas) {
+                                                         double* __restrict__ tag_out, int cap_ctas, double* __restrict__ tag_cor) {
   if ((int)blockIdx.x < cap_ctas) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cap) return;
@@ -131,6 +133,12 @@ __global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double
     double2* o = reinterpret_cast<double2*>(tag_out + (size_t)kTagPre * i);
 #pragma unroll
     for (int k = 0; k < kTagPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    if (tag_cor) {
+      double2* c = reinterpret_cast<double2*>(tag_cor + (size_t)12 * i);
+      const double w[12] = {rec[0], rec[1], rec[2], rec[12], rec[13], rec[14], rec[24], rec[25], rec[26], rec[36], rec[37], rec[38]};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c[k] = make_double2(w[2 * k], w[2 * k + 1]);
+    }
   }
 }
 
@@ -640,7 +648,7 @@ struct CandArgs {
   const int32_t* oth_idx;
   const double* obs;
   const double* cap_pre_c; // prep records at x + delta
-  const double* tag_pre_c;
+  const double* tag_cor_c; // [n_tag][12] world corners at x + delta
   const double* cam_c;
   double* warp_out;        // [grid] CTA partials of the candidate's sum r^2
   unsigned* ticket;
@@ -664,12 +672,21 @@ __global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
         cp[2 * k + 1] = v.y;
       }
     }
-    const double* tpc = a.tag_pre_c + (size_t)kTagPre * tag;
+    double wc[12];
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.tag_cor_c + (size_t)12 * tag);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double2 v = __ldg(src + k);
+        wc[2 * k] = v.x;
+        wc[2 * k + 1] = v.y;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const double ox = a.obs[(size_t)(2 * i) * a.plane + pos];
       const double oy = a.obs[(size_t)(2 * i + 1) * a.plane + pos];
-      double tp3[3] = {__ldg(tpc + 12 * i), __ldg(tpc + 12 * i + 1), __ldg(tpc + 12 * i + 2)};
+      double tp3[3] = {wc[3 * i], wc[3 * i + 1], wc[3 * i + 2]};
       double rc[2];
       corner_residual_m<MODEL>(cp, tp3, cm, ox, oy, rc);
       c2 += rc[0] * rc[0] + rc[1] * rc[1];
