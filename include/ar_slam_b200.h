@@ -124,7 +124,9 @@ const char* arslam_last_error(const arslam_solver* s); /* s may be NULL: creatio
 int arslam_set_options(arslam_solver* s, const arslam_options* opt);
 /* Run all work of this handle on the caller's CUDA stream (a cudaStream_t cast
  * to void*; NULL restores the handle's own stream), e.g. to bracket calls with
- * the caller's CUDA events. */
+ * the caller's CUDA events.  (The dense factorisation forks part of its
+ * trailing update to an internal lower-priority stream and joins it back
+ * before it returns, so stream order is preserved for the caller.) */
 int arslam_set_stream(arslam_solver* s, void* cuda_stream);
 
 /* Replaces resetProblem (ar_slam_util.cpp:1021-1025) + the AddResidualBlock
