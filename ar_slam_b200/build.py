@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libar_slam_b200.so")
 SOURCES = ["arslam.cu"]
-HEADERS = ["model.cuh", "kernels.cuh", "schur.cuh", "cholesky.cuh", "localize.cuh", "pcg.cuh",
+HEADERS = ["model.cuh", "kernels.cuh", "accum_pipe.cuh", "schur.cuh", "cholesky.cuh", "localize.cuh", "pcg.cuh",
            os.path.join("..", "..", "include", "ar_slam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -33,10 +33,12 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
+    tmp = LIB + ".tmp%d" % os.getpid()   # never leave a half-written library where a snapshot could pick it up
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
+          ["-o", tmp] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
     subprocess.check_call(cmd, cwd=CSRC, env=env)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -144,6 +144,11 @@ class Solver:
     def set_profiling(self, on):
         self._check(self._lib.arslam_set_profiling(self._h, C.c_int(1 if on else 0)))
 
+    def set_tuning(self, key, value):
+        """Kernel-variant switch for A/B measurements (see arslam_set_tuning in the header)."""
+        self._lib.arslam_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        self._check(self._lib.arslam_set_tuning(self._h, key.encode(), C.c_int64(int(value))))
+
     def kernel_times(self):
         buf = (KernelTime * 64)()
         n = self._check(self._lib.arslam_kernel_times(self._h, buf, C.c_int32(64)))

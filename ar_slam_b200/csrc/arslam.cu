@@ -21,6 +21,7 @@
 #include "../../include/ar_slam_b200.h"
 #include "cholesky.cuh"
 #include "kernels.cuh"
+#include "accum_pipe.cuh"
 #include "localize.cuh"
 #include "pcg.cuh"
 #include "schur.cuh"
@@ -205,7 +206,7 @@ struct arslam_solver {
   long long problem_version = 0, pcg_version = -1;
   int pcg_side = -1, n_sm = 0;
   // parameters: two sets (current / candidate)
-  DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2], tag_cor[2];
+  DevBuf<double> cam[2], cap[2], tag[2], cap_pre[2], tag_pre[2], tag_cor[2], cap_rt[2];
   int cur = 0;
   // normal equations
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
@@ -232,6 +233,8 @@ struct arslam_solver {
   // stats
   long long launches = 0;
   Profiler prof;
+  // tuning switches (arslam_set_tuning), per handle
+  int tune_accum_pipe = 1, tune_pcg_smem = 1, tune_pcg_pipelined = 1;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   int fail(int code, const char* fmt, ...) {
@@ -343,7 +346,13 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
       cudaMallocHost(&s->h_sc, 256 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
       schur_kernel_attributes<SparseTarget, 1>() != cudaSuccess || schur_kernel_attributes<DenseTarget, 1>() != cudaSuccess ||
       schur_kernel_attributes<DenseTarget, 3>() != cudaSuccess ||
-      pcg_init() != cudaSuccess) {
+      pcg_init() != cudaSuccess ||
+      cudaFuncSetAttribute(accum_e_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEPipeSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(accum_e_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEPipeSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(accum_f_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFPipeSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(accum_f_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFPipeSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(accum_e_pipe_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+      cudaFuncSetAttribute(accum_f_pipe_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
     return ARSLAM_ERR_CUDA;
@@ -387,6 +396,16 @@ int arslam_set_profiling(arslam_solver* s, int on) {
   return ARSLAM_OK;
 }
 
+int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value) {
+  if (!s || !key) return ARSLAM_ERR_INVALID;
+  const std::string k(key);
+  if (k == "accum_pipe") s->tune_accum_pipe = value != 0;
+  else if (k == "pcg_smem") s->tune_pcg_smem = value != 0;
+  else if (k == "pcg_pipelined") s->tune_pcg_pipelined = value != 0;
+  else return s->fail(ARSLAM_ERR_INVALID, "set_tuning: unknown key '%s'", key);
+  return ARSLAM_OK;
+}
+
 int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap) {
   if (!s) return ARSLAM_ERR_INVALID;
   int n = 0;
@@ -405,10 +424,8 @@ namespace {
 // validates blocks [first, first + n_new) and moves them into the original-order arrays
 int store_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t first, int64_t n_new, const int32_t* cap_idx,
                  const int32_t* tag_idx, const double* rect8, int32_t* lo_out, int32_t* hi_out) {
-  // the observations (the bulk of the upload) start moving first; the index check below runs on
-  // the host while the DMA is in flight (when the caller's arrays are pinned)
-  CU(s->o_obs.grow_keep((size_t)(first + n_new) * 8, (size_t)first * 8, s->stream));
-  CU(cudaMemcpyAsync(s->o_obs.p + 8 * first, rect8, sizeof(double) * 8 * n_new, cudaMemcpyHostToDevice, s->stream));
+  // validate BEFORE any copy is enqueued: an error return must not leave a DMA reading the caller's
+  // (possibly pinned, possibly about to be freed) arrays
   int32_t lo = cap_idx[0], hi = cap_idx[0];
   for (int64_t b = 0; b < n_new; ++b) {
     if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
@@ -416,6 +433,8 @@ int store_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t first, 
     lo = std::min(lo, cap_idx[b]);
     hi = std::max(hi, cap_idx[b]);
   }
+  CU(s->o_obs.grow_keep((size_t)(first + n_new) * 8, (size_t)first * 8, s->stream));
+  CU(cudaMemcpyAsync(s->o_obs.p + 8 * first, rect8, sizeof(double) * 8 * n_new, cudaMemcpyHostToDevice, s->stream));
   CU(s->o_cap.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
   CU(s->o_tag.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
   CU(cudaMemcpyAsync(s->o_cap.p + first, cap_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
@@ -459,7 +478,7 @@ int rebuild_views(arslam_solver* s) {
   for (int k = 0; k < 2; ++k) {
     CU(s->cam[k].ensure(4)); CU(s->cap[k].ensure((size_t)6 * s->n_cap)); CU(s->tag[k].ensure((size_t)6 * s->n_tag));
     CU(s->cap_pre[k].ensure((size_t)kCapPre * s->n_cap)); CU(s->tag_pre[k].ensure((size_t)kTagPre * s->n_tag));
-    CU(s->tag_cor[k].ensure((size_t)12 * s->n_tag));
+    CU(s->tag_cor[k].ensure((size_t)12 * s->n_tag)); CU(s->cap_rt[k].ensure((size_t)12 * s->n_cap));
   }
   CU(s->W.ensure((size_t)36 * plane));
   CU(s->warp_cam.ensure((size_t)4 * s->n_warp)); CU(s->warp_cand.ensure((size_t)2 * s->n_warp + 8));
@@ -507,12 +526,14 @@ int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t
   if (s->n_blk + n_new > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
     return s->fail(ARSLAM_ERR_INVALID, "append_blocks: problem too large for 32-bit block indices");
   CU(cudaSetDevice(s->device));
+  const bool had_params = s->have_params;
   s->have_problem = false;
   s->have_params = false;
   int32_t lo = 0, hi = 0;
   const int rc = store_blocks(s, n_cap, n_tag, s->n_blk, n_new, cap_idx, tag_idx, rect8, &lo, &hi);
-  if (rc) {  // the earlier blocks are intact
+  if (rc) {  // nothing was enqueued: the earlier blocks and parameters are intact
     s->have_problem = true;
+    s->have_params = had_params;
     return rc;
   }
   s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk += (int)n_new;
@@ -555,7 +576,7 @@ static int launch_prep(arslam_solver* s, int k) {
   const int cap_ctas = cdiv(s->n_cap, 128);
   LAUNCH("prep_poses", (48.0 + 8.0 * kCapPre) * s->n_cap + (48.0 + 8.0 * kTagPre) * s->n_tag,
          prep_poses_kernel<<<cap_ctas + cdiv(s->n_tag, 128), 128, 0, s->stream>>>(s->n_cap, s->cap[k].p, s->cap_pre[k].p, s->n_tag, s->tag[k].p,
-                                                                               s->opt.tag_size, s->tag_pre[k].p, cap_ctas, s->tag_cor[k].p));
+                                                                               s->opt.tag_size, s->tag_pre[k].p, cap_ctas, s->tag_cor[k].p, s->cap_rt[k].p));
   return ARSLAM_OK;
 }
 
@@ -740,8 +761,6 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   return ARSLAM_OK;
 }
 
-static inline bool use_smem_flag(const PcgWorkspace& w) { return w.smem_ok && !getenv("ARSLAM_PCG_NO_SMEM"); }
-
 int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, const double* sc, const double* cam_minus,
                      double radius, double* x_out) {
   PcgWorkspace& w = s->pcg;
@@ -765,15 +784,9 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
   a.partial = w.partial; a.scal = w.scal; a.trace = nullptr;
   a.sigF = s->sigF.p; a.uF = s->uF.p; a.sc = const_cast<double*>(sc);
-  static unsigned long long* d_trace = nullptr;
-  if (getenv("ARSLAM_PCG_TRACE")) {
-    if (!d_trace) cudaMalloc(&d_trace, sizeof(unsigned long long) * 64 * 1024 * 8);
-    cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 64 * 1024 * 8, s->stream);
-    a.trace = d_trace;
-  }
   sa.cta_row = w.cta_row; sa.halo_ptr = w.halo_ptr; sa.halo_col = w.halo_col; sa.lcol = w.lcol;
   sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots; sa.max_rows = w.max_rows;
-  const bool use_smem = use_smem_flag(w);
+  const bool use_smem = w.smem_ok && s->tune_pcg_smem;
   void* args_g[] = {(void*)&a};
   void* args_s[] = {(void*)&sa};
   Profiler::Rec r{0, nullptr, nullptr};
@@ -783,7 +796,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   }
   // one barrier per iteration for the inexact-Newton tolerances; the classic recurrence when the
   // system is to be solved tightly (its attainable accuracy is higher)
-  const bool pipelined = use_smem && s->opt.pcg_tolerance >= 1e-6 && !getenv("ARSLAM_PCG_CLASSIC");
+  const bool pipelined = use_smem && s->opt.pcg_tolerance >= 1e-6 && s->tune_pcg_pipelined;
   if (pipelined)
     CU(cudaLaunchCooperativeKernel((void*)pcg_pipe_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
   else if (use_smem)
@@ -793,25 +806,6 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   if (s->prof.on) {
     cudaEventRecord(r.b, s->stream);
     s->prof.recs.push_back(r);
-  }
-  if (a.trace) {
-    std::vector<unsigned long long> h((size_t)64 * 1024 * 8);
-    cudaStreamSynchronize(s->stream);
-    cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
-    const int G = use_smem ? w.smem_grid : w.grid;
-    for (int it = 0; it < 6; ++it) {
-      unsigned long long t0 = ~0ull, mx[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mn[8];
-      for (int k = 0; k < 8; ++k) mn[k] = ~0ull;
-      for (int c = 0; c < G; ++c) if (h[((size_t)it * G + c) * 8]) t0 = std::min(t0, h[((size_t)it * G + c) * 8]);
-      if (t0 == ~0ull) break;
-      for (int c = 0; c < G; ++c)
-        for (int k = 0; k < 8; ++k) {
-          const unsigned long long v = h[((size_t)it * G + c) * 8 + k];
-          if (v) { mx[k] = std::max(mx[k], v - t0); mn[k] = std::min(mn[k], v - t0); }
-        }
-      std::fprintf(stderr, "pcg trace it %d (ns): startA %llu..%llu | gathered %llu..%llu | row0 done %llu..%llu | endA %llu..%llu | sums1 %llu..%llu | endB %llu..%llu | sums2 %llu..%llu\n",
-                   it, mn[0], mx[0], mn[5], mx[5], mn[6], mx[6], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3], mn[4], mx[4]);
-    }
   }
   ++s->launches;
   return ARSLAM_OK;
@@ -827,6 +821,7 @@ struct Sides {
 int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, double* HFx, double* head) {
   const int nb = s->n_blk, plane = s->plane, grid = cdiv(plane, kAccumThreads);
   const bool dist = s->opt.num_intrinsics == 3;
+  int pipe_grid = 0;  // CTAs of the pipelined E pass (its camera partials), 0: accum_kernel ran
   for (int pass = 0; pass < 2; ++pass) {
     const int side = pass == 0 ? sd.e : sd.f;
     const int n_own = side == 0 ? s->n_cap : s->n_tag;
@@ -844,7 +839,19 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
       if (dist) LAUNCH(NAME_, BYTES_, accum_kernel<SIDE_, W_, 1><<<grid, kAccumThreads, 0, s->stream>>>(a));    \
       else LAUNCH(NAME_, BYTES_, accum_kernel<SIDE_, W_, 0><<<grid, kAccumThreads, 0, s->stream>>>(a));         \
     } while (0)
-    if (pass == 0) {
+    // the hot role/side combinations (captures eliminated) run the cross-block pipelined kernels
+    const int n_chunks = cdiv(nb, kPipeThreads);
+    if (pass == 0 && side == 0 && s->tune_accum_pipe) {
+      pipe_grid = std::min(n_chunks, 2 * s->n_sm);
+      if (dist) LAUNCH("accum_E", bytes_e, accum_e_pipe_kernel<1><<<pipe_grid, kPipeThreads, kEPipeSmem, s->stream>>>(a, n_chunks));
+      else LAUNCH("accum_E", bytes_e, accum_e_pipe_kernel<0><<<pipe_grid, kPipeThreads, kEPipeSmem, s->stream>>>(a, n_chunks));
+    } else if (pass == 1 && side == 1 && s->tune_accum_pipe) {
+      AccumFArgs fa;
+      fa.a = a; fa.cap_rt = s->cap_rt[k].p;
+      const int g = std::min(n_chunks, 3 * s->n_sm);
+      if (dist) LAUNCH("accum_F", bytes_f, accum_f_pipe_kernel<1><<<g, kPipeThreads, kFPipeSmem, s->stream>>>(fa, n_chunks));
+      else LAUNCH("accum_F", bytes_f, accum_f_pipe_kernel<0><<<g, kPipeThreads, kFPipeSmem, s->stream>>>(fa, n_chunks));
+    } else if (pass == 0) {
       if (side == 0) ARS_ACC(0, true, "accum_E", bytes_e); else ARS_ACC(1, true, "accum_E", bytes_e);
     } else {
       if (side == 0) ARS_ACC(0, false, "accum_F", bytes_f); else ARS_ACC(1, false, "accum_F", bytes_f);
@@ -872,7 +879,7 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
              seg_fixup_kernel<<<cdiv((long long)n_own * NVX, 256), 256, 0, s->stream>>>(n_own, NVX, s->s_off[side].p, s->partialx[side].p, c.out_seg));
     }
   }
-  LAUNCH("reduce_partials", 32.0 * grid, reduce_partials_kernel<4, false><<<1, 1024, 0, s->stream>>>(s->warp_cam.p, grid, head));
+  LAUNCH("reduce_partials", 32.0 * grid, reduce_partials_kernel<4, false><<<1, 1024, 0, s->stream>>>(s->warp_cam.p, pipe_grid ? pipe_grid : grid, head));
   if (dist) launch_colsum(s, s->n_warp, 8, s->warp_cam8.p, head + 4);
   return ARSLAM_OK;
 }
@@ -1288,7 +1295,7 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   CU(cudaMemcpyAsync(d_tagpose.p, tag_pose6, sizeof(double) * 6 * n_tag, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(d_pose.p, cap_pose6, sizeof(double) * 6 * n_loc, cudaMemcpyHostToDevice, s->stream));
   LAUNCH("prep_poses", 8.0 * (6 + kTagPre) * n_tag,
-         prep_poses_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>(0, nullptr, nullptr, (int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p, 0, nullptr));
+         prep_poses_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>(0, nullptr, nullptr, (int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p, 0, nullptr, nullptr));
   LocArgs a;
   a.n_loc = (int)n_loc; a.blk_off = d_off.p; a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
   a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p;

@@ -444,8 +444,7 @@ struct DenseCholesky {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int free_sms = 8;   // measured best of 0 / 8 / 16 / 24 / 32 at n = 12 003 (34.0 / 36.8 ms with 8 / 0); ARSLAM_CHOL_FREE_SMS overrides
-        if (const char* e = getenv("ARSLAM_CHOL_FREE_SMS")) free_sms = atoi(e);
+        const int free_sms = 8;   // measured best of 0 / 8 / 16 / 24 / 32 at n = 12 003 (34.0 / 36.8 ms with 8 / 0)
         rest_ctas = std::max(1, sms - free_sms);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);

@@ -110,9 +110,12 @@ __device__ __forceinline__ void grid_reduce_last_cta(const double (&v)[M], doubl
 // both pose sides in one launch: CTAs [0, cap_ctas) prepare captures, the rest tags
 // tag_cor (optional): the four world corners alone, 12 contiguous doubles per tag, for the residual-only
 // kernels (six 128-bit loads instead of twelve scalar ones spread over the 384-byte record)
+// cap_rt (optional): R | t alone, 12 contiguous doubles per capture, for the passes that never form the
+// capture-rotation columns (accum_f_pipe_kernel)
 __global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double* __restrict__ cap_pose, double* __restrict__ cap_out,
                                                          int n_tag, const double* __restrict__ tag_pose, double tag_size,
-                                                         double* __restrict__ tag_out, int cap_ctas, double* __restrict__ tag_cor) {
+                                                         double* __restrict__ tag_out, int cap_ctas, double* __restrict__ tag_cor,
+                                                         double* __restrict__ cap_rt) {
   if ((int)blockIdx.x < cap_ctas) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cap) return;
@@ -123,6 +126,13 @@ __global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double
     double2* o = reinterpret_cast<double2*>(cap_out + (size_t)kCapPre * i);
 #pragma unroll
     for (int k = 0; k < kCapPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    if (cap_rt) {
+      double2* c = reinterpret_cast<double2*>(cap_rt + (size_t)12 * i);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+      c[4] = make_double2(rec[8], rec[18]);
+      c[5] = make_double2(rec[19], rec[20]);
+    }
   } else {
     const int i = (blockIdx.x - cap_ctas) * blockDim.x + threadIdx.x;
     if (i >= n_tag) return;

@@ -297,6 +297,8 @@ def main():
     ap.add_argument("--cpu-sample-captures", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
+                    help="kernel-variant switch passed to arslam_set_tuning (A/B measurements), e.g. accum_pipe=0")
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="weak: every GPU gets the workload's captures (the map, i.e. the tags, is shared); strong: the workload is split")
     args = ap.parse_args()
@@ -342,6 +344,9 @@ def main():
 
     opts = bench_options(ar, ITERS_PER_SOLVE, args)
     s = ar.Solver(device=local_rank, options=opts)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        s.set_tuning(k, int(v))
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)
     if world > 1:

@@ -213,6 +213,13 @@ typedef struct arslam_kernel_time {
   double algorithmic_bytes; /* per launch, by the formulas in DESIGN.md */
 } arslam_kernel_time;
 int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch with CUDA events */
+/* Kernel-variant switches for A/B measurements (bench.py, tests): per handle, never read from the
+ * environment.  Keys: "accum_pipe" (1: cross-block pipelined accumulation kernels, default; 0: the
+ * thread-per-block kernels that start every block cold); "pcg_smem" (1: the PCG kernels that keep the
+ * reduced matrix in shared memory, default); "pcg_pipelined" (1: one-barrier pipelined recurrence for
+ * pcg_tolerance >= 1e-6, default; 0: always the classic two-barrier recurrence).
+ * Unknown key: ARSLAM_ERR_INVALID. */
+int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value);
 int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap); /* returns rows */
 
 #ifdef __cplusplus
