@@ -192,6 +192,26 @@ class Solver:
         self._check(self._lib.arslam_get_params(self._h, _p(cam), _p(cap), _p(tag)))
         return cam, cap, tag
 
+    def set_constant(self, camera=False, cap=None, tag=None):
+        """SetParameterBlockConstant: camera (all intrinsics), per-capture and per-tag masks (bool arrays or None)."""
+        cm = np.ascontiguousarray(cap, dtype=np.uint8) if cap is not None else None
+        tm = np.ascontiguousarray(tag, dtype=np.uint8) if tag is not None else None
+        if (cm is not None and cm.size != self.n_cap) or (tm is not None and tm.size != self.n_tag):
+            raise ValueError("mask sizes do not match the problem")
+        self._lib.arslam_set_constant.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        self._check(self._lib.arslam_set_constant(self._h, C.c_int(1 if camera else 0), _p(cm, C.c_uint8), _p(tm, C.c_uint8)))
+
+    def normal_equations(self):
+        """(eliminated_side, blk_cap, blk_tag, W [n_blk,6,6], H_cap [n_cap,33], H_tag [n_tag,33], camera4)."""
+        nb = self.n_blk
+        side = C.c_int32(0)
+        bc, bt = np.zeros(nb, dtype=np.int32), np.zeros(nb, dtype=np.int32)
+        W = np.zeros((nb, 6, 6))
+        Hc, Ht, cam4 = np.zeros((self.n_cap, 33)), np.zeros((self.n_tag, 33)), np.zeros(4)
+        self._check(self._lib.arslam_get_normal_equations(self._h, C.byref(side), _p(bc, C.c_int32), _p(bt, C.c_int32),
+                                                          _p(W), _p(Hc), _p(Ht), _p(cam4)))
+        return side.value, bc, bt, W, Hc, Ht, cam4
+
     def evaluate(self, jacobians=True, residuals=True):
         nb = self.n_blk
         res = np.zeros((nb, 8)) if residuals else None

@@ -64,6 +64,43 @@ __device__ __forceinline__ void segment_flush_slice(const double (*st)[kStageLd]
   if (tail_open && sg[32] >= 0) partial[((size_t)gwarp * 2 + (first ? 0 : 1)) * NV + V0 + v] = acc;
 }
 
+// the serial walk of kernels.cuh's segment_flush (run by run, loads and adds chained), same order of additions
+template <int NVT, int V0>
+__device__ __forceinline__ void segment_flush_slice_serial(const double (*st)[kStageLd], const int* sg, int own, int lane, int gwarp,
+                                                           double* __restrict__ out_seg, double* __restrict__ partial) {
+  const unsigned ends = __ballot_sync(0xffffffffu, sg[lane + 2] != own);
+  if (lane >= NVT) return;
+  const bool head_open = sg[0] == sg[1];
+  const bool tail_open = !((ends >> 31) & 1u);
+  const int v = lane;
+  const double* col = st[v];
+  double acc = 0.0;
+  unsigned m = ends;
+  int j0 = 0;
+  while (m) {
+    const int j1 = __ffs(m) - 1;
+    m &= m - 1;
+    for (int j = j0; j <= j1; ++j) acc += col[j];
+    const int sj = sg[j1 + 1];
+    if (sj >= 0) {
+      if (j0 == 0 && head_open) partial[((size_t)gwarp * 2 + 0) * NV + V0 + v] = acc;
+      else out_seg[(size_t)sj * NV + V0 + v] = acc;
+    }
+    acc = 0.0;
+    j0 = j1 + 1;
+  }
+  if (tail_open && sg[32] >= 0) {
+    for (int j = j0; j < 32; ++j) acc += col[j];
+    partial[((size_t)gwarp * 2 + (j0 == 0 ? 0 : 1)) * NV + V0 + v] = acc;
+  }
+}
+template <bool UNROLLED, int NVT, int V0>
+__device__ __forceinline__ void flush_slice(const double (*st)[kStageLd], const int* sg, int own, int lane, int gwarp,
+                                            double* __restrict__ out_seg, double* __restrict__ partial) {
+  if (UNROLLED) segment_flush_slice<NVT, V0>(st, sg, own, lane, gwarp, out_seg, partial);
+  else segment_flush_slice_serial<NVT, V0>(st, sg, own, lane, gwarp, out_seg, partial);
+}
+
 constexpr int kPipeThreads = 128;
 constexpr int kPipeWarps = kPipeThreads / 32;
 constexpr int kPipeStages = 3;        // corner c + 2 is in flight while corner c is computed
@@ -78,7 +115,7 @@ constexpr size_t kEPipeSmem = (size_t)kPipeThreads * (kPipeStages * kESlot + kEC
                               (size_t)kPipeWarps * kPipeHalf * kStageLd * sizeof(double) + kPipeWarps * 36 * sizeof(int) +
                               kPipeWarps * 4 * sizeof(double);
 
-template <int MODEL>
+template <int MODEL, bool UNROLLED>
 __global__ void __launch_bounds__(kPipeThreads, 2) accum_e_pipe_kernel(const AccumArgs a, int n_chunks) {
   extern __shared__ __align__(16) unsigned char pipe_sm[];
   unsigned char* ring = pipe_sm;                                               // [stage][thread][112]
@@ -249,7 +286,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) accum_e_pipe_kernel(const Acc
       st[tri6(2, 3)][lane] = AO[6]; st[tri6(2, 4)][lane] = AO[7]; st[tri6(2, 5)][lane] = AO[8];
       st[tri6(3, 3)][lane] = OO[0]; st[tri6(3, 4)][lane] = OO[1];  // tri6(3, 4) == 16: the last row of the first slice
       __syncwarp();
-      segment_flush_slice<kPipeHalf, 0>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
+      flush_slice<UNROLLED, kPipeHalf, 0>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
       __syncwarp();
       st[tri6(3, 5) - kPipeHalf][lane] = OO[2];
       st[tri6(4, 4) - kPipeHalf][lane] = OO[3]; st[tri6(4, 5) - kPipeHalf][lane] = OO[4];
@@ -262,7 +299,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) accum_e_pipe_kernel(const Acc
         st[30 + p - kPipeHalf][lane] = OK[p];
       }
       __syncwarp();
-      segment_flush_slice<NV - kPipeHalf, kPipeHalf>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
+      flush_slice<UNROLLED, NV - kPipeHalf, kPipeHalf>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
       __syncwarp();
     }
     pos = npos; valid = nvalid; own = nown; oth = noth;
@@ -288,7 +325,7 @@ struct AccumFArgs {
   const double* cap_rt;  // [n_cap][12]  R (9) | t (3)
 };
 
-template <int MODEL>
+template <int MODEL, bool UNROLLED>
 __global__ void __launch_bounds__(kPipeThreads, 3) accum_f_pipe_kernel(const AccumFArgs fa, int n_chunks) {
   const AccumArgs& a = fa.a;
   extern __shared__ __align__(16) unsigned char pipe_sm[];
@@ -429,7 +466,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) accum_f_pipe_kernel(const Acc
       st[tri6(2, 3)][lane] = AO[6]; st[tri6(2, 4)][lane] = AO[7]; st[tri6(2, 5)][lane] = AO[8];
       st[tri6(3, 3)][lane] = OO[0]; st[tri6(3, 4)][lane] = OO[1];  // tri6(3, 4) == 16: the last row of the first slice
       __syncwarp();
-      segment_flush_slice<kPipeHalf, 0>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
+      flush_slice<UNROLLED, kPipeHalf, 0>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
       __syncwarp();
       st[tri6(3, 5) - kPipeHalf][lane] = OO[2];
       st[tri6(4, 4) - kPipeHalf][lane] = OO[3]; st[tri6(4, 5) - kPipeHalf][lane] = OO[4];
@@ -442,7 +479,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) accum_f_pipe_kernel(const Acc
         st[30 + p - kPipeHalf][lane] = OK[p];
       }
       __syncwarp();
-      segment_flush_slice<NV - kPipeHalf, kPipeHalf>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
+      flush_slice<UNROLLED, NV - kPipeHalf, kPipeHalf>(st, sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
       __syncwarp();
     }
     slot ^= 1;

@@ -215,6 +215,10 @@ struct arslam_solver {
   DenseCholesky::LookAhead lookahead;  // second stream + events of the dense factorisation
   DevBuf<double> f_blocks;   // multi-GPU: per F pose, number of blocks over all ranks
   DevBuf<unsigned> tickets;  // one ticket per in-kernel grid reduction (kernels.cuh), zero between launches
+  // constant parameter blocks (arslam_set_constant); cleared by set_problem / append_blocks
+  DevBuf<unsigned char> const_cap, const_tag;
+  bool have_const = false;
+  int cam_const = 0;
   DevBuf<double> Hx[2], partialx[2], warp_cam8;  // radial model: l1, l2 borders per pose side
   DevBuf<unsigned long long> sort_keys[2];
   DevBuf<int32_t> sort_vals[2];
@@ -234,7 +238,7 @@ struct arslam_solver {
   long long launches = 0;
   Profiler prof;
   // tuning switches (arslam_set_tuning), per handle
-  int tune_accum_pipe = 1, tune_pcg_smem = 1, tune_pcg_pipelined = 1;
+  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   int fail(int code, const char* fmt, ...) {
@@ -286,6 +290,19 @@ cudaError_t schur_kernel_attributes() {
 }
 
 
+
+static cudaError_t pipe_kernel_attributes() {
+  cudaError_t e = cudaSuccess;
+#define ARS_ATTR(K_, BYTES_)                                                                                  \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES_)); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+  ARS_ATTR((accum_e_pipe_kernel<0, false>), kEPipeSmem); ARS_ATTR((accum_e_pipe_kernel<0, true>), kEPipeSmem);
+  ARS_ATTR((accum_e_pipe_kernel<1, false>), kEPipeSmem); ARS_ATTR((accum_e_pipe_kernel<1, true>), kEPipeSmem);
+  ARS_ATTR((accum_f_pipe_kernel<0, false>), kFPipeSmem); ARS_ATTR((accum_f_pipe_kernel<0, true>), kFPipeSmem);
+  ARS_ATTR((accum_f_pipe_kernel<1, false>), kFPipeSmem); ARS_ATTR((accum_f_pipe_kernel<1, true>), kFPipeSmem);
+#undef ARS_ATTR
+  return e;
+}
 
 extern "C" {
 
@@ -347,12 +364,7 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
       schur_kernel_attributes<SparseTarget, 1>() != cudaSuccess || schur_kernel_attributes<DenseTarget, 1>() != cudaSuccess ||
       schur_kernel_attributes<DenseTarget, 3>() != cudaSuccess ||
       pcg_init() != cudaSuccess ||
-      cudaFuncSetAttribute(accum_e_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEPipeSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(accum_e_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEPipeSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(accum_f_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFPipeSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(accum_f_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFPipeSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(accum_e_pipe_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-      cudaFuncSetAttribute(accum_f_pipe_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) {
+      pipe_kernel_attributes() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
     return ARSLAM_ERR_CUDA;
@@ -399,7 +411,8 @@ int arslam_set_profiling(arslam_solver* s, int on) {
 int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value) {
   if (!s || !key) return ARSLAM_ERR_INVALID;
   const std::string k(key);
-  if (k == "accum_pipe") s->tune_accum_pipe = value != 0;
+  if (k == "accum_pipe") s->tune_accum_pipe = (int)value & 3;  // bit 0: E pass, bit 1: F pass
+  else if (k == "accum_flush") s->tune_accum_flush = value != 0;
   else if (k == "pcg_smem") s->tune_pcg_smem = value != 0;
   else if (k == "pcg_pipelined") s->tune_pcg_pipelined = value != 0;
   else return s->fail(ARSLAM_ERR_INVALID, "set_tuning: unknown key '%s'", key);
@@ -485,6 +498,8 @@ int rebuild_views(arslam_solver* s) {
   if (!s->tickets.p) { CU(s->tickets.ensure(16)); CU(cudaMemsetAsync(s->tickets.p, 0, 16 * sizeof(unsigned), s->stream)); }
   CU(s->d_cam.ensure(4)); CU(s->sc.ensure(kNumScalars)); CU(s->cam_minus.ensure(12)); CU(s->colsum_part.ensure(12 * kColsumChunks)); CU(s->linv.ensure(CB * CB));
   s->have_problem = true;
+  s->have_const = false;
+  s->cam_const = 0;
   ++s->problem_version;
   return ARSLAM_OK;
 }
@@ -539,6 +554,21 @@ int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t
   s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk += (int)n_new;
   s->n_cap_global = (int)n_cap;
   return rebuild_views(s);
+}
+
+int arslam_set_constant(arslam_solver* s, int camera_constant, const uint8_t* cap_constant, const uint8_t* tag_constant) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem) return s->fail(ARSLAM_ERR_INVALID, "set_constant before set_problem");
+  CU(cudaSetDevice(s->device));
+  CU(s->const_cap.ensure((size_t)s->n_cap)); CU(s->const_tag.ensure((size_t)s->n_tag));
+  if (cap_constant) CU(cudaMemcpyAsync(s->const_cap.p, cap_constant + s->cap_lo, (size_t)s->n_cap, cudaMemcpyHostToDevice, s->stream));
+  else CU(cudaMemsetAsync(s->const_cap.p, 0, (size_t)s->n_cap, s->stream));
+  if (tag_constant) CU(cudaMemcpyAsync(s->const_tag.p, tag_constant, (size_t)s->n_tag, cudaMemcpyHostToDevice, s->stream));
+  else CU(cudaMemsetAsync(s->const_tag.p, 0, (size_t)s->n_tag, s->stream));
+  CU(cudaStreamSynchronize(s->stream));  // the caller may reuse its arrays
+  s->cam_const = camera_constant != 0;
+  s->have_const = cap_constant || tag_constant;
+  return ARSLAM_OK;
 }
 
 int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6, const double* tag_pose6) {
@@ -841,16 +871,20 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
     } while (0)
     // the hot role/side combinations (captures eliminated) run the cross-block pipelined kernels
     const int n_chunks = cdiv(nb, kPipeThreads);
-    if (pass == 0 && side == 0 && s->tune_accum_pipe) {
+    if (pass == 0 && side == 0 && (s->tune_accum_pipe & 1)) {
       pipe_grid = std::min(n_chunks, 2 * s->n_sm);
-      if (dist) LAUNCH("accum_E", bytes_e, accum_e_pipe_kernel<1><<<pipe_grid, kPipeThreads, kEPipeSmem, s->stream>>>(a, n_chunks));
-      else LAUNCH("accum_E", bytes_e, accum_e_pipe_kernel<0><<<pipe_grid, kPipeThreads, kEPipeSmem, s->stream>>>(a, n_chunks));
-    } else if (pass == 1 && side == 1 && s->tune_accum_pipe) {
+#define ARS_EP(M_, U_) LAUNCH("accum_E", bytes_e, accum_e_pipe_kernel<M_, U_><<<pipe_grid, kPipeThreads, kEPipeSmem, s->stream>>>(a, n_chunks))
+      if (dist) { if (s->tune_accum_flush) ARS_EP(1, true); else ARS_EP(1, false); }
+      else { if (s->tune_accum_flush) ARS_EP(0, true); else ARS_EP(0, false); }
+#undef ARS_EP
+    } else if (pass == 1 && side == 1 && (s->tune_accum_pipe & 2)) {
       AccumFArgs fa;
       fa.a = a; fa.cap_rt = s->cap_rt[k].p;
       const int g = std::min(n_chunks, 3 * s->n_sm);
-      if (dist) LAUNCH("accum_F", bytes_f, accum_f_pipe_kernel<1><<<g, kPipeThreads, kFPipeSmem, s->stream>>>(fa, n_chunks));
-      else LAUNCH("accum_F", bytes_f, accum_f_pipe_kernel<0><<<g, kPipeThreads, kFPipeSmem, s->stream>>>(fa, n_chunks));
+#define ARS_FP(M_, U_) LAUNCH("accum_F", bytes_f, accum_f_pipe_kernel<M_, U_><<<g, kPipeThreads, kFPipeSmem, s->stream>>>(fa, n_chunks))
+      if (dist) { if (s->tune_accum_flush) ARS_FP(1, true); else ARS_FP(1, false); }
+      else { if (s->tune_accum_flush) ARS_FP(0, true); else ARS_FP(0, false); }
+#undef ARS_FP
     } else if (pass == 0) {
       if (side == 0) ARS_ACC(0, true, "accum_E", bytes_e); else ARS_ACC(1, true, "accum_E", bytes_e);
     } else {
@@ -884,11 +918,11 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
   return ARSLAM_OK;
 }
 
-__global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled, int nk) {
+__global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled, int nk, int cam_const) {
   const double h[3] = {sc[0], sc[26], sc[28]};  // H_ff, H_l1l1, H_l2l2
   const int slot[3] = {14, 34, 35};
   for (int q = 0; q < nk; ++q) {
-    const double sg = enabled ? 1.0 / (1.0 + sqrt(h[q])) : 1.0;
+    const double sg = cam_const ? 0.0 : (enabled ? 1.0 / (1.0 + sqrt(h[q])) : 1.0);
     sc[slot[q]] = sg;
     sigF_cam[q] = sg;
   }
@@ -919,6 +953,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   sd.f = 1 - sd.e;
   sd.n_e = sd.e == 0 ? s->n_cap : s->n_tag;
   sd.n_f = sd.f == 0 ? s->n_cap : s->n_tag;
+  const unsigned char* const_e = s->have_const ? (sd.e == 0 ? s->const_cap.p : s->const_tag.p) : nullptr;
+  const unsigned char* const_f = s->have_const ? (sd.f == 0 ? s->const_cap.p : s->const_tag.p) : nullptr;
   const int nk = o.num_intrinsics == 3 ? 3 : 1;  // live intrinsics: focal (+ l1, l2 of the radial model)
   const bool dist = nk == 3;
   const int n = 6 * sd.n_f + nk;  // reduced dimension (F poses + intrinsics)
@@ -1025,7 +1061,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     cudaEventRecord(s->ev[0], s->stream);
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_e,
-             sigma_pose_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->H[sd.e].p, o.jacobi_scaling, s->sigE.p));
+             sigma_pose_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->H[sd.e].p, o.jacobi_scaling, s->sigE.p, const_e));
     }
     SchurArgs schur_args;
     {
@@ -1058,13 +1094,13 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (rc) return rc;
     }
     if (fresh_linearisation) {
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16, sc_head, sc, nk, nullptr));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, nullptr, nullptr, nk, f_blocks_all));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16, sc_head, sc, nk, nullptr, const_e));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, nullptr, nullptr, nk, f_blocks_all, const_f));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
-             sigma_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, o.jacobi_scaling, s->sigF.p));
-      LAUNCH("cam_sigma", 16.0, cam_sigma_kernel<<<1, 1, 0, s->stream>>>(sc, s->sigF.p + cam_row, o.jacobi_scaling, nk));
+             sigma_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, o.jacobi_scaling, s->sigF.p, const_f));
+      LAUNCH("cam_sigma", 16.0, cam_sigma_kernel<<<1, 1, 0, s->stream>>>(sc, s->sigF.p + cam_row, o.jacobi_scaling, nk, s->cam_const));
       have_sigma = true;
     }
     if (lin == ARSLAM_LINSOLVE_DENSE) {
@@ -1106,14 +1142,14 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     {
       ApplyArgs ap;
       ap.uF_cam = s->uF.p + cam_row;
-      ap.blocks_all = nullptr;
+      ap.blocks_all = nullptr; ap.constant = const_e;
       ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
       ap.rec = s->H[sd.e].p; ap.recx = dist ? s->Hx[sd.e].p : nullptr;
       ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
       ap.ticket = s->tickets.p + 5; ap.out = sc + 6;
       ap.cam = nullptr; ap.cam_c = nullptr; ap.d_cam = nullptr; ap.sc = sc; ap.nk = nk;
       LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
-      ap.blocks_all = f_blocks_all;
+      ap.blocks_all = f_blocks_all; ap.constant = const_f;
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
       ap.rec = HF; ap.recx = HFx;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
@@ -1160,8 +1196,11 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (lin == ARSLAM_LINSOLVE_PCG) summary->linear_solver_iterations += (long long)h[18];
     if (fresh_linearisation) {
       x_cost = 0.5 * h[2];
-      grad_max = std::max(std::max(h[16], h[17]), std::fabs(h[1]));
-      if (dist) grad_max = std::max(grad_max, std::max(std::fabs(h[29]), std::fabs(h[30])));
+      grad_max = std::max(h[16], h[17]);
+      if (!s->cam_const) {
+        grad_max = std::max(grad_max, std::fabs(h[1]));
+        if (dist) grad_max = std::max(grad_max, std::max(std::fabs(h[29]), std::fabs(h[30])));
+      }
       if (iteration == 0) { summary->initial_cost = x_cost; log_iter(0, x_cost, 0.0, 0.0, 0.0, 1, 1); }
     }
     fresh_linearisation = false;
@@ -1173,7 +1212,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     last_successful = false;
     const double f_cur = h[15];
     const double l1_cur = dist ? h[36] : s->h_cam[1], l2_cur = dist ? h[37] : s->h_cam[2];
-    x_norm = std::sqrt(h[7] + h[10] + f_cur * f_cur + l1_cur * l1_cur + l2_cur * l2_cur);
+    // Ceres' x is the reduced parameter vector: constant blocks are not part of it
+    x_norm = std::sqrt(h[7] + h[10] + (s->cam_const ? 0.0 : f_cur * f_cur + l1_cur * l1_cur + l2_cur * l2_cur));
     const double step_norm = std::sqrt(h[6] + h[9] + h[13] * h[13] + (dist ? h[32] * h[32] + h[33] * h[33] : 0.0));
     // model_cost_change = -(J d).(r + J d / 2) = -(g.d + d^T H d / 2), assembled from the block pieces
     const double d_focal = -h[13];
@@ -1261,6 +1301,57 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   summary->eval_ms = eval_ms;
   summary->linsolve_ms = lin_ms;
   summary->total_ms = wall_ms() - t_start;
+  return ARSLAM_OK;
+}
+
+// ------------------------------------------------- normal equations (parity) ---
+int arslam_get_normal_equations(arslam_solver* s, int32_t* eliminated_side, int32_t* blk_cap, int32_t* blk_tag,
+                                double* W36, double* H_cap, double* H_tag, double* camera4) {
+  if (!s) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem || !s->have_params) return s->fail(ARSLAM_ERR_INVALID, "get_normal_equations needs set_problem and set_params");
+  if (s->opt.num_intrinsics != 1) return s->fail(ARSLAM_ERR_UNSUPPORTED, "get_normal_equations: focal-only model");
+  if (s->world > 1) return s->fail(ARSLAM_ERR_UNSUPPORTED, "get_normal_equations: single-GPU handles only");
+  CU(cudaSetDevice(s->device));
+  s->prof.clear();
+  Sides sd;
+  int elim = s->opt.elimination;
+  if (elim == ARSLAM_ELIM_AUTO) elim = s->n_cap >= s->n_tag ? ARSLAM_ELIM_CAPTURES : ARSLAM_ELIM_TAGS;
+  sd.e = elim == ARSLAM_ELIM_CAPTURES ? 0 : 1;
+  sd.f = 1 - sd.e;
+  sd.n_e = sd.e == 0 ? s->n_cap : s->n_tag;
+  sd.n_f = sd.f == 0 ? s->n_cap : s->n_tag;
+  if (eliminated_side) *eliminated_side = elim;
+  CU(s->eval_out.ensure((size_t)sd.n_f * NV + 16));
+  double* HF = s->eval_out.p;
+  double* head = HF + (size_t)sd.n_f * NV;
+  launch_prep(s, s->cur);
+  launch_accumulate(s, sd, s->cur, HF, nullptr, head);
+  CU(cudaGetLastError());
+  const int nb = s->n_blk;
+  const size_t ps = s->plane;
+  // W leaves the device as it is stored (36 planes in E-sorted order) and is turned into one 6 x 6
+  // row-major block per residual block here
+  std::vector<double> planes;
+  if (W36) {
+    planes.resize((size_t)36 * ps);
+    CU(cudaMemcpyAsync(planes.data(), s->W.p, sizeof(double) * 36 * ps, cudaMemcpyDeviceToHost, s->stream));
+  }
+  int32_t* out_own = sd.e == 0 ? blk_cap : blk_tag;
+  int32_t* out_oth = sd.e == 0 ? blk_tag : blk_cap;
+  if (out_own) CU(cudaMemcpyAsync(out_own, s->s_own[sd.e].p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s->stream));
+  if (out_oth) CU(cudaMemcpyAsync(out_oth, s->s_oth[sd.e].p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s->stream));
+  double* out_e = sd.e == 0 ? H_cap : H_tag;
+  double* out_f = sd.e == 0 ? H_tag : H_cap;
+  if (out_e) CU(cudaMemcpyAsync(out_e, s->H[sd.e].p, sizeof(double) * NV * sd.n_e, cudaMemcpyDeviceToHost, s->stream));
+  if (out_f) CU(cudaMemcpyAsync(out_f, HF, sizeof(double) * NV * sd.n_f, cudaMemcpyDeviceToHost, s->stream));
+  if (camera4) CU(cudaMemcpyAsync(camera4, head, sizeof(double) * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->prof.resolve();
+  if (W36)
+    for (int b = 0; b < nb; ++b)
+      for (int q = 0; q < 36; ++q) W36[(size_t)36 * b + q] = planes[(size_t)q * ps + b];
+  if (out_own && s->cap_lo && sd.e == 0)
+    for (int b = 0; b < nb; ++b) out_own[b] += s->cap_lo;
   return ARSLAM_OK;
 }
 

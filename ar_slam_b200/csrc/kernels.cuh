@@ -709,14 +709,19 @@ __global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
 // ------------------------------------------------------------ LM vectors ---
 // sigma = 1 / (1 + sqrt(H_jj)) once at iteration 0 (Ceres jacobi_scaling).
 // One thread per pose; rec = out_seg layout.
+// A constant pose (arslam_set_constant; ceres::Problem::SetParameterBlockConstant) gets sigma = 0:
+// its scaled block is then D^2 alone, its gradient and every cross term vanish, so its row of the
+// (reduced) system decouples and its step is exactly zero -- the same system Ceres solves after
+// removing the block from the program.
 __global__ void sigma_pose_kernel(int n_pose, const double* __restrict__ rec, int enabled,
-                                  double* __restrict__ sigma) {
+                                  double* __restrict__ sigma, const unsigned char* __restrict__ constant) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pose) return;
+  const bool fixed = constant && constant[i];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     const double h = rec[(size_t)i * NV + tri6(k, k)];
-    sigma[6 * (size_t)i + k] = enabled ? 1.0 / (1.0 + sqrt(h)) : 1.0;
+    sigma[6 * (size_t)i + k] = fixed ? 0.0 : (enabled ? 1.0 / (1.0 + sqrt(h)) : 1.0);
   }
 }
 

@@ -494,6 +494,7 @@ struct ApplyArgs {
   int n_pose;
   const int32_t* seg_off;   // [n_pose + 1] (sorted by this side)
   const double* blocks_all; // multi-GPU, F side: blocks of the pose summed over all ranks (a rank may hold none), else null
+  const unsigned char* constant; // [n_pose] != 0: the pose is held constant (arslam_set_constant), or null
   const double* x;          // [6 n_pose]
   const double* step;       // [6 n_pose]: d_e (already the step) or uF (to be negated)
   int negate;
@@ -527,7 +528,7 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
   }
   double d2 = 0.0, x2 = 0.0, mq = 0.0;
   if (i < a.n_pose) {
-    const bool active = a.blocks_all ? a.blocks_all[i] > 0.0 : a.seg_off[i + 1] > a.seg_off[i];
+    const bool active = (a.blocks_all ? a.blocks_all[i] > 0.0 : a.seg_off[i + 1] > a.seg_off[i]) && !(a.constant && a.constant[i]);
     double d[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -569,13 +570,13 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
 __global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
                                                       double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out,
                                                       const double* __restrict__ head, double* __restrict__ sc, int nk,
-                                                      const double* __restrict__ blocks_all) {
+                                                      const double* __restrict__ blocks_all, const unsigned char* __restrict__ constant) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   // the freshly summed camera scalars move next to the other LM scalars (head may be null)
   if (head && i < 3) sc[i] = head[i];
   if (head && nk == 3 && i >= 4 && i < 12) sc[24 + (i - 4)] = head[i];
   double m = 0.0;
-  if (i < n_pose && (blocks_all ? blocks_all[i] > 0.0 : seg_off[i + 1] > seg_off[i])) {
+  if (i < n_pose && (blocks_all ? blocks_all[i] > 0.0 : seg_off[i + 1] > seg_off[i]) && !(constant && constant[i])) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) m = fmax(m, fabs(rec[(size_t)i * NV + 21 + k]));
   }

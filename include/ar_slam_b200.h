@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define ARSLAM_ABI_VERSION 2 /* 2: arslam_append_blocks, device-resident parameters */
+#define ARSLAM_ABI_VERSION 3 /* 2: arslam_append_blocks, device-resident parameters; 3: arslam_set_constant,
+                                arslam_get_normal_equations, arslam_set_tuning */
 
 enum {
   ARSLAM_OK = 0,
@@ -165,6 +166,16 @@ int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap
                       const double* tag_pose6);
 int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, double* tag_pose6);
 
+/* Replaces ceres::Problem::SetParameterBlockConstant (ar_slam_util.cpp:965 camera, :972 tags in
+ * localizeOne; the disabled gauge fix of the first capture at :697-700, :776-779) for the blocks of
+ * arslam_set_problem: camera_constant != 0 holds all intrinsics, cap_constant[c] / tag_constant[t]
+ * != 0 hold that pose (arrays over the global indices; NULL = none).  A constant block keeps its
+ * value, is left out of the step, of the gradient and parameter norms of the convergence tests and
+ * of the linear system -- what Ceres does by removing it from the program.  The masks are cleared
+ * by arslam_set_problem / arslam_append_blocks. */
+int arslam_set_constant(arslam_solver* s, int camera_constant, const uint8_t* cap_constant,
+                        const uint8_t* tag_constant);
+
 /* What ceres::Problem::Evaluate would return for the current parameters:
  * cost = 1/2 sum r^2, residuals [8 n_blk] (x0,y0,..,y3 per block,
  * ar_slam_util.cpp:207-208) and the AutoDiffCostFunction<..,8,3,6,6>
@@ -173,6 +184,18 @@ int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, doub
  * Host pointers. */
 int arslam_evaluate(arslam_solver* s, double* cost, double* residuals, double* jac_cam,
                     double* jac_cap, double* jac_tag);
+
+/* Parity hook for the fused evaluation + accumulation kernels (kernels (1)+(2)): the block pieces
+ * of J^T J and J^T r at the current parameters, exactly as the LM loop consumes them.  Focal-only
+ * model, single GPU.  Any output may be NULL; all are host pointers.
+ *   eliminated_side  ARSLAM_ELIM_CAPTURES / _TAGS actually used (the E side owns the rows of W)
+ *   blk_cap, blk_tag [n_blk]      the blocks in the order W36 is returned in (sorted by E pose)
+ *   W36     [n_blk][6][6]         J_E^T J_F of each block, rows = the E pose's (t, w), cols = the F pose's
+ *   H_cap   [n_cap][33]           per capture: upper triangle of J_c^T J_c (21, row-major) | J_c^T r (6) | J_c^T J_f (6)
+ *   H_tag   [n_tag][33]           the same per tag
+ *   camera4                       sum (dr/df)^2, sum (dr/df) r, sum r^2, 0 */
+int arslam_get_normal_equations(arslam_solver* s, int32_t* eliminated_side, int32_t* blk_cap, int32_t* blk_tag,
+                                double* W36, double* H_cap, double* H_tag, double* camera4);
 
 /* Replaces ArSlamSolver::optimize == ceres::Solve (ar_slam_util.cpp:1001-1018)
  * on the blocks of arslam_set_problem, starting from arslam_set_params.
@@ -214,8 +237,9 @@ typedef struct arslam_kernel_time {
 } arslam_kernel_time;
 int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch with CUDA events */
 /* Kernel-variant switches for A/B measurements (bench.py, tests): per handle, never read from the
- * environment.  Keys: "accum_pipe" (1: cross-block pipelined accumulation kernels, default; 0: the
- * thread-per-block kernels that start every block cold); "pcg_smem" (1: the PCG kernels that keep the
+ * environment.  Keys: "accum_pipe" (bit 0: E pass, bit 1: F pass on the cross-block pipelined
+ * accumulation kernels instead of the thread-per-block ones that start every block cold; default 2:
+ * measured faster for the F pass only); "accum_flush" (1: unrolled segment flush in those kernels); "pcg_smem" (1: the PCG kernels that keep the
  * reduced matrix in shared memory, default); "pcg_pipelined" (1: one-barrier pipelined recurrence for
  * pcg_tolerance >= 1e-6, default; 0: always the classic two-barrier recurrence).
  * Unknown key: ARSLAM_ERR_INVALID. */
