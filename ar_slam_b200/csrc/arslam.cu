@@ -226,6 +226,9 @@ struct arslam_solver {
   // localisation batch buffers (kept between calls)
   DevBuf<int32_t> l_off, l_tag, l_seed, l_it, l_term;
   DevBuf<double> l_obs, l_tagpose, l_tagpre, l_pose, l_cost;
+  DevBuf<int> l_invalid;
+  cudaStream_t loc_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t loc_done[3] = {nullptr, nullptr, nullptr}, loc_ready = nullptr;
   double* h_sc = nullptr;  // pinned
   long long ld = 0;
   int n_pad = 0;
@@ -238,7 +241,8 @@ struct arslam_solver {
   long long launches = 0;
   Profiler prof;
   // tuning switches (arslam_set_tuning), per handle
-  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1;
+  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1, tune_schur_bulk = 1;
+  long long tune_loc_chunk = 0;  // captures per localisation chunk (0: default)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   int fail(int code, const char* fmt, ...) {
@@ -275,10 +279,15 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 // main launch + the launch for the products whose partner sits in another CTA (schur.cuh)
 template <typename Target, int NK>
-void launch_schur(arslam_solver* s, const SchurArgs& a, const Target& t, const int32_t* e_idx, double bytes) {
+void launch_schur(arslam_solver* s, const SchurArgs& a, const Target& t, const int32_t* e_idx, double bytes, bool bulk = false) {
   const int grid = cdiv(s->n_blk, kSchurThreads);
-  LAUNCH("schur_eliminate", bytes, schur_eliminate_kernel<Target, NK, false><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
-  LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+  if (bulk) {
+    LAUNCH("schur_eliminate", bytes, schur_eliminate_kernel<Target, NK, false, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+    LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+  } else {
+    LAUNCH("schur_eliminate", bytes, schur_eliminate_kernel<Target, NK, false><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+    LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+  }
 }
 template <typename Target, int NK>
 cudaError_t schur_kernel_attributes() {
@@ -286,6 +295,12 @@ cudaError_t schur_kernel_attributes() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
   // three CTAs of 75 KB per SM need the full shared-memory carve-out
   if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return e;
+}
+static cudaError_t schur_bulk_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e;
 }
 
@@ -363,7 +378,7 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
       cudaMallocHost(&s->h_sc, 256 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
       schur_kernel_attributes<SparseTarget, 1>() != cudaSuccess || schur_kernel_attributes<DenseTarget, 1>() != cudaSuccess ||
       schur_kernel_attributes<DenseTarget, 3>() != cudaSuccess ||
-      pcg_init() != cudaSuccess ||
+      pcg_init() != cudaSuccess || schur_bulk_attributes() != cudaSuccess ||
       pipe_kernel_attributes() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -381,6 +396,9 @@ void arslam_destroy(arslam_solver* s) {
   cudaStreamSynchronize(s->stream);
   if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& st : s->loc_stream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (auto& ev : s->loc_done) if (ev) cudaEventDestroy(ev);
+  if (s->loc_ready) cudaEventDestroy(s->loc_ready);
   if (s->h_sc) cudaFreeHost(s->h_sc);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
@@ -414,6 +432,8 @@ int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value) {
   if (k == "accum_pipe") s->tune_accum_pipe = (int)value & 3;  // bit 0: E pass, bit 1: F pass
   else if (k == "accum_flush") s->tune_accum_flush = value != 0;
   else if (k == "pcg_smem") s->tune_pcg_smem = value != 0;
+  else if (k == "schur_bulk") s->tune_schur_bulk = value != 0;
+  else if (k == "loc_chunk") s->tune_loc_chunk = value;
   else if (k == "pcg_pipelined") s->tune_pcg_pipelined = value != 0;
   else return s->fail(ARSLAM_ERR_INVALID, "set_tuning: unknown key '%s'", key);
   return ARSLAM_OK;
@@ -787,7 +807,10 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   t.pair_slot = s->pcg.pair_slot; t.lower_of = s->pcg.src_slot;
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
-  launch_schur<SparseTarget, 1>(s, a2, t, e_idx, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnzb);
+  // compulsory bytes: W read once (288 B / block) + indices (8 B / block) + E records and Z / YB (264 + 128 B / pose)
+  // + the lower blocks of the reduced system written once (288 B each)
+  launch_schur<SparseTarget, 1>(s, a2, t, e_idx, (288.0 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnz_lower,
+                                s->tune_schur_bulk != 0);
   return ARSLAM_OK;
 }
 
@@ -1077,8 +1100,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
-        if (dist) launch_schur<DenseTarget, 3>(s, a, t, s->s_own[sd.e].p, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e);
-        else launch_schur<DenseTarget, 1>(s, a, t, s->s_own[sd.e].p, (288.0 * 2 + 8) * s->n_blk + (264.0 + 128) * sd.n_e);
+        if (dist) launch_schur<DenseTarget, 3>(s, a, t, s->s_own[sd.e].p, (288.0 + 8) * s->n_blk + (264.0 + 128) * sd.n_e + 8.0 * n * (double)n / 2);
+        else launch_schur<DenseTarget, 1>(s, a, t, s->s_own[sd.e].p, (288.0 + 8) * s->n_blk + (264.0 + 128) * sd.n_e + 8.0 * n * (double)n / 2);
       } else {
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;
@@ -1365,12 +1388,6 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
     return s->fail(ARSLAM_ERR_INVALID, "localize_batch: null pointer or empty batch");
   const int64_t nb = blk_offsets[n_loc];
   if (blk_offsets[0] != 0 || nb < 0 || nb > (1LL << 28)) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: bad block offsets");
-  for (int64_t i = 0; i < n_loc; ++i) {
-    const int32_t k = blk_offsets[i + 1] - blk_offsets[i];
-    if (k < 0 || seed_block[i] >= k) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: capture %lld has bad offsets/seed", (long long)i);
-  }
-  for (int64_t b = 0; b < nb; ++b)
-    if (tag_idx[b] < 0 || tag_idx[b] >= n_tag) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: tag index out of range");
   CU(cudaSetDevice(s->device));
   s->prof.clear();
   s->launches = 0;
@@ -1378,18 +1395,24 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   DevBuf<double>&d_obs = s->l_obs, &d_tagpose = s->l_tagpose, &d_tagpre = s->l_tagpre, &d_pose = s->l_pose, &d_cost = s->l_cost;
   CU(d_off.ensure(n_loc + 1)); CU(d_tag.ensure(nb)); CU(d_seed.ensure(n_loc)); CU(d_it.ensure(n_loc)); CU(d_term.ensure(n_loc));
   CU(d_obs.ensure((size_t)8 * nb)); CU(d_tagpose.ensure((size_t)6 * n_tag)); CU(d_tagpre.ensure((size_t)kTagPre * n_tag));
-  CU(d_pose.ensure((size_t)6 * n_loc)); CU(d_cost.ensure(n_loc));
-  CU(cudaMemcpyAsync(d_off.p, blk_offsets, sizeof(int32_t) * (n_loc + 1), cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(d_tag.p, tag_idx, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(d_seed.p, seed_block, sizeof(int32_t) * n_loc, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(d_obs.p, rect8, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, s->stream));
+  CU(d_pose.ensure((size_t)6 * n_loc)); CU(d_cost.ensure(n_loc)); CU(s->l_invalid.ensure(1));
+  // chunk streams: the upload of chunk i + 1 runs under the kernel of chunk i, the download of chunk i - 1 under both
+  constexpr int kLocStreams = 3;
+  if (!s->loc_stream[0]) {
+    for (int i = 0; i < kLocStreams; ++i) {
+      CU(cudaStreamCreateWithFlags(&s->loc_stream[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&s->loc_done[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&s->loc_ready, cudaEventDisableTiming));
+  }
+  CU(cudaMemsetAsync(s->l_invalid.p, 0, sizeof(int), s->stream));
   CU(cudaMemcpyAsync(d_tagpose.p, tag_pose6, sizeof(double) * 6 * n_tag, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(d_pose.p, cap_pose6, sizeof(double) * 6 * n_loc, cudaMemcpyHostToDevice, s->stream));
   LAUNCH("prep_poses", 8.0 * (6 + kTagPre) * n_tag,
          prep_poses_kernel<<<cdiv(n_tag, 128), 128, 0, s->stream>>>(0, nullptr, nullptr, (int)n_tag, d_tagpose.p, s->opt.tag_size, d_tagpre.p, 0, nullptr, nullptr));
+  CU(cudaEventRecord(s->loc_ready, s->stream));
   LocArgs a;
-  a.n_loc = (int)n_loc; a.blk_off = d_off.p; a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
-  a.seed_block = d_seed.p; a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p;
+  a.tag_idx = d_tag.p; a.obs = reinterpret_cast<const double2*>(d_obs.p);
+  a.tag_pose = d_tagpose.p; a.tag_pre = d_tagpre.p;
   a.cam[0] = camera3[0]; a.cam[1] = camera3[1]; a.cam[2] = camera3[2];
   const arslam_options& o = s->opt;
   a.o.max_num_iterations = o.max_num_iterations; a.o.max_invalid = o.max_num_consecutive_invalid_steps;
@@ -1398,18 +1421,56 @@ int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_of
   a.o.min_relative_decrease = o.min_relative_decrease; a.o.min_diag = o.min_lm_diagonal; a.o.max_diag = o.max_lm_diagonal;
   a.o.function_tolerance = o.function_tolerance; a.o.gradient_tolerance = o.gradient_tolerance;
   a.o.parameter_tolerance = o.parameter_tolerance; a.o.tag_size = o.tag_size;
-  a.pose = d_pose.p; a.iterations = d_it.p; a.final_cost = d_cost.p; a.termination = d_term.p;
-  if (s->opt.num_intrinsics == 3)
-    LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc, localize_kernel<1><<<cdiv(n_loc * kLocGroup, 128), 128, 0, s->stream>>>(a));
-  else
-    LAUNCH("localize", 17.0 * 4 * nb + 116.0 * n_loc, localize_kernel<0><<<cdiv(n_loc * kLocGroup, 128), 128, 0, s->stream>>>(a));
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(cap_pose6, d_pose.p, sizeof(double) * 6 * n_loc, cudaMemcpyDeviceToHost, s->stream));
-  if (iterations) CU(cudaMemcpyAsync(iterations, d_it.p, sizeof(int32_t) * n_loc, cudaMemcpyDeviceToHost, s->stream));
-  if (final_cost) CU(cudaMemcpyAsync(final_cost, d_cost.p, sizeof(double) * n_loc, cudaMemcpyDeviceToHost, s->stream));
-  if (termination) CU(cudaMemcpyAsync(termination, d_term.p, sizeof(int32_t) * n_loc, cudaMemcpyDeviceToHost, s->stream));
+  a.invalid = s->l_invalid.p;
+  // ~128 k captures per chunk (64 MB of observations): large enough for full-rate DMA and a full grid
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_loc, s->tune_loc_chunk > 0 ? s->tune_loc_chunk : (1 << 17)));
+  const int n_chunks = (int)((n_loc + chunk - 1) / chunk);
+  for (int c = 0; c < n_chunks; ++c) {
+    cudaStream_t st = s->loc_stream[c % kLocStreams];
+    const int64_t c0 = c * chunk, c1 = std::min<int64_t>(n_loc, c0 + chunk), nc = c1 - c0;
+    const int64_t b0 = blk_offsets[c0], b1 = blk_offsets[c1];
+    if (b0 < 0 || b1 < b0 || b1 > nb) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: block offsets are not monotone");
+    if (c < kLocStreams) CU(cudaStreamWaitEvent(st, s->loc_ready, 0));
+    CU(cudaMemcpyAsync(d_off.p + c0, blk_offsets + c0, sizeof(int32_t) * (nc + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_seed.p + c0, seed_block + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, st));
+    if (b1 > b0) {
+      CU(cudaMemcpyAsync(d_tag.p + b0, tag_idx + b0, sizeof(int32_t) * (b1 - b0), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_obs.p + 8 * b0, rect8 + 8 * b0, sizeof(double) * 8 * (b1 - b0), cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(d_pose.p + 6 * c0, cap_pose6 + 6 * c0, sizeof(double) * 6 * nc, cudaMemcpyHostToDevice, st));
+    loc_validate_kernel<<<cdiv(nc, 256), 256, 0, st>>>((int)nc, d_off.p + c0, d_tag.p, d_seed.p + c0, (int)n_tag, (int)b0, (int)b1, s->l_invalid.p);
+    a.n_loc = (int)nc; a.blk_off = d_off.p + c0; a.seed_block = d_seed.p + c0;
+    a.pose = d_pose.p + 6 * c0; a.iterations = d_it.p + c0; a.final_cost = d_cost.p + c0; a.termination = d_term.p + c0;
+    {
+      Profiler::Rec r{0, nullptr, nullptr};
+      if (s->prof.on) {
+        r = Profiler::Rec{s->prof.id_of("localize", 17.0 * 4 * nb + 116.0 * n_loc), s->prof.ev(), s->prof.ev()};
+        cudaEventRecord(r.a, st);
+      }
+      if (s->opt.num_intrinsics == 3) localize_kernel<1><<<cdiv(nc * kLocGroup, 128), 128, 0, st>>>(a);
+      else localize_kernel<0><<<cdiv(nc * kLocGroup, 128), 128, 0, st>>>(a);
+      if (s->prof.on) {
+        cudaEventRecord(r.b, st);
+        s->prof.recs.push_back(r);
+      }
+      s->launches += 2;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cap_pose6 + 6 * c0, d_pose.p + 6 * c0, sizeof(double) * 6 * nc, cudaMemcpyDeviceToHost, st));
+    if (iterations) CU(cudaMemcpyAsync(iterations + c0, d_it.p + c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, st));
+    if (final_cost) CU(cudaMemcpyAsync(final_cost + c0, d_cost.p + c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+    if (termination) CU(cudaMemcpyAsync(termination + c0, d_term.p + c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, st));
+  }
+  // join the chunk streams back into the handle's stream, then wait for it
+  for (int i = 0; i < std::min(kLocStreams, n_chunks); ++i) {
+    CU(cudaEventRecord(s->loc_done[i], s->loc_stream[i]));
+    CU(cudaStreamWaitEvent(s->stream, s->loc_done[i], 0));
+  }
+  int h_invalid = 0;
+  CU(cudaMemcpyAsync(&h_invalid, s->l_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   s->prof.resolve();
+  if (h_invalid) return s->fail(ARSLAM_ERR_INVALID, "localize_batch: bad block offsets, seed block or tag index (checked on the device; no result was written)");
   return ARSLAM_OK;
 }
 

@@ -35,7 +35,23 @@ struct LocArgs {
   int32_t* iterations;        // optional
   double* final_cost;         // optional
   int32_t* termination;       // optional
+  const int* invalid;         // device flag written by loc_validate_kernel: != 0 -> do nothing (indices cannot be trusted)
 };
+
+// Index validation on the device (the host used to walk 1 M offsets + 8 M tag indices serially inside
+// the timed path): per capture 0 <= blocks, seed < blocks, block range inside [0, n_blk_total]; per block
+// 0 <= tag < n_tag.  One thread per capture, its blocks' tags checked by the same thread.
+__global__ void loc_validate_kernel(int n_loc, const int32_t* __restrict__ blk_off, const int32_t* __restrict__ tag_idx,
+                                    const int32_t* __restrict__ seed_block, int n_tag, int b_lo, int b_hi,
+                                    int* __restrict__ invalid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_loc) return;
+  const int b0 = blk_off[i], b1 = blk_off[i + 1];
+  bool bad = b0 < b_lo || b1 > b_hi || b1 < b0 || seed_block[i] >= b1 - b0;
+  if (!bad)
+    for (int b = b0; b < b1; ++b) bad = bad || tag_idx[b] < 0 || tag_idx[b] >= n_tag;
+  if (bad) atomicExch(invalid, 1);
+}
 
 // Eight lanes per capture (one lane per residual block, its four corners in sequence), four
 // captures per warp: the scalar LM control code, the pose prep (sincos) and the 6x6 Cholesky
@@ -117,6 +133,7 @@ __global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
   const int lane = threadIdx.x & 31, gl = lane & (kLocGroup - 1);
   const unsigned mask = ((1u << kLocGroup) - 1u) << (lane & ~(kLocGroup - 1));
   if (cap >= a.n_loc) return;
+  if (a.invalid && *a.invalid) return;
   const int b0 = a.blk_off[cap], nb = a.blk_off[cap + 1] - b0;
   const int seed = a.seed_block[cap];
   if (seed < 0 || nb <= 0) {

@@ -127,7 +127,21 @@ __device__ __forceinline__ void chol6_backward(const double L[36], double b[6]) 
 }
 
 constexpr int kSchurThreads = 128;
-constexpr size_t kSchurSmem = (size_t)(kSchurThreads * 37 + 4 * 32 * 37) * sizeof(double);
+constexpr int kSchurStageLd = 38;  // staged 6x6 product per thread: 36 doubles, 16-byte aligned rows (bulk reduction source)
+constexpr size_t kSchurSmem = (size_t)(kSchurThreads * 37 + 4 * 32 * kSchurStageLd) * sizeof(double);
+
+// One TMA bulk reduction adds a staged, contiguous block of doubles to global memory
+// (cp.reduce.async.bulk ... .add.f64): the 36 elements of a Schur product travel as one request
+// instead of 36 per-lane FP64 reductions.  src: shared memory, 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_reduce_add_f64(double* dst_global, const double* src_shared, unsigned bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy stores that staged the block
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst_global)),
+               "r"((unsigned)__cvta_generic_to_shared(src_shared)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // One thread per residual block (E-sorted order).  With Ht_ee = L L^T the Schur term of a
 // segment is sum_ij V_i^T V_j, V_j = L^-1 (sig_e W_j).  Thread j
@@ -143,12 +157,14 @@ constexpr size_t kSchurSmem = (size_t)(kSchurThreads * 37 + 4 * 32 * 37) * sizeo
 // CTA) is not in shared memory.  Those products are left to a second launch of the same kernel
 // with STRADDLE = true, which rebuilds the partner's V column by column from W (same L); the
 // main launch then does not need L after V and fits three CTAs per SM.
-template <typename Target, int NK, bool STRADDLE>
+// BULK (sparse target only: its blocks are 36 contiguous doubles): every thread hands its staged product to
+// the TMA engine as ONE bulk reduction instead of the warp adding it element by element.
+template <typename Target, int NK, bool STRADDLE, bool BULK = false>
 __global__ void __launch_bounds__(kSchurThreads, STRADDLE ? 1 : 3)
 schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32_t* __restrict__ e_idx) {
   extern __shared__ __align__(16) double schur_sm[];
   double(*Vs)[37] = reinterpret_cast<double(*)[37]>(schur_sm);                       // [128][37]
-  double(*stage)[32][37] = reinterpret_cast<double(*)[32][37]>(schur_sm + kSchurThreads * 37);  // [4][32][37]
+  double(*stage)[32][kSchurStageLd] = reinterpret_cast<double(*)[32][kSchurStageLd]>(schur_sm + kSchurThreads * 37);  // [4][32][38]
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   const int cta0 = blockIdx.x * blockDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -280,6 +296,7 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
         const bool diag = fa == fb, twice = diag && d != 0;
         blk = t.block(fa, fb, (a.pair_off ? (long long)a.pair_off[pos] : 0) + d);
         double* st = stage[wid][lane];
+        if (BULK) bulk_wait_read();  // the engine has read the product staged in the previous round
         // m1 = V^T P, P the partner's V.  The product wanted is M = V_a^T V_b (element
         // (6 fa + r, 6 fb + c)), stored transposed in the lower block (fb, fa): with the own block
         // first that is m1^T, with the partner first it is m1 itself; on the diagonal (same F
@@ -315,8 +332,10 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
               st[c * 6 + r] = v;
             }
         }
+        if (BULK) bulk_reduce_add_f64(blk, st, 36 * sizeof(double));
       }
     }
+    if (BULK) continue;
     __syncwarp();
     const unsigned m = __ballot_sync(0xffffffffu, active);
     // lanes 0..31 of the warp add elements 0..31 of every staged block; the 4-element tails
@@ -335,6 +354,7 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
     }
     __syncwarp();
   }
+  if (BULK) bulk_wait_all();  // the reductions are complete (and visible) before the thread exits
 }
 
 // E poses without blocks never reach schur_eliminate_kernel: clear their records.

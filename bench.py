@@ -15,6 +15,13 @@ value  = observation corners processed per second by the whole job
          stream, max over ranks), problem resident in HBM.
 e2e    = the same through the C-ABI with host buffers: set_problem +
          set_params + solve + get_params inside the timed region.
+
+With N > 1 the NAMED shape is split across the ranks (strong scaling, the
+default); `extra.weak` carries a short weak-scaling measurement (every rank
+brings the workload's captures against the same map).  `n_gpu_check` compares
+the sharded solve's cost with a single-GPU solve of the same problem.
+At N = 1 short runs of the other BASELINE configurations ride along in
+`extra_workloads`.
 """
 import argparse
 import json
@@ -37,6 +44,20 @@ WORKLOADS = {
     "loc_1m_5k": (1000000, 5000, 8, 4),   # batched localisation (kernel 5), a step = one full batch
 }
 ITERS_PER_SOLVE = 5  # LM iterations per solve call; the solve restarts from the same initial state
+INIT_STATE = ("ground truth perturbed by N(0, 2 cm) / N(0, 2 deg) per pose component, f0 = 800 px (true 760); "
+              "NOT the reference's f0 = 3000 + heuristic seeds (those are exercised by the schedule tests)")
+# what bounds each kernel; bytes are the compulsory HBM bytes the library reports per launch
+KERNEL_BOUND = {"dense_cholesky": "tensor"}
+KERNEL_NOTE = {
+    "accum_E": "fused evaluation + accumulation, J never in HBM: 18 B/corner in + 72 B/corner W out + 264 B/pose",
+    "accum_F": "tag-sorted pass, Jacobians recomputed: 18 B/corner in + 264 B/pose out",
+    "schur_eliminate": "W read once (72 B/corner) + E records + the lower reduced blocks written once; limited by FP64 reductions into L2",
+    "pcg_solve": "persistent cooperative PCG, matrix resident in shared memory: compulsory HBM bytes = the block values "
+                 "read once per solve; bound by grid-barrier + halo latency per iteration, not by bandwidth",
+    "backsub": "W read once (72 B/corner) + E records",
+    "candidate": "residual-only cost at x + delta: 18 B/corner",
+    "localize": "whole LM solve per capture in registers: FP64-latency bound, not HBM bound",
+}
 
 
 def read_peaks():
@@ -45,6 +66,27 @@ def read_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def dgemm_peak():
+    fp = os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")
+    if os.path.exists(fp):
+        with open(fp) as f:
+            return max(json.load(f).values()), "measured cuBLAS DGEMM on this pool's B200 (profiles/r1_fp64_peaks.json)"
+    return 35.5, "cuBLAS DGEMM measured in round 1"
+
+
+def static_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (static:
+    the profiler cannot run inside a timed bench)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                v = json.load(f).get(workload, {}).get(kernel)
+            if v is not None:
+                return v, "profiles/" + name
+    return None, None
 
 
 class ClockSampler:
@@ -115,21 +157,73 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
-def bench_options(ar, iters, args):
+class Ctx:
+    """What every measurement needs: the torch / distributed handles and this rank's place in the job."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = self.dist = self.ar = self.synth = None
+
+    def init_gpu(self):
+        import torch
+        import ar_slam_b200 as ar
+        from ar_slam_b200 import synth
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.torch, self.ar, self.synth = torch, ar, synth
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def pinned(self, a):
+        torch = self.torch
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.ascontiguousarray(a[:0])).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    def comm_init(self, s):
+        torch, dist = self.torch, self.dist
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if self.rank == 0:
+            uid = torch.frombuffer(bytearray(self.ar.Solver.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        s.comm_init(self.rank, self.world, bytes(uid.cpu().numpy().tobytes()))
+
+
+def bench_options(ar, iters, args, linear_solver=None, num_intrinsics=None, pcg_tolerance=None, exact_iters=True):
     o = ar.default_options()
     o.max_num_iterations = iters
-    # run exactly `iters` LM iterations: switch the convergence tests off
-    o.function_tolerance = 0.0
-    o.parameter_tolerance = 0.0
-    o.gradient_tolerance = 0.0
-    if args.linear_solver == "dense":
+    if exact_iters:   # run exactly `iters` LM iterations: switch the convergence tests off
+        o.function_tolerance = 0.0
+        o.parameter_tolerance = 0.0
+        o.gradient_tolerance = 0.0
+    linear_solver = linear_solver or args.linear_solver
+    num_intrinsics = num_intrinsics or args.num_intrinsics
+    if linear_solver == "dense":
         o.linear_solver = ar.LINSOLVE_DENSE
         o.dense_max_dim = 1 << 20
-    elif args.linear_solver == "pcg":
+    elif linear_solver == "pcg":
         o.linear_solver = ar.LINSOLVE_PCG
-    o.pcg_tolerance = args.pcg_tolerance
-    o.num_intrinsics = args.num_intrinsics
-    if args.num_intrinsics == 3 and args.linear_solver == "auto":
+    o.pcg_tolerance = args.pcg_tolerance if pcg_tolerance is None else pcg_tolerance
+    o.num_intrinsics = num_intrinsics
+    if num_intrinsics == 3 and linear_solver == "auto":
         o.dense_max_dim = 1 << 20   # the radial model is solved with the dense Cholesky
     return o
 
@@ -147,10 +241,10 @@ def shard(m, rank, world):
     return m.cap_idx[lo:hi], m.tag_idx[lo:hi], m.obs[lo:hi]
 
 
-def run_solves(s, m, total_iters, start=None):
+def run_solves(s, total_iters, start):
     """Runs solves of ITERS_PER_SOLVE iterations from the same start until total_iters are done.
-    start = (cam, cap, tag) arrays to restart from (pinned copies of the initial state)."""
-    cam0, cap0, tag0 = start if start is not None else (m.cam0, m.cap0, m.tag0)
+    start = (cam, cap, tag) pinned copies of the initial state."""
+    cam0, cap0, tag0 = start
     done, summaries = 0, []
     while done < total_iters:
         n = min(ITERS_PER_SOLVE, total_iters - done)
@@ -166,11 +260,11 @@ def run_solves(s, m, total_iters, start=None):
     return summaries
 
 
-def cpu_baseline(args, steps, warmup, threads=None):
+def cpu_baseline(args, workload, steps, warmup, threads=None):
     """Times the oracle (restated reference, not Ceres) on a bounded sample of the workload."""
     from ar_slam_b200 import synth
     from oracle import pyoracle as po
-    n_cap, n_tag, tpc, _ = WORKLOADS[args.workload]
+    n_cap, n_tag, tpc, _ = WORKLOADS[workload]
     scale = max(1, n_cap // args.cpu_sample_captures)
     sc, st = max(50, n_cap // scale), max(10, n_tag // scale)
     m = synth.make_map(sc, st, tpc, seed=0xA55A0000 + 100)
@@ -189,65 +283,287 @@ def cpu_baseline(args, steps, warmup, threads=None):
         run(min(warmup, 2))
     dt, summ = run(steps)
     its = max(1, summ["iterations"])
+    same = (sc == n_cap and st == n_tag)
     return {"value": nc * its / dt, "unit": "corners/s", "cores": threads, "kind": "port",
-            "lm_iters_per_sec": its / dt, "reduced_dim": summ["reduced_dim"],
+            "lm_iters_per_sec": its / dt, "reduced_dim": summ["reduced_dim"], "same_config": same,
             "sample": "%d captures x %d tags (%d corners), same generator and density as %s, %d LM iterations, "
-                      "restated reference (not Ceres): Jet autodiff + dense Schur, OpenMP x%d"
-                      % (sc, st, nc, args.workload, its, threads)}, dt, its
+                      "restated reference (not Ceres): Jet autodiff + dense Schur, OpenMP x%d%s"
+                      % (sc, st, nc, workload, its, threads,
+                         "" if same else "; NOT the named shape: the reference's DENSE_SCHUR is cubic in the tag count "
+                                         "(reduced dimension %d here, %d at the named shape), so corners/s at the named "
+                                         "shape would be lower still" % (summ["reduced_dim"], 6 * n_tag + 1))}, dt, its
 
 
-def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
+# --------------------------------------------------------------------------------------------- roofline
+def kernel_rooflines(kt, reduced_dim, workload):
+    """One entry per profiled kernel: achieved = compulsory bytes (or flops) per launch / CUDA-event time per launch."""
+    hbm_peak, hbm_how = read_peaks()
+    tot = sum(k["total_ms"] for k in kt) or 1.0
+    out = []
+    for k in kt:
+        if k["launches"] <= 0 or k["total_ms"] <= 0:
+            continue
+        sec = k["total_ms"] / k["launches"] * 1e-3
+        share = k["total_ms"] / tot
+        name = k["name"]
+        if KERNEL_BOUND.get(name) == "tensor":
+            n = reduced_dim
+            flops = n ** 3 / 3.0 + 2.0 * n * n
+            peak, how = dgemm_peak()
+            e = {"kernel": name, "bound": "tensor", "achieved": flops / sec / 1e12, "peak": peak, "unit": "TFLOP/s",
+                 "frac": flops / sec / 1e12 / peak, "peak_source": how, "algorithmic_flops": flops,
+                 "note": "FP64 DMMA (mma.sync.m8n8k4.f64) blocked Cholesky + solve, n^3/3 + 2 n^2 flop, n = %d; the peak is "
+                         "FP64 DGEMM, not the bf16 figure of MEASURED_PEAKS.json" % n}
+        else:
+            b = k["algorithmic_bytes"]
+            if b <= 0:
+                continue
+            e = {"kernel": name, "bound": "hbm", "achieved": b / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": b / sec / 1e9 / hbm_peak, "peak_source": hbm_how, "algorithmic_bytes": b}
+            if name in KERNEL_NOTE:
+                e["note"] = KERNEL_NOTE[name]
+        e["us_per_launch"] = sec * 1e6
+        e["launches"] = k["launches"]
+        e["share_of_step"] = share
+        tr, src = static_traffic(workload, name)
+        e["traffic"] = tr
+        if tr is not None:
+            e["traffic_source"] = src + " (ncu --set full, static)"
+        out.append(e)
+    out.sort(key=lambda e: -e["share_of_step"])
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- BA
+def bench_ba(ctx, workload, steps, warmup, scaling="strong", linear_solver=None, num_intrinsics=None,
+             e2e=True, profile=True, converge=False, check=False, clocks=True):
+    """One bundle-adjustment workload on the job's GPUs.  Returns the fields of a bench line (rank 0) or None."""
+    args, torch, ar, synth = ctx.args, ctx.torch, ctx.ar, ctx.synth
+    rank, world = ctx.rank, ctx.world
+    n_cap, n_tag, tpc, cfg_id = WORKLOADS[workload]
+    num_intrinsics = num_intrinsics or args.num_intrinsics
+    if scaling == "weak":
+        n_cap *= world
+    m = synth.make_map(n_cap, n_tag, tpc, seed=0xA55A0000 + cfg_id,
+                       distortion=(-0.05, 0.01) if num_intrinsics == 3 else (0.0, 0.0))
+    cap_idx, tag_idx, obs = shard(m, rank, world)
+    n_corner_total = 4 * len(m.cap_idx)
+
+    opts = bench_options(ar, ITERS_PER_SOLVE, args, linear_solver, num_intrinsics)
+    s = ar.Solver(device=ctx.local_rank, options=opts)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        s.set_tuning(k, int(v))
+    stream = torch.cuda.Stream()
+    s.set_stream(stream.cuda_stream)
+    if world > 1:
+        ctx.comm_init(s)
+    s.set_problem(m.n_cap, m.n_tag, cap_idx, tag_idx, obs)
+
+    # every solve restarts from the same initial state, re-sent from pinned host memory (the only
+    # host -> device traffic inside the timed region: 4.9 MB per 5 LM iterations)
+    keep_start = [ctx.pinned(a) for a in (m.cam0, m.cap0, m.tag0)]
+    start = tuple(t.numpy() for t in keep_start)
+    if warmup > 0:
+        run_solves(s, warmup, start)
+    # ---- timed region: exactly `steps` LM iterations, CUDA events on the solver's stream
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0 and clocks:
+        sampler.start()
+    ctx.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        summaries = run_solves(s, steps, start)
+        ev1.record(stream)
+    ctx.barrier()
+    ms, = ctx.max_over_ranks(ev0.elapsed_time(ev1))
+    clk = sampler.stop() if (rank == 0 and clocks) else None
+    launches = int(sum(x["gpu_launches"] for x in summaries))
+    pcg_its = int(sum(x["linear_solver_iterations"] for x in summaries))
+    final_cost = summaries[-1]["final_cost"]
+
+    # ---- end to end through the C-ABI with host buffers
+    e2e_out = None
+    if e2e:
+        # what ArSlamSolver::optimize does per call (ar_slam_util.cpp:1001-1018 with the blocks of
+        # :720-727): the whole problem and the parameters go host -> device from pinned host memory,
+        # ITERS_PER_SOLVE LM iterations run, the parameters come back.  One untimed call first.
+        keep = [ctx.pinned(a) for a in (cap_idx, tag_idx, obs, m.cam0, m.cap0, m.tag0)]
+        p_cap_idx, p_tag_idx, p_obs, p_cam0, p_cap0, p_tag0 = [t.numpy() for t in keep]
+        if s.options.max_num_iterations != ITERS_PER_SOLVE:
+            s.options.max_num_iterations = ITERS_PER_SOLVE
+            s.set_options(s.options)
+        keep_out = [torch.empty((m.n_cap, 6), dtype=torch.float64, pin_memory=True),
+                    torch.empty((m.n_tag, 6), dtype=torch.float64, pin_memory=True)]
+        out = tuple(t.numpy() for t in keep_out)
+
+        def one_call():
+            s.set_problem(m.n_cap, m.n_tag, p_cap_idx, p_tag_idx, p_obs)
+            s.set_params(p_cam0, p_cap0, p_tag0)
+            summ, _ = s.solve(log=False)
+            s.get_params(out=out)
+            return summ
+        one_call()
+        n_solves = max(1, -(-steps // ITERS_PER_SOLVE))
+        ctx.barrier()
+        t0 = time.perf_counter()
+        e2e_iters = 0
+        for _ in range(n_solves):
+            e2e_iters += one_call()["iterations"]
+        ctx.barrier()
+        dt, = ctx.max_over_ranks(time.perf_counter() - t0)
+        param_bytes = 8 * (3 + 6 * m.n_cap + 6 * m.n_tag)
+        h2d = n_solves * (obs.nbytes + cap_idx.nbytes + tag_idx.nbytes + param_bytes)
+        d2h = n_solves * param_bytes + 8 * 40 * e2e_iters
+        e2e_out = {"value": n_corner_total * e2e_iters / dt, "unit": "corners/s",
+                   "h2d_bytes_per_step": int(h2d / e2e_iters), "d2h_bytes_per_step": int(d2h / e2e_iters),
+                   "lm_iters_per_sec": e2e_iters / dt, "lm_iterations": e2e_iters,
+                   "what": "%d x (arslam_set_problem, set_params, solve of %d LM iterations, get_params) from pinned host "
+                           "arrays, wall clock; a step is one LM iteration" % (n_solves, ITERS_PER_SOLVE)}
+
+    # ---- per-kernel device times (separate profiled solve; events around every launch)
+    rooflines = None
+    if profile:
+        if rank == 0:
+            s.set_profiling(True)
+        run_solves(s, ITERS_PER_SOLVE, start)
+        if rank == 0:
+            kt = s.kernel_times()
+            s.set_profiling(False)
+            rooflines = kernel_rooflines(kt, summaries[0]["reduced_dim"], workload)
+
+    # ---- time to converge with the reference's own stopping rule (function_tolerance 1e-6, <= 50 iterations)
+    conv = None
+    if converge:
+        conv = {}
+        runs = [("default", None, None)]
+        if summaries[0]["linear_solver"] == 2 and world == 1:
+            runs.append(("pcg_tight_1e-8", "pcg", 1e-8))
+        for label, ls, tol in runs:
+            o = bench_options(ar, 50, args, ls or linear_solver, num_intrinsics, tol, exact_iters=False)
+            s.set_options(o)
+            s.set_params(*start)
+            s.solve(log=False)   # warm (symbolic phase of a solver switch)
+            ctx.barrier()
+            with torch.cuda.stream(stream):
+                s.set_params(*start)
+                ev0.record(stream)
+                summ, _ = s.solve(log=False)
+                ev1.record(stream)
+            ctx.barrier()
+            cms, = ctx.max_over_ranks(ev0.elapsed_time(ev1))
+            conv[label] = {"ms": cms, "lm_iterations": summ["iterations"], "final_cost": summ["final_cost"],
+                           "termination": summ["reason_name"], "pcg_iterations": int(summ["linear_solver_iterations"]),
+                           "pcg_tolerance": o.pcg_tolerance if summ["linear_solver"] == 2 else None}
+        s.set_options(opts)
+
+    # ---- N-GPU gate: the sharded solve must reproduce the single-GPU cost (tight linear solves, 2 LM iterations)
+    gate = None
+    if check and world > 1:
+        tight = bench_options(ar, 2, args, "pcg" if summaries[0]["linear_solver"] == 2 else "dense", num_intrinsics, 1e-11)
+        s.set_options(tight)
+        s.set_params(*start)
+        summ_n, _ = s.solve(log=False)
+        ctx.barrier()
+        if rank == 0:
+            s1 = ar.Solver(device=ctx.local_rank, options=tight)
+            s1.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+            s1.set_params(m.cam0, m.cap0, m.tag0)
+            summ_1, _ = s1.solve(log=False)
+            s1.close()
+            gate = {"cost_%dgpu" % world: summ_n["final_cost"], "cost_1gpu": summ_1["final_cost"],
+                    "cost_vs_1gpu_rel": abs(summ_n["final_cost"] - summ_1["final_cost"]) / summ_1["final_cost"],
+                    "what": "2 LM iterations from the bench's initial state, PCG tolerance 1e-11, same problem solved "
+                            "sharded over %d ranks and on rank 0's GPU alone" % world}
+        ctx.barrier()
+        s.set_options(opts)
+    s.close()
+    if rank != 0:
+        return None
+    value = n_corner_total * steps / (ms * 1e-3)
+    lin = {1: "dense_cholesky_dmma", 2: "pcg"}[summaries[0]["linear_solver"]]
+    res = {"metric": "observation_corners_per_sec", "value": value, "unit": "corners/s", "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+           "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "lm_iters_per_sec": steps / (ms * 1e-3),
+           "config": {"workload": workload, "captures": m.n_cap, "tags": m.n_tag, "tags_per_capture": tpc,
+                      "blocks": int(len(m.cap_idx)), "corners": int(n_corner_total), "linear_solver": lin,
+                      "pcg_tolerance": opts.pcg_tolerance if lin == "pcg" else None,
+                      "intrinsics": "f, l1, l2 (radial model)" if num_intrinsics == 3 else "f (focal only, the reference's live model)",
+                      "eliminated": {1: "tags", 2: "captures"}[summaries[0]["eliminated_side"]],
+                      "reduced_dim": summaries[0]["reduced_dim"], "iters_per_solve": ITERS_PER_SOLVE,
+                      "initial_state": INIT_STATE,
+                      "l2_policy": "inputs larger than L2 (W + observations > 126 MB) for ba_100k_5k; no explicit flush",
+                      "final_cost": final_cost, "pcg_iterations": pcg_its,
+                      "pcg_iterations_per_lm_iteration": pcg_its / max(1, steps) if lin == "pcg" else None},
+           "clocks": clk, "e2e": e2e_out, "gpu_launches": launches}
+    if rooflines:
+        res["roofline"] = dict(rooflines[0])
+        res["roofline"]["why_this_kernel"] = "largest share of the LM iteration"
+        res["rooflines"] = [r for r in rooflines if r["share_of_step"] >= 0.05]
+        res["kernels"] = {r["kernel"]: {"us_per_launch": r["us_per_launch"], "launches": r["launches"],
+                                        "share_of_step": r["share_of_step"]} for r in rooflines}
+    if conv:
+        res["time_to_converge"] = conv
+    if gate:
+        res["n_gpu_check"] = gate
+    return res
+
+
+# ------------------------------------------------------------------------------------------ localisation
+def bench_localization(ctx, workload, steps, warmup, cpu=True, clocks=True):
     """BASELINE config 4: captures are sharded evenly, no communication at all."""
-    n_loc, n_tag, tpc, cfg_id = WORKLOADS[args.workload]
+    args, torch, ar, synth = ctx.args, ctx.torch, ctx.ar, ctx.synth
+    rank, world = ctx.rank, ctx.world
+    n_loc, n_tag, tpc, cfg_id = WORKLOADS[workload]
     m = synth.make_localization_batch(n_loc, n_tag, tpc, seed=0xA55A0000 + cfg_id)
     lo, hi = n_loc * rank // world, n_loc * (rank + 1) // world
     b0, b1 = m.blk_offsets[lo], m.blk_offsets[hi]
     offs = (m.blk_offsets[lo:hi + 1] - b0).astype(np.int32)
     tag_idx, obs, seed = m.tag_idx[b0:b1], m.obs[b0:b1], m.seed_block[lo:hi]
-    s = ar.Solver(device=local_rank)
+    s = ar.Solver(device=ctx.local_rank)
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)
-
-    def pinned(a):  # the batch arrives in pinned host memory; results go back into pinned arrays
-        t = torch.empty(a.shape, dtype=torch.from_numpy(np.ascontiguousarray(a[:0])).dtype, pin_memory=True)
-        t.numpy()[...] = a
-        return t
-    keep = [pinned(a) for a in (offs, tag_idx, obs, seed)]
+    keep = [ctx.pinned(a) for a in (offs, tag_idx, obs, seed)]   # the batch arrives in pinned host memory
     offs, tag_idx, obs, seed = [t.numpy() for t in keep]
     keep_out = [torch.empty((hi - lo, 6), dtype=torch.float64, pin_memory=True), torch.empty(hi - lo, dtype=torch.int32, pin_memory=True),
                 torch.empty(hi - lo, dtype=torch.float64, pin_memory=True), torch.empty(hi - lo, dtype=torch.int32, pin_memory=True)]
     out = tuple(t.numpy() for t in keep_out)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, warmup)):
         pose, its, cost, term = s.localize_batch(offs, tag_idx, obs, seed, m.cam_true, m.tag_true, out=out)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    barrier()
-    t0 = time.perf_counter()
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0 and clocks:
+        sampler.start()
+    # ---- value: the kernel alone, inputs resident (one chunk: no copy or other chunk runs beside it)
+    s.set_tuning("loc_chunk", hi - lo)
     s.set_profiling(True)
-    kms = []
-    for _ in range(args.steps):
+    kms, launches = [], 0
+    ctx.barrier()
+    for _ in range(steps):
         pose, its, cost, term = s.localize_batch(offs, tag_idx, obs, seed, m.cam_true, m.tag_true, out=out)
-        kms.append([k for k in s.kernel_times() if k["name"] == "localize"][0]["total_ms"])
-    barrier()
+        kt = s.kernel_times()
+        kms.append(sum(k["total_ms"] for k in kt if k["name"] == "localize"))
+        launches += int(sum(k["launches"] for k in kt))
+    s.set_profiling(False)
+    # ---- e2e: the call as a user makes it (chunked upload / kernel / download pipeline on three streams)
+    s.set_tuning("loc_chunk", 0)
+    s.localize_batch(offs, tag_idx, obs, seed, m.cam_true, m.tag_true, out=out)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pose, its, cost, term = s.localize_batch(offs, tag_idx, obs, seed, m.cam_true, m.tag_true, out=out)
+    ctx.barrier()
     dt = time.perf_counter() - t0
-    ms_kernel = float(np.sum(kms))
-    if dist is not None:
-        t = torch.tensor([dt, ms_kernel], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, ms_kernel = float(t[0]), float(t[1])
-    clk = clocks.stop() if rank == 0 else None
+    dt, ms_kernel = ctx.max_over_ranks(dt, float(np.sum(kms)))
+    clk = sampler.stop() if (rank == 0 and clocks) else None
+    res = None
     if rank == 0:
         nc = 4 * len(m.tag_idx)
         peak, how = read_peaks()
         err = np.abs(pose - m.cap_true[lo:hi])
         cb = None
-        if not args.no_cpu_baseline and world == 1:
+        if cpu and world == 1:
             from oracle import pyoracle as po
             ns = min(n_loc, 50000)
             threads = len(os.sched_getaffinity(0))
@@ -256,31 +572,35 @@ def bench_localization(args, ar, synth, torch, dist, rank, world, local_rank):
                               m.seed_block[:ns], m.cam_true, m.tag_true, num_threads=threads)
             dtc = time.perf_counter() - t1
             cb = {"value": 4 * int(m.blk_offsets[ns]) / dtc, "unit": "corners/s", "cores": threads, "kind": "port",
-                  "captures_per_sec": ns / dtc,
+                  "captures_per_sec": ns / dtc, "same_config": ns == n_loc,
                   "sample": "first %d captures of the same batch, restated localizeOne (not Ceres), OpenMP x%d" % (ns, threads)}
         alg = 17.0 * 4 * len(tag_idx) + 116.0 * (hi - lo)
-        line = {"metric": "observation_corners_per_sec", "value": nc * args.steps / (ms_kernel * 1e-3), "unit": "corners/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "captures_per_sec": n_loc * args.steps / (ms_kernel * 1e-3),
-                "config": {"workload": args.workload, "captures": n_loc, "tags": n_tag, "tags_per_capture": tpc,
-                           "corners": nc, "mean_lm_iterations": float(its.mean()),
-                           "median_abs_pose_error": float(np.median(err)), "l2_policy": "inputs larger than L2"},
-                "clocks": clk, "gpu_launches": 2 * args.steps,
-                "e2e": {"value": nc * args.steps / dt, "unit": "corners/s", "captures_per_sec": n_loc * args.steps / dt,
-                        "h2d_bytes_per_step": int(obs.nbytes + tag_idx.nbytes + offs.nbytes + seed.nbytes),
-                        "d2h_bytes_per_step": int(pose.nbytes + its.nbytes + cost.nbytes + term.nbytes),
-                        "what": "arslam_localize_batch from pinned host arrays (H2D, kernel, D2H), wall clock"},
-                "roofline": {"bound": "hbm", "kernel": "localize", "achieved": alg * args.steps / (ms_kernel * 1e-3) / 1e9,
-                             "peak": peak, "unit": "GB/s", "frac": alg * args.steps / (ms_kernel * 1e-3) / 1e9 / peak,
-                             "traffic": None, "peak_source": how,
-                             "note": "whole LM solve per capture in registers: FP64-latency bound, not HBM bound"},
-                "cpu_baseline": cb}
-        print(json.dumps(line))
+        ach = alg * steps / (ms_kernel * 1e-3) / 1e9
+        res = {"metric": "observation_corners_per_sec", "value": nc * steps / (ms_kernel * 1e-3), "unit": "corners/s",
+               "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_kernel / steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "captures_per_sec": n_loc * steps / (ms_kernel * 1e-3),
+               "config": {"workload": workload, "captures": n_loc, "tags": n_tag, "tags_per_capture": tpc,
+                          "corners": nc, "mean_lm_iterations": float(its.mean()),
+                          "median_abs_pose_error": float(np.median(err)), "l2_policy": "inputs larger than L2",
+                          "sharding": "captures split evenly over the ranks, no communication"},
+               "clocks": clk, "gpu_launches": launches,
+               "e2e": {"value": nc * steps / dt, "unit": "corners/s", "captures_per_sec": n_loc * steps / dt,
+                       "h2d_bytes_per_step": int(obs.nbytes + tag_idx.nbytes + offs.nbytes + seed.nbytes),
+                       "d2h_bytes_per_step": int(pose.nbytes + its.nbytes + cost.nbytes + term.nbytes),
+                       "what": "arslam_localize_batch from pinned host arrays (H2D, validation + kernel, D2H, in 128 k-capture "
+                               "chunks on three streams), wall clock"},
+               "roofline": {"bound": "hbm", "kernel": "localize", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": static_traffic(workload, "localize")[0], "peak_source": how,
+                            "algorithmic_bytes": alg, "note": KERNEL_NOTE["localize"]},
+               "cpu_baseline": cb}
     s.close()
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+    return res
+
+
+def short(res, keys=("ms_per_step", "value", "unit", "lm_iters_per_sec", "captures_per_sec", "config", "e2e", "roofline",
+                     "gpu_launches", "steps", "warmup", "time_to_converge")):
+    return {k: res[k] for k in keys if res and k in res}
 
 
 def main():
@@ -297,24 +617,24 @@ def main():
     ap.add_argument("--cpu-sample-captures", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads / extra.weak / time_to_converge / n_gpu_check")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="kernel-variant switch passed to arslam_set_tuning (A/B measurements), e.g. accum_pipe=0")
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
-                    help="weak: every GPU gets the workload's captures (the map, i.e. the tags, is shared); strong: the workload is split")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the named workload is split over the GPUs; weak: every GPU gets the workload's "
+                         "captures (the map, i.e. the tags, is shared)")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = Ctx(args)
     n_cap, n_tag, tpc, cfg_id = WORKLOADS[args.workload]
 
     if args.impl == "reference":
-        if rank != 0:
+        if ctx.rank != 0:
             return 0
-        cb, dt, its = cpu_baseline(args, args.steps, args.warmup)
+        cb, dt, its = cpu_baseline(args, args.workload, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "observation_corners_per_sec", "value": cb["value"], "unit": "corners/s",
                 "n_gpus": args.gpus, "steps": its, "warmup": args.warmup, "ms_per_step": 1e3 * dt / its,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "lm_iters_per_sec": cb["lm_iters_per_sec"],
+                "data": "synthetic", "lm_iters_per_sec": cb["lm_iters_per_sec"], "same_config": cb["same_config"],
                 "config": {"workload": args.workload, "captures": n_cap, "tags": n_tag, "tags_per_capture": tpc,
                            "note": "CPU arm runs the bounded sample described in cpu_baseline.sample"},
                 "cpu_baseline": cb,
@@ -322,195 +642,34 @@ def main():
         print(json.dumps(line))
         return 0
 
-    import torch
-    import ar_slam_b200 as ar
-    from ar_slam_b200 import synth
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    ctx.init_gpu()
+    extra_on = not args.no_extra
     if args.workload.startswith("loc_"):
-        return bench_localization(args, ar, synth, torch, dist, rank, world, local_rank)
-    if args.scaling == "weak":
-        n_cap *= world
-    m = synth.make_map(n_cap, n_tag, tpc, seed=0xA55A0000 + cfg_id,
-                       distortion=(-0.05, 0.01) if args.num_intrinsics == 3 else (0.0, 0.0))
-    cap_idx, tag_idx, obs = shard(m, rank, world)
-    n_corner_total = 4 * len(m.cap_idx)
-
-    opts = bench_options(ar, ITERS_PER_SOLVE, args)
-    s = ar.Solver(device=local_rank, options=opts)
-    for kv in args.tune:
-        k, v = kv.split("=")
-        s.set_tuning(k, int(v))
-    stream = torch.cuda.Stream()
-    s.set_stream(stream.cuda_stream)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(ar.Solver.comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        s.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-    s.set_problem(m.n_cap, m.n_tag, cap_idx, tag_idx, obs)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # every solve restarts from the same initial state, re-sent from pinned host memory (the only
-    # host -> device traffic inside the timed region: 4.9 MB per 5 LM iterations)
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.from_numpy(np.ascontiguousarray(a[:0])).dtype, pin_memory=True)
-        t.numpy()[...] = a
-        return t
-    keep_start = [pinned(a) for a in (m.cam0, m.cap0, m.tag0)]
-    start = tuple(t.numpy() for t in keep_start)
-    # ---- warm-up
-    if args.warmup > 0:
-        run_solves(s, m, args.warmup, start)
-    # ---- timed region: exactly --steps LM iterations, CUDA events on the solver's stream
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        summaries = run_solves(s, m, args.steps, start)
-        ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clk = clocks.stop() if rank == 0 else None
-    launches = int(sum(x["gpu_launches"] for x in summaries))
-    pcg_its = int(sum(x["linear_solver_iterations"] for x in summaries))
-    final_cost = summaries[-1]["final_cost"]
-
-    # ---- end to end through the C-ABI with host buffers
-    e2e = None
-    if not args.no_e2e:
-        # what ArSlamSolver::optimize does per call (ar_slam_util.cpp:1001-1018 with the blocks of
-        # :720-727): the whole problem and the parameters go host -> device from pinned host memory,
-        # ITERS_PER_SOLVE LM iterations run, the parameters come back.  One untimed call first.
-        keep = [pinned(a) for a in (cap_idx, tag_idx, obs, m.cam0, m.cap0, m.tag0)]
-        p_cap_idx, p_tag_idx, p_obs, p_cam0, p_cap0, p_tag0 = [t.numpy() for t in keep]
-        if s.options.max_num_iterations != ITERS_PER_SOLVE:
-            s.options.max_num_iterations = ITERS_PER_SOLVE
-            s.set_options(s.options)
-
-        keep_out = [torch.empty((m.n_cap, 6), dtype=torch.float64, pin_memory=True),
-                    torch.empty((m.n_tag, 6), dtype=torch.float64, pin_memory=True)]
-        out = tuple(t.numpy() for t in keep_out)
-
-        def one_call():
-            s.set_problem(m.n_cap, m.n_tag, p_cap_idx, p_tag_idx, p_obs)
-            s.set_params(p_cam0, p_cap0, p_tag0)
-            summ, _ = s.solve(log=False)
-            s.get_params(out=out)
-            return summ
-        one_call()
-        n_solves = max(1, -(-args.steps // ITERS_PER_SOLVE))
-        barrier()
-        t0 = time.perf_counter()
-        e2e_iters = 0
-        for _ in range(n_solves):
-            e2e_iters += one_call()["iterations"]
-        barrier()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        param_bytes = 8 * (3 + 6 * m.n_cap + 6 * m.n_tag)
-        h2d = n_solves * (obs.nbytes + cap_idx.nbytes + tag_idx.nbytes + param_bytes)
-        d2h = n_solves * param_bytes + 8 * 40 * e2e_iters
-        e2e = {"value": n_corner_total * e2e_iters / dt, "unit": "corners/s",
-               "h2d_bytes_per_step": int(h2d / e2e_iters), "d2h_bytes_per_step": int(d2h / e2e_iters),
-               "lm_iters_per_sec": e2e_iters / dt, "lm_iterations": e2e_iters,
-               "what": "%d x (arslam_set_problem, set_params, solve of %d LM iterations, get_params) from pinned host "
-                       "arrays, wall clock; a step is one LM iteration" % (n_solves, ITERS_PER_SOLVE)}
-
-    # ---- per-kernel device times (separate profiled solve; events around every launch)
-    roofline = None
-    kernels = None
-    if rank == 0:
-        s.set_profiling(True)
-    if True:
-        run_solves(s, m, ITERS_PER_SOLVE, start)
-    if rank == 0:
-        kt = s.kernel_times()
-        s.set_profiling(False)
-        kernels = {k["name"]: {"ms_per_launch": k["total_ms"] / max(1, k["launches"]), "launches": k["launches"],
-                               "algorithmic_bytes": k["algorithmic_bytes"]} for k in kt}
-        peak, how = read_peaks()
-        cand = [k for k in kt if k["name"] in ("accum_E", "accum_F") and k["launches"] > 0]
-        if cand:
-            top = max(cand, key=lambda k: k["total_ms"])
-            sec = top["total_ms"] / top["launches"] * 1e-3
-            ach = top["algorithmic_bytes"] / sec / 1e9
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-            if os.path.exists(tp):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
-                with open(tp) as f:
-                    traffic = json.load(f).get(args.workload, {}).get(top["name"])
-            roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": traffic, "peak_source": how,
-                        "us_per_launch": sec * 1e6, "algorithmic_bytes": top["algorithmic_bytes"],
-                        "note": "fused evaluation+accumulation, J never in HBM: 18 B/corner in + 72 B/corner W out + "
-                                "264 B/pose; the kernel is also FP64-pipe bound (800 FP64 instructions per block)"}
-            tot = sum(k["total_ms"] for k in kt)
-            roofline["share_of_step"] = top["total_ms"] / tot if tot else None
-            by_time = sorted(kt, key=lambda k: -k["total_ms"])[:3]
-            roofline["largest_kernels"] = [{"kernel": k["name"], "share_of_step": k["total_ms"] / tot} for k in by_time]
-        # dense path: the blocked Cholesky dominates; its roofline is the FP64 tensor (DMMA) pipe
-        chol = [k for k in kt if k["name"] == "dense_cholesky" and k["launches"] > 0]
-        if chol and cand and chol[0]["total_ms"] > max(k["total_ms"] for k in cand):
-            n = summaries[0]["reduced_dim"]
-            sec = chol[0]["total_ms"] / chol[0]["launches"] * 1e-3
-            flops = n ** 3 / 3.0 + 2.0 * n * n
-            dg_peak, dg_how = 35.5, "measured cuBLAS DGEMM on this pool's B200 (profiles/r1_fp64_peaks.json)"
-            fp = os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")
-            if os.path.exists(fp):
-                with open(fp) as f:
-                    dg_peak = max(json.load(f).values())
-            roofline = {"bound": "tensor", "kernel": "dense_cholesky", "achieved": flops / sec / 1e12, "peak": dg_peak,
-                        "unit": "TFLOP/s", "frac": flops / sec / 1e12 / dg_peak, "traffic": None, "peak_source": dg_how,
-                        "us_per_launch": sec * 1e6, "algorithmic_flops": flops,
-                        "note": "FP64 DMMA (mma.sync.m8n8k4.f64) blocked Cholesky + solve, n^3/3 + 2 n^2 flop, n = %d; "
-                                "the peak is FP64, not the bf16 figure of MEASURED_PEAKS.json" % n}
-
-    if rank == 0:
-        cb = None
-        if not args.no_cpu_baseline and world == 1:
-            cb, _, _ = cpu_baseline(args, 2, 1)
-        value = n_corner_total * args.steps / (ms * 1e-3)
-        line = {"metric": "observation_corners_per_sec", "value": value, "unit": "corners/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "lm_iters_per_sec": args.steps / (ms * 1e-3),
-                "config": {"workload": args.workload, "captures": m.n_cap, "tags": m.n_tag, "tags_per_capture": tpc,
-                           "blocks": int(len(m.cap_idx)), "corners": int(n_corner_total),
-                           "linear_solver": {1: "dense_cholesky_dmma", 2: "pcg"}[summaries[0]["linear_solver"]],
-                           "intrinsics": "f, l1, l2 (radial model)" if args.num_intrinsics == 3 else "f (focal only, the reference's live model)",
-                           "eliminated": {1: "tags", 2: "captures"}[summaries[0]["eliminated_side"]],
-                           "reduced_dim": summaries[0]["reduced_dim"], "iters_per_solve": ITERS_PER_SOLVE,
-                           "l2_policy": "inputs larger than L2 (W + observations > 126 MB) for ba_100k_5k; "
-                                        "no explicit flush", "final_cost": final_cost,
-                           "pcg_iterations": pcg_its},
-                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
-                "kernels": kernels}
+        line = bench_localization(ctx, args.workload, args.steps, args.warmup, cpu=not args.no_cpu_baseline)
+    else:
+        line = bench_ba(ctx, args.workload, args.steps, args.warmup, scaling=args.scaling, e2e=not args.no_e2e,
+                        converge=extra_on, check=extra_on)
+        if ctx.rank == 0 and not args.no_cpu_baseline and ctx.world == 1:
+            line["cpu_baseline"], _, _ = cpu_baseline(args, args.workload, 2, 1)
+        elif ctx.rank == 0:
+            line["cpu_baseline"] = None
+        if extra_on and ctx.world > 1 and args.scaling == "strong":
+            # short weak-scaling measurement: every rank brings the workload's captures against the same map
+            w = bench_ba(ctx, args.workload, min(args.steps, 20), min(args.warmup, 5), scaling="weak", e2e=False,
+                         profile=False, clocks=False)
+            if ctx.rank == 0:
+                line["extra"] = {"weak": short(w)}
+        if extra_on and ctx.world == 1 and args.workload == "ba_100k_5k":
+            # the other BASELINE configurations, short runs, so that one invocation witnesses them all
+            ex = {}
+            ex["ba_1k_200"] = short(bench_ba(ctx, "ba_1k_200", 40, 10, e2e=True, clocks=False, converge=True))
+            ex["ba_20k_2k_radial_dense"] = short(bench_ba(ctx, "ba_20k_2k", 5, 3, num_intrinsics=3, e2e=False, clocks=False))
+            ex["loc_1m_5k"] = short(bench_localization(ctx, "loc_1m_5k", 3, 2, cpu=False, clocks=False))
+            line["extra_workloads"] = ex
+    if ctx.rank == 0:
         print(json.dumps(line))
-    s.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
     return 0
 
 

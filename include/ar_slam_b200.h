@@ -211,7 +211,11 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
  * shared with the map (:911-927) and seeds the pose through initCapturePose
  * (:91-108); seed_block[i] < 0 leaves capture i untouched (:929-933).
  * cap_pose6 [6 n_loc] out; iterations / final_cost / termination are optional
- * per-capture outputs (host pointers). */
+ * per-capture outputs (host pointers).  The batch is processed in chunks on three
+ * internal streams (upload of chunk i + 1 under the kernel of chunk i, download of
+ * chunk i - 1 under both; pinned host arrays make the copies asynchronous) which are
+ * joined into the handle's stream before the call returns.  Offsets, seed blocks and
+ * tag indices are validated on the device; on ARSLAM_ERR_INVALID no result is valid. */
 int arslam_localize_batch(arslam_solver* s, int64_t n_loc, const int32_t* blk_offsets,
                           const int32_t* tag_idx, const double* rect8, const int32_t* seed_block,
                           int64_t n_tag, const double* camera3, const double* tag_pose6,
@@ -239,7 +243,10 @@ int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch wit
 /* Kernel-variant switches for A/B measurements (bench.py, tests): per handle, never read from the
  * environment.  Keys: "accum_pipe" (bit 0: E pass, bit 1: F pass on the cross-block pipelined
  * accumulation kernels instead of the thread-per-block ones that start every block cold; default 2:
- * measured faster for the F pass only); "accum_flush" (1: unrolled segment flush in those kernels); "pcg_smem" (1: the PCG kernels that keep the
+ * measured faster for the F pass only); "accum_flush" (1: unrolled segment flush in those kernels); "schur_bulk" (1: the Schur products reach the
+ * block-sparse reduced system as TMA bulk reductions, default; 0: per-lane FP64 reductions);
+ * "loc_chunk" (captures per chunk of arslam_localize_batch's upload / kernel / download pipeline, 0:
+ * default 131072); "pcg_smem" (1: the PCG kernels that keep the
  * reduced matrix in shared memory, default); "pcg_pipelined" (1: one-barrier pipelined recurrence for
  * pcg_tolerance >= 1e-6, default; 0: always the classic two-barrier recurrence).
  * Unknown key: ARSLAM_ERR_INVALID. */

@@ -80,3 +80,38 @@ def test_batch_radial_model(gpu_solver_cls, oracle):
     assert np.abs(pose[same] - po[same]).max() < 1e-8
     err = np.abs(pose - m.cap_true)
     assert np.median(err[:, :3]) < 5e-3 and np.median(err[:, 3:]) < 5e-3
+
+
+def test_chunked_pipeline_equals_one_chunk_and_rejects_bad_indices(gpu_solver_cls):
+    """arslam_localize_batch uploads / solves / downloads in chunks on three streams: any chunk size gives
+    the same bits; indices are validated on the device and a bad batch returns ARSLAM_ERR_INVALID."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_localization_batch(5000, 200, seed=6)
+    outs = []
+    for chunk in (0, 700, 4999, 1):
+        s = gpu_solver_cls()
+        s.set_tuning("loc_chunk", chunk if chunk != 1 else 333)
+        outs.append(s.localize_batch(m.blk_offsets, m.tag_idx, m.obs, m.seed_block, m.cam_true, m.tag_true))
+        s.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    s = gpu_solver_cls()
+    bad_tag = m.tag_idx.copy()
+    bad_tag[1234] = 200                      # == n_tag
+    with pytest.raises(ar_slam_b200.ArslamError) as e:
+        s.localize_batch(m.blk_offsets, bad_tag, m.obs, m.seed_block, m.cam_true, m.tag_true)
+    assert e.value.code == -1
+    bad_seed = m.seed_block.copy()
+    bad_seed[77] = 50                        # beyond the capture's blocks
+    with pytest.raises(ar_slam_b200.ArslamError):
+        s.localize_batch(m.blk_offsets, m.tag_idx, m.obs, bad_seed, m.cam_true, m.tag_true)
+    bad_off = m.blk_offsets.copy()
+    bad_off[100] = bad_off[101] + 1          # not monotone
+    with pytest.raises(ar_slam_b200.ArslamError):
+        s.localize_batch(bad_off, m.tag_idx, m.obs, m.seed_block, m.cam_true, m.tag_true)
+    # the handle is still usable
+    pose, its, cost, term = s.localize_batch(m.blk_offsets, m.tag_idx, m.obs, m.seed_block, m.cam_true, m.tag_true)
+    assert np.array_equal(pose, outs[0][0])
+    s.close()
