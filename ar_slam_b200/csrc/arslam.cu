@@ -213,6 +213,7 @@ struct arslam_solver {
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
   DenseCholesky::LookAhead lookahead;  // second stream + events of the dense factorisation
+  DevBuf<long long> agree;   // multi-GPU: status word of comm_agree / capture ranges of the ranks
   DevBuf<double> f_blocks;   // multi-GPU: per F pose, number of blocks over all ranks
   DevBuf<unsigned> tickets;  // one ticket per in-kernel grid reduction (kernels.cuh), zero between launches
   // constant parameter blocks (arslam_set_constant); cleared by set_problem / append_blocks
@@ -526,29 +527,49 @@ int rebuild_views(arslam_solver* s) {
 
 }  // namespace
 
+namespace { int comm_agree(arslam_solver* s, int local, const char* what); }
+
 int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_blk, const int32_t* cap_idx,
                        const int32_t* tag_idx, const double* rect8) {
   if (!s) return ARSLAM_ERR_INVALID;
+  int rc = ARSLAM_OK;
   if (n_cap <= 0 || n_tag <= 0 || n_blk <= 0 || !cap_idx || !tag_idx || !rect8)
-    return s->fail(ARSLAM_ERR_INVALID, "set_problem: empty problem or null pointer");
-  if (n_blk > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
-    return s->fail(ARSLAM_ERR_INVALID, "set_problem: problem too large for 32-bit block indices");
+    rc = s->fail(ARSLAM_ERR_INVALID, "set_problem: empty problem or null pointer%s", s->world > 1 ? " (every rank needs at least one block)" : "");
+  else if (n_blk > (1LL << 28) || n_cap > (1LL << 28) || n_tag > (1LL << 28))
+    rc = s->fail(ARSLAM_ERR_INVALID, "set_problem: problem too large for 32-bit block indices");
   CU(cudaSetDevice(s->device));
   s->have_problem = false;
   s->have_params = false;
   int32_t lo = 0, hi = 0;
-  const int rc = store_blocks(s, n_cap, n_tag, 0, n_blk, cap_idx, tag_idx, rect8, &lo, &hi);
+  if (!rc) rc = store_blocks(s, n_cap, n_tag, 0, n_blk, cap_idx, tag_idx, rect8, &lo, &hi);
+  // under arslam_comm_init every rank learns here whether ALL ranks declared a valid shard
+  rc = comm_agree(s, rc, "set_problem");
   if (rc) return rc;
   s->cap_lo = 0;
   s->n_cap_global = (int)n_cap;
   if (s->world > 1) {
-    // a rank only ever touches the captures of its own blocks: work on that index range alone
+    // a rank only ever touches the captures of its own blocks: work on that index range alone.  The
+    // ranges of the ranks must not overlap: a capture whose blocks sit on two ranks would be eliminated
+    // twice from partial blocks (silently wrong Schur complement).
+    CU(s->agree.ensure((size_t)2 * s->world));
+    long long mine[2] = {lo, hi};
+    std::vector<long long> all((size_t)2 * s->world);
+    CU(cudaMemcpyAsync(s->agree.p + 2 * s->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, s->stream));
+    const int nrc = g_nccl.AllGather(s->agree.p + 2 * s->rank, s->agree.p, 2, kNcclInt64, s->comm, s->stream);
+    if (nrc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllGather(ranges): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+    CU(cudaMemcpyAsync(all.data(), s->agree.p, sizeof(long long) * 2 * s->world, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int a = 0; a < s->world; ++a)
+      for (int b = a + 1; b < s->world; ++b)
+        if (all[2 * a] <= all[2 * b + 1] && all[2 * b] <= all[2 * a + 1])  // identical on every rank: all fail together
+          return s->fail(ARSLAM_ERR_INVALID, "set_problem: ranks %d and %d declare overlapping capture ranges [%lld, %lld] and [%lld, %lld]; "
+                         "all blocks of a capture must be on one rank", a, b, all[2 * a], all[2 * a + 1], all[2 * b], all[2 * b + 1]);
     s->cap_lo = lo;
     n_cap = (int64_t)hi - lo + 1;
     if (s->cap_lo) shift_index_kernel<<<cdiv(n_blk, 256), 256, 0, s->stream>>>((int)n_blk, s->o_cap.p, -s->cap_lo);
   }
   s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk = (int)n_blk;
-  return rebuild_views(s);
+  return comm_agree(s, rebuild_views(s), "set_problem");
 }
 
 int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n_new, const int32_t* cap_idx,
@@ -720,6 +741,23 @@ int nccl_sum(arslam_solver* s, double* buf, size_t count) {
   return ARSLAM_OK;
 }
 
+// Multi-GPU: a rank-local failure (bad index, allocation) must fail EVERY rank, or the others wait in
+// the next collective forever.  Max-reduces |code| over the ranks; returns `local` when this rank
+// failed, ARSLAM_ERR_INVALID-style "a peer failed" otherwise, ARSLAM_OK when all are fine.
+int comm_agree(arslam_solver* s, int local, const char* what) {
+  if (s->world <= 1) return local;
+  if (s->agree.ensure(1) != cudaSuccess) return s->fail(ARSLAM_ERR_CUDA, "comm_agree: allocation failed");
+  long long v = local < 0 ? -local : local, worst = 0;
+  CU(cudaMemcpyAsync(s->agree.p, &v, sizeof(v), cudaMemcpyHostToDevice, s->stream));
+  const int rc = g_nccl.AllReduce(s->agree.p, s->agree.p, 1, kNcclInt64, kNcclMax, s->comm, s->stream);
+  if (rc) return s->fail(ARSLAM_ERR_NCCL, "ncclAllReduce(status): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  CU(cudaMemcpyAsync(&worst, s->agree.p, sizeof(worst), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (local) return local;
+  if (worst) return s->fail(-(int)worst, "%s: another rank failed (code %d); this rank stops with it", what, -(int)worst);
+  return ARSLAM_OK;
+}
+
 // sums the eight block-local LM scalars; max of gmax_e via per-rank slots
 int small_allreduce(arslam_solver* s, double* sc) {
   CU(s->small.ensure(8 + s->world));
@@ -776,11 +814,13 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
   std::string err;
   int rc = pcg_symbolic_keys(s->pcg, n_e, n_f, s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->s_oth[side_e].p, s->stream, err);
-  if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
+  rc = comm_agree(s, rc ? s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str()) : ARSLAM_OK, "pcg symbolic phase");
+  if (rc) return rc;
   const int urc = union_keys_across_ranks(s);
   if (urc) return urc;
   rc = pcg_symbolic_build(s->pcg, s->stream, err, s->n_sm, (size_t)227 * 1024 - 2048);
-  if (rc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
+  rc = comm_agree(s, rc ? s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str()) : ARSLAM_OK, "pcg symbolic phase");
+  if (rc) return rc;
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel, kPcgThreads, 0));
   if (occ < 1) return s->fail(ARSLAM_ERR_CUDA, "pcg_kernel cannot be made resident");
@@ -875,6 +915,18 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
   const int nb = s->n_blk, plane = s->plane, grid = cdiv(plane, kAccumThreads);
   const bool dist = s->opt.num_intrinsics == 3;
   int pipe_grid = 0;  // CTAs of the pipelined E pass (its camera partials), 0: accum_kernel ran
+  FixupJobs fix;
+  fix.n = 0;
+  int fix_ctas = 0;
+  auto add_fixup = [&](int side, int n_own, int nv, const double* partial, double* out_seg) {
+    FixupJob& f = fix.j[fix.n++];
+    f.n_pose = n_own; f.n_blk = nb; f.nv = nv;
+    f.own_idx = s->s_own[side].p; f.seg_off = s->s_off[side].p; f.partial = partial; f.out_seg = out_seg;
+    fix_ctas += cdiv((long long)std::max(s->n_warp - 1, 0) * nv, 256);
+    f.cta_zero = fix_ctas;
+    fix_ctas += cdiv(n_own, 256);
+    f.cta_end = fix_ctas;
+  };
   for (int pass = 0; pass < 2; ++pass) {
     const int side = pass == 0 ? sd.e : sd.f;
     const int n_own = side == 0 ? s->n_cap : s->n_tag;
@@ -914,8 +966,7 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
       if (side == 0) ARS_ACC(0, false, "accum_F", bytes_f); else ARS_ACC(1, false, "accum_F", bytes_f);
     }
 #undef ARS_ACC
-    LAUNCH("seg_fixup", 8.0 * NV * n_own,
-           seg_fixup_kernel<<<cdiv((long long)n_own * NV, 256), 256, 0, s->stream>>>(n_own, NV, s->s_off[side].p, s->partial[side].p, a.out_seg));
+    add_fixup(side, n_own, NV, s->partial[side].p, a.out_seg);
     if (dist) {  // the l1, l2 columns
       AccumCamArgs c;
       c.n_blk = nb; c.plane = plane;
@@ -932,10 +983,11 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
         if (side == 0) LAUNCH("accum_cam_F", bytes_c, accum_cam_kernel<0, false><<<grid, kAccumThreads, 0, s->stream>>>(c));
         else LAUNCH("accum_cam_F", bytes_c, accum_cam_kernel<1, false><<<grid, kAccumThreads, 0, s->stream>>>(c));
       }
-      LAUNCH("seg_fixup", 8.0 * NVX * n_own,
-             seg_fixup_kernel<<<cdiv((long long)n_own * NVX, 256), 256, 0, s->stream>>>(n_own, NVX, s->s_off[side].p, s->partialx[side].p, c.out_seg));
+      add_fixup(side, n_own, NVX, s->partialx[side].p, c.out_seg);
     }
   }
+  // the pieces of segments that straddle warps, all records of both passes in one launch
+  LAUNCH("seg_fixup", 16.0 * NV * s->n_warp, seg_fixup_kernel<<<fix_ctas, 256, 0, s->stream>>>(fix));
   LAUNCH("reduce_partials", 32.0 * grid, reduce_partials_kernel<4, false><<<1, 1024, 0, s->stream>>>(s->warp_cam.p, pipe_grid ? pipe_grid : grid, head));
   if (dist) launch_colsum(s, s->n_warp, 8, s->warp_cam8.p, head + 4);
   return ARSLAM_OK;
@@ -955,7 +1007,6 @@ __global__ void cam_sigma_kernel(double* sc, double* sigF_cam, int enabled, int 
 
 int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, int32_t log_rows) {
   if (!s || !summary) return ARSLAM_ERR_INVALID;
-  if (!s->have_problem || !s->have_params) return s->fail(ARSLAM_ERR_INVALID, "solve needs set_problem and set_params");
   CU(cudaSetDevice(s->device));
   const double t_start = wall_ms();
   const arslam_options& o = s->opt;
@@ -970,8 +1021,17 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   // rank's range) and are the only side that can be eliminated locally
   if (elim == ARSLAM_ELIM_AUTO)
     elim = (s->world > 1 || s->n_cap >= s->n_tag) ? ARSLAM_ELIM_CAPTURES : ARSLAM_ELIM_TAGS;
-  if (s->world > 1 && elim != ARSLAM_ELIM_CAPTURES)
-    return s->fail(ARSLAM_ERR_UNSUPPORTED, "multi-GPU solve shards captures and must eliminate them");
+  {
+    // every rank-local reason to refuse is settled among the ranks before the first collective
+    int pre = ARSLAM_OK;
+    if (!s->have_problem || !s->have_params) pre = s->fail(ARSLAM_ERR_INVALID, "solve needs set_problem and set_params");
+    else if (s->world > 1 && elim != ARSLAM_ELIM_CAPTURES)
+      pre = s->fail(ARSLAM_ERR_UNSUPPORTED, "multi-GPU solve shards captures and must eliminate them");
+    else if (o.num_intrinsics == 3 && o.linear_solver == ARSLAM_LINSOLVE_PCG)
+      pre = s->fail(ARSLAM_ERR_UNSUPPORTED, "the radial model (num_intrinsics = 3) is solved with the dense Cholesky only");
+    pre = comm_agree(s, pre, "solve");
+    if (pre) return pre;
+  }
   sd.e = elim == ARSLAM_ELIM_CAPTURES ? 0 : 1;
   sd.f = 1 - sd.e;
   sd.n_e = sd.e == 0 ? s->n_cap : s->n_tag;
@@ -985,8 +1045,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   // AUTO: the dense DMMA Cholesky where the reduced matrix is actually dense (>= 25 % of its
   // 6x6 blocks are structurally non-zero, or it is tiny), block-sparse PCG otherwise
   int lin = o.linear_solver;
-  if (dist && lin == ARSLAM_LINSOLVE_PCG)
-    return s->fail(ARSLAM_ERR_UNSUPPORTED, "the radial model (num_intrinsics = 3) is solved with the dense Cholesky only");
   if (dist) lin = ARSLAM_LINSOLVE_DENSE;
   if (lin == ARSLAM_LINSOLVE_AUTO) {
     lin = ARSLAM_LINSOLVE_PCG;
@@ -1005,12 +1063,15 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
 
   // ---- buffers that depend on the roles
   CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * nk * sd.n_e)); CU(s->seg_cam.ensure((size_t)12 * cdiv(s->n_blk, kSchurThreads)));
+  // E poses without blocks never reach the elimination kernel: their Z / YB stay zero for the whole solve
+  CU(cudaMemsetAsync(s->Z.p, 0, sizeof(double) * 8 * sd.n_e, s->stream));
+  CU(cudaMemsetAsync(s->YB.p, 0, sizeof(double) * 6 * nk * sd.n_e, s->stream));
   if (dist) {
     CU(s->Hx[sd.e].ensure((size_t)NVX * sd.n_e));
     for (int side = 0; side < 2; ++side) CU(s->partialx[side].ensure((size_t)s->n_warp * 2 * NVX));
     CU(s->warp_cam8.ensure((size_t)8 * s->n_warp));
   }
-  CU(s->seg_cross.ensure((size_t)cdiv((long long)sd.n_e * kBsGroup, 128) + 1));
+  CU(s->seg_cross.ensure((size_t)5 * (cdiv((long long)sd.n_e * kBsGroup, 128) + 1)));
   CU(s->sigE.ensure((size_t)6 * sd.n_e)); CU(s->sigF.ensure((size_t)n + 1)); CU(s->uF.ensure((size_t)n + 1));
   size_t s_elems = 0;
   if (lin == ARSLAM_LINSOLVE_DENSE) {
@@ -1093,10 +1154,9 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       a.e_off = s->s_off[sd.e].p; a.f_idx = s->s_oth[sd.e].p;
       a.HE = s->H[sd.e].p; a.HEx = dist ? s->Hx[sd.e].p : nullptr; a.W = s->W.p; a.sig_e = s->sigE.p;
       a.radius = radius; a.inv_radius = 1.0 / radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
-      a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr;
+      a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr; a.e_const = const_e;
       schur_args = a;
       CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
-      LAUNCH("schur_empty", 8.0 * sd.n_e, schur_empty_kernel<<<cdiv(std::max(sd.n_e, 1), 256), 256, 0, s->stream>>>(a, nk, sc + 12));
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
@@ -1106,8 +1166,9 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
         if (rc) return rc;
       }
-      LAUNCH("reduce_partials", 96.0 * cdiv(s->n_blk, kSchurThreads),
-             reduce_partials_kernel<12, false><<<1, 1024, 0, s->stream>>>(s->seg_cam.p, cdiv(s->n_blk, kSchurThreads), cam_minus));
+      // closes the elimination: cam_minus, max |g_e| -> sc[16], and the failure flag of the solve that starts here
+      LAUNCH("schur_finish", 96.0 * cdiv(s->n_blk, kSchurThreads),
+             schur_finish_kernel<<<1, 1024, 0, s->stream>>>(s->seg_cam.p, cdiv(s->n_blk, kSchurThreads), cam_minus, sc));
     }
     if (s->world > 1) {
       // one allreduce per linearisation: partial Schur terms (+ on a fresh
@@ -1117,8 +1178,9 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       if (rc) return rc;
     }
     if (fresh_linearisation) {
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_e, gradmax_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(sd.n_e, s->s_off[sd.e].p, s->H[sd.e].p, s->warp_gmax[sd.e].p, s->tickets.p + 2, sc + 16, sc_head, sc, nk, nullptr, const_e));
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, nullptr, nullptr, nk, f_blocks_all, const_f));
+      // (the E side's maximum comes out of the elimination kernel; this launch also moves the freshly summed
+      // camera scalars next to the other LM scalars)
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, sc_head, sc, nk, f_blocks_all, const_f));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
@@ -1151,27 +1213,27 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     }
     if (lin == ARSLAM_LINSOLVE_DENSE)  // (the PCG kernels write uF themselves)
       LAUNCH("scale_uF", 24.0 * n, scale_uF_kernel<<<cdiv(n, 256), 256, 0, s->stream>>>(n, s->yF.p, s->sigF.p, s->uF.p));
-    {
-      BacksubArgs b;
-      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk;
-      b.d_e = s->d_pose[sd.e].p; b.seg_cross = s->seg_cross.p; b.ticket = s->tickets.p + 4; b.out_cross = sc + 4;
-      LAUNCH("backsub", 292.0 * s->n_blk + 400.0 * sd.n_e,
-             backsub_kernel<<<cdiv((long long)sd.n_e * kBsGroup, 128), 128, 0, s->stream>>>(b));
-    }
     double* x_e = sd.e == 0 ? s->cap[k].p : s->tag[k].p;
     double* x_f = sd.f == 0 ? s->cap[k].p : s->tag[k].p;
     double* xc_e = sd.e == 0 ? s->cap[kc].p : s->tag[kc].p;
     double* xc_f = sd.f == 0 ? s->cap[kc].p : s->tag[kc].p;
     {
+      // back-substitution + the E side of the step: candidate poses, norms, model-cost terms and the
+      // candidate's prep records all come out of this one launch
+      BacksubArgs b;
+      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk;
+      b.d_e = s->d_pose[sd.e].p; b.seg_part = s->seg_cross.p; b.ticket = s->tickets.p + 4; b.out5 = sc + 4;
+      b.x_e = x_e; b.x_cand = xc_e; b.e_is_capture = sd.e == 0; b.tag_size = o.tag_size;
+      // (the candidate's prep records stay with prep_poses_kernel: one lane in eight would run the sincos /
+      // Rodrigues chain here, measured +40 us on this kernel against 19 us for the separate launch)
+      b.cap_pre_c = nullptr; b.cap_rt_c = nullptr; b.tag_pre_c = nullptr; b.tag_cor_c = nullptr;
+      LAUNCH("backsub", 292.0 * s->n_blk + (400.0 + 96.0) * sd.n_e,
+             backsub_kernel<<<cdiv((long long)sd.n_e * kBsGroup, 128), 128, 0, s->stream>>>(b));
+    }
+    {
       ApplyArgs ap;
       ap.uF_cam = s->uF.p + cam_row;
-      ap.blocks_all = nullptr; ap.constant = const_e;
-      ap.n_pose = sd.n_e; ap.seg_off = s->s_off[sd.e].p; ap.x = x_e; ap.step = s->d_pose[sd.e].p; ap.negate = 0;
-      ap.rec = s->H[sd.e].p; ap.recx = dist ? s->Hx[sd.e].p : nullptr;
-      ap.delta = s->d_pose[sd.e].p; ap.x_cand = xc_e; ap.warp_out = s->warp_norm[sd.e].p; ap.count_norms = 1;
-      ap.ticket = s->tickets.p + 5; ap.out = sc + 6;
-      ap.cam = nullptr; ap.cam_c = nullptr; ap.d_cam = nullptr; ap.sc = sc; ap.nk = nk;
-      LAUNCH("apply_step", 144.0 * sd.n_e + 8.0 * NV * sd.n_e, apply_step_kernel<<<cdiv(sd.n_e, 128), 128, 0, s->stream>>>(ap));
+      ap.sc = sc; ap.nk = nk;
       ap.blocks_all = f_blocks_all; ap.constant = const_f;
       ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
       ap.rec = HF; ap.recx = HFx;
@@ -1179,7 +1241,10 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       ap.ticket = s->tickets.p + 6; ap.out = sc + 9;
       ap.cam = s->cam[k].p; ap.cam_c = s->cam[kc].p; ap.d_cam = s->d_cam.p;  // this launch also steps the intrinsics
       ap.count_norms = (s->rank == 0) ? 1 : 0;
-      LAUNCH("apply_step", 144.0 * sd.n_f + 8.0 * NV * sd.n_f, apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
+      ap.pose_is_capture = sd.f == 0; ap.tag_size = o.tag_size;
+      ap.cap_pre_c = nullptr; ap.cap_rt_c = nullptr; ap.tag_pre_c = nullptr; ap.tag_cor_c = nullptr;
+      LAUNCH("apply_step", (144.0 + 8.0 * NV) * sd.n_f,
+             apply_step_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(ap));
     }
     cudaEventRecord(s->ev[1], s->stream);
     // ---------------- candidate point: cost at x + delta (residuals only)

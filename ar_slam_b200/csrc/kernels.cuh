@@ -41,7 +41,8 @@ __device__ __forceinline__ double warp_max(double v) {
 //                          only; the heavy ones write partials and leave the sum to
 //                          reduce_partials_kernel.
 __host__ __device__ constexpr int grid_reduce_scratch_doubles(int M, int WARPS) { return (WARPS + (WARPS * 32) / M) * M + 2; }
-template <int M, bool MAX, int WARPS>
+// MAXCOL >= 0: that one column is combined with max instead of + (a sum-type reduction that carries one maximum)
+template <int M, bool MAX, int WARPS, int MAXCOL = -1>
 __device__ __forceinline__ bool cta_partial(const double (&v)[M], double* __restrict__ part, double* scratch) {
   double(*gr_sm)[M] = reinterpret_cast<double(*)[M]>(scratch);  // [WARPS][M]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -50,33 +51,43 @@ __device__ __forceinline__ bool cta_partial(const double (&v)[M], double* __rest
     for (int c = 0; c < M; ++c) gr_sm[wid][c] = v[c];
   __syncthreads();
   if (threadIdx.x < M) {
+    const bool mx = MAX || (int)threadIdx.x == MAXCOL;
     double t = gr_sm[0][threadIdx.x];
 #pragma unroll
-    for (int w = 1; w < WARPS; ++w) t = MAX ? fmax(t, gr_sm[w][threadIdx.x]) : t + gr_sm[w][threadIdx.x];
+    for (int w = 1; w < WARPS; ++w) t = mx ? fmax(t, gr_sm[w][threadIdx.x]) : t + gr_sm[w][threadIdx.x];
     __stcg(part + (size_t)blockIdx.x * M + threadIdx.x, t);
     return true;
   }
   return false;
 }
-template <int M, bool MAX, int THREADS>
+template <int M, bool MAX, int THREADS, int MAXCOL = -1>
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int n, double* __restrict__ out,
                                                 double* scratch /* [THREADS / M][M] */) {
-  // thread (g, c): partial rows g, g + G, ... of column c; then the G groups in order
+  // thread (g, c): partial rows g, g + G, ... of column c; then the G groups in order.  The rows are
+  // loaded eight at a time before they are added (same order of additions): this kernel is one CTA
+  // deep on the critical path of every LM iteration, and a load -> add chain per row made it
+  // latency bound (13 us for 6250 rows, round 1).
   constexpr int G = THREADS / M;
   double(*gr_fin)[M] = reinterpret_cast<double(*)[M]>(scratch);
   const int c = threadIdx.x % M, g = threadIdx.x / M;
+  const bool mx = MAX || c == MAXCOL;
   if (g < G) {
     double t = 0.0;
-    for (int i = g; i < n; i += G) {
-      const double x = __ldcg(part + (size_t)i * M + c);
-      t = MAX ? fmax(t, x) : t + x;
+    for (int i = g; i < n; i += 8 * G) {
+      double x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (i + k * G < n) ? __ldcg(part + (size_t)(i + k * G) * M + c) : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (i + k * G < n) t = mx ? fmax(t, x[k]) : t + x[k];
     }
     gr_fin[g][c] = t;
   }
   __syncthreads();
   if (threadIdx.x < M) {
+    const bool mxo = MAX || (int)threadIdx.x == MAXCOL;
     double r = gr_fin[0][threadIdx.x];
-    for (int q = 1; q < G; ++q) r = MAX ? fmax(r, gr_fin[q][threadIdx.x]) : r + gr_fin[q][threadIdx.x];
+    for (int q = 1; q < G; ++q) r = mxo ? fmax(r, gr_fin[q][threadIdx.x]) : r + gr_fin[q][threadIdx.x];
     out[threadIdx.x] = r;
   }
 }
@@ -579,23 +590,52 @@ __global__ void __launch_bounds__(kAccumThreads) accum_cam_kernel(const AccumCam
   segment_flush<NVX>(stage[wid], sseg[wid], own, lane, gwarp, a.out_seg, a.partial);
 }
 
-// Sums the pieces of poses whose blocks straddle warps (fixed order), and
-// zero-fills poses without blocks.  One thread per (pose, value).
-__global__ void seg_fixup_kernel(int n_pose, int nv, const int32_t* __restrict__ seg_off,
-                                 const double* __restrict__ partial, double* __restrict__ out_seg) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_pose * nv) return;
-  const int s = t / nv, v = t - s * nv;
-  const int b0 = seg_off[s], b1 = seg_off[s + 1];
-  if (b1 == b0) { out_seg[t] = 0.0; return; }
-  const int w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
-  if (w0 == w1) return;
-  double acc = 0.0;
-  for (int w = w0; w <= w1; ++w) {
-    const int slot = (w == w0 && (b0 & 31) != 0) ? 1 : 0;
-    acc += partial[((size_t)w * 2 + slot) * nv + v];
+// Sums the pieces of poses whose blocks straddle warps (fixed order), and zero-fills poses without
+// blocks.  A segment can only be cut where a warp ends, so the work is indexed by warp boundary:
+// thread (w, v) looks at the boundary between sorted positions 32 w - 1 and 32 w and, when a
+// segment crosses it for the FIRST time there, adds that segment's pieces of value v in warp order.
+// (Round 1 ran one thread per (pose, value) -- 3.3 M threads per side at config 3, 13.6 us each.)
+// Up to four records are fixed in one launch: both pose sides and, for the radial model, their
+// l1 / l2 border records.
+struct FixupJob {
+  int n_pose, n_blk, nv;
+  const int32_t* own_idx;   // [n_blk] sorted pose index
+  const int32_t* seg_off;   // [n_pose + 1]
+  const double* partial;    // [n_warp][2][nv]
+  double* out_seg;          // [n_pose][nv]
+  int cta_end;              // this job owns CTAs [previous cta_end, cta_end)
+  int cta_zero;             // of those, CTAs >= cta_zero zero-fill the poses without blocks
+};
+struct FixupJobs {
+  FixupJob j[4];
+  int n;
+};
+__global__ void __launch_bounds__(256) seg_fixup_kernel(const FixupJobs jobs) {
+  int q = 0;
+  while (q + 1 < jobs.n && (int)blockIdx.x >= jobs.j[q].cta_end) ++q;
+  const FixupJob& f = jobs.j[q];
+  const int cta0 = q ? jobs.j[q - 1].cta_end : 0;
+  if ((int)blockIdx.x >= f.cta_zero) {  // poses without blocks: their records are never written by the accumulation
+    const int s = ((int)blockIdx.x - f.cta_zero) * 256 + threadIdx.x;
+    if (s < f.n_pose && f.seg_off[s + 1] == f.seg_off[s])
+      for (int v = 0; v < f.nv; ++v) f.out_seg[(size_t)s * f.nv + v] = 0.0;
+    return;
   }
-  out_seg[t] = acc;
+  const int t = ((int)blockIdx.x - cta0) * 256 + threadIdx.x;
+  const int w = 1 + t / f.nv, v = t % f.nv;
+  const int blk = w << 5;
+  if (blk >= f.n_blk) return;
+  const int s = f.own_idx[blk - 1];
+  if (f.own_idx[blk] != s) return;             // no segment crosses this boundary
+  const int b0 = f.seg_off[s], b1 = f.seg_off[s + 1];
+  const int w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
+  if (w0 != w - 1) return;                     // the segment was already open at the previous boundary
+  double acc = 0.0;
+  for (int ww = w0; ww <= w1; ++ww) {
+    const int slot = (ww == w0 && (b0 & 31) != 0) ? 1 : 0;
+    acc += f.partial[((size_t)ww * 2 + slot) * f.nv + v];
+  }
+  f.out_seg[(size_t)s * f.nv + v] = acc;
 }
 
 // Deterministic column sums of a [n][m] array (m <= 12) into out[m]: every CTA

@@ -28,7 +28,8 @@ struct SchurArgs {
   double radius, inv_radius, min_diag, max_diag;  // inv_radius = 1 / radius (host)
   double* Z;              // [n_e][8]: z = Ht_ee^-1 sig_e g_e (6), ok flag, pad
   double* YB;             // [n_e][6 NK]: Ht_ee^-1 sig_e H_e,intrinsic_q
-  double* seg_cam;        // [grid][12] CTA partials of M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | 0 0
+  double* seg_cam;        // [grid][12] CTA partials of M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | max |g_e| | 0
+  const unsigned char* e_const;  // [n_e] != 0: E pose held constant (left out of the gradient norm), or null
 };
 
 // FP64 add to global memory without a return value.  atomicAdd through a pointer whose address
@@ -226,6 +227,13 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
 #pragma unroll
         for (int i = 0; i < 12; ++i) sg[i] = 0.0;
         sg[0] = m00; sg[6] = v0; sg[9] = ok ? 0.0 : 1.0;
+        if (!(a.e_const && a.e_const[e])) {  // max |g| of this E pose (unscaled), for the gradient convergence test
+          const double* rec = a.HE + (size_t)e * NV;
+          double gm = 0.0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) gm = fmax(gm, fabs(rec[21 + i]));
+          sg[10] = gm;
+        }
         if (NK == 3) {
           double yb1[6], yb2[6];
 #pragma unroll
@@ -272,7 +280,8 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
     double cm[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) cm[i] = (NK == 3 || i == 0 || i == 6 || i == 9) ? warp_sum(cs[threadIdx.x][i]) : 0.0;
-    cta_partial<12, false, kSchurThreads / 32>(cm, a.seg_cam, schur_sm + kSchurThreads * 37 + kSchurThreads * 12);
+    cm[10] = warp_max(cs[threadIdx.x][10]);
+    cta_partial<12, false, kSchurThreads / 32, 10>(cm, a.seg_cam, schur_sm + kSchurThreads * 37 + kSchurThreads * 12);
     __syncthreads();  // the staging area is reused by the products
   }
   const int my_pairs = valid ? schur_pairs_of(j, k) : 0;
@@ -357,13 +366,17 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
   if (BULK) bulk_wait_all();  // the reductions are complete (and visible) before the thread exits
 }
 
-// E poses without blocks never reach schur_eliminate_kernel: clear their records.
-__global__ void schur_empty_kernel(const SchurArgs a, int nk, double* __restrict__ fail_flag) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e == 0) *fail_flag = 0.0;  // LmScalars::chol_fail of the linear solve that starts here
-  if (e >= a.n_e || a.e_off[e + 1] > a.e_off[e]) return;
-  for (int i = 0; i < 8; ++i) a.Z[8 * (size_t)e + i] = 0.0;
-  for (int i = 0; i < 6 * nk; ++i) a.YB[6 * nk * (size_t)e + i] = 0.0;
+// One CTA closes the elimination: column sums of the CTA partials (cam_minus[0..9], fixed order), the
+// maximum of the E poses' gradient entries, and the failure flag of the linear solve that starts here.
+__global__ void __launch_bounds__(1024) schur_finish_kernel(const double* __restrict__ seg_cam, int n, double* __restrict__ cam_minus,
+                                                            double* __restrict__ sc) {
+  __shared__ double scratch[(1024 / 12) * 12];
+  reduce_partials<12, false, 1024, 10>(seg_cam, n, cam_minus, scratch);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sc[16] = cam_minus[10];  // LmScalars::gmax_e
+    sc[12] = 0.0;            // LmScalars::chol_fail (the solvers raise it; the E-pose failures travel in cam_minus[9])
+  }
 }
 
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
@@ -448,15 +461,53 @@ struct BacksubArgs {
   const double* uF;   // [6 n_f + nk]
   int cam_row, nk;
   double* d_e;        // [6 n_e] step of the E poses
-  double* seg_cross;  // [grid] CTA partials of the cross term -sum_j d_e^T W_j u_j
+  double* seg_part;   // [grid][5] CTA partials of (cross term -sum_j d_e^T W_j u_j, 0, |x - x_cand|^2, |x|^2, model terms)
   unsigned* ticket;
-  double* out_cross;  // [1]
+  double* out5;       // -> LmScalars::cross (5 consecutive scalars: cross, cand_r2 (rewritten later), step2_e, xnorm2_e, mq_e)
+  // the E side of the step (what apply_step_kernel does for the F side), folded in: candidate point,
+  // norms, model-cost terms and the candidate's prep record
+  const double* x_e;      // [6 n_e] current E poses
+  double* x_cand;         // [6 n_e] out: x + d
+  int e_is_capture;       // which prep record the E poses get
+  double tag_size;
+  double* cap_pre_c;      // candidate prep records (E = captures): [n_e][kCapPre], cap_rt_c [n_e][12]
+  double* cap_rt_c;
+  double* tag_pre_c;      // (E = tags): [n_e][kTagPre], tag_cor_c [n_e][12]
+  double* tag_cor_c;
 };
 constexpr int kBsGroup = 8;  // lanes per E pose: four poses per warp (8 blocks per capture is the common case)
 __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
   for (int o = kBsGroup / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+__device__ __forceinline__ void store_cap_prep(const double pose[6], double* __restrict__ cap_pre, double* __restrict__ cap_rt, size_t i) {
+  double rec[kCapPre];
+  prep_capture(pose, rec);
+  double2* o = reinterpret_cast<double2*>(cap_pre + (size_t)kCapPre * i);
+#pragma unroll
+  for (int k = 0; k < kCapPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+  if (cap_rt) {
+    double2* c = reinterpret_cast<double2*>(cap_rt + (size_t)12 * i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    c[4] = make_double2(rec[8], rec[18]);
+    c[5] = make_double2(rec[19], rec[20]);
+  }
+}
+__device__ __forceinline__ void store_tag_prep(const double pose[6], double tag_size, double* __restrict__ tag_pre,
+                                               double* __restrict__ tag_cor, size_t i) {
+  double rec[kTagPre];
+  prep_tag(pose, tag_size, rec);
+  double2* o = reinterpret_cast<double2*>(tag_pre + (size_t)kTagPre * i);
+#pragma unroll
+  for (int k = 0; k < kTagPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+  if (tag_cor) {
+    double2* c = reinterpret_cast<double2*>(tag_cor + (size_t)12 * i);
+    const double w[12] = {rec[0], rec[1], rec[2], rec[12], rec[13], rec[14], rec[24], rec[25], rec[26], rec[36], rec[37], rec[38]};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c[k] = make_double2(w[2 * k], w[2 * k + 1]);
+  }
 }
 __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,6 +536,8 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   for (int i = 0; i < 6; ++i) t[i] = group_sum(t[i]);
   double de[6] = {0, 0, 0, 0, 0, 0};
   double cross = 0.0;
+  // a constant E pose has sig_e = 0: everything below then gives d = 0 exactly
+  const bool active = k > 0 && !(a.sa.e_const && a.sa.e_const[e]);
   if (k > 0) {
     double tr[6];  // sum_j W_j u_j, unscaled
 #pragma unroll
@@ -495,17 +548,46 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
       double ybu = a.sa.YB[6 * a.nk * (size_t)e + i] * a.uF[a.cam_row];
       if (a.nk == 3)
         ybu += a.sa.YB[18 * (size_t)e + 6 + i] * a.uF[a.cam_row + 1] + a.sa.YB[18 * (size_t)e + 12 + i] * a.uF[a.cam_row + 2];
-      de[i] = -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - ybu);
+      de[i] = active ? -s[i] * (a.sa.Z[8 * (size_t)e + i] - t[i] - ybu) : 0.0;
       // cross term of the model cost change, -sum_j d_e^T W_j u_j = -d_e . (sum_j W_j u_j)
       cross -= de[i] * tr[i];
     }
   }
-  if (valid && gl == 0) {
+  // ---- the step of this E pose: candidate point, norms, model-cost terms (one row of H per lane)
+  double d2 = 0.0, x2 = 0.0, mq = 0.0;
+  if (valid) {
+    const double* rec = a.sa.HE + (size_t)e * NV;
+    if (active && gl < 6) {
+      double hd = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) a.d_e[6 * (size_t)e + i] = de[i];
+      for (int c = 0; c < 6; ++c) hd += rec[gl <= c ? tri6(gl, c) : tri6(c, gl)] * de[c];
+      double border = -a.uF[a.cam_row] * rec[27 + gl];
+      if (a.sa.HEx) border += -a.uF[a.cam_row + 1] * a.sa.HEx[(size_t)e * NVX + gl] - a.uF[a.cam_row + 2] * a.sa.HEx[(size_t)e * NVX + 6 + gl];
+      double dg = 0.0;  // de[gl] without dynamic register indexing
+#pragma unroll
+      for (int c = 0; c < 6; ++c) dg = c == gl ? de[c] : dg;
+      mq = dg * (rec[21 + gl] + 0.5 * hd + border);
+    }
+    if (gl == 0) {
+      double xc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double x = a.x_e[6 * (size_t)e + i];
+        xc[i] = x + de[i];
+        a.d_e[6 * (size_t)e + i] = de[i];
+        a.x_cand[6 * (size_t)e + i] = xc[i];
+        if (active) {
+          const double dd = x - xc[i];  // Ceres: (x - candidate_x).norm()
+          d2 += dd * dd;
+          x2 += x * x;
+        }
+      }
+      if (a.e_is_capture) { if (a.cap_pre_c) store_cap_prep(xc, a.cap_pre_c, a.cap_rt_c, (size_t)e); }
+      else if (a.tag_pre_c) store_tag_prep(xc, a.tag_size, a.tag_pre_c, a.tag_cor_c, (size_t)e);
+    }
   }
-  const double v[1] = {warp_sum(valid && gl == 0 ? cross : 0.0)};
-  grid_reduce_last_cta<1, false, 4>(v, a.seg_cross, a.ticket, a.out_cross);
+  const double v[5] = {warp_sum(valid && gl == 0 ? cross : 0.0), 0.0, warp_sum(d2), warp_sum(x2), warp_sum(mq)};
+  grid_reduce_last_cta<5, false, 4>(v, a.seg_part, a.ticket, a.out5);
 }
 
 // delta_F = -uF ; candidate = x + delta on both pose sides and the camera;
@@ -533,6 +615,13 @@ struct ApplyArgs {
   double* d_cam;            // [3] step
   double* sc;               // LmScalars
   int nk;
+  // prep record of the candidate point (saves the separate prep launch): pose_is_capture selects which
+  int pose_is_capture;
+  double tag_size;
+  double* cap_pre_c;        // [n_pose][kCapPre] / cap_rt_c [n_pose][12], or
+  double* cap_rt_c;
+  double* tag_pre_c;        // [n_pose][kTagPre] / tag_cor_c [n_pose][12]; all null: no prep
+  double* tag_cor_c;
 };
 __global__ void apply_step_kernel(const ApplyArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -549,7 +638,7 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
   double d2 = 0.0, x2 = 0.0, mq = 0.0;
   if (i < a.n_pose) {
     const bool active = (a.blocks_all ? a.blocks_all[i] > 0.0 : a.seg_off[i + 1] > a.seg_off[i]) && !(a.constant && a.constant[i]);
-    double d[6];
+    double d[6], xcand[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const double x = a.x[6 * (size_t)i + k];
@@ -557,6 +646,7 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
       dk = active ? (a.negate ? -dk : dk) : 0.0;
       d[k] = dk;
       const double xc = x + dk;
+      xcand[k] = xc;
       a.delta[6 * (size_t)i + k] = dk;
       a.x_cand[6 * (size_t)i + k] = xc;
       if (active && a.count_norms) {
@@ -581,6 +671,8 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
       }
       mq = q;
     }
+    if (a.pose_is_capture) { if (a.cap_pre_c) store_cap_prep(xcand, a.cap_pre_c, a.cap_rt_c, (size_t)i); }
+    else if (a.tag_pre_c) store_tag_prep(xcand, a.tag_size, a.tag_pre_c, a.tag_cor_c, (size_t)i);
   }
   const double v[3] = {warp_sum(d2), warp_sum(x2), warp_sum(mq)};
   grid_reduce_last_cta<3, false, 4>(v, a.warp_out, a.ticket, a.out);

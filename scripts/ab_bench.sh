@@ -9,7 +9,7 @@ import json,sys
 try:
     d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
     k=d['kernels']
-    print("%-44s ms/step %.4f  E %.1f F %.1f schur %.1f pcg %.1f backsub %.1f cand %.1f cost %.6f" % (sys.argv[1], d['ms_per_step'], k['accum_E']['ms_per_launch']*1e3, k['accum_F']['ms_per_launch']*1e3, k['schur_eliminate']['ms_per_launch']*1e3, k.get('pcg_solve',{'ms_per_launch':0})['ms_per_launch']*1e3, k['backsub']['ms_per_launch']*1e3, k['candidate']['ms_per_launch']*1e3, d['config']['final_cost']))
+    print("%-44s ms/step %.4f  E %.1f F %.1f schur %.1f pcg %.1f backsub %.1f cand %.1f cost %.6f" % (sys.argv[1], d['ms_per_step'], k['accum_E']['us_per_launch'], k['accum_F']['us_per_launch'], k['schur_eliminate']['us_per_launch'], k.get('pcg_solve',{'us_per_launch':0})['us_per_launch'], k['backsub']['us_per_launch'], k['candidate']['us_per_launch'], d['config']['final_cost']))
 except Exception as e:
     print(sys.argv[1], 'FAILED', e)
 PY

@@ -56,6 +56,34 @@ for name, ls, (nc, nt) in (("dense", ar.LINSOLVE_DENSE, (3000, 400)), ("pcg", ar
         print("%s: world %d  iterations %d vs %d  final cost %.9g vs %.9g  max trajectory diff %.2e  max param diff %.2e  %s"
               % (name, world, summ["iterations"], summ1["iterations"], summ["final_cost"], summ1["final_cost"], dcost, dp,
                  "OK" if good else "MISMATCH"), flush=True)
+# ---- rank-consistent failure: overlapping capture ranges and a rank-local bad index must fail on EVERY rank
+# (round 1 hung the healthy ranks in the next collective)
+m = synth.make_map(2000, 200, seed=32)
+for case in ("overlap", "bad_index", "no_params"):
+    s = ar.Solver(device=local, options=ar.default_options())
+    s.comm_init(rank, world, fresh_uid())
+    ci, ti, ob = bench.shard(m, rank, world)
+    if case == "overlap" and rank == 1:      # rank 1 also claims the first capture of rank 0
+        ci, ti, ob = np.concatenate([[0], ci]).astype(np.int32), np.concatenate([[ti[0]], ti]).astype(np.int32), np.concatenate([ob[:1], ob])
+    if case == "bad_index" and rank == world - 1:
+        ti = ti.copy()
+        ti[3] = m.n_tag
+    failed = False
+    try:
+        s.set_problem(m.n_cap, m.n_tag, ci, ti, ob)
+        if case != "no_params" or rank != 0:
+            s.set_params(m.cam0, m.cap0, m.tag0)
+        s.solve()
+    except ar.ArslamError as e:
+        failed = True
+        msg = str(e)
+    s.close()
+    flags = torch.tensor([1.0 if failed else 0.0], device="cuda")
+    dist.all_reduce(flags)
+    good = int(flags.item()) == world
+    ok = ok and good
+    if rank == 0:
+        print("%s: %d of %d ranks raised (%s)  %s" % (case, int(flags.item()), world, msg if failed else "-", "OK" if good else "MISMATCH"), flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
