@@ -181,6 +181,33 @@ class Solver:
             raise ValueError("parameter array sizes do not match the problem")
         self._check(self._lib.arslam_set_params(self._h, _p(cam), _p(cap), _p(tag)))
 
+    # device-resident parameters (incremental schedules)
+    def set_camera(self, cam):
+        cam = _f64(cam)
+        self._lib.arslam_set_camera.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._check(self._lib.arslam_set_camera(self._h, _p(cam)))
+
+    def set_poses(self, which, first, pose6):
+        pose6 = _f64(pose6).reshape(-1, 6)
+        self._lib.arslam_set_poses.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_double)]
+        self._check(self._lib.arslam_set_poses(self._h, which, first, len(pose6), _p(pose6)))
+
+    def get_poses(self, which, first, count):
+        out = np.zeros((count, 6))
+        self._lib.arslam_get_poses.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_double)]
+        self._check(self._lib.arslam_get_poses(self._h, which, first, count, _p(out)))
+        return out
+
+    def seed_captures(self, cap_idx, tag_idx, rect8):
+        cap_idx, tag_idx, rect8 = _i32(cap_idx), _i32(tag_idx), _f64(rect8).reshape(-1)
+        self._lib.arslam_seed_captures.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        self._check(self._lib.arslam_seed_captures(self._h, len(cap_idx), _p(cap_idx, C.c_int32), _p(tag_idx, C.c_int32), _p(rect8)))
+
+    def seed_tags(self, tag_idx, cap_idx, rect8):
+        cap_idx, tag_idx, rect8 = _i32(cap_idx), _i32(tag_idx), _f64(rect8).reshape(-1)
+        self._lib.arslam_seed_tags.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        self._check(self._lib.arslam_seed_tags(self._h, len(tag_idx), _p(tag_idx, C.c_int32), _p(cap_idx, C.c_int32), _p(rect8)))
+
     def get_params(self, out=None):
         """(camera3, cap_pose [n_cap, 6], tag_pose [n_tag, 6]); out = caller-owned (cap, tag) arrays, e.g. pinned.
         In a multi-GPU solve only the rank's own capture range of cap_pose is written."""

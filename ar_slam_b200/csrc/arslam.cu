@@ -85,6 +85,12 @@ struct DevBuf {
     if (e == cudaSuccess) n = count;
     return e;
   }
+  // exactly like grow_keep, and the elements [keep, count) are zero afterwards (also when no reallocation happened)
+  cudaError_t grow_keep_zero(size_t count, size_t keep, cudaStream_t st) {
+    cudaError_t e = grow_keep(count, keep, st);
+    if (e == cudaSuccess && count > keep) e = cudaMemsetAsync(p + keep, 0, (count - keep) * sizeof(T), st);
+    return e;
+  }
   // capacity >= count with the first `keep` elements preserved (amortised growth)
   cudaError_t grow_keep(size_t count, size_t keep, cudaStream_t st) {
     if (count <= n && p) return cudaSuccess;
@@ -194,6 +200,8 @@ struct arslam_solver {
   // problem
   int n_cap = 0, n_tag = 0, n_blk = 0, plane = 0, n_warp = 0;
   bool have_problem = false, have_params = false;
+  bool keep_params = false;           // rebuild_views: keep the current parameter set (append_blocks with parameters on the device)
+  int param_caps = 0, param_tags = 0; // poses that hold parameters
   std::vector<double> h_cam;  // host mirror of the camera (poses stay on the device between calls)
   // multi-GPU: captures are re-indexed to the rank's own range [cap_lo, cap_lo + n_cap) of the n_cap_global captures
   int cap_lo = 0, n_cap_global = 0;
@@ -228,6 +236,8 @@ struct arslam_solver {
   DevBuf<int32_t> l_off, l_tag, l_seed, l_it, l_term;
   DevBuf<double> l_obs, l_tagpose, l_tagpre, l_pose, l_cost;
   DevBuf<int> l_invalid;
+  DevBuf<int32_t> seed_idx;   // arslam_seed_*: staged indices and observations
+  DevBuf<double> seed_rect;
   cudaStream_t loc_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t loc_done[3] = {nullptr, nullptr, nullptr}, loc_ready = nullptr;
   double* h_sc = nullptr;  // pinned
@@ -510,7 +520,12 @@ int rebuild_views(arslam_solver* s) {
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
   for (int k = 0; k < 2; ++k) {
-    CU(s->cam[k].ensure(4)); CU(s->cap[k].ensure((size_t)6 * s->n_cap)); CU(s->tag[k].ensure((size_t)6 * s->n_tag));
+    CU(s->cam[k].ensure(4));
+    // the current parameter set survives a growing problem (arslam_append_blocks): poses that did not exist
+    // before are zero until arslam_set_poses / arslam_seed_* / arslam_set_params fills them
+    const bool keep = s->keep_params && k == s->cur;
+    CU(s->cap[k].grow_keep_zero((size_t)6 * s->n_cap, keep ? (size_t)6 * s->param_caps : 0, s->stream));
+    CU(s->tag[k].grow_keep_zero((size_t)6 * s->n_tag, keep ? (size_t)6 * s->param_tags : 0, s->stream));
     CU(s->cap_pre[k].ensure((size_t)kCapPre * s->n_cap)); CU(s->tag_pre[k].ensure((size_t)kTagPre * s->n_tag));
     CU(s->tag_cor[k].ensure((size_t)12 * s->n_tag)); CU(s->cap_rt[k].ensure((size_t)12 * s->n_cap));
   }
@@ -569,6 +584,7 @@ int arslam_set_problem(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t n
     if (s->cap_lo) shift_index_kernel<<<cdiv(n_blk, 256), 256, 0, s->stream>>>((int)n_blk, s->o_cap.p, -s->cap_lo);
   }
   s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk = (int)n_blk;
+  s->keep_params = false;
   return comm_agree(s, rebuild_views(s), "set_problem");
 }
 
@@ -594,7 +610,15 @@ int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t
   }
   s->n_cap = (int)n_cap; s->n_tag = (int)n_tag; s->n_blk += (int)n_new;
   s->n_cap_global = (int)n_cap;
-  return rebuild_views(s);
+  // the parameters on the device stay (the incremental schedules continue from the previous solve's result);
+  // poses that are new are zero until they are set or seeded
+  s->keep_params = had_params;
+  const int rrc = rebuild_views(s);
+  s->keep_params = false;
+  if (rrc) return rrc;
+  s->have_params = had_params;
+  s->param_caps = s->n_cap; s->param_tags = s->n_tag;
+  return ARSLAM_OK;
 }
 
 int arslam_set_constant(arslam_solver* s, int camera_constant, const uint8_t* cap_constant, const uint8_t* tag_constant) {
@@ -627,6 +651,123 @@ int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap
   CU(cudaStreamSynchronize(s->stream));  // the caller may reuse its arrays
   s->cur = 0;
   s->have_params = true;
+  s->param_caps = s->n_cap; s->param_tags = s->n_tag;
+  return ARSLAM_OK;
+}
+
+// ---- parameters that stay on the device between solves (the incremental schedules) -----------------
+namespace {
+__global__ void seed_captures_kernel(int n, const int32_t* __restrict__ cap_idx, const int32_t* __restrict__ tag_idx,
+                                     const double* __restrict__ rect8, const double* __restrict__ cam, const double* __restrict__ tag_pose,
+                                     double tag_size, double* __restrict__ cap_pose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rect[8], tp[6], out[6];
+  for (int k = 0; k < 8; ++k) rect[k] = rect8[8 * (size_t)i + k];
+  for (int k = 0; k < 6; ++k) tp[k] = tag_pose[6 * (size_t)tag_idx[i] + k];
+  seed_capture_pose(rect, cam[0], tp, tag_size, out);  // initCapturePose, ar_slam_util.cpp:91-108
+  for (int k = 0; k < 6; ++k) cap_pose[6 * (size_t)cap_idx[i] + k] = out[k];
+}
+__global__ void seed_tags_kernel(int n, const int32_t* __restrict__ tag_idx, const int32_t* __restrict__ cap_idx,
+                                 const double* __restrict__ rect8, const double* __restrict__ cam, const double* __restrict__ cap_pose,
+                                 double tag_size, double* __restrict__ tag_pose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rect[8], cp[6], out[6];
+  for (int k = 0; k < 8; ++k) rect[k] = rect8[8 * (size_t)i + k];
+  for (int k = 0; k < 6; ++k) cp[k] = cap_pose[6 * (size_t)cap_idx[i] + k];
+  seed_tag_pose(rect, cam[0], cp, tag_size, out);      // initArPose, ar_slam_util.cpp:111-128
+  for (int k = 0; k < 6; ++k) tag_pose[6 * (size_t)tag_idx[i] + k] = out[k];
+}
+}  // namespace
+
+static int pose_range_ok(arslam_solver* s, int which, int64_t first, int64_t count, const char* what) {
+  if (!s->have_problem || !s->have_params) return s->fail(ARSLAM_ERR_INVALID, "%s needs set_problem and parameters on the device", what);
+  if (s->world > 1) return s->fail(ARSLAM_ERR_UNSUPPORTED, "%s: single-GPU handles only", what);
+  const int64_t n = which == 0 ? s->n_cap : s->n_tag;
+  if ((which != 0 && which != 1) || first < 0 || count < 0 || first + count > n)
+    return s->fail(ARSLAM_ERR_INVALID, "%s: pose range [%lld, %lld) outside the problem's %lld poses", what, (long long)first,
+                   (long long)(first + count), (long long)n);
+  return ARSLAM_OK;
+}
+
+int arslam_set_poses(arslam_solver* s, int which, int64_t first, int64_t count, const double* pose6) {
+  if (!s || !pose6) return ARSLAM_ERR_INVALID;
+  const int rc = pose_range_ok(s, which, first, count, "set_poses");
+  if (rc || count == 0) return rc;
+  CU(cudaSetDevice(s->device));
+  double* dst = (which == 0 ? s->cap[s->cur].p : s->tag[s->cur].p) + 6 * first;
+  CU(cudaMemcpyAsync(dst, pose6, sizeof(double) * 6 * count, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return ARSLAM_OK;
+}
+
+int arslam_get_poses(arslam_solver* s, int which, int64_t first, int64_t count, double* pose6) {
+  if (!s || !pose6) return ARSLAM_ERR_INVALID;
+  const int rc = pose_range_ok(s, which, first, count, "get_poses");
+  if (rc || count == 0) return rc;
+  CU(cudaSetDevice(s->device));
+  const double* src = (which == 0 ? s->cap[s->cur].p : s->tag[s->cur].p) + 6 * first;
+  CU(cudaMemcpyAsync(pose6, src, sizeof(double) * 6 * count, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return ARSLAM_OK;
+}
+
+int arslam_set_camera(arslam_solver* s, const double* camera3) {
+  if (!s || !camera3) return ARSLAM_ERR_INVALID;
+  if (!s->have_problem) return s->fail(ARSLAM_ERR_INVALID, "set_camera before set_problem");
+  CU(cudaSetDevice(s->device));
+  s->h_cam.assign(camera3, camera3 + 3);
+  double* cam4 = s->h_sc + 200;
+  cam4[0] = camera3[0]; cam4[1] = camera3[1]; cam4[2] = camera3[2]; cam4[3] = 0.0;
+  CU(cudaMemcpyAsync(s->cam[s->cur].p, cam4, 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (!s->have_params) {  // a fresh problem whose poses will all be set / seeded on the device: they start at zero
+    CU(cudaMemsetAsync(s->cap[s->cur].p, 0, sizeof(double) * 6 * s->n_cap, s->stream));
+    CU(cudaMemsetAsync(s->tag[s->cur].p, 0, sizeof(double) * 6 * s->n_tag, s->stream));
+    s->have_params = true;
+    s->param_caps = s->n_cap; s->param_tags = s->n_tag;
+  }
+  return ARSLAM_OK;
+}
+
+static int seed_common(arslam_solver* s, int64_t n, const int32_t* a_idx, int64_t n_a, const int32_t* b_idx, int64_t n_b,
+                       const double* rect8, const char* what, int32_t** d_a, int32_t** d_b, double** d_rect) {
+  if (!s->have_problem || !s->have_params) return s->fail(ARSLAM_ERR_INVALID, "%s needs set_problem and parameters on the device", what);
+  if (s->world > 1) return s->fail(ARSLAM_ERR_UNSUPPORTED, "%s: single-GPU handles only", what);
+  for (int64_t i = 0; i < n; ++i)
+    if (a_idx[i] < 0 || a_idx[i] >= n_a || b_idx[i] < 0 || b_idx[i] >= n_b) return s->fail(ARSLAM_ERR_INVALID, "%s: index out of range", what);
+  CU(s->seed_idx.ensure((size_t)2 * n)); CU(s->seed_rect.ensure((size_t)8 * n));
+  CU(cudaMemcpyAsync(s->seed_idx.p, a_idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->seed_idx.p + n, b_idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->seed_rect.p, rect8, sizeof(double) * 8 * n, cudaMemcpyHostToDevice, s->stream));
+  *d_a = s->seed_idx.p; *d_b = s->seed_idx.p + n; *d_rect = s->seed_rect.p;
+  return ARSLAM_OK;
+}
+
+int arslam_seed_captures(arslam_solver* s, int64_t n, const int32_t* cap_idx, const int32_t* tag_idx, const double* rect8) {
+  if (!s || n < 0 || (n > 0 && (!cap_idx || !tag_idx || !rect8))) return ARSLAM_ERR_INVALID;
+  if (n == 0) return ARSLAM_OK;
+  CU(cudaSetDevice(s->device));
+  int32_t *d_c, *d_t; double* d_r;
+  const int rc = seed_common(s, n, cap_idx, s->n_cap, tag_idx, s->n_tag, rect8, "seed_captures", &d_c, &d_t, &d_r);
+  if (rc) return rc;
+  seed_captures_kernel<<<cdiv(n, 128), 128, 0, s->stream>>>((int)n, d_c, d_t, d_r, s->cam[s->cur].p, s->tag[s->cur].p, s->opt.tag_size, s->cap[s->cur].p);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));  // the caller may reuse its arrays
+  return ARSLAM_OK;
+}
+
+int arslam_seed_tags(arslam_solver* s, int64_t n, const int32_t* tag_idx, const int32_t* cap_idx, const double* rect8) {
+  if (!s || n < 0 || (n > 0 && (!cap_idx || !tag_idx || !rect8))) return ARSLAM_ERR_INVALID;
+  if (n == 0) return ARSLAM_OK;
+  CU(cudaSetDevice(s->device));
+  int32_t *d_t, *d_c; double* d_r;
+  const int rc = seed_common(s, n, tag_idx, s->n_tag, cap_idx, s->n_cap, rect8, "seed_tags", &d_t, &d_c, &d_r);
+  if (rc) return rc;
+  seed_tags_kernel<<<cdiv(n, 128), 128, 0, s->stream>>>((int)n, d_t, d_c, d_r, s->cam[s->cur].p, s->cap[s->cur].p, s->opt.tag_size, s->tag[s->cur].p);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
   return ARSLAM_OK;
 }
 

@@ -298,15 +298,52 @@ std::optional<CaptureHandle> ArSlamSolver::addDetections(const ar_slam_interface
   return capture.handle;
 }
 
+static void rect_of(const Block& block, double rect[8]) {
+  for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
+}
+
+// initCapturePose (ar_slam_util.cpp:91-108): on the host arrays, or queued for the device while the
+// parameters live there (the tag pose it reads is the previous solve's result, which only the GPU has)
+void ArSlamSolver::seedCapture(Capture& capture, const Block& from_block) {
+  double rect[8];
+  rect_of(from_block, rect);
+  if (host_stale_) {
+    PendingSeed p{true, (int32_t)capture.handle.idx, (int32_t)from_block.aruco.idx, {}};
+    std::copy_n(rect, 8, p.rect);
+    pending_seeds_.push_back(p);
+  } else {
+    ars::seed_capture_pose(rect, camera_.params[0], at(from_block.aruco).data(), options_.tag_size, capture.data());
+  }
+}
+// initArPose (ar_slam_util.cpp:111-128)
+void ArSlamSolver::seedAruco(Aruco& aruco, const Capture& from_capture, const Block& block) {
+  double rect[8];
+  rect_of(block, rect);
+  if (host_stale_) {
+    PendingSeed p{false, (int32_t)aruco.handle.idx, (int32_t)from_capture.handle.idx, {}};
+    std::copy_n(rect, 8, p.rect);
+    pending_seeds_.push_back(p);
+  } else {
+    ars::seed_tag_pose(rect, camera_.params[0], from_capture.data(), options_.tag_size, aruco.data());
+  }
+}
+
+void ArSlamSolver::syncFromDevice() {
+  if (!host_stale_ || !gpu_) { host_stale_ = false; return; }
+  std::vector<double> cap(6 * device_captures_), tag(6 * device_arucos_);
+  check(gpu_, arslam_get_params(gpu_, camera_.params.data(), cap.data(), tag.data()), "get_params");
+  for (size_t i = 0; i < device_captures_; ++i) std::copy_n(cap.begin() + 6 * i, 6, captures_[i].data());
+  for (size_t i = 0; i < device_arucos_; ++i) std::copy_n(tag.begin() + 6 * i, 6, arucos_[i].data());
+  host_stale_ = false;
+}
+
 void ArSlamSolver::addCaptureBlocksToProblem(Capture& capture) {
   for (BlockHandle bh : capture.blocks) {
     Block& block = at(bh);
     Aruco& aruco = at(block.aruco);
-    double rect[8];
-    for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
     if (!aruco.initialized) {
       aruco.initialized = true;
-      ars::seed_tag_pose(rect, camera_.params[0], capture.data(), options_.tag_size, aruco.data());  // initArPose
+      seedAruco(aruco, capture, block);  // initArPose
     }
     if (block.added) throw std::runtime_error("block for capture was somehow already added?");
     block.added = true;
@@ -315,12 +352,7 @@ void ArSlamSolver::addCaptureBlocksToProblem(Capture& capture) {
 }
 
 void ArSlamSolver::solveCapture(Capture& capture, std::optional<BlockHandle> init_block_handle) {
-  if (init_block_handle.has_value()) {
-    const Block& block = at(init_block_handle.value());
-    double rect[8];
-    for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
-    ars::seed_capture_pose(rect, camera_.params[0], at(block.aruco).data(), options_.tag_size, capture.data());  // initCapturePose
-  }
+  if (init_block_handle.has_value()) seedCapture(capture, at(init_block_handle.value()));  // initCapturePose
   addCaptureBlocksToProblem(capture);
   optimize(capture);
 }
@@ -350,6 +382,7 @@ void ArSlamSolver::solveIncremental() {
       if (itr == unsolved_captures_.end()) break;
     }
   } while (repeat_solve);
+  syncFromDevice();  // the callers (detection_callback: getTransforms / markers) read the host arrays
 }
 
 void ArSlamSolver::solve() {
@@ -366,20 +399,22 @@ void ArSlamSolver::solve() {
   best_capture.init_block = BlockHandle(~0u);  // prevents the capture from being queued again
   open_captures.emplace_back(best_capture.handle);
   while (!open_captures.empty()) {
-    CaptureHandle h = open_captures.front();
-    open_captures.pop_front();
-    std::cout << "Processing capture " << h.idx << std::endl;
-    Capture& capture = at(h);
-    if (h.idx != best_cap_idx) {
-      const Block& block = at(capture.init_block.value());
-      double rect[8];
-      for (unsigned i = 0; i < 4; ++i) { rect[2 * i] = block.aruco_rect.corners[i].x; rect[2 * i + 1] = block.aruco_rect.corners[i].y; }
-      ars::seed_capture_pose(rect, camera_.params[0], at(block.aruco).data(), options_.tag_size, at(block.capture).data());
+    // captures_per_solve_ captures join the problem per optimize() call (1: the reference's schedule;
+    // more: its TODO at ar_slam_util.cpp:810)
+    Capture* last = nullptr;
+    for (unsigned batch = 0; batch < std::max(1u, captures_per_solve_) && !open_captures.empty(); ++batch) {
+      CaptureHandle h = open_captures.front();
+      open_captures.pop_front();
+      std::cout << "Processing capture " << h.idx << std::endl;
+      Capture& capture = at(h);
+      if (h.idx != best_cap_idx) seedCapture(capture, at(capture.init_block.value()));  // initCapturePose
+      addCaptureBlocksToProblem(capture);
+      addConnectedCaptures(capture, open_captures);  // structure only: the queue is the same as when it follows optimize()
+      last = &capture;
     }
-    addCaptureBlocksToProblem(capture);
-    optimize(capture);
-    addConnectedCaptures(capture, open_captures);
+    optimize(*last);
   }
+  syncFromDevice();
 }
 
 void ArSlamSolver::addConnectedCaptures(const Capture& base, std::deque<CaptureHandle>& open_captures) {
@@ -467,27 +502,156 @@ void ArSlamSolver::optimize(const Capture&) {
       for (const Point& p : b.aruco_rect.corners) { rect.push_back(p.x); rect.push_back(p.y); }
     }
   }
-  std::vector<double> cap(6 * captures_.size()), tag(6 * arucos_.size());
-  for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(captures_[i].data(), 6, cap.begin() + 6 * i);
-  for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(arucos_[i].data(), 6, tag.begin() + 6 * i);
   arslam_solver* g = handle();
   std::cout << "Starting solver..." << std::endl;
   check(g, arslam_set_options(g, &options_), "set_options");
-  if (is_extension)
+  const bool on_device = device_resident_ && device_params_ && host_stale_ && is_extension;
+  if (on_device) {
+    // the parameters of everything solved so far are on the GPU: append the new blocks (parameters stay),
+    // then seed the new captures / tags there, in the order the schedule asked for them
     check(g, arslam_append_blocks(g, captures_.size(), arucos_.size(), ci.size(), ci.data(), ti.data(), rect.data()), "append_blocks");
-  else if (!is_same)
-    check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), ci.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+    size_t i = 0;
+    while (i < pending_seeds_.size()) {
+      size_t j = i;
+      std::vector<int32_t> tgt, src;
+      std::vector<double> rr;
+      while (j < pending_seeds_.size() && pending_seeds_[j].is_capture == pending_seeds_[i].is_capture) {
+        tgt.push_back(pending_seeds_[j].target); src.push_back(pending_seeds_[j].source);
+        rr.insert(rr.end(), pending_seeds_[j].rect, pending_seeds_[j].rect + 8);
+        ++j;
+      }
+      if (pending_seeds_[i].is_capture) check(g, arslam_seed_captures(g, tgt.size(), tgt.data(), src.data(), rr.data()), "seed_captures");
+      else check(g, arslam_seed_tags(g, tgt.size(), tgt.data(), src.data(), rr.data()), "seed_tags");
+      i = j;
+    }
+    pending_seeds_.clear();
+  } else {
+    if (host_stale_) syncFromDevice();
+    if (!pending_seeds_.empty()) throw std::runtime_error("optimize: seeds were queued for the device but the problem is not an extension");
+    std::vector<double> cap(6 * captures_.size()), tag(6 * arucos_.size());
+    for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(captures_[i].data(), 6, cap.begin() + 6 * i);
+    for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(arucos_[i].data(), 6, tag.begin() + 6 * i);
+    if (is_extension)
+      check(g, arslam_append_blocks(g, captures_.size(), arucos_.size(), ci.size(), ci.data(), ti.data(), rect.data()), "append_blocks");
+    else if (!is_same)
+      check(g, arslam_set_problem(g, captures_.size(), arucos_.size(), ci.size(), ci.data(), ti.data(), rect.data()), "set_problem");
+    check(g, arslam_set_params(g, camera_.params.data(), cap.data(), tag.data()), "set_params");
+  }
   device_blocks_ = problem_blocks_;
   device_captures_ = captures_.size();
   device_arucos_ = arucos_.size();
-  check(g, arslam_set_params(g, camera_.params.data(), cap.data(), tag.data()), "set_params");
   // like the reference, a solver that does not converge is not an error (summary discarded at :1013-1017);
   // API misuse and CUDA failures are
   check(g, arslam_solve(g, &last_summary_, nullptr, 0), "solve");
   summaries_.push_back(last_summary_);
-  check(g, arslam_get_params(g, camera_.params.data(), cap.data(), tag.data()), "get_params");
-  for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(cap.begin() + 6 * i, 6, captures_[i].data());
-  for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(tag.begin() + 6 * i, 6, arucos_[i].data());
+  if (device_resident_) {
+    // only the intrinsics come back (the seeds of the next capture need the focal length; it is mirrored on
+    // the host by the library, so this moves nothing); the poses stay on the GPU until the schedule returns
+    check(g, arslam_get_params(g, camera_.params.data(), nullptr, nullptr), "get_params");
+    device_params_ = true;
+    host_stale_ = true;
+  } else {
+    std::vector<double> cap(6 * captures_.size()), tag(6 * arucos_.size());
+    check(g, arslam_get_params(g, camera_.params.data(), cap.data(), tag.data()), "get_params");
+    for (size_t i = 0; i < captures_.size(); ++i) std::copy_n(cap.begin() + 6 * i, 6, captures_[i].data());
+    for (size_t i = 0; i < arucos_.size(); ++i) std::copy_n(tag.begin() + 6 * i, 6, arucos_[i].data());
+  }
 }
 
 void ArSlamSolver::resetProblem() { problem_blocks_.clear(); }
+
+// ---------------------------------------------------------------- ROS outputs ---
+// What ArSlam::detection_callback publishes after every solveIncremental (reference
+// ar_slam/src/ar_slam.cpp:133 tf, :145 CameraInfo, :154 markers).  Same conventions as
+// ar_slam_util.cpp:1027-1162: tags are forward poses (world <- tag: translation and rotation as
+// stored), captures are INVERSE poses (p_cam = R(w)(p_world + t)): the published world <- camera
+// transform negates both the translation and the angle-axis vector; quaternions leave Ceres'
+// AngleAxisToQuaternion as (w, x, y, z) and are written into the message's x, y, z, w fields.
+namespace {
+void angle_axis_to_quaternion(const double aa[3], double q[4]) {  // ceres::AngleAxisToQuaternion, w first
+  ars::aa_to_quat(aa, q);
+}
+template <typename Stamp, typename T> void set_stamp(Stamp& dst, const T& src) { dst = src; }
+}  // namespace
+
+std::vector<geometry_msgs::msg::TransformStamped> ArSlamSolver::getTransforms(const arslam_ros::Time& stamp) const {
+  std::vector<geometry_msgs::msg::TransformStamped> transforms;
+  transforms.reserve(captures_.size() + arucos_.size());
+  for (const Aruco& aruco : arucos_) {
+    transforms.emplace_back();
+    auto& t = transforms.back();
+    set_stamp(t.header.stamp, stamp);
+    t.header.frame_id = "world";
+    t.child_frame_id = aruco.id.id;
+    const auto& pose = aruco.pose.params;
+    t.transform.translation.x = pose[0];
+    t.transform.translation.y = pose[1];
+    t.transform.translation.z = pose[2];
+    double q[4];
+    angle_axis_to_quaternion(&pose[3], q);
+    t.transform.rotation.w = q[0];
+    t.transform.rotation.x = q[1];
+    t.transform.rotation.y = q[2];
+    t.transform.rotation.z = q[3];
+  }
+  for (const Capture& capture : captures_) {
+    transforms.emplace_back();
+    auto& t = transforms.back();
+    set_stamp(t.header.stamp, stamp);
+    t.header.frame_id = "world";
+    t.child_frame_id = capture.uid.uid;
+    const auto& inv_pose = capture.inv_pose.params;
+    const double rot[3] = {-inv_pose[3], -inv_pose[4], -inv_pose[5]};
+    double q[4];
+    angle_axis_to_quaternion(rot, q);
+    t.transform.rotation.w = q[0];
+    t.transform.rotation.x = q[1];
+    t.transform.rotation.y = q[2];
+    t.transform.rotation.z = q[3];
+    t.transform.translation.x = -inv_pose[0];
+    t.transform.translation.y = -inv_pose[1];
+    t.transform.translation.z = -inv_pose[2];
+  }
+  return transforms;
+}
+
+sensor_msgs::msg::CameraInfo ArSlamSolver::getCameraInfo() const {
+  sensor_msgs::msg::CameraInfo info;
+  info.distortion_model = sensor_msgs::distortion_models::PLUMB_BOB;
+  info.d = {0, 0, 0, 0, 0};  // plumb_bob: k1, k2, t1, t2, k3 -- the live model has no distortion
+  const double fx = camera_.params[0], fy = camera_.params[0];
+  if (!camera_.size.has_value()) throw std::runtime_error("getCameraInfo: image size unknown (no detections yet)");
+  const double cx = camera_.size->first * 0.5, cy = camera_.size->second * 0.5;  // width, height
+  info.k = {fx, 0.0, cx, 0.0, fy, cy, 0.0, 0.0, 1.0};
+  info.r = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+  info.p = {fx, 0.0, cx, 0.0, 0.0, fy, cy, 0.0, 0.0, 0.0, 1.0, 0.0};
+  return info;
+}
+
+void ArSlamSolver::appendArucoMarkers(std::vector<visualization_msgs::msg::Marker>& markers, arslam_ros::Time stamp) const {
+  markers.reserve(markers.size() + arucos_.size() + 1);
+  {
+    markers.emplace_back();
+    auto& marker = markers.back();
+    set_stamp(marker.header.stamp, stamp);
+    marker.action = marker.DELETEALL;
+    marker.ns = "arucos";
+  }
+  for (unsigned idx = 0; idx < arucos_.size(); ++idx) {
+    const Aruco& aruco = arucos_[idx];
+    markers.emplace_back();
+    auto& marker = markers.back();
+    set_stamp(marker.header.stamp, stamp);
+    marker.header.frame_id = aruco.id.id;
+    marker.type = marker.CUBE;
+    marker.action = marker.ADD;
+    marker.ns = "arucos";
+    marker.id = idx;
+    marker.scale.x = aruco_size;
+    marker.scale.y = aruco_size;
+    marker.scale.z = 0.01;  // 1 cm thick
+    marker.color.a = 0.8;
+    marker.color.r = 1.0;
+    marker.frame_locked = true;
+  }
+}

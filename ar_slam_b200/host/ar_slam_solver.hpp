@@ -10,9 +10,12 @@
 // keeps the data store, the schedules and map.yaml.
 //
 // Built without ROS2 / OpenCV / yaml-cpp / Ceres (none exist in this
-// environment): image ingest, debug display and the ROS message getters
-// (loadImages, displayDebug, getTransforms, getCameraInfo, appendArucoMarkers;
-// SURVEY.md section 2 rows 9-11) are outside the hot path and not provided.
+// environment): image ingest and the debug display (loadImages, displayDebug;
+// SURVEY.md section 2 rows 10-11) are outside the hot path and not provided.
+// The ROS output getters (getTransforms, getCameraInfo, appendArucoMarkers;
+// reference ar_slam_util.cpp:1027-1162, called at ar_slam.cpp:133,145,154) ARE
+// provided: they fill the real ROS2 messages when built with -DARSLAM_WITH_ROS
+// and same-named plain structs otherwise (ros_msgs_lite.hpp).
 #pragma once
 #include <array>
 #include <deque>
@@ -25,6 +28,7 @@
 
 #include "../../include/ar_slam_b200.h"
 #include "detections_msg.hpp"
+#include "ros_msgs_lite.hpp"
 
 struct Point {
   double x = 0.0, y = 0.0;
@@ -115,6 +119,11 @@ public:
   void localizeMany(unsigned first_loc_cap_idx);
   std::optional<CaptureHandle> addDetections(const ar_slam_interfaces::msg::Detections& detections);
 
+  // ROS outputs of the live component (reference ar_slam_util.cpp:1027-1162)
+  std::vector<geometry_msgs::msg::TransformStamped> getTransforms(const arslam_ros::Time& stamp) const;
+  sensor_msgs::msg::CameraInfo getCameraInfo() const;
+  void appendArucoMarkers(std::vector<visualization_msgs::msg::Marker>& markers, arslam_ros::Time stamp) const;
+
   bool& display_debug() { return display_debug_; }
   double& display_wait_duration() { return display_wait_duration_; }
 
@@ -125,7 +134,18 @@ public:
   Block& at(BlockHandle h) { return blocks_[h.idx]; }
   const Block& at(BlockHandle h) const { return blocks_[h.idx]; }
 
-  // additions (not in the reference): the summary Ceres would have returned, and the solver options
+  // additions (not in the reference)
+  // Schedules with the parameters resident on the GPU (default): between the optimize() calls of one
+  // solve() / solveIncremental() nothing but the new capture's blocks crosses the bus -- new captures and
+  // tags are seeded on the device (arslam_seed_captures / arslam_seed_tags) from the previous solve's result,
+  // and the poses come back once, when the schedule returns.  false: every optimize() uploads and downloads
+  // all parameters, like the reference's Ceres calls touch the caller's arrays.
+  bool& device_resident_schedule() { return device_resident_; }
+  // The reference's own TODO (ar_slam_util.cpp:810): add this many captures to the problem per optimize()
+  // call in solve().  1 reproduces the reference's schedule; larger values trade its exact trajectory for
+  // fewer (quadratically growing) solves.
+  unsigned& captures_per_solve() { return captures_per_solve_; }
+  // the summary Ceres would have returned, and the solver options
   const arslam_summary& lastSummary() const { return last_summary_; }
   const std::vector<arslam_summary>& summaries() const { return summaries_; }
   arslam_options& options() { return options_; }
@@ -145,6 +165,16 @@ protected:
   void optimize(const Capture& capture);
   void resetProblem();
   arslam_solver* handle();
+  // seeds go to the host arrays, or -- while the parameters live on the GPU -- are queued for the device
+  void seedCapture(Capture& capture, const Block& from_block);
+  void seedAruco(Aruco& aruco, const Capture& from_capture, const Block& block);
+  void syncFromDevice();   // downloads the parameters when the host copies are stale
+  struct PendingSeed { bool is_capture; int32_t target, source; double rect[8]; };
+  std::vector<PendingSeed> pending_seeds_;
+  bool device_resident_ = true;   // option
+  bool device_params_ = false;    // the GPU holds the current parameters of the device_captures_ / device_arucos_ poses
+  bool host_stale_ = false;       // ... and the host copies are older than those
+  unsigned captures_per_solve_ = 1;
 
   arslam_solver* gpu_ = nullptr;              // replaces `ceres::Problem problem_` (hpp:473)
   arslam_options options_;

@@ -6,8 +6,8 @@
 #include "ar_slam_solver.hpp"
 
 int main(int argc, char** argv) {
-  if (argc < 2 || (std::string(argv[1]) == "roundtrip" && argc < 3)) {
-    std::cerr << "usage: host_selftest roundtrip in.yaml | detections" << std::endl;
+  if (argc < 2 || ((std::string(argv[1]) == "roundtrip" || std::string(argv[1]) == "rosout") && argc < 3)) {
+    std::cerr << "usage: host_selftest roundtrip in.yaml | detections | rosout map.yaml" << std::endl;
     return 1;
   }
   const std::string mode = argv[1];
@@ -16,6 +16,31 @@ int main(int argc, char** argv) {
       ArSlamSolver s;
       s.loadYaml(argv[2]);
       s.saveYaml(std::cout);
+      return 0;
+    }
+    if (mode == "rosout") {
+      // the ROS outputs of the live component for a saved map, one record per line (17 significant digits)
+      ArSlamSolver s;
+      s.loadYaml(argv[2]);
+      arslam_ros::Time stamp;
+      stamp.sec = 12; stamp.nanosec = 345;
+      std::cout.precision(17);
+      for (const auto& t : s.getTransforms(stamp))
+        std::cout << "tf " << t.header.frame_id << " " << t.child_frame_id << " " << t.header.stamp.sec << " " << t.header.stamp.nanosec << " "
+                  << t.transform.translation.x << " " << t.transform.translation.y << " " << t.transform.translation.z << " "
+                  << t.transform.rotation.x << " " << t.transform.rotation.y << " " << t.transform.rotation.z << " " << t.transform.rotation.w << "\n";
+      const auto info = s.getCameraInfo();
+      std::cout << "caminfo " << info.distortion_model << " " << info.d.size();
+      for (double v : info.k) std::cout << " " << v;
+      for (double v : info.r) std::cout << " " << v;
+      for (double v : info.p) std::cout << " " << v;
+      std::cout << "\n";
+      std::vector<visualization_msgs::msg::Marker> markers;
+      s.appendArucoMarkers(markers, stamp);
+      for (const auto& m : markers)
+        std::cout << "marker " << (m.header.frame_id.empty() ? "-" : m.header.frame_id) << " " << m.ns << " " << m.id << " " << m.type << " " << m.action << " "
+                  << m.scale.x << " " << m.scale.y << " " << m.scale.z << " " << m.color.r << " " << m.color.g << " " << m.color.b << " " << m.color.a << " "
+                  << (m.frame_locked ? 1 : 0) << "\n";
       return 0;
     }
     if (mode == "detections") {

@@ -160,3 +160,22 @@ def make_localization_batch(n_loc, n_tag, tags_per_capture=8, seed=0xA55A0004, n
     m.blk_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     m.seed_block = np.zeros(n_loc, dtype=np.int32)  # first block: every tag is in the map
     return m
+
+
+def write_detections_yaml(m, path, width=IMG_W, height=IMG_H, f0=3000.0):
+    """The synthetic map's observations in the reference's detections / map.yaml layout
+    (ar_slam_util.cpp:304-465: blocks, captures, arucos, camera), poses at zero and f at the reference's
+    initial 3000 (ar_slam_util.hpp:69), so that ar_slam_cli builds the map from scratch with the
+    reference's own schedule and seed heuristics."""
+    with open(path, "w") as f:
+        f.write("blocks:\n")
+        for c, t, r in zip(m.cap_idx, m.tag_idx, m.obs):
+            f.write("  - capture: cap_%d\n    aruco: aruco_4X4_50_%d\n    aruco_rect: [%s]\n"
+                    % (c, t, ", ".join(repr(float(v)) for v in r)))
+        f.write("captures:\n")
+        for c in range(m.n_cap):
+            f.write("  cap_%d:\n    inv_pose: [0, 0, 0, 0, 0, 0]\n    img_fn: cap_%d.jpg\n" % (c, c))
+        f.write("arucos:\n")
+        for t in range(m.n_tag):
+            f.write("  aruco_4X4_50_%d:\n    pose: [0, 0, 0, 0, 0, 0]\n" % t)
+        f.write("camera:\n  params: [%r, 0, 0]\n  width: %d\n  height: %d\n" % (float(f0), width, height))

@@ -31,7 +31,8 @@ extern "C" {
 #endif
 
 #define ARSLAM_ABI_VERSION 3 /* 2: arslam_append_blocks, device-resident parameters; 3: arslam_set_constant,
-                                arslam_get_normal_equations, arslam_set_tuning */
+                                arslam_get_normal_equations, arslam_set_tuning, device-resident schedule entries
+                                (arslam_set_camera / set_poses / get_poses / seed_captures / seed_tags) */
 
 enum {
   ARSLAM_OK = 0,
@@ -165,6 +166,23 @@ int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t
 int arslam_set_params(arslam_solver* s, const double* camera3, const double* cap_pose6,
                       const double* tag_pose6);
 int arslam_get_params(arslam_solver* s, double* camera3, double* cap_pose6, double* tag_pose6);
+
+/* Device-resident parameters for the incremental schedules (solveIncremental :629-678, solveCapture
+ * :680-742, solve :744-866: one optimize() per added capture).  Between two solves only the new
+ * capture's pose and the poses of tags seen for the first time change on the host side of the
+ * reference; with these entries nothing else crosses the bus:
+ *   arslam_set_camera      intrinsics alone (on a fresh problem it also zeroes all poses, so that a
+ *                          schedule can start without arslam_set_params)
+ *   arslam_set_poses / arslam_get_poses   `count` poses from index `first`; which: 0 captures, 1 tags
+ *   arslam_seed_captures   initCapturePose (:91-108) on the device: capture cap_idx[i] is seeded from the
+ *                          quad rect8[8 i ..] of tag tag_idx[i], whose pose is read from the device
+ *   arslam_seed_tags       initArPose (:111-128): tag tag_idx[i] from the quad seen by capture cap_idx[i]
+ * All use the current focal length on the device (camera_.params[0] in the reference).  Single GPU. */
+int arslam_set_camera(arslam_solver* s, const double* camera3);
+int arslam_set_poses(arslam_solver* s, int which, int64_t first, int64_t count, const double* pose6);
+int arslam_get_poses(arslam_solver* s, int which, int64_t first, int64_t count, double* pose6);
+int arslam_seed_captures(arslam_solver* s, int64_t n, const int32_t* cap_idx, const int32_t* tag_idx, const double* rect8);
+int arslam_seed_tags(arslam_solver* s, int64_t n, const int32_t* tag_idx, const int32_t* cap_idx, const double* rect8);
 
 /* Replaces ceres::Problem::SetParameterBlockConstant (ar_slam_util.cpp:965 camera, :972 tags in
  * localizeOne; the disabled gauge fix of the first capture at :697-700, :776-779) for the blocks of
