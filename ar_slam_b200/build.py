@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libar_slam_b200.so")
 SOURCES = ["arslam.cu"]
-HEADERS = ["model.cuh", "kernels.cuh", "accum_pipe.cuh", "schur.cuh", "cholesky.cuh", "localize.cuh", "pcg.cuh",
+HEADERS = ["model.cuh", "kernels.cuh", "accum_pipe.cuh", "schur.cuh", "schur_local.cuh", "cholesky.cuh", "localize.cuh", "pcg.cuh",
            os.path.join("..", "..", "include", "ar_slam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

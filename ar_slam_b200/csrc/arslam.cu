@@ -25,6 +25,7 @@
 #include "localize.cuh"
 #include "pcg.cuh"
 #include "schur.cuh"
+#include "schur_local.cuh"
 
 using namespace ars;
 
@@ -78,11 +79,16 @@ struct DevBuf {
   size_t n = 0;
   ~DevBuf() { release(); }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  // contents are NOT preserved.  A buffer that has to grow a second time grows by half again: the
+  // incremental schedules enlarge the problem by one capture per solve, and a cudaFree + cudaMalloc per buffer
+  // per solve cost more than the solve itself (3.5 ms per optimize() on a 1600-block map).  The first
+  // allocation is exact, so one-shot problems (config 3: 230 MB of W) do not over-allocate.
   cudaError_t ensure(size_t count) {
     if (count <= n && p) return cudaSuccess;
+    const size_t cap = p ? count + count / 2 + 16 : std::max<size_t>(count, 1);
     release();
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-    if (e == cudaSuccess) n = count;
+    cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
+    if (e == cudaSuccess) n = cap;
     return e;
   }
   // exactly like grow_keep, and the elements [keep, count) are zero afterwards (also when no reallocation happened)
@@ -153,20 +159,69 @@ __global__ void shift_index_kernel(int n, int32_t* idx, int32_t by) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < n) idx[b] += by;
 }
-__global__ void segment_sizes_kernel(int n, const int32_t* __restrict__ off, double* __restrict__ out) {
+__global__ void segment_sizes_kernel(int n, const int32_t* __restrict__ off, const int32_t* __restrict__ end, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (double)(off[i + 1] - off[i]);
+  if (i < n) out[i] = (double)(end[i] - off[i]);
+}
+// ---- locality order of the capture-sorted copy: captures sorted by their smallest tag ---------------
+// (captures that share it see overlapping tag sets; the elimination kernel pre-reduces the products of such
+// neighbours inside a CTA, schur_local.cuh, and the tag records their blocks gather share cache lines)
+__global__ void fill_i32_kernel(int n, int32_t* out, int32_t v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+__global__ void min_other_kernel(int n_blk, const int32_t* __restrict__ own, const int32_t* __restrict__ oth, int32_t* __restrict__ min_oth) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_blk) atomicMin(min_oth + own[b], oth[b]);
+}
+__global__ void locality_keys_kernel(int n_own, const int32_t* __restrict__ min_oth, unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_own) keys[i] = ((unsigned long long)(unsigned)min_oth[i] << 32) | (unsigned)i;  // poses without blocks (INT_MAX) last
+}
+__global__ void locality_rank_kernel(int n_own, const unsigned long long* __restrict__ sorted, int32_t* __restrict__ by_rank, int32_t* __restrict__ rank) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_own) return;
+  const int i = (int)(sorted[r] & 0xffffffffu);
+  by_rank[r] = i;
+  rank[i] = r;
+}
+__global__ void make_sort_keys_ranked_kernel(int n, const int32_t* __restrict__ own, const int32_t* __restrict__ oth, const int32_t* __restrict__ rank,
+                                             unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  keys[b] = ((unsigned long long)(unsigned)rank[own[b]] << 32) | (unsigned)oth[b];
+  vals[b] = b;
+}
+// segment bounds when the sorted order is by rank: start_by_rank[r] = first position whose rank is >= r (r = 0 .. n_own)
+__global__ void rank_offsets_kernel(int n, int n_own, const unsigned long long* __restrict__ sorted_keys, int32_t* __restrict__ start_by_rank) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_own) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)(sorted_keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+  }
+  start_by_rank[r] = lo;
+}
+__global__ void rank_bounds_kernel(int n_own, const int32_t* __restrict__ start_by_rank, const int32_t* __restrict__ by_rank,
+                                   int32_t* __restrict__ off, int32_t* __restrict__ end) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_own) return;
+  const int i = by_rank[r];
+  off[i] = start_by_rank[r];
+  end[i] = start_by_rank[r + 1];
 }
 // sorted position p takes block perm[p]: indices and the 8 observation planes
 __global__ void gather_sorted_kernel(int n, int plane, const int32_t* __restrict__ perm,
                                      const unsigned long long* __restrict__ keys, const double* __restrict__ rect8,
-                                     int32_t* __restrict__ s_own, int32_t* __restrict__ s_oth, double* __restrict__ s_obs) {
+                                     int32_t* __restrict__ s_own, int32_t* __restrict__ s_oth, double* __restrict__ s_obs,
+                                     const int32_t* __restrict__ by_rank /* key's high word is a rank: pose = by_rank[rank]; or null */) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= plane) return;
   if (p < n) {
     const int b = perm[p];
     const unsigned long long k = keys[p];
-    s_own[p] = (int32_t)(k >> 32);
+    s_own[p] = by_rank ? by_rank[(int32_t)(k >> 32)] : (int32_t)(k >> 32);
     s_oth[p] = (int32_t)(k & 0xffffffffu);
     const double2* src = reinterpret_cast<const double2*>(rect8 + 8 * (size_t)b);
 #pragma unroll
@@ -210,6 +265,11 @@ struct arslam_solver {
   DevBuf<double> o_obs;
   // sorted copies: side 0 capture-sorted, side 1 tag-sorted
   DevBuf<int32_t> s_own[2], s_oth[2], s_off[2];
+  // side 0 (captures) is stored in locality order: its segments are not in index order and carry explicit ends
+  DevBuf<int32_t> s_end0, rank0, by_rank0, min_oth0, start_by_rank0;
+  bool locality0 = false;
+  const int32_t* seg_end(int side) const { return (side == 0 && locality0) ? s_end0.p : s_off[side].p + 1; }
+  const int32_t* order(int side) const { return (side == 0 && locality0) ? by_rank0.p : nullptr; }
   DevBuf<double> s_obs[2];
   long long problem_version = 0, pcg_version = -1;
   int pcg_side = -1, n_sm = 0;
@@ -245,6 +305,7 @@ struct arslam_solver {
   int n_pad = 0;
   // pcg
   PcgWorkspace pcg;
+  SchurLocalPlan schur_plan;   // locality-ordered elimination with in-CTA pre-reduction (schur_local.cuh)
   // comm
   void* comm = nullptr;
   int rank = 0, world = 1;
@@ -252,7 +313,7 @@ struct arslam_solver {
   long long launches = 0;
   Profiler prof;
   // tuning switches (arslam_set_tuning), per handle
-  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1, tune_schur_bulk = 1;
+  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1, tune_schur_bulk = 1, tune_schur_local = 0, tune_locality = 0;  // the locality-ordered elimination is parked: measured slower
   long long tune_loc_chunk = 0;  // captures per localisation chunk (0: default)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -306,6 +367,13 @@ cudaError_t schur_kernel_attributes() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
   // three CTAs of 75 KB per SM need the full shared-memory carve-out
   if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<Target, NK, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return e;
+}
+static cudaError_t schur_local_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(schur_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_local_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_local_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e;
 }
 static cudaError_t schur_bulk_attributes() {
@@ -389,7 +457,7 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
       cudaMallocHost(&s->h_sc, 256 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
       schur_kernel_attributes<SparseTarget, 1>() != cudaSuccess || schur_kernel_attributes<DenseTarget, 1>() != cudaSuccess ||
       schur_kernel_attributes<DenseTarget, 3>() != cudaSuccess ||
-      pcg_init() != cudaSuccess || schur_bulk_attributes() != cudaSuccess ||
+      pcg_init() != cudaSuccess || schur_bulk_attributes() != cudaSuccess || schur_local_attributes() != cudaSuccess ||
       pipe_kernel_attributes() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -444,6 +512,8 @@ int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value) {
   else if (k == "accum_flush") s->tune_accum_flush = value != 0;
   else if (k == "pcg_smem") s->tune_pcg_smem = value != 0;
   else if (k == "schur_bulk") s->tune_schur_bulk = value != 0;
+  else if (k == "locality") s->tune_locality = value != 0;  // takes effect at the next arslam_set_problem / append_blocks
+  else if (k == "schur_local") { s->tune_schur_local = value != 0; s->pcg.valid = false; }  // the plan is (re)built with the symbolic phase
   else if (k == "loc_chunk") s->tune_loc_chunk = value;
   else if (k == "pcg_pipelined") s->tune_pcg_pipelined = value != 0;
   else return s->fail(ARSLAM_ERR_INVALID, "set_tuning: unknown key '%s'", key);
@@ -501,16 +571,39 @@ int rebuild_views(arslam_solver* s) {
     const int n_own = side == 0 ? s->n_cap : s->n_tag;
     CU(s->s_own[side].ensure(plane)); CU(s->s_oth[side].ensure(plane)); CU(s->s_off[side].ensure(n_own + 1));
     CU(s->s_obs[side].ensure((size_t)8 * plane));
-    make_sort_keys_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, d_own, d_oth, s->sort_keys[0].p, s->sort_vals[0].p);
+    const bool ranked = side == 0 && s->tune_locality;
+    if (side == 0) s->locality0 = ranked;
     size_t tmp_bytes = 0;
+    if (ranked) {
+      // captures in locality order: sort them by (smallest tag, index), then sort the blocks by (rank, tag)
+      CU(s->min_oth0.ensure(n_own)); CU(s->rank0.ensure(n_own)); CU(s->by_rank0.ensure(n_own)); CU(s->s_end0.ensure(n_own));
+      CU(s->start_by_rank0.ensure(n_own + 1));
+      CU(s->sort_keys[0].ensure(std::max(nb, n_own))); CU(s->sort_keys[1].ensure(std::max(nb, n_own)));
+      fill_i32_kernel<<<cdiv(n_own, 256), 256, 0, s->stream>>>(n_own, s->min_oth0.p, 0x7fffffff);
+      min_other_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, d_own, d_oth, s->min_oth0.p);
+      locality_keys_kernel<<<cdiv(n_own, 256), 256, 0, s->stream>>>(n_own, s->min_oth0.p, s->sort_keys[0].p);
+      CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, s->sort_keys[0].p, s->sort_keys[1].p, n_own, 0, 64, s->stream));
+      CU(s->sort_tmp.ensure(tmp_bytes));
+      CU(cub::DeviceRadixSort::SortKeys(s->sort_tmp.p, tmp_bytes, s->sort_keys[0].p, s->sort_keys[1].p, n_own, 0, 64, s->stream));
+      locality_rank_kernel<<<cdiv(n_own, 256), 256, 0, s->stream>>>(n_own, s->sort_keys[1].p, s->by_rank0.p, s->rank0.p);
+      make_sort_keys_ranked_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, d_own, d_oth, s->rank0.p, s->sort_keys[0].p, s->sort_vals[0].p);
+    } else {
+      make_sort_keys_kernel<<<cdiv(nb, 256), 256, 0, s->stream>>>(nb, d_own, d_oth, s->sort_keys[0].p, s->sort_vals[0].p);
+    }
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s->sort_keys[0].p, s->sort_keys[1].p, s->sort_vals[0].p,
                                        s->sort_vals[1].p, nb, 0, 64, s->stream));
     CU(s->sort_tmp.ensure(tmp_bytes));
     CU(cub::DeviceRadixSort::SortPairs(s->sort_tmp.p, tmp_bytes, s->sort_keys[0].p, s->sort_keys[1].p, s->sort_vals[0].p,
                                        s->sort_vals[1].p, nb, 0, 64, s->stream));
     gather_sorted_kernel<<<cdiv(plane, 256), 256, 0, s->stream>>>(nb, plane, s->sort_vals[1].p, s->sort_keys[1].p, s->o_obs.p,
-                                                                 s->s_own[side].p, s->s_oth[side].p, s->s_obs[side].p);
-    segment_offsets_kernel<<<cdiv(n_own + 1, 256), 256, 0, s->stream>>>(nb, n_own, s->s_own[side].p, s->s_off[side].p);
+                                                                 s->s_own[side].p, s->s_oth[side].p, s->s_obs[side].p,
+                                                                 ranked ? s->by_rank0.p : nullptr);
+    if (ranked) {
+      rank_offsets_kernel<<<cdiv(n_own + 1, 256), 256, 0, s->stream>>>(nb, n_own, s->sort_keys[1].p, s->start_by_rank0.p);
+      rank_bounds_kernel<<<cdiv(n_own, 256), 256, 0, s->stream>>>(n_own, s->start_by_rank0.p, s->by_rank0.p, s->s_off[side].p, s->s_end0.p);
+    } else {
+      segment_offsets_kernel<<<cdiv(n_own + 1, 256), 256, 0, s->stream>>>(nb, n_own, s->s_own[side].p, s->s_off[side].p);
+    }
     CU(s->H[side].ensure((size_t)n_own * NV));
     CU(s->partial[side].ensure((size_t)s->n_warp * 2 * NV));
     CU(s->d_pose[side].ensure((size_t)6 * n_own));
@@ -954,7 +1047,7 @@ int union_keys_across_ranks(arslam_solver* s) {
 int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   if (s->pcg.valid && s->pcg_version == s->problem_version && s->pcg_side == side_e) return ARSLAM_OK;
   std::string err;
-  int rc = pcg_symbolic_keys(s->pcg, n_e, n_f, s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->s_oth[side_e].p, s->stream, err);
+  int rc = pcg_symbolic_keys(s->pcg, n_e, n_f, s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->seg_end(side_e), s->s_oth[side_e].p, s->stream, err);
   rc = comm_agree(s, rc ? s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str()) : ARSLAM_OK, "pcg symbolic phase");
   if (rc) return rc;
   const int urc = union_keys_across_ranks(s);
@@ -971,8 +1064,14 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
     t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx; t.Sraw = nullptr; t.borderm = nullptr; t.rhsm = nullptr;
     t.pair_slot = nullptr; t.lower_of = s->pcg.src_slot;
     LAUNCH("pair_slot", 4.0 * s->pcg.n_pairs,
-           pair_slot_kernel<<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p,
+           pair_slot_kernel<<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->seg_end(side_e),
                                                                       s->s_oth[side_e].p, s->pcg.pair_off, t, s->pcg.pair_slot));
+  }
+  // the locality plan of the elimination kernel hangs off the same pair-slot table
+  s->schur_plan.valid = false;
+  if (s->pcg.pair_slot && s->tune_schur_local) {
+    const int prc = schur_local_build(s->schur_plan, s->pcg, n_e, s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->seg_end(side_e), s->s_oth[side_e].p, s->n_sm, s->stream, err);
+    if (prc) return s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str());
   }
   s->pcg_version = s->problem_version;
   s->pcg_side = side_e;
@@ -988,6 +1087,16 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   t.pair_slot = s->pcg.pair_slot; t.lower_of = s->pcg.src_slot;
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
+  if (s->schur_plan.valid && s->tune_schur_local) {
+    // locality-ordered CTAs, products pre-reduced per destination inside the CTA; no straddle launch
+    const double bytes = (288.0 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnz_lower + 2.0 * s->schur_plan.n_pairs;
+    const SchurLocalView v = s->schur_plan.view();
+    if (s->tune_schur_bulk)
+      LAUNCH("schur_eliminate", bytes, schur_local_kernel<true><<<s->schur_plan.n_cta, kSlThreads, kSlSmem, s->stream>>>(a2, t, s->n_blk, e_idx, v));
+    else
+      LAUNCH("schur_eliminate", bytes, schur_local_kernel<false><<<s->schur_plan.n_cta, kSlThreads, kSlSmem, s->stream>>>(a2, t, s->n_blk, e_idx, v));
+    return ARSLAM_OK;
+  }
   // compulsory bytes: W read once (288 B / block) + indices (8 B / block) + E records and Z / YB (264 + 128 B / pose)
   // + the lower blocks of the reduced system written once (288 B each)
   launch_schur<SparseTarget, 1>(s, a2, t, e_idx, (288.0 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnz_lower,
@@ -1062,7 +1171,7 @@ int launch_accumulate(arslam_solver* s, const Sides& sd, int k, double* HF, doub
   auto add_fixup = [&](int side, int n_own, int nv, const double* partial, double* out_seg) {
     FixupJob& f = fix.j[fix.n++];
     f.n_pose = n_own; f.n_blk = nb; f.nv = nv;
-    f.own_idx = s->s_own[side].p; f.seg_off = s->s_off[side].p; f.partial = partial; f.out_seg = out_seg;
+    f.own_idx = s->s_own[side].p; f.seg_off = s->s_off[side].p; f.seg_end = s->seg_end(side); f.partial = partial; f.out_seg = out_seg;
     fix_ctas += cdiv((long long)std::max(s->n_warp - 1, 0) * nv, 256);
     f.cta_zero = fix_ctas;
     fix_ctas += cdiv(n_own, 256);
@@ -1203,7 +1312,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   summary->reduced_dim = n;
 
   // ---- buffers that depend on the roles
-  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * nk * sd.n_e)); CU(s->seg_cam.ensure((size_t)12 * cdiv(s->n_blk, kSchurThreads)));
+  CU(s->Z.ensure((size_t)8 * sd.n_e)); CU(s->YB.ensure((size_t)6 * nk * sd.n_e)); CU(s->seg_cam.ensure((size_t)12 * (cdiv(s->n_blk, 90) + 2)));  // CTA partials of either elimination kernel (the local one packs >= 96 blocks per CTA)
   // E poses without blocks never reach the elimination kernel: their Z / YB stay zero for the whole solve
   CU(cudaMemsetAsync(s->Z.p, 0, sizeof(double) * 8 * sd.n_e, s->stream));
   CU(cudaMemsetAsync(s->YB.p, 0, sizeof(double) * 6 * nk * sd.n_e, s->stream));
@@ -1245,7 +1354,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   const double* f_blocks_all = nullptr;
   if (s->world > 1) {
     CU(s->f_blocks.ensure((size_t)sd.n_f));
-    segment_sizes_kernel<<<cdiv(sd.n_f, 256), 256, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, s->f_blocks.p);
+    segment_sizes_kernel<<<cdiv(sd.n_f, 256), 256, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, s->seg_end(sd.f), s->f_blocks.p);
     int rcb = nccl_sum(s, s->f_blocks.p, (size_t)sd.n_f);
     if (rcb) return rcb;
     f_blocks_all = s->f_blocks.p;
@@ -1292,7 +1401,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     {
       SchurArgs a;
       a.n_e = sd.n_e; a.plane = s->plane;
-      a.e_off = s->s_off[sd.e].p; a.f_idx = s->s_oth[sd.e].p;
+      a.e_off = s->s_off[sd.e].p; a.e_end = s->seg_end(sd.e); a.f_idx = s->s_oth[sd.e].p;
       a.HE = s->H[sd.e].p; a.HEx = dist ? s->Hx[sd.e].p : nullptr; a.W = s->W.p; a.sig_e = s->sigE.p;
       a.radius = radius; a.inv_radius = 1.0 / radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
       a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr; a.e_const = const_e;
@@ -1308,8 +1417,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         if (rc) return rc;
       }
       // closes the elimination: cam_minus, max |g_e| -> sc[16], and the failure flag of the solve that starts here
-      LAUNCH("schur_finish", 96.0 * cdiv(s->n_blk, kSchurThreads),
-             schur_finish_kernel<<<1, 1024, 0, s->stream>>>(s->seg_cam.p, cdiv(s->n_blk, kSchurThreads), cam_minus, sc));
+      const int schur_ctas = (lin != ARSLAM_LINSOLVE_DENSE && s->schur_plan.valid && s->tune_schur_local) ? s->schur_plan.n_cta : cdiv(s->n_blk, kSchurThreads);
+      LAUNCH("schur_finish", 96.0 * schur_ctas, schur_finish_kernel<<<1, 1024, 0, s->stream>>>(s->seg_cam.p, schur_ctas, cam_minus, sc));
     }
     if (s->world > 1) {
       // one allreduce per linearisation: partial Schur terms (+ on a fresh
@@ -1321,7 +1430,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (fresh_linearisation) {
       // (the E side's maximum comes out of the elimination kernel; this launch also moves the freshly summed
       // camera scalars next to the other LM scalars)
-      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, sc_head, sc, nk, f_blocks_all, const_f));
+      LAUNCH("gradmax", 8.0 * 6 * sd.n_f, gradmax_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, s->s_off[sd.f].p, s->seg_end(sd.f), HF, s->warp_gmax[sd.f].p, s->tickets.p + 3, sc + 17, sc_head, sc, nk, f_blocks_all, const_f));
     }
     if (!have_sigma) {
       LAUNCH("sigma", 8.0 * 12 * sd.n_f,
@@ -1362,7 +1471,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       // back-substitution + the E side of the step: candidate poses, norms, model-cost terms and the
       // candidate's prep records all come out of this one launch
       BacksubArgs b;
-      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk;
+      b.sa = schur_args; b.uF = s->uF.p; b.cam_row = cam_row; b.nk = nk; b.e_order = s->order(sd.e);
       b.d_e = s->d_pose[sd.e].p; b.seg_part = s->seg_cross.p; b.ticket = s->tickets.p + 4; b.out5 = sc + 4;
       b.x_e = x_e; b.x_cand = xc_e; b.e_is_capture = sd.e == 0; b.tag_size = o.tag_size;
       // (the candidate's prep records stay with prep_poses_kernel: one lane in eight would run the sincos /
@@ -1376,7 +1485,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       ap.uF_cam = s->uF.p + cam_row;
       ap.sc = sc; ap.nk = nk;
       ap.blocks_all = f_blocks_all; ap.constant = const_f;
-      ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
+      ap.n_pose = sd.n_f; ap.seg_off = s->s_off[sd.f].p; ap.seg_end = s->seg_end(sd.f); ap.x = x_f; ap.step = s->uF.p; ap.negate = 1;
       ap.rec = HF; ap.recx = HFx;
       ap.delta = s->d_pose[sd.f].p; ap.x_cand = xc_f; ap.warp_out = s->warp_norm[sd.f].p;
       ap.ticket = s->tickets.p + 6; ap.out = sc + 9;

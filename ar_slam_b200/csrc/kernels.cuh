@@ -600,7 +600,8 @@ __global__ void __launch_bounds__(kAccumThreads) accum_cam_kernel(const AccumCam
 struct FixupJob {
   int n_pose, n_blk, nv;
   const int32_t* own_idx;   // [n_blk] sorted pose index
-  const int32_t* seg_off;   // [n_pose + 1]
+  const int32_t* seg_off;   // [n_pose] first sorted position of the pose's segment
+  const int32_t* seg_end;   // [n_pose] one past its last position (== seg_off + 1 when the segments are in index order)
   const double* partial;    // [n_warp][2][nv]
   double* out_seg;          // [n_pose][nv]
   int cta_end;              // this job owns CTAs [previous cta_end, cta_end)
@@ -617,7 +618,7 @@ __global__ void __launch_bounds__(256) seg_fixup_kernel(const FixupJobs jobs) {
   const int cta0 = q ? jobs.j[q - 1].cta_end : 0;
   if ((int)blockIdx.x >= f.cta_zero) {  // poses without blocks: their records are never written by the accumulation
     const int s = ((int)blockIdx.x - f.cta_zero) * 256 + threadIdx.x;
-    if (s < f.n_pose && f.seg_off[s + 1] == f.seg_off[s])
+    if (s < f.n_pose && f.seg_end[s] == f.seg_off[s])
       for (int v = 0; v < f.nv; ++v) f.out_seg[(size_t)s * f.nv + v] = 0.0;
     return;
   }
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(256) seg_fixup_kernel(const FixupJobs jobs) {
   if (blk >= f.n_blk) return;
   const int s = f.own_idx[blk - 1];
   if (f.own_idx[blk] != s) return;             // no segment crosses this boundary
-  const int b0 = f.seg_off[s], b1 = f.seg_off[s + 1];
+  const int b0 = f.seg_off[s], b1 = f.seg_end[s];
   const int w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
   if (w0 != w - 1) return;                     // the segment was already open at the previous boundary
   double acc = 0.0;

@@ -31,9 +31,10 @@ struct PcgBuf {
   size_t cap = 0;
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
+    // a buffer that grows AGAIN grows by half as much again (the incremental schedules append one capture per solve)
+    const size_t want = p ? n + n / 2 + 64 : n + n / 8 + 64;
     cudaFree(p);
     p = nullptr; cap = 0;
-    const size_t want = n + n / 8 + 64;
     const cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
@@ -90,23 +91,23 @@ struct PcgWorkspace {
 // shared-memory solver and their halo lists) is derived from the sorted keys by bisection, so
 // the host only ever sees a handful of counts.
 __global__ void sym_counts_kernel(int n_blk, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
-                                  long long* __restrict__ n_keys, long long* __restrict__ n_pairs) {
+                                  const int32_t* __restrict__ e_end, long long* __restrict__ n_keys, long long* __restrict__ n_pairs) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos > n_blk) return;
   if (pos == n_blk) { n_keys[pos] = 0; n_pairs[pos] = 0; return; }  // the scans' totals land here
   const int e = e_idx[pos];
-  const int beg = e_off[e], k = e_off[e + 1] - beg;
+  const int beg = e_off[e], k = e_end[e] - beg;
   n_keys[pos] = k;
   n_pairs[pos] = schur_pairs_of(pos - beg, k);
 }
 __global__ void sym_emit_keys_kernel(int n_blk, int n_f, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
-                                     const int32_t* __restrict__ f_idx, const long long* __restrict__ key_off,
+                                     const int32_t* __restrict__ e_end, const int32_t* __restrict__ f_idx, const long long* __restrict__ key_off,
                                      unsigned long long* __restrict__ keys) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos < n_f) keys[key_off[n_blk] + pos] = (unsigned long long)pos * n_f + pos;  // every diagonal block exists
   if (pos >= n_blk) return;
   const int e = e_idx[pos];
-  const int beg = e_off[e], k = e_off[e + 1] - beg;
+  const int beg = e_off[e], k = e_end[e] - beg;
   const unsigned long long row = (unsigned long long)f_idx[pos] * n_f;
   unsigned long long* out = keys + key_off[pos];
   for (int q = 0; q < k; ++q) out[q] = row + f_idx[beg + q];
@@ -229,7 +230,7 @@ inline cudaError_t pcg_sort_unique(PcgWorkspace& ws, int n, int bits, cudaStream
 }
 
 // phase 1: the sorted unique keys of this rank's blocks -> ws.keys[0][0 .. ws.nnzb), and pair_off
-inline int pcg_symbolic_keys(PcgWorkspace& ws, int n_e, int n_f, int n_blk, const int32_t* e_idx, const int32_t* e_off,
+inline int pcg_symbolic_keys(PcgWorkspace& ws, int n_e, int n_f, int n_blk, const int32_t* e_idx, const int32_t* e_off, const int32_t* e_end,
                              const int32_t* f_idx, cudaStream_t st, std::string& err) {
   (void)n_e;
   ws.valid = false;
@@ -240,7 +241,7 @@ inline int pcg_symbolic_keys(PcgWorkspace& ws, int n_e, int n_f, int n_blk, cons
   PCG_TRY(ws.off_keys.ensure((size_t)n_blk + 1)); PCG_TRY(ws.off_pairs.ensure((size_t)n_blk + 1));
   PCG_TRY(ws.counts.ensure(8));
   if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
-  sym_counts_kernel<<<(n_blk + 256) / 256, 256, 0, st>>>(n_blk, e_idx, e_off, ws.cnt_keys.p, ws.cnt_pairs.p);
+  sym_counts_kernel<<<(n_blk + 256) / 256, 256, 0, st>>>(n_blk, e_idx, e_off, e_end, ws.cnt_keys.p, ws.cnt_pairs.p);
   size_t t1 = 0;
   PCG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t1, ws.cnt_keys.p, ws.off_keys.p, n_blk + 1, st));
   PCG_TRY(ws.tmp.ensure(t1));
@@ -265,7 +266,7 @@ inline int pcg_symbolic_keys(PcgWorkspace& ws, int n_e, int n_f, int n_blk, cons
     ws.pair_off = nullptr; ws.pair_slot = nullptr;
   }
   if (ce != cudaSuccess) { err = std::string("pcg workspace: ") + cudaGetErrorString(ce); return -2; }
-  sym_emit_keys_kernel<<<(std::max(n_blk, n_f) + 255) / 256, 256, 0, st>>>(n_blk, n_f, e_idx, e_off, f_idx, ws.off_keys.p, ws.keys[0].p);
+  sym_emit_keys_kernel<<<(std::max(n_blk, n_f) + 255) / 256, 256, 0, st>>>(n_blk, n_f, e_idx, e_off, e_end, f_idx, ws.off_keys.p, ws.keys[0].p);
   int nn = 0;
   PCG_TRY(pcg_sort_unique(ws, (int)n_keys, sym_key_bits(n_f), st, &nn));
   if (ce != cudaSuccess) { err = std::string("pcg symbolic (sort): ") + cudaGetErrorString(ce); return -2; }
@@ -390,12 +391,12 @@ struct SparseTarget {
 // fills pair_slot once per problem: thread per E-sorted block, same partner enumeration as
 // schur_eliminate_kernel
 __global__ void pair_slot_kernel(int n_blk, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
-                                 const int32_t* __restrict__ f_idx, const int32_t* __restrict__ pair_off,
+                                 const int32_t* __restrict__ e_end, const int32_t* __restrict__ f_idx, const int32_t* __restrict__ pair_off,
                                  SparseTarget t, int32_t* __restrict__ out) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n_blk) return;
   const int e = e_idx[pos];
-  const int beg = e_off[e], k = e_off[e + 1] - beg, j = pos - beg;
+  const int beg = e_off[e], k = e_end[e] - beg, j = pos - beg;
   const int fj = f_idx[pos];
   const int np = schur_pairs_of(j, k);
   for (int d = 0; d < np; ++d) {

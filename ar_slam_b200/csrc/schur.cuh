@@ -18,7 +18,8 @@ namespace ars {
 
 struct SchurArgs {
   int n_e, plane;
-  const int32_t* e_off;   // [n_e + 1] block offsets (E-sorted order)
+  const int32_t* e_off;   // [n_e] first block of each E pose's segment (E-sorted order)
+  const int32_t* e_end;   // [n_e] one past its last block (== e_off + 1 when the segments are in index order)
   const int32_t* f_idx;   // [n_blk]   F pose per E-sorted block
   const int32_t* pair_off; // [n_blk]  number of (partner, block) pairs before each block (sparse target)
   const double* HE;       // [n_e][NV]
@@ -172,7 +173,7 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
   bool valid = pos < n_blk;
   const int e = valid ? e_idx[pos] : 0;
   const int beg = valid ? a.e_off[e] : 0;
-  const int k = valid ? a.e_off[e + 1] - beg : 0;
+  const int k = valid ? a.e_end[e] - beg : 0;
   const int j = valid ? pos - beg : 0;
   // the second launch only concerns segments that leave their CTA
   if (STRADDLE) valid = valid && (beg < cta0 || beg + k > cta0 + kSchurThreads);
@@ -459,6 +460,7 @@ __global__ void scale_uF_kernel(int n, const double* __restrict__ y, const doubl
 struct BacksubArgs {
   SchurArgs sa;       // HE, W, sig_e, radius, e_off, f_idx, Z, YB
   const double* uF;   // [6 n_f + nk]
+  const int32_t* e_order;  // [n_e] E pose handled by each thread group (storage order of the segments), or null: index order
   int cam_row, nk;
   double* d_e;        // [6 n_e] step of the E poses
   double* seg_part;   // [grid][5] CTA partials of (cross term -sum_j d_e^T W_j u_j, 0, |x - x_cand|^2, |x|^2, model terms)
@@ -511,9 +513,11 @@ __device__ __forceinline__ void store_tag_prep(const double pose[6], double tag_
 }
 __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = gid / kBsGroup, gl = gid % kBsGroup;
-  const bool valid = e < a.sa.n_e;
-  const int beg = valid ? a.sa.e_off[e] : 0, k = valid ? a.sa.e_off[e + 1] - beg : 0;
+  const int slot = gid / kBsGroup, gl = gid % kBsGroup;
+  const bool valid = slot < a.sa.n_e;
+  // groups walk the E poses in the order their segments are stored (e_order: locality rank -> pose), so that W streams
+  const int e = valid ? (a.e_order ? a.e_order[slot] : slot) : 0;
+  const int beg = valid ? a.sa.e_off[e] : 0, k = valid ? a.sa.e_end[e] - beg : 0;
   double L[36], zt[6], hk[6], s[6];
   if (k > 0) {
     load_scaled_E(a.sa, e, L, zt, hk, s);
@@ -594,7 +598,8 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
 // per-warp partials of ||delta||^2 and ||x||^2 over poses that own blocks.
 struct ApplyArgs {
   int n_pose;
-  const int32_t* seg_off;   // [n_pose + 1] (sorted by this side)
+  const int32_t* seg_off;   // [n_pose] segment start / seg_end [n_pose] segment end (sorted by this side)
+  const int32_t* seg_end;
   const double* blocks_all; // multi-GPU, F side: blocks of the pose summed over all ranks (a rank may hold none), else null
   const unsigned char* constant; // [n_pose] != 0: the pose is held constant (arslam_set_constant), or null
   const double* x;          // [6 n_pose]
@@ -637,7 +642,7 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
   }
   double d2 = 0.0, x2 = 0.0, mq = 0.0;
   if (i < a.n_pose) {
-    const bool active = (a.blocks_all ? a.blocks_all[i] > 0.0 : a.seg_off[i + 1] > a.seg_off[i]) && !(a.constant && a.constant[i]);
+    const bool active = (a.blocks_all ? a.blocks_all[i] > 0.0 : a.seg_end[i] > a.seg_off[i]) && !(a.constant && a.constant[i]);
     double d[6], xcand[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -679,7 +684,8 @@ __global__ void apply_step_kernel(const ApplyArgs a) {
 }
 
 // max |g| over poses that own blocks
-__global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const double* __restrict__ rec,
+__global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_end,
+                                                      const double* __restrict__ rec,
                                                       double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out,
                                                       const double* __restrict__ head, double* __restrict__ sc, int nk,
                                                       const double* __restrict__ blocks_all, const unsigned char* __restrict__ constant) {
@@ -688,7 +694,7 @@ __global__ void __launch_bounds__(128) gradmax_kernel(int n_pose, const int32_t*
   if (head && i < 3) sc[i] = head[i];
   if (head && nk == 3 && i >= 4 && i < 12) sc[24 + (i - 4)] = head[i];
   double m = 0.0;
-  if (i < n_pose && (blocks_all ? blocks_all[i] > 0.0 : seg_off[i + 1] > seg_off[i]) && !(constant && constant[i])) {
+  if (i < n_pose && (blocks_all ? blocks_all[i] > 0.0 : seg_end[i] > seg_off[i]) && !(constant && constant[i])) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) m = fmax(m, fabs(rec[(size_t)i * NV + 21 + k]));
   }

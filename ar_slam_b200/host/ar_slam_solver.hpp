@@ -145,6 +145,9 @@ public:
   // call in solve().  1 reproduces the reference's schedule; larger values trade its exact trajectory for
   // fewer (quadratically growing) solves.
   unsigned& captures_per_solve() { return captures_per_solve_; }
+  // creates the GPU handle now (CUDA context, kernel attributes: about a second in a fresh process) instead of
+  // inside the first optimize(); a long-lived node pays this once at start-up
+  void prepareDevice() { handle(); }
   // the summary Ceres would have returned, and the solver options
   const arslam_summary& lastSummary() const { return last_summary_; }
   const std::vector<arslam_summary>& summaries() const { return summaries_; }

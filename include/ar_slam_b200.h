@@ -263,7 +263,11 @@ int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch wit
  * accumulation kernels instead of the thread-per-block ones that start every block cold; default 2:
  * measured faster for the F pass only); "accum_flush" (1: unrolled segment flush in those kernels); "schur_bulk" (1: the Schur products reach the
  * block-sparse reduced system as TMA bulk reductions, default; 0: per-lane FP64 reductions);
- * "loc_chunk" (captures per chunk of arslam_localize_batch's upload / kernel / download pipeline, 0:
+ * "locality" (1: the capture-sorted copy of the blocks is stored with the captures ordered by their
+ * smallest tag; 0, default: by capture index; read by the next arslam_set_problem / append_blocks);
+ * "schur_local" (1: elimination CTAs hold whole segments and pre-reduce the products per destination
+ * inside the CTA -- an experiment kept for reference, measured slower than the default; 0, default: one
+ * reduction per product); "loc_chunk" (captures per chunk of arslam_localize_batch's upload / kernel / download pipeline, 0:
  * default 131072); "pcg_smem" (1: the PCG kernels that keep the
  * reduced matrix in shared memory, default); "pcg_pipelined" (1: one-barrier pipelined recurrence for
  * pcg_tolerance >= 1e-6, default; 0: always the classic two-barrier recurrence).

@@ -175,8 +175,10 @@ def test_device_resident_schedule_equals_host_round_trips(host_tools, tmp_path, 
     from ar_slam_b200 import synth
     from oracle import schedule
     m = synth.make_map(60, 25, 6, seed=77)
-    # some tags may be unobserved in such a small map: keep the observed ones only (the yaml lists every tag it names)
-    synth.write_detections_yaml(m, str(tmp_path / "det.yaml"))
+    # f0 = 800 instead of the reference's 3000: from 3000 the first solves of this schedule (one capture, all its tags
+    # and the focal length free) are so under-determined that rounding decides which way they wander, and no two
+    # implementations -- or runs -- walk the same trajectory (scripts/schedule_bench.py runs that case)
+    synth.write_detections_yaml(m, str(tmp_path / "det.yaml"), f0=800.0)
     maps, lines = {}, {}
     for name, flags in (("device", []), ("host", ["--host-params"]), ("k4", ["--captures-per-solve", "4"])):
         r = subprocess.run([os.path.join(host_tools, "ar_slam_cli"), "--quiet", "--output", name + ".yaml"] + flags + ["det.yaml"],
