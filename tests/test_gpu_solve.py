@@ -402,3 +402,27 @@ def test_pipelined_accumulation_is_bit_identical(gpu_solver_cls):
     assert np.allclose(logs[0][0][:, 0], logs[1][0][:, 0], rtol=1e-11, atol=0), (logs[0][0][:, 0] - logs[1][0][:, 0])
     assert np.allclose(logs[0][2], logs[1][2], rtol=0, atol=1e-9), np.abs(logs[0][2] - logs[1][2]).max()
     assert np.allclose(logs[0][3], logs[1][3], rtol=0, atol=1e-9), np.abs(logs[0][3] - logs[1][3]).max()
+
+
+def test_locality_order_and_local_elimination_equal_default(gpu_solver_cls):
+    """The capture-sorted copy stored in locality order (captures sorted by their smallest tag, segments with
+    explicit ends) and the elimination kernel that pre-reduces products inside the CTA (schur_local.cuh) are
+    parked experiments (measured slower), but they stay correct: same LM trajectory as the default path."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(3000, 150, seed=13)
+    logs = []
+    for locality, local in ((0, 0), (1, 0), (1, 1), (0, 1)):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ar_slam_b200.LINSOLVE_PCG, pcg_tolerance=1e-12,
+                                                                 pcg_max_iterations=3000, max_num_iterations=4))
+        s.set_tuning("locality", locality)
+        s.set_tuning("schur_local", local)
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        summ, log = s.solve()
+        cam, cap, tag = s.get_params()
+        s.close()
+        logs.append((log, cam, cap, tag))
+    for other in logs[1:]:
+        assert np.allclose(other[0][:, 0], logs[0][0][:, 0], rtol=1e-10, atol=0)
+        assert np.abs(other[2] - logs[0][2]).max() <= 1e-8 and np.abs(other[3] - logs[0][3]).max() <= 1e-8
