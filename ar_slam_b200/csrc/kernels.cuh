@@ -170,54 +170,70 @@ __global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double
 // 16 B of residuals, 48 B of jac_cam, 96 B of jac_cap and of jac_tag, all
 // contiguous across consecutive threads (coalesced 128-bit stores).
 // Algorithmic bytes per corner: 16 obs + 2 idx + 16 r + 240 J = 274.
+// The outputs are written through a per-warp shared-memory transpose: a thread's rows are 16 / 48 / 96 / 96
+// contiguous bytes, so direct 128-bit stores would leave every warp-wide store touching 32 half-filled
+// sectors (ncu, round 2: 243 us, lg_throttle + mio_throttle 20 stall cycles per issue, L2 at 61 %).  Staged,
+// every store instruction of a warp covers 512 contiguous bytes.
+constexpr int kEvalThreads = 256;
+template <int N2 /* double2 per thread */>
+__device__ __forceinline__ void warp_store_rows(double2* __restrict__ dst_warp, const double2 (&v)[N2], double2* stage, int lane, int n_valid_threads) {
+  // stage[thread][N2] -> dst_warp[0 .. 32 N2): the same linear order, written 32 consecutive double2 at a time
+#pragma unroll
+  for (int k = 0; k < N2; ++k) stage[lane * N2 + k] = v[k];
+  __syncwarp();
+  const int n = n_valid_threads * N2;
+#pragma unroll
+  for (int k = 0; k < N2; ++k) {
+    const int i = k * 32 + lane;
+    if (i < n) dst_warp[i] = stage[i];
+  }
+  __syncwarp();
+}
 template <int MODEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kEvalThreads)
 eval_jacobian_kernel(int n_corner, const int32_t* __restrict__ cap_idx, const int32_t* __restrict__ tag_idx,
                      const double2* __restrict__ obs /* [n_corner] (x,y) */,
                      const double* __restrict__ cap_pre, const double* __restrict__ tag_pre,
                      const double* __restrict__ cam, double2* __restrict__ res /* may be null */,
                      double2* __restrict__ jac_cam, double2* __restrict__ jac_cap,
                      double2* __restrict__ jac_tag, double* __restrict__ warp_cost) {
+  __shared__ double2 stage_all[kEvalThreads / 32][32 * 6];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double2* stage = stage_all[threadIdx.x >> 5];
+  const int warp_first = t - lane;                              // first corner of this warp
+  const int n_valid = min(32, max(0, n_corner - warp_first));   // corners of this warp that exist
   double rr = 0.0;
+  CornerJ j;
+  double Kl[2][2] = {{0, 0}, {0, 0}};
   if (t < n_corner) {
     const int b = t >> 2, i = t & 3;
     const double cm[3] = {cam[0], cam[1], cam[2]};
     const double2 o = obs[t];
     const double* cp = cap_pre + (size_t)kCapPre * cap_idx[b];
     const double* tp = tag_pre + (size_t)kTagPre * tag_idx[b] + 12 * i;
-    CornerJ j;
-    double Kl[2][2];
     corner_jacobian_m<MODEL>(cp, tp, cm, o.x, o.y, j, Kl);
     rr = j.r[0] * j.r[0] + j.r[1] * j.r[1];
-    if (res) res[t] = make_double2(j.r[0], j.r[1]);
+    if (res) res[t] = make_double2(j.r[0], j.r[1]);   // 16 B per thread: already contiguous across the warp
+  }
+  if (n_valid > 0) {
     if (jac_cam) {
-      double2* d = jac_cam + 3 * (size_t)t;
-      d[0] = make_double2(j.K[0], Kl[0][0]);
-      d[1] = make_double2(Kl[0][1], j.K[1]);
-      d[2] = make_double2(Kl[1][0], Kl[1][1]);
+      const double2 v[3] = {make_double2(j.K[0], Kl[0][0]), make_double2(Kl[0][1], j.K[1]), make_double2(Kl[1][0], Kl[1][1])};
+      warp_store_rows<3>(jac_cam + 3 * (size_t)warp_first, v, stage, lane, n_valid);
     }
     if (jac_cap) {
-      double2* d = jac_cap + 6 * (size_t)t;
-      d[0] = make_double2(j.A[0][0], j.A[0][1]);
-      d[1] = make_double2(j.A[0][2], j.B[0][0]);
-      d[2] = make_double2(j.B[0][1], j.B[0][2]);
-      d[3] = make_double2(j.A[1][0], j.A[1][1]);
-      d[4] = make_double2(j.A[1][2], j.B[1][0]);
-      d[5] = make_double2(j.B[1][1], j.B[1][2]);
+      const double2 v[6] = {make_double2(j.A[0][0], j.A[0][1]), make_double2(j.A[0][2], j.B[0][0]), make_double2(j.B[0][1], j.B[0][2]),
+                            make_double2(j.A[1][0], j.A[1][1]), make_double2(j.A[1][2], j.B[1][0]), make_double2(j.B[1][1], j.B[1][2])};
+      warp_store_rows<6>(jac_cap + 6 * (size_t)warp_first, v, stage, lane, n_valid);
     }
     if (jac_tag) {
-      double2* d = jac_tag + 6 * (size_t)t;
-      d[0] = make_double2(j.A[0][0], j.A[0][1]);
-      d[1] = make_double2(j.A[0][2], j.C[0][0]);
-      d[2] = make_double2(j.C[0][1], j.C[0][2]);
-      d[3] = make_double2(j.A[1][0], j.A[1][1]);
-      d[4] = make_double2(j.A[1][2], j.C[1][0]);
-      d[5] = make_double2(j.C[1][1], j.C[1][2]);
+      const double2 v[6] = {make_double2(j.A[0][0], j.A[0][1]), make_double2(j.A[0][2], j.C[0][0]), make_double2(j.C[0][1], j.C[0][2]),
+                            make_double2(j.A[1][0], j.A[1][1]), make_double2(j.A[1][2], j.C[1][0]), make_double2(j.C[1][1], j.C[1][2])};
+      warp_store_rows<6>(jac_tag + 6 * (size_t)warp_first, v, stage, lane, n_valid);
     }
   }
   rr = warp_sum(rr);
-  if ((threadIdx.x & 31) == 0) warp_cost[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = rr;
+  if (lane == 0) warp_cost[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = rr;
 }
 
 // Reduces the staged per-lane values ([value][lane], padded) over the runs of lanes that share

@@ -56,6 +56,8 @@ KERNEL_NOTE = {
                  "read once per solve; bound by grid-barrier + halo latency per iteration, not by bandwidth",
     "backsub": "W read once (72 B/corner) + E records",
     "candidate": "residual-only cost at x + delta: 18 B/corner",
+    "eval_jacobian": "kernel (1) with J materialised (arslam_evaluate, the Problem::Evaluate parity API; not on the LM path, which "
+                     "fuses it into accum_E/F): 18 B/corner in + 16 B r + 240 B J out = 274 B/corner, stores staged per warp",
     "localize": "whole LM solve per capture in registers: FP64-latency bound, not HBM bound",
 }
 
@@ -433,6 +435,24 @@ def bench_ba(ctx, workload, steps, warmup, scaling="strong", linear_solver=None,
             s.set_profiling(False)
             rooflines = kernel_rooflines(kt, summaries[0]["reduced_dim"], workload)
 
+    # ---- kernel (1) on its own: residuals + Jacobians materialised, as ceres::Problem::Evaluate would return them
+    eval_roofline = None
+    if profile and world == 1 and rank == 0 and n_corner_total <= 4000000:
+        s.set_params(*start)
+        s.set_profiling(True)
+        times = []
+        for _ in range(3):
+            s.evaluate(jacobians=True)
+            times += [k for k in s.kernel_times() if k["name"] == "eval_jacobian"]
+        s.set_profiling(False)
+        best = min(times, key=lambda k: k["total_ms"])
+        hbm_peak, hbm_how = read_peaks()
+        sec = best["total_ms"] * 1e-3
+        eval_roofline = {"kernel": "eval_jacobian", "bound": "hbm", "achieved": best["algorithmic_bytes"] / sec / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": best["algorithmic_bytes"] / sec / 1e9 / hbm_peak, "peak_source": hbm_how,
+                         "algorithmic_bytes": best["algorithmic_bytes"], "us_per_launch": sec * 1e6, "launches": 3,
+                         "share_of_step": 0.0, "traffic": static_traffic(workload, "eval_jacobian")[0], "note": KERNEL_NOTE["eval_jacobian"]}
+
     # ---- time to converge with the reference's own stopping rule (function_tolerance 1e-6, <= 50 iterations)
     conv = None
     if converge:
@@ -501,7 +521,7 @@ def bench_ba(ctx, workload, steps, warmup, scaling="strong", linear_solver=None,
     if rooflines:
         res["roofline"] = dict(rooflines[0])
         res["roofline"]["why_this_kernel"] = "largest share of the LM iteration"
-        res["rooflines"] = [r for r in rooflines if r["share_of_step"] >= 0.05]
+        res["rooflines"] = [r for r in rooflines if r["share_of_step"] >= 0.05] + ([eval_roofline] if eval_roofline else [])
         res["kernels"] = {r["kernel"]: {"us_per_launch": r["us_per_launch"], "launches": r["launches"],
                                         "share_of_step": r["share_of_step"]} for r in rooflines}
     if conv:
