@@ -33,7 +33,8 @@ class Options(C.Structure):
                 ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
                 ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
-                ("parameter_tolerance", C.c_double), ("pcg_tolerance", C.c_double), ("tag_size", C.c_double),
+                ("parameter_tolerance", C.c_double), ("pcg_tolerance", C.c_double), ("pcg_q_tolerance", C.c_double),
+                ("tag_size", C.c_double),
                 ("dense_max_dim", C.c_int64)]
 
 

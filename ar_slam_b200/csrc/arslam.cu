@@ -424,6 +424,7 @@ void arslam_default_options(arslam_options* o) {
   o->gradient_tolerance = 1e-10;
   o->parameter_tolerance = 1e-8;
   o->pcg_tolerance = 0.1;  // inexact-Newton forcing term, the value of Ceres' Solver::Options::eta
+  o->pcg_q_tolerance = 0.0;
   o->tag_size = 0.0635;  // ar_slam_util.hpp:319
   o->dense_max_dim = 16384;
 }
@@ -1121,7 +1122,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
          pcg_finalize_kernel<<<cdiv(std::max(n_f, 1), 64), 64, 0, s->stream>>>(f, w.diag_slot));
   PcgSmemArgs sa;
   PcgArgs& a = sa.a;
-  a.n_f = n_f; a.max_iter = s->opt.pcg_max_iterations; a.tol = s->opt.pcg_tolerance;
+  a.n_f = n_f; a.max_iter = s->opt.pcg_max_iterations; a.tol = s->opt.pcg_tolerance; a.q_tol = s->opt.pcg_q_tolerance;
   a.row_ptr = w.row_ptr; a.col_idx = w.col_idx; a.S = w.Sfin; a.Minv = w.Minv;
   a.border = f.border; a.rhs = f.rhs;
   a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
@@ -1139,7 +1140,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   }
   // one barrier per iteration for the inexact-Newton tolerances; the classic recurrence when the
   // system is to be solved tightly (its attainable accuracy is higher)
-  const bool pipelined = use_smem && s->opt.pcg_tolerance >= 1e-6 && s->tune_pcg_pipelined;
+  const bool pipelined = use_smem && (s->opt.pcg_tolerance >= 1e-6 || s->opt.pcg_q_tolerance > 0.0) && s->tune_pcg_pipelined;
   if (pipelined)
     CU(cudaLaunchCooperativeKernel((void*)pcg_pipe_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
   else if (use_smem)

@@ -518,6 +518,7 @@ struct PcgArgs {
   double* q;
   double* partial;       // [grid][8]
   double* scal;          // [0] S_kk [1] 1/S_kk [2] iterations (out) [3] fail (in/out)
+  double q_tol;               // quadratic-model termination (pipelined kernel): 0 = off
   unsigned long long* trace;  // debug: [iteration][cta][5] globaltimer stamps, or null
   // results go straight to the LM loop: unscaled step uF = sigF . x, iteration count -> sc[18],
   // failure -> sc[12]
@@ -998,8 +999,8 @@ __device__ __forceinline__ double reduce6_halving(const double (&ac)[6], int lan
 __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemArgs A) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ double sm[(kPcgWarps + 1) * 4 + 12];
-  constexpr int kVk = (kPcgWarps + 1) * 4 + 4;  // camera component of the gathered vector; S_kk, 1 / S_kk next to it
+  __shared__ double sm[(kPcgWarps + 1) * 6 + 12];
+  constexpr int kVk = (kPcgWarps + 1) * 6 + 4;  // camera component of the gathered vector; S_kk, 1 / S_kk next to it
   const PcgArgs& a = A.a;
   double* Ss = reinterpret_cast<double*>(dyn);                       // [cap_slots][36]
   double* xs = Ss + (size_t)A.cap_slots * 36;                        // [max_halo][6]
@@ -1097,6 +1098,8 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
   double* buf[2] = {a.p0, a.p1};
   // r0 = rhs (x0 = 0), u0 = M^-1 r0, w0 = A u0
   if (owner) r = a.rhs[gi];
+  const double b0 = r;      // this lane's component of the right-hand side (quadratic-model termination)
+  double Q_prev = 0.0;      // Q(x) = x'Ax - 2 b'x = -x.(b + r); Q(0) = 0
   u = precond(r);
   if (owner) buf[0][gi] = u;
   double s2[2] = {isRow ? bd * u : 0.0, owner ? r * r : 0.0};
@@ -1113,11 +1116,20 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
       const double m = precond(w);
       double* mb = buf[(it + 1) & 1];
       if (owner) mb[gi] = m;
-      double sv[4] = {owner ? r * u : 0.0, owner ? w * u : 0.0, owner ? r * r : 0.0, isRow ? bd * m : 0.0};
-      grid_sums_atomic<4>(grid, sv, a.partial, sm, round);
+      double sv[6] = {owner ? r * u : 0.0, owner ? w * u : 0.0, owner ? r * r : 0.0, isRow ? bd * m : 0.0,
+                      owner ? x * b0 : 0.0, owner ? x * r : 0.0};
+      grid_sums_atomic<6>(grid, sv, a.partial, sm, round);
       const double gamma = sv[0], delta = sv[1];
       if (!isfinite(sv[2])) { fail = true; break; }
       if (sv[2] <= thresh) break;
+      if (a.q_tol > 0.0 && it >= 1) {
+        // Ceres' ConjugateGradientsSolver rule, the one its trust-region strategies use for inexact steps
+        // (q_tolerance = eta, r_tolerance off): stop when zeta = i (Q_i - Q_{i-1}) / Q_i < q_tolerance
+        const double Q = -(sv[4] + sv[5]);
+        const double zeta = (double)it * (Q - Q_prev) / Q;
+        Q_prev = Q;
+        if (zeta < a.q_tol) break;
+      }
       double beta = 0.0, alpha;
       if (it == 0) {
         if (!(delta > 0.0) || !isfinite(delta)) { fail = true; break; }

@@ -85,6 +85,10 @@ typedef struct arslam_options {
                                                 PCG stops (inexact Newton; Ceres' eta).  >= 1e-6
                                                 runs the one-barrier pipelined recurrence, tighter
                                                 values the classic one                          */
+  double pcg_q_tolerance;                    /* 0: off.  > 0: PCG also stops when i (Q_i - Q_{i-1}) / Q_i < this, Q(x) = x'Sx - 2 b'x
+                                                -- the rule Ceres' own ConjugateGradientsSolver applies for the
+                                                inexact steps of its trust-region strategies (q_tolerance = eta = 0.1,
+                                                r_tolerance off); pipelined PCG kernel only          */
   double tag_size;                           /* 0.0635 m (ar_slam_util.hpp:319)                */
   int64_t dense_max_dim;                     /* AUTO never picks the dense Cholesky above this
                                                 reduced dimension (default 16384)              */

@@ -426,3 +426,24 @@ def test_locality_order_and_local_elimination_equal_default(gpu_solver_cls):
     for other in logs[1:]:
         assert np.allclose(other[0][:, 0], logs[0][0][:, 0], rtol=1e-10, atol=0)
         assert np.abs(other[2] - logs[0][2]).max() <= 1e-8 and np.abs(other[3] - logs[0][3]).max() <= 1e-8
+
+
+def test_pcg_quadratic_model_termination(gpu_solver_cls):
+    """pcg_q_tolerance: Ceres' ConjugateGradientsSolver rule (stop when i (Q_i - Q_{i-1}) / Q_i < q, Q(x) = x'Sx - 2b'x; what
+    its trust-region strategies use for inexact steps with q = eta = 0.1).  Same minimum as the tightly solved
+    problem, far fewer PCG iterations."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(4000, 400, seed=17)
+    res = {}
+    for name, kw in (("tight", dict(pcg_tolerance=1e-10)), ("q", dict(pcg_tolerance=0.0, pcg_q_tolerance=0.1))):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ar_slam_b200.LINSOLVE_PCG, pcg_max_iterations=3000, **kw))
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        res[name], _ = s.solve()
+        s.close()
+    assert res["q"]["termination"] == 0 and res["tight"]["termination"] == 0
+    assert abs(res["q"]["final_cost"] - res["tight"]["final_cost"]) <= 1e-5 * res["tight"]["final_cost"]
+    assert res["q"]["linear_solver_iterations"] < 0.5 * res["tight"]["linear_solver_iterations"]
+    # the rule actually stops the solves: nowhere near the iteration cap
+    assert res["q"]["linear_solver_iterations"] < 0.5 * 3000 * res["q"]["iterations"]
