@@ -313,7 +313,7 @@ struct arslam_solver {
   long long launches = 0;
   Profiler prof;
   // tuning switches (arslam_set_tuning), per handle
-  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1, tune_schur_bulk = 1, tune_schur_local = 0, tune_locality = 0;  // the locality-ordered elimination is parked: measured slower
+  int tune_accum_pipe = 2, tune_accum_flush = 0, tune_pcg_smem = 1, tune_pcg_pipelined = 1, tune_schur_bulk = 1, tune_schur_local = 0, tune_locality = 0, tune_chol_chain = 1;  // the locality-ordered elimination is parked: measured slower
   long long tune_loc_chunk = 0;  // captures per localisation chunk (0: default)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -517,6 +517,8 @@ int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value) {
   else if (k == "schur_local") { s->tune_schur_local = value != 0; s->pcg.valid = false; }  // the plan is (re)built with the symbolic phase
   else if (k == "loc_chunk") s->tune_loc_chunk = value;
   else if (k == "pcg_pipelined") s->tune_pcg_pipelined = value != 0;
+  else if (k == "chol_chain") s->tune_chol_chain = value != 0;
+  else if (k == "chol_big") s->lookahead.variant = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
   else return s->fail(ARSLAM_ERR_INVALID, "set_tuning: unknown key '%s'", key);
   return ARSLAM_OK;
 }
@@ -1451,12 +1453,12 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         Profiler::Rec r{s->prof.id_of("dense_cholesky", 0.0), s->prof.ev(), s->prof.ev()};
         cudaEventRecord(r.a, s->stream);
         s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream, s->lookahead);
-        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, s->stream);
+        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, sc + 12, s->stream, s->lookahead, s->tune_chol_chain != 0);
         cudaEventRecord(r.b, s->stream);
         s->prof.recs.push_back(r);
       } else {
         s->launches += DenseCholesky::factor(S, s->ld, s->n_pad, s->linv.p, sc + 12, s->stream, s->lookahead);
-        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, s->stream);
+        s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, sc + 12, s->stream, s->lookahead, s->tune_chol_chain != 0);
       }
     } else {
       rc = pcg_launch_solve(s, sd.n_f, S, HF, sc, cam_minus, radius, s->yF.p);

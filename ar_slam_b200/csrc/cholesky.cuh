@@ -336,6 +336,160 @@ __global__ void __launch_bounds__(kBigThreads, 1) syrk_big_dmma_kernel(double* _
   }
 }
 
+// --- trailing update, asynchronous version ---------------------------------------------------
+// Same tiles and the same arithmetic as syrk_big_dmma_kernel (every C element still receives ONE
+// contribution per launch, so the factor stays bit-reproducible), built so that the DMMA pipe does
+// not wait for memory at the two ends of a tile:
+//   * the operand chunks of ALL the tiles a persistent CTA walks form one cp.async stream (k chunks of
+//     16, STAGES deep, one CTA barrier per chunk): the first chunks of the next tile are in flight
+//     while the current tile finishes;
+//   * C is never read into the SM: the negated accumulators are staged in shared memory EPI_ROWS
+//     rows at a time and handed to the TMA engine as one bulk reduction per row
+//     (cp.reduce.async.bulk ... .add.f64: C += (-acc) in L2), which drains under the next tile's MMAs.
+constexpr int BK2 = 16;                 // k chunk
+constexpr int BK2_LD = BK2 + 4;         // conflict-free DMMA fragment loads, 16-byte aligned rows
+constexpr int CS_LD = BT + 8;           // staging row stride: conflict-free 16-byte stores of the accumulator fragments
+constexpr int kStage2 = 2 * BT * BK2_LD;  // doubles per stage (both operands)
+template <int STAGES, int EPI_ROWS>
+constexpr size_t big2_smem() { return (size_t)(STAGES * kStage2 + EPI_ROWS * CS_LD) * sizeof(double); }
+__device__ __forceinline__ void tile_of(int p, int nt, int tile_off, int strip_cols, int& ti, int& tj) {
+  if (strip_cols > 0) {  // column by column through the strip, rows ti >= tj
+    tj = 0;
+    while (p >= nt - tj) { p -= nt - tj; ++tj; }
+    ti = tj + p;
+  } else {               // linear id over the triangle ti >= tj >= tile_off
+    ti = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+    while (ti * (ti + 1) / 2 > p) --ti;
+    tj = p - ti * (ti + 1) / 2 + tile_off;
+    ti += tile_off;
+  }
+}
+template <int STAGES, int EPI_ROWS>
+__global__ void __launch_bounds__(kBigThreads, 1) syrk_big_async_kernel(double* __restrict__ A, long long ld, int K0, int kw, int n_pad,
+                                                                        int nt, int tile_off, int strip_cols, int n_tiles) {
+  extern __shared__ __align__(16) double sm[];
+  double* cs = sm + STAGES * kStage2;  // [EPI_ROWS][CS_LD]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int base = K0 + kw;
+  const int nchunk = kw / BK2;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * nchunk;  // chunks in this CTA's stream
+  // the load side of the stream: chunk ld_kc of tile ld_p
+  int ld_i = 0, ld_kc = 0, ld_r0 = 0, ld_c0 = 0;
+  {
+    int ti, tj;
+    tile_of(blockIdx.x, nt, tile_off, strip_cols, ti, tj);
+    ld_r0 = base + ti * BT;
+    ld_c0 = base + tj * BT;
+  }
+  auto load_next = [&]() {
+    if (ld_i < total) {
+      double* st = sm + (size_t)(ld_i % STAGES) * kStage2;
+      // 2 x (128 rows x 16 doubles) = 2048 16-byte pieces, 8 per thread; 8 threads cover 128 contiguous bytes of a row
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int e = tid + it * kBigThreads;
+        const int which = e >> 10, q = e & 1023;
+        const int r = q >> 3, c2 = (q & 7) * 2;
+        const int gr = (which == 0 ? ld_r0 : ld_c0) + r;
+        double* dst = st + (which * BT + r) * BK2_LD + c2;
+        if (gr < n_pad) cp_async16(dst, A + (size_t)gr * ld + K0 + ld_kc * BK2 + c2);
+        else { dst[0] = 0.0; dst[1] = 0.0; }
+      }
+      ++ld_i;
+      if (++ld_kc == nchunk) {
+        ld_kc = 0;
+        if (ld_i < total) {
+          int ti, tj;
+          tile_of(blockIdx.x + (ld_i / nchunk) * gridDim.x, nt, tile_off, strip_cols, ti, tj);
+          ld_r0 = base + ti * BT;
+          ld_c0 = base + tj * BT;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // an empty group keeps the wait distance constant
+  };
+#pragma unroll
+  for (int q = 0; q < STAGES - 1; ++q) load_next();
+  const int rb = (w >> 2) * 64, cb = (w & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  int i = 0;
+  for (int mt = 0; mt < my_tiles; ++mt) {
+    double acc[4][4][4];  // 4 x 4 MMA tiles of 16 x 8
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0;
+    for (int kc = 0; kc < nchunk; ++kc, ++i) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");  // chunk i has landed (this thread's pieces)
+      __syncthreads();  // ... everybody's; and every warp is done with chunk i - 1, whose stage the next load overwrites
+      load_next();      // chunk i + STAGES - 1
+      const double* Pi = sm + (size_t)(i % STAGES) * kStage2;
+      const double* Pj = Pi + BT * BK2_LD;
+#pragma unroll
+      for (int kk = 0; kk < BK2; kk += 8) {
+        double af[4][4], bf[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          const double* r0p = Pi + (rb + mi * 16 + g) * BK2_LD + kk + t;
+          af[mi][0] = r0p[0];
+          af[mi][1] = r0p[8 * BK2_LD];
+          af[mi][2] = r0p[4];
+          af[mi][3] = r0p[8 * BK2_LD + 4];
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const double* c0p = Pj + (cb + ni * 8 + g) * BK2_LD + kk + t;
+          bf[ni][0] = c0p[0];
+          bf[ni][1] = c0p[4];
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma1688(acc[mi][ni], af[mi], bf[ni]);
+      }
+    }
+    // epilogue: C(tile) += -acc through the staging rows
+    int ti, tj;
+    tile_of(blockIdx.x + mt * gridDim.x, nt, tile_off, strip_cols, ti, tj);
+    const int r0 = base + ti * BT, c0 = base + tj * BT;
+    const unsigned row_bytes = (unsigned)(min(BT, n_pad - c0) * (int)sizeof(double));
+#pragma unroll
+    for (int ph = 0; ph < BT / EPI_ROWS; ++ph) {
+      if (tid < EPI_ROWS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the previous rows
+      __syncthreads();
+      if ((w >> 2) == (ph * EPI_ROWS) / 64) {
+#pragma unroll
+        for (int mm = 0; mm < EPI_ROWS / 16; ++mm) {
+          const int mi = ((ph * EPI_ROWS) % 64) / 16 + mm;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+              *reinterpret_cast<double2*>(cs + (mm * 16 + g + 8 * h) * CS_LD + cb + ni * 8 + 2 * t) =
+                  make_double2(-acc[mi][ni][2 * h], -acc[mi][ni][2 * h + 1]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the bulk engine
+      }
+      __syncthreads();
+      if (tid < EPI_ROWS) {
+        const int gr = r0 + ph * EPI_ROWS + tid;
+        if (gr < n_pad)
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(
+                           __cvta_generic_to_global(A + (size_t)gr * ld + c0)),
+                       "r"((unsigned)__cvta_generic_to_shared(cs + tid * CS_LD)), "r"(row_bytes)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tid < EPI_ROWS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // complete (and visible) before the CTA retires
+}
+
 // --- panel solve as a GEMM: X = A_tile Linv^T on 64x64 tiles (in place), DMMA ----------------
 __global__ void __launch_bounds__(128) trsm_dmma_kernel(double* __restrict__ A, long long ld, int k0,
                                                         const double* __restrict__ Linv) {
@@ -419,6 +573,84 @@ __global__ void __launch_bounds__(256) backsolve_step_kernel(double* __restrict_
   if (grp == 0 && j < k0) A[(size_t)rhs_row * ld + j] -= (part[0][jl] + part[1][jl]) + (part[2][jl] + part[3][jl]);
 }
 
+// --- the whole of L^T y = w in ONE launch ------------------------------------------------------
+// CTA j owns the unknowns of 64-block j: it folds y_k (k from the last block down to j + 1) into its right-hand
+// side, then forms y_j = Linv_j^T w_j.  The CTAs are chained through y itself: y is preset to an all-ones bit
+// pattern (a NaN no computation produces) and a reader polls the 64 values it needs until they are numbers, so
+// the dependent chain is one L2 round trip + 16 FMAs + one 64 x 64 mat-vec per block instead of a launch.  The L
+// block of the NEXT step is already in registers when y_k arrives.  Launched cooperatively (all CTAs resident;
+// producers carry the lowest block indices); summation order is fixed, so the result is reproducible.
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int kChainSpinLimit = 1 << 22;  // ~ seconds; a reader that gives up raises *fail instead of hanging the GPU
+__global__ void __launch_bounds__(256, 2) backsolve_chain_kernel(const double* __restrict__ A, long long ld, int n, int rhs_row,
+                                                                 double* y, const double* __restrict__ linv, double* __restrict__ fail) {
+  __shared__ __align__(16) double Ls[CB * CB];  // Linv_j
+  __shared__ double yv[2][CB], part[4][CB], wv[CB];
+  const int nblk = gridDim.x;
+  const int j = nblk - 1 - (int)blockIdx.x;
+  const int tid = threadIdx.x, c = tid & 63, grp = tid >> 6;
+  const int nv_j = min(CB, n - j * CB);
+#pragma unroll
+  for (int it = 0; it < CB * CB / 2 / 256; ++it) {
+    const int e = tid + it * 256;
+    cp_async16(Ls + 2 * e, linv + (size_t)j * CB * CB + 2 * e);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const double w0 = (tid < nv_j) ? A[(size_t)rhs_row * ld + j * CB + tid] : 0.0;
+  auto load_blk = [&](double(&dst)[16], int k) {
+    const int nv = min(CB, n - k * CB);
+    const double* src = A + (size_t)(k * CB + grp * 16) * ld + j * CB + c;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) dst[q] = (grp * 16 + q < nv) ? src[(size_t)q * ld] : 0.0;
+  };
+  double s = 0.0;
+  auto step = [&](const double(&cur)[16], double(&nxt)[16], int k) {
+    if (k - 1 > j) load_blk(nxt, k - 1);
+    if (tid < CB) {
+      const double* src = y + (size_t)k * CB + tid;
+      double v = ld_volatile_f64(src);
+      int spins = 0;
+      while (__double_as_longlong(v) == -1ll && ++spins < kChainSpinLimit) v = ld_volatile_f64(src);
+      if (spins >= kChainSpinLimit) { *fail = 1.0; v = 0.0; }
+      yv[k & 1][tid] = v;
+    }
+    __syncthreads();
+    const double* yk = yv[k & 1] + grp * 16;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += cur[q] * yk[q];
+  };
+  double Lb0[16], Lb1[16];
+  int k = nblk - 1;
+  if (k > j) load_blk(Lb0, k);
+  while (k > j) {
+    step(Lb0, Lb1, k);
+    if (--k <= j) break;
+    step(Lb1, Lb0, k);
+    --k;
+  }
+  part[grp][c] = s;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (tid < CB) wv[tid] = w0 - ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
+  __syncthreads();
+  {
+    // y_r = sum_{cc >= r} Linv[cc][r] w_cc: four lanes per r
+    const int r = tid >> 2, p4 = tid & 3;
+    double acc = 0.0;
+    for (int cc = r + p4; cc < nv_j; cc += 4) acc += Ls[cc * CB + r] * wv[cc];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (p4 == 0) {
+      const double v = r < nv_j ? acc : 0.0;
+      asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(y + (size_t)j * CB + r), "d"(v) : "memory");
+    }
+  }
+}
+
 struct DenseCholesky {
   static constexpr size_t kTileSmem = 2 * CB * CB_LD * sizeof(double);
   static cudaError_t init() {
@@ -428,7 +660,18 @@ struct DenseCholesky {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(syrk_big_async_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big2_smem<3, 64>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(syrk_big_async_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big2_smem<4, 32>());
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(syrk_big_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
+  }
+  static void launch_big(int variant, int grid, cudaStream_t st, double* A, long long ld, int K0, int kw, int n_pad, int nt, int tile_off,
+                         int strip_cols, int n_tiles) {
+    if (variant == 2)
+      syrk_big_async_kernel<4, 32><<<grid, kBigThreads, big2_smem<4, 32>(), st>>>(A, ld, K0, kw, n_pad, nt, tile_off, strip_cols, n_tiles);
+    else
+      syrk_big_async_kernel<3, 64><<<grid, kBigThreads, big2_smem<3, 64>(), st>>>(A, ld, K0, kw, n_pad, nt, tile_off, strip_cols, n_tiles);
   }
   static constexpr int NB = 256;  // outer panel width
   // Second stream + events for the look-ahead: after outer panel P is factored, the update of the
@@ -437,11 +680,14 @@ struct DenseCholesky {
   // so the latency-bound factorisation kernels get SM slots first).
   struct LookAhead {
     cudaStream_t aux = nullptr;
+    int chain_capacity = -1;      // CTAs of backsolve_chain_kernel the GPU holds at once (-1: not asked yet)
+    int variant = 1;              // trailing update: 0 synchronous epilogue (round 1), 1 / 2 asynchronous (3 stages x 64 rows / 4 x 32)
+    int sms = 148;
     int rest_ctas = 140;          // persistent CTAs of the rest update (one per SM): the other SMs serve the factorisation chain
     std::vector<cudaEvent_t> ev;  // [2 P]: panel P factored, [2 P + 1]: rest(P) done
     cudaError_t ensure(int panels) {
       if (!aux) {
-        int dev = 0, sms = 148;
+        int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int free_sms = 8;   // measured best of 0 / 8 / 16 / 24 / 32 at n = 12 003 (34.0 / 36.8 ms with 8 / 0)
@@ -499,13 +745,21 @@ struct DenseCholesky {
       if (two_streams) cudaEventRecord(la.ev[2 * P], st);  // panel P is factored
       // the strip reads and writes columns that rest(P - 1) wrote
       if (two_streams && last_rest >= 0) cudaStreamWaitEvent(st, la.ev[2 * last_rest + 1], 0);
-      syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip, 0);
+      if (la.variant == 0) {
+        syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip, 0);
+      } else {
+        const int stiles = nt * strip - strip * (strip - 1) / 2;
+        launch_big(la.variant, std::min(stiles, la.sms), st, A, ld, K0, kw, n_pad, nt, 0, strip, stiles);
+      }
       ++launches;
       if (nt > strip) {
         const int m = nt - strip;
         if (two_streams) cudaStreamWaitEvent(aux, la.ev[2 * P], 0);
         const int tiles = m * (m + 1) / 2;
-        syrk_big_dmma_kernel<<<std::min(tiles, la.rest_ctas), kBigThreads, kBigSmem, aux>>>(A, ld, K0, kw, n_pad, strip, 0, tiles);
+        if (la.variant == 0)
+          syrk_big_dmma_kernel<<<std::min(tiles, la.rest_ctas), kBigThreads, kBigSmem, aux>>>(A, ld, K0, kw, n_pad, strip, 0, tiles);
+        else
+          launch_big(la.variant, std::min(tiles, la.rest_ctas), aux, A, ld, K0, kw, n_pad, nt, strip, 0, tiles);
         if (two_streams) cudaEventRecord(la.ev[2 * P + 1], aux);
         last_rest = P;
         ++launches;
@@ -515,8 +769,24 @@ struct DenseCholesky {
     return launches;
   }
   // solves L^T y = w for the leading n unknowns; w is row rhs_row (== n) and is destroyed
-  static int backsolve(double* A, long long ld, int n, int rhs_row, double* y, const double* linv, cudaStream_t st) {
+  // y must hold ceil(n / 64) * 64 doubles
+  static int backsolve(double* A, long long ld, int n, int rhs_row, double* y, const double* linv, double* fail, cudaStream_t st, LookAhead& la,
+                       bool chained = true) {
     int launches = 0;
+    const int nblk = (n + CB - 1) / CB;
+    if (la.chain_capacity < 0) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      la.chain_capacity = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, backsolve_chain_kernel, 256, 0) == cudaSuccess ? per_sm * sms : 0;
+    }
+    if (chained && nblk <= la.chain_capacity) {
+      cudaMemsetAsync(y, 0xFF, (size_t)nblk * CB * sizeof(double), st);
+      const double* Ac = A;
+      void* args[] = {(void*)&Ac, (void*)&ld, (void*)&n, (void*)&rhs_row, (void*)&y, (void*)&linv, (void*)&fail};
+      if (cudaLaunchCooperativeKernel((void*)backsolve_chain_kernel, dim3(nblk), dim3(256), args, 0, st) == cudaSuccess) return 2;
+      cudaGetLastError();  // fall through to the stepwise path
+    }
     for (int k0 = ((n - 1) / CB) * CB; k0 >= 0; k0 -= CB) {
       const int grid = k0 > 0 ? (k0 + CB - 1) / CB : 1;
       backsolve_step_kernel<<<grid, 256, 0, st>>>(A, ld, k0, n, rhs_row, y, linv + (size_t)(k0 / CB) * CB * CB);
