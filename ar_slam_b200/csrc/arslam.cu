@@ -518,7 +518,9 @@ int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value) {
   else if (k == "loc_chunk") s->tune_loc_chunk = value;
   else if (k == "pcg_pipelined") s->tune_pcg_pipelined = value != 0;
   else if (k == "chol_chain") s->tune_chol_chain = value != 0;
-  else if (k == "chol_big") s->lookahead.variant = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
+  else if (k == "chol_big") s->lookahead.variant = value != 0;
+  else if (k == "chol_nb") s->lookahead.nb = (int)std::max<int64_t>(128, std::min<int64_t>(1024, value / 128 * 128));
+  else if (k == "chol_free_sms") { s->lookahead.free_sms = (int)std::max<int64_t>(0, std::min<int64_t>(64, value)); s->lookahead.rest_ctas = std::max(1, s->lookahead.sms - s->lookahead.free_sms); }
   else return s->fail(ARSLAM_ERR_INVALID, "set_tuning: unknown key '%s'", key);
   return ARSLAM_OK;
 }

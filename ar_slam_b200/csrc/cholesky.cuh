@@ -170,6 +170,23 @@ __device__ __forceinline__ void dmma1688(double (&d)[4], const double (&a)[4], c
                : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+// both 64 x 64 operands of a tile kernel, 128 threads: 2 x 2048 16-byte pieces, ALL in flight at once (these kernels sit on the
+// factorisation's critical path with one CTA per SM or fewer: their time is load latency, so it is paid once)
+__device__ __forceinline__ void load_two_tiles_async(double (*Pi)[CB + 4], double (*Pj)[CB + 4], const double* gi, long long ldi, const double* gj,
+                                                     long long ldj) {
+#pragma unroll
+  for (int it = 0; it < CB * CB / 2 / 128; ++it) {
+    const int e = threadIdx.x + it * 128;
+    const int r = e >> 5, c2 = (e & 31) * 2;
+    cp_async16(&Pi[r][c2], gi + (size_t)r * ldi + c2);
+    cp_async16(&Pj[r][c2], gj + (size_t)r * ldj + c2);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 // --- in-panel update C(ti,tj) -= P(ti) P(tj)^T on 64x64 tiles, tj <= ti, tj inside the outer panel ----
 // 4 warps per CTA, each a 32x32 quadrant = 4x4 DMMA tiles, K = 64.
 __global__ void __launch_bounds__(128) syrk_dmma_kernel(double* __restrict__ A, long long ld, int k0) {
@@ -181,14 +198,17 @@ __global__ void __launch_bounds__(128) syrk_dmma_kernel(double* __restrict__ A, 
   if (ti < tj) return;
   const int r0 = k0 + CB + ti * CB, c0 = k0 + CB + tj * CB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int e = tid; e < CB * CB; e += 128) {
-    const int r = e / CB, c = e % CB;
-    Pi[r][c] = A[(size_t)(r0 + r) * ld + k0 + c];
-    Pj[r][c] = A[(size_t)(c0 + r) * ld + k0 + c];
-  }
-  __syncthreads();
+  load_two_tiles_async(Pi, Pj, A + (size_t)r0 * ld + k0, ld, A + (size_t)c0 * ld + k0, ld);
   const int rb = (w >> 1) * 32, cb = (w & 1) * 32;
   const int fr = lane >> 2, fk = lane & 3;
+  double2 cv[4][4];  // the C fragments travel while the operands land
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+      cv[mi][ni] = *reinterpret_cast<const double2*>(A + (size_t)(r0 + rb + mi * 8 + fr) * ld + c0 + cb + ni * 8 + 2 * fk);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   double acc[4][4][2];
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(128) syrk_dmma_kernel(double* __restrict__ A, 
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
       double2* c = reinterpret_cast<double2*>(A + (size_t)(r0 + rb + mi * 8 + fr) * ld + c0 + cb + ni * 8 + 2 * fk);
-      double2 v = *c;
+      double2 v = cv[mi][ni];
       v.x -= acc[mi][ni][0];
       v.y -= acc[mi][ni][1];
       *c = v;
@@ -226,10 +246,6 @@ constexpr int BK = 32;           // k chunk
 constexpr int BK_LD = BK + 4;    // shared-memory row stride: conflict-free DMMA fragment loads, 16-byte aligned rows
 constexpr int kBigThreads = 256;
 constexpr size_t kBigSmem = (size_t)2 /*stages*/ * 2 /*Pi, Pj*/ * BT * BK_LD * sizeof(double);
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
 // Tiles: strip_cols > 0: grid (row tiles, strip_cols) = the tile columns [0, strip_cols) (the next outer
 // panel, updated first so that its factorisation can start); else a linear id over the triangle of the
 // tiles with ti >= tj >= tile_off (the rest, which runs beside that factorisation on a second stream).
@@ -498,11 +514,8 @@ __global__ void __launch_bounds__(128) trsm_dmma_kernel(double* __restrict__ A, 
   double(*Pj)[CB_LD] = reinterpret_cast<double(*)[CB_LD]>(sm + CB * CB_LD);
   const int r0 = k0 + CB + blockIdx.x * CB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int e = tid; e < CB * CB; e += 128) {
-    const int r = e / CB, c = e % CB;
-    Pi[r][c] = A[(size_t)(r0 + r) * ld + k0 + c];
-    Pj[r][c] = Linv[e];
-  }
+  load_two_tiles_async(Pi, Pj, A + (size_t)r0 * ld + k0, ld, Linv, CB);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const int rb = (w >> 1) * 32, cb = (w & 1) * 32;
   const int fr = lane >> 2, fk = lane & 3;
@@ -662,18 +675,12 @@ struct DenseCholesky {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(syrk_big_async_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big2_smem<3, 64>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(syrk_big_async_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big2_smem<4, 32>());
-    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(syrk_big_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
   }
-  static void launch_big(int variant, int grid, cudaStream_t st, double* A, long long ld, int K0, int kw, int n_pad, int nt, int tile_off,
-                         int strip_cols, int n_tiles) {
-    if (variant == 2)
-      syrk_big_async_kernel<4, 32><<<grid, kBigThreads, big2_smem<4, 32>(), st>>>(A, ld, K0, kw, n_pad, nt, tile_off, strip_cols, n_tiles);
-    else
-      syrk_big_async_kernel<3, 64><<<grid, kBigThreads, big2_smem<3, 64>(), st>>>(A, ld, K0, kw, n_pad, nt, tile_off, strip_cols, n_tiles);
+  static void launch_big(int grid, cudaStream_t st, double* A, long long ld, int K0, int kw, int n_pad, int nt, int tile_off, int strip_cols,
+                         int n_tiles) {
+    syrk_big_async_kernel<3, 64><<<grid, kBigThreads, big2_smem<3, 64>(), st>>>(A, ld, K0, kw, n_pad, nt, tile_off, strip_cols, n_tiles);
   }
-  static constexpr int NB = 256;  // outer panel width
   // Second stream + events for the look-ahead: after outer panel P is factored, the update of the
   // NEXT panel's columns (strip) stays on the caller's stream, followed by that panel's
   // factorisation, while the update of everything beyond (rest) runs on `aux` (lower priority,
@@ -681,7 +688,9 @@ struct DenseCholesky {
   struct LookAhead {
     cudaStream_t aux = nullptr;
     int chain_capacity = -1;      // CTAs of backsolve_chain_kernel the GPU holds at once (-1: not asked yet)
-    int variant = 1;              // trailing update: 0 synchronous epilogue (round 1), 1 / 2 asynchronous (3 stages x 64 rows / 4 x 32)
+    int variant = 1;              // trailing update: 0 synchronous epilogue (round 1), 1 asynchronous
+    int nb = 256;                 // outer panel width (a multiple of 128)
+    int free_sms = 8;             // SMs the persistent rest update leaves to the factorisation chain
     int sms = 148;
     int rest_ctas = 140;          // persistent CTAs of the rest update (one per SM): the other SMs serve the factorisation chain
     std::vector<cudaEvent_t> ev;  // [2 P]: panel P factored, [2 P + 1]: rest(P) done
@@ -690,7 +699,6 @@ struct DenseCholesky {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int free_sms = 8;   // measured best of 0 / 8 / 16 / 24 / 32 at n = 12 003 (34.0 / 36.8 ms with 8 / 0)
         rest_ctas = std::max(1, sms - free_sms);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -714,6 +722,7 @@ struct DenseCholesky {
   // returns the number of launches
   static int factor(double* A, long long ld, int n_pad, double* linv, double* fail, cudaStream_t st, LookAhead& la) {
     int launches = 0;
+    const int NB = la.nb;
     const int panels = (n_pad + NB - 1) / NB;
     // without the second stream (creation failed) everything runs in order on the caller's stream
     const bool two_streams = la.ensure(panels) == cudaSuccess;
@@ -749,7 +758,7 @@ struct DenseCholesky {
         syrk_big_dmma_kernel<<<dim3(nt, strip), kBigThreads, kBigSmem, st>>>(A, ld, K0, kw, n_pad, 0, strip, 0);
       } else {
         const int stiles = nt * strip - strip * (strip - 1) / 2;
-        launch_big(la.variant, std::min(stiles, la.sms), st, A, ld, K0, kw, n_pad, nt, 0, strip, stiles);
+        launch_big(std::min(stiles, la.sms), st, A, ld, K0, kw, n_pad, nt, 0, strip, stiles);
       }
       ++launches;
       if (nt > strip) {
@@ -759,7 +768,7 @@ struct DenseCholesky {
         if (la.variant == 0)
           syrk_big_dmma_kernel<<<std::min(tiles, la.rest_ctas), kBigThreads, kBigSmem, aux>>>(A, ld, K0, kw, n_pad, strip, 0, tiles);
         else
-          launch_big(la.variant, std::min(tiles, la.rest_ctas), aux, A, ld, K0, kw, n_pad, nt, strip, 0, tiles);
+          launch_big(std::min(tiles, la.rest_ctas), aux, A, ld, K0, kw, n_pad, nt, strip, 0, tiles);
         if (two_streams) cudaEventRecord(la.ev[2 * P + 1], aux);
         last_rest = P;
         ++launches;

@@ -459,7 +459,7 @@ def test_dense_cholesky_variants_agree(gpu_solver_cls):
     from ar_slam_b200 import synth
     m = synth.make_map(2500, 420, seed=23)
     runs = {}
-    for name, tune in (("default", {}), ("sync", {"chol_big": 0}), ("async4x32", {"chol_big": 2}), ("stepwise", {"chol_chain": 0})):
+    for name, tune in (("default", {}), ("sync", {"chol_big": 0}), ("wide_panel", {"chol_nb": 512}), ("stepwise", {"chol_chain": 0})):
         s = gpu_solver_cls(options=ar_slam_b200.default_options(linear_solver=ar_slam_b200.LINSOLVE_DENSE, max_num_iterations=4))
         for k, v in tune.items():
             s.set_tuning(k, v)
@@ -470,7 +470,7 @@ def test_dense_cholesky_variants_agree(gpu_solver_cls):
         s.close()
     ref = runs["default"]
     assert ref[0]["termination"] in (0, 1)
-    for name in ("sync", "async4x32"):
+    for name in ("sync", "wide_panel"):
         # the reduced system itself is summed with FP64 reductions in arrival order (schur_eliminate), so two runs
         # agree to rounding, not to the bit; the factorisation variants add nothing to that
         assert np.allclose(runs[name][1][:, 0], ref[1][:, 0], rtol=1e-11, atol=0), name
