@@ -1411,7 +1411,12 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       a.radius = radius; a.inv_radius = 1.0 / radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
       a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr; a.e_const = const_e;
       schur_args = a;
-      CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
+      if (lin == ARSLAM_LINSOLVE_DENSE) {
+        LAUNCH("dense_zero", 4.0 * s->n_pad * (double)s->n_pad,
+               dense_zero_lower_kernel<<<dim3(cdiv(s->n_pad, kDenseTileCols), cdiv(s->n_pad, kDenseTileRows)), 256, 0, s->stream>>>(S, s->ld, s->n_pad));
+      } else {
+        CU(cudaMemsetAsync(S, 0, s_elems * sizeof(double), s->stream));
+      }
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         DenseTarget t;
         t.S = S; t.ld = s->ld; t.cam_row = cam_row; t.rhs_row = rhs_row;
@@ -1444,8 +1449,8 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       have_sigma = true;
     }
     if (lin == ARSLAM_LINSOLVE_DENSE) {
-      dim3 blk(32, 8), grd(cdiv(n, 32), cdiv(n + 1, 8));
-      LAUNCH("dense_scale", 8.0 * n * n, dense_scale_kernel<<<grd, blk, 0, s->stream>>>(S, s->ld, rhs_row, s->sigF.p));
+      LAUNCH("dense_scale", 8.0 * n * n,
+             dense_scale_kernel<<<dim3(cdiv(n, kDenseTileCols), cdiv(n + 1, kDenseTileRows)), 256, 0, s->stream>>>(S, s->ld, rhs_row, s->sigF.p));
       LAUNCH("dense_add_pose", 8.0 * NV * sd.n_f,
              dense_add_pose_kernel<<<cdiv(sd.n_f, 128), 128, 0, s->stream>>>(sd.n_f, HF, HFx, s->sigF.p, radius, o.min_lm_diagonal, o.max_lm_diagonal, S, s->ld, cam_row, rhs_row));
       LAUNCH("dense_add_camera", 64.0,

@@ -380,14 +380,45 @@ __global__ void __launch_bounds__(1024) schur_finish_kernel(const double* __rest
   }
 }
 
+// The dense reduced system is only ever read on and below the diagonal (and inside the 128 x 128 diagonal tiles
+// of the factorisation): the two full-matrix passes touch 64 x 32 tiles of that region only.
+constexpr int kDenseTileCols = 64, kDenseTileRows = 32;
+// zero the rows [0, rows) up to the end of the 128-wide tile that holds the diagonal
+__global__ void __launch_bounds__(256) dense_zero_lower_kernel(double* __restrict__ S, long long ld, int rows) {
+  const int j0 = blockIdx.x * kDenseTileCols, i0 = blockIdx.y * kDenseTileRows;
+  if (j0 >= ((i0 + kDenseTileRows - 1) / 128 + 1) * 128) return;
+  const int j = j0 + (threadIdx.x & 31) * 2;
+  const int ib = i0 + (threadIdx.x >> 5) * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = ib + q;
+    if (i < rows && j < ld) *reinterpret_cast<double2*>(S + (size_t)i * ld + j) = make_double2(0.0, 0.0);
+  }
+}
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
-__global__ void dense_scale_kernel(double* __restrict__ S, long long ld, int n /* = rhs_row */,
-                                   const double* __restrict__ sigF) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i > n || j >= n || j > i) return;
-  const double si = (i == n) ? 1.0 : sigF[i];
-  S[(size_t)i * ld + j] = -si * sigF[j] * S[(size_t)i * ld + j];
+__global__ void __launch_bounds__(256) dense_scale_kernel(double* __restrict__ S, long long ld, int n /* = rhs_row */,
+                                                          const double* __restrict__ sigF) {
+  const int j0 = blockIdx.x * kDenseTileCols, i0 = blockIdx.y * kDenseTileRows;
+  if (j0 > i0 + kDenseTileRows - 1) return;
+  const int j = j0 + (threadIdx.x & 31) * 2;
+  const int ib = i0 + (threadIdx.x >> 5) * 4;
+  if (j >= n) return;
+  const double sj0 = sigF[j], sj1 = j + 1 < n ? sigF[j + 1] : 0.0;
+  double2 v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = ib + q;
+    v[q] = (i <= n && j <= i) ? *reinterpret_cast<const double2*>(S + (size_t)i * ld + j) : make_double2(0.0, 0.0);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = ib + q;
+    if (i > n || j > i) continue;
+    const double si = (i == n) ? 1.0 : sigF[i];
+    double* dst = S + (size_t)i * ld + j;
+    dst[0] = -si * sj0 * v[q].x;
+    if (j + 1 <= i && j + 1 < n) dst[1] = -si * sj1 * v[q].y;
+  }
 }
 
 // Adds the F-pose diagonal blocks sig H_ff sig + D^2, the camera border and
