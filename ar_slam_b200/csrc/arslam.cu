@@ -278,7 +278,7 @@ struct arslam_solver {
   int cur = 0;
   // normal equations
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
-  DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red;  // red: S | cam_minus | HF | sc head
+  DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red, tri;  // tri: packed lower region of the dense system (multi-GPU sum)  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
   DenseCholesky::LookAhead lookahead;  // second stream + events of the dense factorisation
   DevBuf<long long> agree;   // multi-GPU: status word of comm_agree / capture ranges of the ranks
@@ -1335,6 +1335,11 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     s_elems = (size_t)s->n_pad * s->ld;
     CU(s->linv.ensure((size_t)(s->n_pad / CB) * CB * CB));
     CU(s->yF.ensure((size_t)s->n_pad));
+    if (s->world > 1) {
+      const size_t had = s->tri.n;
+      CU(s->tri.ensure(dense_packed_count(s->n_pad)));
+      if (s->tri.n != had) CU(cudaMemsetAsync(s->tri.p, 0, s->tri.n * sizeof(double), s->stream));  // the slots past ld are summed too, never read
+    }
   } else {
     int rc = pcg_prepare(s, sd.e, sd.n_e, sd.n_f);
     if (rc) return rc;
@@ -1433,8 +1438,18 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (s->world > 1) {
       // one allreduce per linearisation: partial Schur terms (+ on a fresh
       // linearisation the partial tag blocks, focal terms and cost)
-      const size_t cnt = fresh_linearisation ? s_elems + red_tail : s_elems + 12;
-      rc = nccl_sum(s, S, cnt);
+      const size_t tail = fresh_linearisation ? red_tail : 12;
+      if (lin == ARSLAM_LINSOLVE_DENSE) {
+        // only the populated region of the square travels (half the bytes), packed into a contiguous buffer
+        const dim3 grd(cdiv(s->n_pad, kDenseTileCols), cdiv(s->n_pad, kDenseTileRows));
+        LAUNCH("dense_pack", 8.0 * s->n_pad * (double)s->n_pad, dense_pack_kernel<false><<<grd, 256, 0, s->stream>>>(S, s->ld, s->n_pad, s->tri.p));
+        rc = nccl_sum(s, s->tri.p, dense_packed_count(s->n_pad));
+        if (rc) return rc;
+        LAUNCH("dense_unpack", 8.0 * s->n_pad * (double)s->n_pad, dense_pack_kernel<true><<<grd, 256, 0, s->stream>>>(S, s->ld, s->n_pad, s->tri.p));
+        rc = nccl_sum(s, S + s_elems, tail);
+      } else {
+        rc = nccl_sum(s, S, s_elems + tail);
+      }
       if (rc) return rc;
     }
     if (fresh_linearisation) {

@@ -395,6 +395,26 @@ __global__ void __launch_bounds__(256) dense_zero_lower_kernel(double* __restric
     if (i < rows && j < ld) *reinterpret_cast<double2*>(S + (size_t)i * ld + j) = make_double2(0.0, 0.0);
   }
 }
+// The same region as a contiguous buffer, for the multi-GPU sum: 128-row bands, band t holding 128 (t + 1) columns.
+__host__ __device__ inline size_t dense_packed_offset(int band) { return (size_t)(128 * 128) * band * (band + 1) / 2; }
+inline size_t dense_packed_count(int n_pad) { return dense_packed_offset((n_pad + 127) / 128); }
+template <bool UNPACK>
+__global__ void __launch_bounds__(256) dense_pack_kernel(double* __restrict__ S, long long ld, int rows, double* __restrict__ packed) {
+  const int j0 = blockIdx.x * kDenseTileCols, i0 = blockIdx.y * kDenseTileRows;
+  const int band = i0 / 128, width = (band + 1) * 128;
+  if (j0 >= width) return;
+  const int j = j0 + (threadIdx.x & 31) * 2;
+  const int ib = i0 + (threadIdx.x >> 5) * 4;
+  if (j >= ld) return;
+  double* pk = packed + dense_packed_offset(band) + (size_t)(ib - band * 128) * width + j;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (ib + q >= rows) break;
+    double2* a = reinterpret_cast<double2*>(S + (size_t)(ib + q) * ld + j);
+    double2* b = reinterpret_cast<double2*>(pk + (size_t)q * width);
+    if (UNPACK) *a = *b; else *b = *a;
+  }
+}
 // S <- -sigF_i sigF_j S on the lower triangle (rhs row: -sigF_j S).
 __global__ void __launch_bounds__(256) dense_scale_kernel(double* __restrict__ S, long long ld, int n /* = rhs_row */,
                                                           const double* __restrict__ sigF) {
