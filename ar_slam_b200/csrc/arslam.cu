@@ -376,10 +376,11 @@ static cudaError_t schur_local_attributes() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_local_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e;
 }
+template <int NK>
 static cudaError_t schur_bulk_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, 1, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaError_t e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, NK, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, NK, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchurSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(schur_eliminate_kernel<SparseTarget, NK, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e;
 }
 
@@ -458,7 +459,8 @@ int arslam_create(int device, const arslam_options* opt, arslam_solver** out) {
       cudaMallocHost(&s->h_sc, 256 * sizeof(double)) != cudaSuccess || DenseCholesky::init() != cudaSuccess ||
       schur_kernel_attributes<SparseTarget, 1>() != cudaSuccess || schur_kernel_attributes<DenseTarget, 1>() != cudaSuccess ||
       schur_kernel_attributes<DenseTarget, 3>() != cudaSuccess ||
-      pcg_init() != cudaSuccess || schur_bulk_attributes() != cudaSuccess || schur_local_attributes() != cudaSuccess ||
+      pcg_init() != cudaSuccess || schur_bulk_attributes<1>() != cudaSuccess || schur_bulk_attributes<3>() != cudaSuccess ||
+      schur_kernel_attributes<SparseTarget, 3>() != cudaSuccess || schur_local_attributes() != cudaSuccess ||
       pipe_kernel_attributes() != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete s;
@@ -1061,12 +1063,12 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   rc = comm_agree(s, rc ? s->fail(ARSLAM_ERR_CUDA, "%s", err.c_str()) : ARSLAM_OK, "pcg symbolic phase");
   if (rc) return rc;
   int occ = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel, kPcgThreads, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_kernel<3>, kPcgThreads, 0));
   if (occ < 1) return s->fail(ARSLAM_ERR_CUDA, "pcg_kernel cannot be made resident");
   s->pcg.grid = std::min(s->n_sm * std::min(occ, 1), 1024);
   if (s->pcg.pair_slot) {
     SparseTarget t;
-    t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx; t.Sraw = nullptr; t.borderm = nullptr; t.rhsm = nullptr;
+    t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx; t.Sraw = nullptr; t.borderm = nullptr; t.rhsm = nullptr; t.borderx = nullptr; t.n_f = s->pcg.n_f;
     t.pair_slot = nullptr; t.lower_of = s->pcg.src_slot;
     LAUNCH("pair_slot", 4.0 * s->pcg.n_pairs,
            pair_slot_kernel<<<cdiv(s->n_blk, 128), 128, 0, s->stream>>>(s->n_blk, s->s_own[side_e].p, s->s_off[side_e].p, s->seg_end(side_e),
@@ -1083,15 +1085,22 @@ int pcg_prepare(arslam_solver* s, int side_e, int n_e, int n_f) {
   return ARSLAM_OK;
 }
 
-int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, const int32_t* e_idx) {
+int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, const int32_t* e_idx, int nk) {
   SparseTarget t;
   t.row_ptr = s->pcg.row_ptr; t.col_idx = s->pcg.col_idx;
   t.Sraw = Sraw;
   t.borderm = Sraw + (size_t)36 * s->pcg.nnz_lower;
   t.rhsm = t.borderm + (size_t)6 * s->pcg.n_f;
+  t.borderx = nk == 3 ? t.rhsm + (size_t)6 * s->pcg.n_f : nullptr;
+  t.n_f = s->pcg.n_f;
   t.pair_slot = s->pcg.pair_slot; t.lower_of = s->pcg.src_slot;
   SchurArgs a2 = a;
   a2.pair_off = s->pcg.pair_slot ? s->pcg.pair_off : nullptr;
+  if (nk == 3) {
+    launch_schur<SparseTarget, 3>(s, a2, t, e_idx, (288.0 + 8) * s->n_blk + (264.0 + 128 + 96) * a.n_e + 288.0 * s->pcg.nnz_lower,
+                                  s->tune_schur_bulk != 0);
+    return ARSLAM_OK;
+  }
   if (s->schur_plan.valid && s->tune_schur_local) {
     // locality-ordered CTAs, products pre-reduced per destination inside the CTA; no straddle launch
     const double bytes = (288.0 + 8) * s->n_blk + (264.0 + 128) * a.n_e + 288.0 * s->pcg.nnz_lower + 2.0 * s->schur_plan.n_pairs;
@@ -1109,10 +1118,10 @@ int pcg_launch_eliminate(arslam_solver* s, const SchurArgs& a, double* Sraw, con
   return ARSLAM_OK;
 }
 
-int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, const double* sc, const double* cam_minus,
-                     double radius, double* x_out) {
+int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, const double* HFx, int nk, const double* sc,
+                     const double* cam_minus, double radius, double* x_out) {
   PcgWorkspace& w = s->pcg;
-  const size_t nvec = (size_t)6 * n_f + 2;
+  const size_t nvec = pcg_nvec(n_f);
   double* v = w.vec;
   PcgFinalizeArgs f;
   f.n_f = n_f; f.nnzb = w.nnzb; f.row_ptr = w.row_ptr; f.col_idx = w.col_idx; f.src_slot = w.src_slot;
@@ -1120,6 +1129,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   f.HF = HF; f.sigF = s->sigF.p; f.sc = reinterpret_cast<const LmScalars*>(sc); f.cam_minus = cam_minus;
   f.radius = radius; f.min_diag = s->opt.min_lm_diagonal; f.max_diag = s->opt.max_lm_diagonal;
   f.Sfin = w.Sfin; f.Minv = w.Minv; f.border = v + 6 * nvec; f.rhs = v + 7 * nvec; f.scal = w.scal; f.partial = w.partial;
+  f.nk = nk; f.HFx = HFx; f.borderx = nk == 3 ? f.rhsm + (size_t)6 * n_f : nullptr; f.border1 = v + 8 * nvec; f.border2 = v + 9 * nvec;
   LAUNCH("pcg_finalize_offdiag", 2.0 * 288.0 * w.nnzb,
          pcg_finalize_offdiag_kernel<<<cdiv((long long)w.nnzb * 6, 256), 256, 0, s->stream>>>(f, w.slot_row));
   LAUNCH("pcg_finalize", 8.0 * (NV + 36 + 36 + 36 + 24) * n_f,
@@ -1128,13 +1138,13 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   PcgArgs& a = sa.a;
   a.n_f = n_f; a.max_iter = s->opt.pcg_max_iterations; a.tol = s->opt.pcg_tolerance; a.q_tol = s->opt.pcg_q_tolerance;
   a.row_ptr = w.row_ptr; a.col_idx = w.col_idx; a.S = w.Sfin; a.Minv = w.Minv;
-  a.border = f.border; a.rhs = f.rhs;
+  a.border = f.border; a.border1 = f.border1; a.border2 = f.border2; a.rhs = f.rhs;
   a.x = x_out; a.r = v + 1 * nvec; a.z = v + 2 * nvec; a.p0 = v + 3 * nvec; a.p1 = v + 4 * nvec; a.q = v + 5 * nvec;
   a.partial = w.partial; a.scal = w.scal; a.trace = nullptr;
   a.sigF = s->sigF.p; a.uF = s->uF.p; a.sc = const_cast<double*>(sc);
   sa.cta_row = w.cta_row; sa.halo_ptr = w.halo_ptr; sa.halo_col = w.halo_col; sa.lcol = w.lcol;
   sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots; sa.max_rows = w.max_rows;
-  const bool use_smem = w.smem_ok && s->tune_pcg_smem;
+  const bool use_smem = w.smem_ok && s->tune_pcg_smem && nk == 1;  // (the radial model's three intrinsics: pcg_kernel<3>)
   void* args_g[] = {(void*)&a};
   void* args_s[] = {(void*)&sa};
   Profiler::Rec r{0, nullptr, nullptr};
@@ -1150,7 +1160,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   else if (use_smem)
     CU(cudaLaunchCooperativeKernel((void*)pcg_smem_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
   else
-    CU(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(w.grid), dim3(kPcgThreads), args_g, 0, s->stream));
+    CU(cudaLaunchCooperativeKernel(nk == 3 ? (void*)pcg_kernel<3> : (void*)pcg_kernel<1>, dim3(w.grid), dim3(kPcgThreads), args_g, 0, s->stream));
   if (s->prof.on) {
     cudaEventRecord(r.b, s->stream);
     s->prof.recs.push_back(r);
@@ -1282,8 +1292,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
     if (!s->have_problem || !s->have_params) pre = s->fail(ARSLAM_ERR_INVALID, "solve needs set_problem and set_params");
     else if (s->world > 1 && elim != ARSLAM_ELIM_CAPTURES)
       pre = s->fail(ARSLAM_ERR_UNSUPPORTED, "multi-GPU solve shards captures and must eliminate them");
-    else if (o.num_intrinsics == 3 && o.linear_solver == ARSLAM_LINSOLVE_PCG)
-      pre = s->fail(ARSLAM_ERR_UNSUPPORTED, "the radial model (num_intrinsics = 3) is solved with the dense Cholesky only");
     pre = comm_agree(s, pre, "solve");
     if (pre) return pre;
   }
@@ -1300,7 +1308,6 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   // AUTO: the dense DMMA Cholesky where the reduced matrix is actually dense (>= 25 % of its
   // 6x6 blocks are structurally non-zero, or it is tiny), block-sparse PCG otherwise
   int lin = o.linear_solver;
-  if (dist) lin = ARSLAM_LINSOLVE_DENSE;
   if (lin == ARSLAM_LINSOLVE_AUTO) {
     lin = ARSLAM_LINSOLVE_PCG;
     if (n <= 128) {
@@ -1343,7 +1350,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
   } else {
     int rc = pcg_prepare(s, sd.e, sd.n_e, sd.n_f);
     if (rc) return rc;
-    s_elems = s->pcg.value_count();  // block values + border + rhs
+    s_elems = s->pcg.value_count(nk);  // block values + border + rhs (+ the l1, l2 borders)
     CU(s->yF.ensure((size_t)n + 1));
   }
   // reduction buffer: [S or sparse values | cam_minus (12) | HF (n_f NV) | HFx (n_f NVX, radial model) | head (12)]
@@ -1428,7 +1435,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         if (dist) launch_schur<DenseTarget, 3>(s, a, t, s->s_own[sd.e].p, (288.0 + 8) * s->n_blk + (264.0 + 128) * sd.n_e + 8.0 * n * (double)n / 2);
         else launch_schur<DenseTarget, 1>(s, a, t, s->s_own[sd.e].p, (288.0 + 8) * s->n_blk + (264.0 + 128) * sd.n_e + 8.0 * n * (double)n / 2);
       } else {
-        rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p);
+        rc = pcg_launch_eliminate(s, a, S, s->s_own[sd.e].p, nk);
         if (rc) return rc;
       }
       // closes the elimination: cam_minus, max |g_e| -> sc[16], and the failure flag of the solve that starts here
@@ -1483,7 +1490,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
         s->launches += DenseCholesky::backsolve(S, s->ld, n, rhs_row, s->yF.p, s->linv.p, sc + 12, s->stream, s->lookahead, s->tune_chol_chain != 0);
       }
     } else {
-      rc = pcg_launch_solve(s, sd.n_f, S, HF, sc, cam_minus, radius, s->yF.p);
+      rc = pcg_launch_solve(s, sd.n_f, S, HF, HFx, nk, sc, cam_minus, radius, s->yF.p);
       if (rc) return rc;
     }
     if (lin == ARSLAM_LINSOLVE_DENSE)  // (the PCG kernels write uF themselves)

@@ -45,6 +45,9 @@ struct PcgBuf {
   ~PcgBuf() { cudaFree(p); }
 };
 
+// length of one PCG vector: the F poses' components + up to three intrinsics (even, so every vector is 16-byte aligned)
+inline size_t pcg_nvec(int n_f) { return (size_t)6 * n_f + 4; }
+
 struct PcgWorkspace {
   int n_f = 0, nnzb = 0, nnz_lower = 0, grid = 0;  // nnz_lower: blocks with col <= row, the ones that are formed
   bool valid = false;
@@ -54,7 +57,7 @@ struct PcgWorkspace {
   int32_t* src_slot = nullptr;  // [nnzb]: index, in the compact array of lower blocks, of the source block (transposed if col > row)
   double* Sfin = nullptr;       // [nnzb][36] final scaled + damped blocks
   double* Minv = nullptr;       // [n_f][36]  inverse diagonal blocks (block-Jacobi)
-  double* vec = nullptr;        // x | r | z | p0 | p1 | q | border | rhs : 8 x (6 n_f + 2)
+  double* vec = nullptr;        // x | r | z | p0 | p1 | q | border | rhs | border_l1 | border_l2 : 10 x pcg_nvec(n_f)
   double* partial = nullptr;    // [grid][8]
   double* scal = nullptr;       // [16]: S_kk, 1/S_kk, iterations, fail, ...
   // shared-memory resident variant: block rows are split into one contiguous range per CTA
@@ -70,7 +73,8 @@ struct PcgWorkspace {
   int32_t* pair_off = nullptr;  // [n_blk] (E-sorted) pairs before each block
   int32_t* pair_slot = nullptr; // [n_pairs]
   long long n_pairs = 0;
-  size_t value_count() const { return (size_t)36 * nnz_lower + (size_t)12 * n_f; }  // lower blocks | border | rhs
+  // lower blocks | border (focal) | rhs | borders of l1, l2 (radial model)
+  size_t value_count(int nk = 1) const { return (size_t)36 * nnz_lower + (size_t)12 * n_f + (nk == 3 ? (size_t)12 * n_f : 0); }
   // storage (grow-only, so a new problem of similar size allocates nothing); the pointers above alias it
   PcgBuf<int32_t> b_lowflag, b_lrank, b_row_ptr, b_col_idx, b_src_slot, b_cta_row, b_halo_ptr, b_halo_col, b_diag_slot, b_slot_row, b_pair_off, b_pair_slot;
   PcgBuf<uint16_t> b_lcol;
@@ -278,10 +282,10 @@ inline int pcg_symbolic_keys(PcgWorkspace& ws, int n_e, int n_f, int n_blk, cons
 // phase 2: everything derived from the sorted keys ws.keys[0][0 .. ws.nnzb)
 inline int pcg_symbolic_build(PcgWorkspace& ws, cudaStream_t st, std::string& err, int n_sm, size_t smem_limit) {
   const int n_f = ws.n_f, nnzb = ws.nnzb, G = n_sm;
-  const size_t nvec = (size_t)6 * n_f + 2;
+  const size_t nvec = pcg_nvec(n_f);
   cudaError_t ce = cudaSuccess;
   PCG_TRY(ws.b_row_ptr.ensure((size_t)n_f + 1)); PCG_TRY(ws.b_col_idx.ensure(nnzb)); PCG_TRY(ws.b_src_slot.ensure(nnzb));
-  PCG_TRY(ws.b_Sfin.ensure((size_t)36 * nnzb)); PCG_TRY(ws.b_Minv.ensure((size_t)36 * n_f)); PCG_TRY(ws.b_vec.ensure(8 * nvec));
+  PCG_TRY(ws.b_Sfin.ensure((size_t)36 * nnzb)); PCG_TRY(ws.b_Minv.ensure((size_t)36 * n_f)); PCG_TRY(ws.b_vec.ensure(10 * nvec));
   PCG_TRY(ws.b_partial.ensure(8 * 4096)); PCG_TRY(ws.b_scal.ensure(16));
   PCG_TRY(ws.b_diag_slot.ensure(std::max(n_f, 1))); PCG_TRY(ws.b_slot_row.ensure(std::max(nnzb, 1)));
   PCG_TRY(ws.b_cta_row.ensure((size_t)G + 1)); PCG_TRY(ws.b_halo_ptr.ensure((size_t)G + 1)); PCG_TRY(ws.b_lcol.ensure(std::max(nnzb, 1)));
@@ -366,11 +370,16 @@ struct SparseTarget {
   double* Sraw;     // [nnzb][36]
   double* borderm;  // [6 n_f]  sum W~^T yb
   double* rhsm;     // [6 n_f]  sum W~^T z
+  double* borderx;  // [2][6 n_f] the same for the columns of l1, l2 (radial model), else null
+  int n_f;
   __device__ __forceinline__ void add_border(int f, int c, double b0, double b1) const {
     red_add_f64(borderm + 6 * (size_t)f + c, b0);
     red_add_f64(rhsm + 6 * (size_t)f + c, b1);
   }
-  __device__ __forceinline__ void add_border_x(int, int, double, double) const {}  // radial model: dense solver only
+  __device__ __forceinline__ void add_border_x(int f, int c, double bl1, double bl2) const {
+    red_add_f64(borderx + 6 * (size_t)f + c, bl1);
+    red_add_f64(borderx + 6 * (size_t)(n_f + f) + c, bl2);
+  }
   const int32_t* pair_slot;  // [n_pairs] precomputed slot of every (partner, block) pair, or null
   // lower block (row fj, col fi): precomputed slot, else bisection in the row's sorted column list
   __device__ __forceinline__ int find(int fi, int fj) const {
@@ -419,7 +428,12 @@ struct PcgFinalizeArgs {
   const double* borderm;
   const double* rhsm;
   const double* HF;       // [n_f][NV]
-  const double* sigF;     // [6 n_f + 1]
+  const double* HFx;      // [n_f][NVX] pose x (l1, l2) terms of the radial model, or null
+  const double* borderx;  // [2][6 n_f] (SparseTarget::borderx), or null
+  int nk;                 // live intrinsics: 1 (focal) or 3 (radial model)
+  double* border1;        // [6 n_f] final S_f,l1
+  double* border2;        // [6 n_f] final S_f,l2
+  const double* sigF;     // [6 n_f + nk]
   const LmScalars* sc;
   const double* cam_minus;
   double radius, min_diag, max_diag;
@@ -427,7 +441,7 @@ struct PcgFinalizeArgs {
   double* Minv;
   double* border;         // [6 n_f] final S_f,cam
   double* rhs;            // [6 n_f + 1] final right-hand side
-  double* scal;           // [0] S_kk  [1] 1/S_kk  [3] fail
+  double* scal;           // [0] S_kk  [1] 1/S_kk  [3] fail; radial model: [4..9] the 3 x 3 intrinsics block (00 01 02 11 12 22), [10..15] its inverse
   double* partial;        // PcgWorkspace::partial (cleared here)
 };
 
@@ -461,6 +475,30 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __re
     a.scal[1] = 1.0 / skk;
     a.rhs[6 * (size_t)a.n_f] = sf * (a.sc->cam_g - a.cam_minus[6]);
     if (!(skk > 0.0) || a.cam_minus[9] != 0.0) a.scal[3] = 1.0;
+    if (a.nk == 3) {
+      // the damped 3 x 3 block of (f, l1, l2) as in dense_add_camera_kernel, and its inverse (adjugate) for the preconditioner
+      const double H[6] = {a.sc->cam_H, a.sc->H_f_l1, a.sc->H_f_l2, a.sc->H_l1_l1, a.sc->H_l1_l2, a.sc->H_l2_l2};
+      const double g[3] = {a.sc->cam_g, a.sc->g_l1, a.sc->g_l2};
+      const double sg[3] = {a.sc->sigma_f, a.sc->sigma_l1, a.sc->sigma_l2};
+      const int idx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+      double K[6];
+      for (int q = 0; q < 3; ++q) {
+        for (int p2 = q; p2 < 3; ++p2) {
+          double v = sg[q] * sg[p2] * (H[idx[q][p2]] - a.cam_minus[idx[q][p2]]);
+          if (p2 == q) v += fmin(fmax(sg[q] * sg[q] * H[idx[q][q]], a.min_diag), a.max_diag) / a.radius;
+          K[idx[q][p2]] = v;
+        }
+        a.rhs[6 * (size_t)a.n_f + q] = sg[q] * (g[q] - a.cam_minus[6 + q]);
+      }
+      const double c00 = K[3] * K[5] - K[4] * K[4], c01 = K[2] * K[4] - K[1] * K[5], c02 = K[1] * K[4] - K[2] * K[3];
+      const double det = K[0] * c00 + K[1] * c01 + K[2] * c02;
+      const double m2 = K[0] * K[3] - K[1] * K[1];
+      if (!(K[0] > 0.0) || !(m2 > 0.0) || !(det > 0.0)) a.scal[3] = 1.0;
+      const double id = 1.0 / det;
+      for (int q = 0; q < 6; ++q) a.scal[4 + q] = K[q];
+      a.scal[10] = c00 * id; a.scal[11] = c01 * id; a.scal[12] = c02 * id;
+      a.scal[13] = (K[0] * K[5] - K[2] * K[2]) * id; a.scal[14] = (K[1] * K[2] - K[0] * K[4]) * id; a.scal[15] = m2 * id;
+    }
   }
   if (row >= a.n_f) return;
   double sr[6];
@@ -472,6 +510,11 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __re
   for (int i = 0; i < 6; ++i) {
     a.border[6 * (size_t)row + i] = sr[i] * scam * (rec[27 + i] - a.borderm[6 * (size_t)row + i]);
     a.rhs[6 * (size_t)row + i] = sr[i] * (rec[21 + i] - a.rhsm[6 * (size_t)row + i]);
+    if (a.nk == 3) {
+      const double* rx = a.HFx + (size_t)row * NVX;
+      a.border1[6 * (size_t)row + i] = sr[i] * a.sigF[6 * (size_t)a.n_f + 1] * (rx[i] - a.borderx[6 * (size_t)row + i]);
+      a.border2[6 * (size_t)row + i] = sr[i] * a.sigF[6 * (size_t)a.n_f + 2] * (rx[6 + i] - a.borderx[6 * (size_t)(a.n_f + row) + i]);
+    }
   }
   const int s = diag_slot[row];
   const double* src = a.Sraw + 36 * (size_t)a.src_slot[s];
@@ -509,7 +552,9 @@ struct PcgArgs {
   const double* S;       // [nnzb][36]
   const double* Minv;    // [n_f][36]
   const double* border;  // [6 n_f]
-  const double* rhs;     // [6 n_f + 1]
+  const double* border1; // [6 n_f] l1, l2 columns (radial model: pcg_kernel<3>)
+  const double* border2;
+  const double* rhs;     // [6 n_f + nk]
   double* x;             // [6 n_f + 1] out
   double* r;
   double* z;
@@ -535,6 +580,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define PCG_TRACE(slot) do { if (a.trace && threadIdx.x == 0 && it <= 64) a.trace[((size_t)(it - 1) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); } while (0)
 
 // deterministic grid-wide sums: every CTA adds the same numbers in the same order
+constexpr int kGsOff = 32 * 4;         // NS <= 4: warp partials in sm[0 .. 128), the second stage behind them
+constexpr int kGsSmem = 2 * kGsOff;
 template <int NS>
 __device__ __forceinline__ void grid_sums(cg::grid_group& grid, double (&v)[NS], double* partial_base, double* sm, int& parity) {
   // two alternating partial buffers: a CTA may start the next reduction while a slower one still reads this one
@@ -566,28 +613,42 @@ __device__ __forceinline__ void grid_sums(cg::grid_group& grid, double (&v)[NS],
     for (int i = 0; i < NS; ++i) acc[i] = warp_sum(acc[i]);
     if (lane == 0)
 #pragma unroll
-      for (int i = 0; i < NS; ++i) sm[64 + wid * NS + i] = acc[i];
+      for (int i = 0; i < NS; ++i) sm[kGsOff + wid * NS + i] = acc[i];
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     double t = 0.0;
-    for (int w = 0; w < nwarp_used; ++w) t += sm[64 + w * NS + i];
+    for (int w = 0; w < nwarp_used; ++w) t += sm[kGsOff + w * NS + i];
     v[i] = t;
   }
   __syncthreads();
 }
 
 
+// NK = live intrinsics: 1 (focal: the scalar S_kk) or 3 (radial model: the 3 x 3 block of f, l1, l2 and three border columns)
+template <int NK>
 __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[64 + 32 * 2 + 8];
+  __shared__ double sm[kGsSmem];
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * kPcgThreads + threadIdx.x) >> 5, nw = (gridDim.x * kPcgThreads) >> 5;
   const int g = lane >> 3, rr_ = lane & 7;  // 4 block groups x 8 lanes (6 active rows)
   const bool act = rr_ < 6;
   const int n_f = a.n_f, camrow = 6 * n_f;
-  const double skk = a.scal[0], iskk = a.scal[1];
+  // intrinsics block K (symmetric) and its inverse Ki
+  double K[NK][NK], Ki[NK][NK];
+  if (NK == 1) {
+    K[0][0] = a.scal[0];
+    Ki[0][0] = a.scal[1];
+  } else {
+    const int idx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+    for (int q = 0; q < NK; ++q)
+#pragma unroll
+      for (int p2 = 0; p2 < NK; ++p2) { K[q][p2] = a.scal[4 + idx[q][p2]]; Ki[q][p2] = a.scal[10 + idx[q][p2]]; }
+  }
+  const double* bcol[3] = {a.border, a.border1, a.border2};
   const bool is_cam_owner = (blockIdx.x == 0 && threadIdx.x == 0);
   int parity = 0;
 
@@ -612,10 +673,18 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
     }
   }
   if (is_cam_owner) {
-    const double rv = a.rhs[camrow], zv = rv * iskk;
-    a.x[camrow] = 0.0; a.r[camrow] = rv; a.z[camrow] = zv; a.p0[camrow] = 0.0;
-    s2[0] += rv * zv;
-    s2[1] += rv * rv;
+    double rv[NK];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) rv[q] = a.rhs[camrow + q];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+      double zv = 0.0;
+#pragma unroll
+      for (int p2 = 0; p2 < NK; ++p2) zv += Ki[q][p2] * rv[p2];
+      a.x[camrow + q] = 0.0; a.r[camrow + q] = rv[q]; a.z[camrow + q] = zv; a.p0[camrow + q] = 0.0;
+      s2[0] += rv[q] * zv;
+      s2[1] += rv[q] * rv[q];
+    }
   }
   grid_sums<2>(grid, s2, a.partial, sm, parity);
   double rz = s2[0];
@@ -632,9 +701,13 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
   }
   while (it < a.max_iter) {
     ++it;
-    // ---- phase A: p_new = z + beta p_old ; q = S p_new ; sums: p.q and the camera row of q
-    double sa[2] = {0.0, 0.0};
-    const double pk = a.z[camrow] + beta * p_old[camrow];
+    // ---- phase A: p_new = z + beta p_old ; q = S p_new ; sums: p.q and the intrinsics rows of q
+    double sa[1 + NK];
+#pragma unroll
+    for (int q = 0; q <= NK; ++q) sa[q] = 0.0;
+    double pk[NK];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) pk[q] = a.z[camrow + q] + beta * p_old[camrow + q];
     for (int f = gw; f < n_f; f += nw) {
       double acc = 0.0, acc2 = 0.0;
       const int s0 = a.row_ptr[f], s1 = a.row_ptr[f + 1];
@@ -665,17 +738,28 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
       if (lane < 6) {
         const double pf = a.z[6 * (size_t)f + lane] + beta * p_old[6 * (size_t)f + lane];
-        const double bd = a.border[6 * (size_t)f + lane];
-        const double qf = acc + bd * pk;
+        double qf = acc;
+#pragma unroll
+        for (int q = 0; q < NK; ++q) {
+          const double bd = bcol[q][6 * (size_t)f + lane];
+          qf += bd * pk[q];
+          sa[1 + q] += bd * pf;
+        }
         p_new[6 * (size_t)f + lane] = pf;
         a.q[6 * (size_t)f + lane] = qf;
         sa[0] += pf * qf;
-        sa[1] += bd * pf;
       }
     }
-    grid_sums<2>(grid, sa, a.partial, sm, parity);
-    const double qk = sa[1] + skk * pk;
-    const double pq = sa[0] + pk * qk;
+    grid_sums<1 + NK>(grid, sa, a.partial, sm, parity);
+    double qk[NK];
+    double pq = sa[0];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+      qk[q] = sa[1 + q];
+#pragma unroll
+      for (int p2 = 0; p2 < NK; ++p2) qk[q] += K[q][p2] * pk[p2];
+      pq += pk[q] * qk[q];
+    }
     if (!(pq > 0.0) || !isfinite(pq)) { fail = true; break; }
     const double alpha = rz / pq;
     // ---- phase B: x += alpha p ; r -= alpha q ; z = M^-1 r ; sums: r.z, r.r
@@ -701,14 +785,23 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
       }
     }
     if (is_cam_owner) {
-      p_new[camrow] = pk;
-      a.x[camrow] += alpha * pk;
-      const double rv = a.r[camrow] - alpha * qk;
-      a.r[camrow] = rv;
-      const double zv = rv * iskk;
-      a.z[camrow] = zv;
-      sb[0] += rv * zv;
-      sb[1] += rv * rv;
+      double rv[NK];
+#pragma unroll
+      for (int q = 0; q < NK; ++q) {
+        p_new[camrow + q] = pk[q];
+        a.x[camrow + q] += alpha * pk[q];
+        rv[q] = a.r[camrow + q] - alpha * qk[q];
+        a.r[camrow + q] = rv[q];
+      }
+#pragma unroll
+      for (int q = 0; q < NK; ++q) {
+        double zv = 0.0;
+#pragma unroll
+        for (int p2 = 0; p2 < NK; ++p2) zv += Ki[q][p2] * rv[p2];
+        a.z[camrow + q] = zv;
+        sb[0] += rv[q] * zv;
+        sb[1] += rv[q] * rv[q];
+      }
     }
     grid_sums<2>(grid, sb, a.partial, sm, parity);
     beta = sb[0] / rz;
@@ -718,7 +811,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_kernel(const PcgArgs a) {
     if (!isfinite(sb[1])) { fail = true; break; }
   }
   // unscaled step for the LM loop (x is complete: the loop leaves through a grid-wide sum)
-  for (int i = blockIdx.x * kPcgThreads + threadIdx.x; i <= camrow; i += gridDim.x * kPcgThreads) a.uF[i] = a.sigF[i] * a.x[i];
+  for (int i = blockIdx.x * kPcgThreads + threadIdx.x; i < camrow + NK; i += gridDim.x * kPcgThreads) a.uF[i] = a.sigF[i] * a.x[i];
   if (is_cam_owner) {
     a.scal[2] = (double)it;
     if (fail) a.scal[3] = 1.0;

@@ -225,8 +225,6 @@ def bench_options(ar, iters, args, linear_solver=None, num_intrinsics=None, pcg_
         o.linear_solver = ar.LINSOLVE_PCG
     o.pcg_tolerance = args.pcg_tolerance if pcg_tolerance is None else pcg_tolerance
     o.num_intrinsics = num_intrinsics
-    if num_intrinsics == 3 and linear_solver == "auto":
-        o.dense_max_dim = 1 << 20   # the radial model is solved with the dense Cholesky
     return o
 
 
@@ -683,7 +681,10 @@ def main():
             # the other BASELINE configurations, short runs, so that one invocation witnesses them all
             ex = {}
             ex["ba_1k_200"] = short(bench_ba(ctx, "ba_1k_200", 40, 10, e2e=True, clocks=False, converge=True))
-            ex["ba_20k_2k_radial_dense"] = short(bench_ba(ctx, "ba_20k_2k", 5, 3, num_intrinsics=3, e2e=False, clocks=False))
+            ex["ba_20k_2k_radial_dense"] = short(bench_ba(ctx, "ba_20k_2k", 5, 3, linear_solver="dense", num_intrinsics=3, e2e=False, converge=True,
+                                                          clocks=False))
+            ex["ba_20k_2k_radial_pcg"] = short(bench_ba(ctx, "ba_20k_2k", 20, 5, linear_solver="pcg", num_intrinsics=3, e2e=False,
+                                                        clocks=False, converge=True))
             ex["loc_1m_5k"] = short(bench_localization(ctx, "loc_1m_5k", 3, 2, cpu=False, clocks=False))
             line["extra_workloads"] = ex
     if ctx.rank == 0:

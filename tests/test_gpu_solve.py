@@ -269,7 +269,8 @@ def test_radial_model_trajectory(gpu_solver_cls, oracle, elim):
     m = _radial_map(oracle, 400, 100, seed=21)
     cam_o, cap_o, tag_o, so, log_o = oracle.solve(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs, m.cam0, m.cap0,
                                                   m.tag0, options=oracle.default_options(num_threads=4), model=1)
-    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, elimination=elim))
+    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, elimination=elim,
+                                                             linear_solver=ar_slam_b200.LINSOLVE_DENSE))
     s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
     s.set_params(m.cam0, m.cap0, m.tag0)
     sg, log_g = s.solve()
@@ -294,16 +295,31 @@ def test_radial_model_trajectory(gpu_solver_cls, oracle, elim):
     assert s1["final_cost"] > 1.5 * sg["final_cost"]
 
 
-def test_radial_model_rejects_pcg(gpu_solver_cls):
+@pytest.mark.parametrize("elim", [1, 2])
+def test_radial_model_pcg_matches_dense(gpu_solver_cls, oracle, elim):
+    """The radial model on the sparse path: three border columns (f, l1, l2) and a 3 x 3 intrinsics block in the
+    block-sparse reduced system (SparseTarget::add_border_x, pcg_finalize_kernel, pcg_kernel<3>).  Solved tightly it
+    walks the dense Cholesky trajectory."""
     import ar_slam_b200
-    from ar_slam_b200 import synth
-    m = synth.make_map(100, 40, seed=3)
-    s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, linear_solver=ar_slam_b200.LINSOLVE_PCG))
-    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
-    s.set_params(m.cam0, m.cap0, m.tag0)
-    with pytest.raises(ar_slam_b200.ArslamError):
-        s.solve()
-    s.close()
+    m = _radial_map(oracle, 1200, 300, seed=29)
+    res = {}
+    for name, ls in (("dense", ar_slam_b200.LINSOLVE_DENSE), ("pcg", ar_slam_b200.LINSOLVE_PCG)):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, elimination=elim, linear_solver=ls,
+                                                                 pcg_tolerance=1e-12, pcg_max_iterations=3000))
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        summ, log = s.solve()
+        res[name] = (summ, log, s.get_params())
+        s.close()
+    (sd, ld, pd), (sp, lp, pp) = res["dense"], res["pcg"]
+    assert sp["linear_solver"] == ar_slam_b200.LINSOLVE_PCG and sp["linear_solver_iterations"] > 0
+    assert sd["termination"] == sp["termination"] == 0
+    assert sp["iterations"] == sd["iterations"]
+    assert np.allclose(lp[:, 0], ld[:, 0], rtol=1e-8)
+    assert np.allclose(lp[1:, 3], ld[1:, 3], rtol=1e-5)
+    assert np.abs(pp[0] - pd[0]).max() <= 1e-7 * max(1.0, np.abs(pd[0]).max())
+    assert np.abs(pp[1] - pd[1]).max() < 1e-6 and np.abs(pp[2] - pd[2]).max() < 1e-6
+    assert abs(pp[0][1] - 0.08) < 0.02
 
 
 def test_parameter_round_trip_and_continued_solve(gpu_solver_cls):
