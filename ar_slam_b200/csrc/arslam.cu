@@ -1144,7 +1144,8 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   a.sigF = s->sigF.p; a.uF = s->uF.p; a.sc = const_cast<double*>(sc);
   sa.cta_row = w.cta_row; sa.halo_ptr = w.halo_ptr; sa.halo_col = w.halo_col; sa.lcol = w.lcol;
   sa.cap_slots = w.cap_slots; sa.max_halo = w.max_halo; sa.max_slots = w.max_slots; sa.max_rows = w.max_rows;
-  const bool use_smem = w.smem_ok && s->tune_pcg_smem && nk == 1;  // (the radial model's three intrinsics: pcg_kernel<3>)
+  const bool smem_fits = w.smem_ok && s->tune_pcg_smem;
+  const bool use_smem = smem_fits && nk == 1;  // the classic shared-memory kernel knows the focal-only border
   void* args_g[] = {(void*)&a};
   void* args_s[] = {(void*)&sa};
   Profiler::Rec r{0, nullptr, nullptr};
@@ -1154,9 +1155,11 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   }
   // one barrier per iteration for the inexact-Newton tolerances; the classic recurrence when the
   // system is to be solved tightly (its attainable accuracy is higher)
-  const bool pipelined = use_smem && (s->opt.pcg_tolerance >= 1e-6 || s->opt.pcg_q_tolerance > 0.0) && s->tune_pcg_pipelined;
+  // (radial model: pcg_pipe_kernel<3>, or pcg_kernel<3> for the tight solves)
+  const bool pipelined = smem_fits && (s->opt.pcg_tolerance >= 1e-6 || s->opt.pcg_q_tolerance > 0.0) && s->tune_pcg_pipelined;
   if (pipelined)
-    CU(cudaLaunchCooperativeKernel((void*)pcg_pipe_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
+    CU(cudaLaunchCooperativeKernel(nk == 3 ? (void*)pcg_pipe_kernel<3> : (void*)pcg_pipe_kernel<1>, dim3(w.smem_grid), dim3(kPcgThreads), args_s,
+                                   w.smem_bytes, s->stream));
   else if (use_smem)
     CU(cudaLaunchCooperativeKernel((void*)pcg_smem_kernel, dim3(w.smem_grid), dim3(kPcgThreads), args_s, w.smem_bytes, s->stream));
   else

@@ -1089,11 +1089,16 @@ __device__ __forceinline__ double reduce6_halving(const double (&ac)[6], int lan
 // 0..5 hold the warp's first row, lanes 8..13 its second, lane 16 of CTA 0 / warp 0 the camera
 // scalar.  Rounding differs from the classic recurrence and the attainable accuracy is lower,
 // so the host picks this kernel for inexact-Newton tolerances only (pcg_tolerance >= 1e-6).
+// NK = 1: the focal length; NK = 3: f, l1, l2 of the radial model in lanes 16..18, their 3 x 3 block and its inverse in
+// shared memory, three border columns (one register each per row lane), three border dots among the fused sums.
+template <int NK>
 __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemArgs A) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ double sm[(kPcgWarps + 1) * 6 + 12];
-  constexpr int kVk = (kPcgWarps + 1) * 6 + 4;  // camera component of the gathered vector; S_kk, 1 / S_kk next to it
+  constexpr int NSUM = 5 + NK;  // r.u  w.u  r.r  x.b  x.r | b_q.m
+  constexpr int kVk = (kPcgWarps + 1) * NSUM + 4;  // intrinsics components of the gathered vector (NK); then K (9) and K^-1 (9)
+  constexpr int kKm = kVk + 4, kKi = kKm + 9;
+  __shared__ double sm[kKi + 9];
   const PcgArgs& a = A.a;
   double* Ss = reinterpret_cast<double*>(dyn);                       // [cap_slots][36]
   double* xs = Ss + (size_t)A.cap_slots * 36;                        // [max_halo][6]
@@ -1109,7 +1114,13 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
   const int s_beg = a.row_ptr[r0], s_end = a.row_ptr[r1];
   const int nslot = s_end - s_beg, ncache = min(nslot, A.cap_slots);
   const int h0 = A.halo_ptr[blockIdx.x], nhalo = A.halo_ptr[blockIdx.x + 1] - h0;
-  if (tid == 0) { sm[kVk + 1] = a.scal[0]; sm[kVk + 2] = a.scal[1]; }
+  if (tid < 9) {
+    // the intrinsics block and its inverse, row-major 3 x 3 (NK = 1: element 0 only)
+    const int q = tid / 3, p2 = tid - 3 * q;
+    const int sym = q <= p2 ? (q == 0 ? p2 : q + p2 + 1) : (p2 == 0 ? q : q + p2 + 1);  // 00 01 02 11 12 22
+    sm[kKm + tid] = NK == 1 ? (tid == 0 ? a.scal[0] : 0.0) : a.scal[4 + sym];
+    sm[kKi + tid] = NK == 1 ? (tid == 0 ? a.scal[1] : 0.0) : a.scal[10 + sym];
+  }
   int round = 0;
   {
     const double* src = a.S + 36 * (size_t)s_beg;
@@ -1124,16 +1135,21 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
     for (int i = tid; i < nrow * 6; i += kPcgThreads) bs[i] = a.border[6 * (size_t)r0 + i];
   }
   __syncthreads();
-  const double skk = sm[kVk + 1], iskk = sm[kVk + 2];
   const int lrA = wid, lrB = wid + 32;
   const bool hasA = lrA < nrow, hasB = lrB < nrow;
   const bool isA = hasA && lane < 6, isB = hasB && lane >= 8 && lane < 14;
-  const bool isK = blockIdx.x == 0 && wid == 0 && lane == 16;
+  const bool isK = blockIdx.x == 0 && wid == 0 && lane >= 16 && lane < 16 + NK;
+  const int kq = isK ? lane - 16 : 0;
   const bool isRow = isA || isB, owner = isRow || isK;
   const int comp = isB ? lane - 8 : (lane < 6 ? lane : 0);
   const int lrow = isB ? lrB : lrA;
-  const size_t gi = isK ? (size_t)camrow : 6 * (size_t)(r0 + lrow) + comp;
-  const double bd = isRow ? bs[6 * lrow + comp] : 0.0;
+  const size_t gi = isK ? (size_t)(camrow + kq) : 6 * (size_t)(r0 + lrow) + comp;
+  double bd[NK];
+  bd[0] = isRow ? bs[6 * lrow + comp] : 0.0;
+  if (NK == 3) {
+    bd[1] = isRow ? a.border1[gi] : 0.0;
+    bd[2] = isRow ? a.border2[gi] : 0.0;
+  }
 
   auto precond = [&](double v) {  // M^-1 v: the row's inverse diagonal block, 1 / S_kk for the camera
     double o = 0.0;
@@ -1143,12 +1159,17 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
       if (isA) o += Ms[36 * lrA + lane * 6 + c] * va;
       else if (isB) o += Ms[36 * lrB + (lane - 8) * 6 + c] * vb;
     }
-    if (isK) o = v * iskk;
+    if (NK == 1) {
+      if (isK) o = v * sm[kKi];
+    } else {
+      const double v0 = __shfl_sync(0xffffffffu, v, 16), v1 = __shfl_sync(0xffffffffu, v, 17), v2 = __shfl_sync(0xffffffffu, v, 18);
+      if (isK) o = sm[kKi + 3 * kq] * v0 + sm[kKi + 3 * kq + 1] * v1 + sm[kKi + 3 * kq + 2] * v2;
+    }
     return o;
   };
   // halo of `buf` -> xs, camera component -> sm[kVk]
   auto gather = [&](const double* buf) {
-    if (tid == 0) sm[kVk] = __ldcg(buf + camrow);
+    if (tid < NK) sm[kVk + tid] = __ldcg(buf + camrow + tid);
     for (int i = tid; i < nhalo * 6; i += kPcgThreads) {
       const int h = i / 6, k = i - h * 6;
       xs[i] = __ldcg(buf + 6 * (size_t)hc[h] + k);
@@ -1156,8 +1177,10 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
     __syncthreads();
   };
   // this lane's component of A v, v gathered in xs / sm[kVk]; bv = b . v over all rows
-  auto product = [&](double bv) {
-    const double vk = sm[kVk];
+  auto product = [&](const double* bv) {  // bv[q] = b_q . v
+    double vk[NK];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) vk[q] = sm[kVk + q];
     double res = 0.0;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
@@ -1181,9 +1204,17 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
       }
       const double tot = reduce6_halving(ac, lane);
       const double mine = __shfl_sync(0xffffffffu, tot, (4 * (which == 0 ? lane : lane - 8)) & 31);
-      if (which == 0 ? isA : isB) res = mine + bd * vk;
+      if (which == 0 ? isA : isB) {
+        res = mine;
+#pragma unroll
+        for (int q = 0; q < NK; ++q) res += bd[q] * vk[q];
+      }
     }
-    if (isK) res = bv + skk * vk;
+    if (isK) {
+      res = bv[kq];
+#pragma unroll
+      for (int q = 0; q < NK; ++q) res += sm[kKm + 3 * kq + q] * vk[q];
+    }
     return res;
   };
 
@@ -1195,30 +1226,36 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
   double Q_prev = 0.0;      // Q(x) = x'Ax - 2 b'x = -x.(b + r); Q(0) = 0
   u = precond(r);
   if (owner) buf[0][gi] = u;
-  double s2[2] = {isRow ? bd * u : 0.0, owner ? r * r : 0.0};
-  grid_sums_atomic<2>(grid, s2, a.partial, sm, round);
-  const double bb = s2[1];
+  double s2[1 + NK];
+  s2[0] = owner ? r * r : 0.0;
+#pragma unroll
+  for (int q = 0; q < NK; ++q) s2[1 + q] = isRow ? bd[q] * u : 0.0;
+  grid_sums_atomic<1 + NK>(grid, s2, a.partial, sm, round);
+  const double bb = s2[0];
   const double thresh = a.tol * a.tol * bb;
   bool fail = !(bb >= 0.0) || !isfinite(bb);
   int it = 0;
   if (!(bb == 0.0 || fail)) {
     gather(buf[0]);
-    w = product(s2[0]);
+    w = product(s2 + 1);
     double gamma_prev = 1.0, alpha_prev = 1.0;
     while (it < a.max_iter) {
       const double m = precond(w);
       double* mb = buf[(it + 1) & 1];
       if (owner) mb[gi] = m;
-      double sv[6] = {owner ? r * u : 0.0, owner ? w * u : 0.0, owner ? r * r : 0.0, isRow ? bd * m : 0.0,
-                      owner ? x * b0 : 0.0, owner ? x * r : 0.0};
-      grid_sums_atomic<6>(grid, sv, a.partial, sm, round);
+      double sv[NSUM];
+      sv[0] = owner ? r * u : 0.0; sv[1] = owner ? w * u : 0.0; sv[2] = owner ? r * r : 0.0;
+      sv[3] = owner ? x * b0 : 0.0; sv[4] = owner ? x * r : 0.0;
+#pragma unroll
+      for (int kq2 = 0; kq2 < NK; ++kq2) sv[5 + kq2] = isRow ? bd[kq2] * m : 0.0;
+      grid_sums_atomic<NSUM>(grid, sv, a.partial, sm, round);
       const double gamma = sv[0], delta = sv[1];
       if (!isfinite(sv[2])) { fail = true; break; }
       if (sv[2] <= thresh) break;
       if (a.q_tol > 0.0 && it >= 1) {
         // Ceres' ConjugateGradientsSolver rule, the one its trust-region strategies use for inexact steps
         // (q_tolerance = eta, r_tolerance off): stop when zeta = i (Q_i - Q_{i-1}) / Q_i < q_tolerance
-        const double Q = -(sv[4] + sv[5]);
+        const double Q = -(sv[3] + sv[4]);
         const double zeta = (double)it * (Q - Q_prev) / Q;
         Q_prev = Q;
         if (zeta < a.q_tol) break;
@@ -1234,7 +1271,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
         alpha = gamma / den;
       }
       gather(mb);
-      const double n = product(sv[3]);
+      const double n = product(sv + 5);
       z = n + beta * z;
       q = m + beta * q;
       s_ = w + beta * s_;
@@ -1258,8 +1295,9 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_pipe_kernel(const PcgSmemA
 }
 
 inline cudaError_t pcg_init() {
-  cudaError_t e = cudaFuncSetAttribute(pcg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(pcg_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  cudaError_t e = cudaFuncSetAttribute(pcg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pcg_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pcg_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
   return e;
 }
 

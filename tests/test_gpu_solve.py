@@ -303,9 +303,10 @@ def test_radial_model_pcg_matches_dense(gpu_solver_cls, oracle, elim):
     import ar_slam_b200
     m = _radial_map(oracle, 1200, 300, seed=29)
     res = {}
-    for name, ls in (("dense", ar_slam_b200.LINSOLVE_DENSE), ("pcg", ar_slam_b200.LINSOLVE_PCG)):
+    for name, ls, tol in (("dense", ar_slam_b200.LINSOLVE_DENSE, 0.1), ("pcg", ar_slam_b200.LINSOLVE_PCG, 1e-12),
+                          ("pipelined", ar_slam_b200.LINSOLVE_PCG, 1e-6)):
         s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, elimination=elim, linear_solver=ls,
-                                                                 pcg_tolerance=1e-12, pcg_max_iterations=3000))
+                                                                 pcg_tolerance=tol, pcg_max_iterations=3000))
         s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
         s.set_params(m.cam0, m.cap0, m.tag0)
         summ, log = s.solve()
@@ -320,6 +321,11 @@ def test_radial_model_pcg_matches_dense(gpu_solver_cls, oracle, elim):
     assert np.abs(pp[0] - pd[0]).max() <= 1e-7 * max(1.0, np.abs(pd[0]).max())
     assert np.abs(pp[1] - pd[1]).max() < 1e-6 and np.abs(pp[2] - pd[2]).max() < 1e-6
     assert abs(pp[0][1] - 0.08) < 0.02
+    # the one-barrier kernel (pcg_pipe_kernel<3>, chosen for pcg_tolerance >= 1e-6) reaches the same minimum
+    sq, lq, pq = res["pipelined"]
+    assert sq["termination"] == 0 and abs(sq["iterations"] - sd["iterations"]) <= 1
+    assert abs(sq["final_cost"] - sd["final_cost"]) <= 1e-6 * sd["final_cost"]
+    assert np.abs(pq[0] - pd[0]).max() <= 1e-4 * max(1.0, np.abs(pd[0]).max())
 
 
 def test_parameter_round_trip_and_continued_solve(gpu_solver_cls):
