@@ -26,10 +26,13 @@ def fresh_uid():
 
 ok = True
 # "few-captures": every rank misses some of the tags, which must move all the same
+# "radial-*": the three-intrinsics model (f, l1, l2); its border columns travel in the same allreduce
 for name, ls, (nc, nt) in (("dense", ar.LINSOLVE_DENSE, (3000, 400)), ("pcg", ar.LINSOLVE_PCG, (20000, 1500)),
-                           ("few-captures", ar.LINSOLVE_DENSE, (40 * world, 200))):
-    m = synth.make_map(nc, nt, seed=31)
-    opts = ar.default_options(linear_solver=ls, pcg_tolerance=1e-10, pcg_max_iterations=3000)
+                           ("few-captures", ar.LINSOLVE_DENSE, (40 * world, 200)),
+                           ("radial-dense", ar.LINSOLVE_DENSE, (3000, 400)), ("radial-pcg", ar.LINSOLVE_PCG, (8000, 900))):
+    radial = name.startswith("radial")
+    m = synth.make_map(nc, nt, seed=31, distortion=(-0.05, 0.01) if radial else (0.0, 0.0))
+    opts = ar.default_options(linear_solver=ls, pcg_tolerance=1e-10, pcg_max_iterations=3000, num_intrinsics=3 if radial else 1)
     s = ar.Solver(device=local, options=opts)
     s.comm_init(rank, world, fresh_uid())
     ci, ti, ob = bench.shard(m, rank, world)

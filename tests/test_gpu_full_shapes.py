@@ -154,12 +154,17 @@ def numpy_radial_first_step(oracle, m, radius=1e4):
     return cost_o, -sk * yF[6 * nt:], -sc * yc, -st * yF[:6 * nt].reshape(nt, 6)
 
 
-def test_config5_radial_first_step_at_full_shape(gpu_solver_cls, oracle):
+@pytest.mark.parametrize("solver", ["dense", "pcg"])
+def test_config5_radial_first_step_at_full_shape(gpu_solver_cls, oracle, solver):
+    """Config 5 at its full shape, first LM step of the radial model: the dense DMMA Cholesky and the block-sparse
+    system with three border columns solved tightly by PCG, both against a scipy solve of the same Schur complement."""
     import ar_slam_b200
     from ar_slam_b200 import synth
     m = synth.make_map(20000, 2000, 8, seed=0xA55A0005, distortion=(-0.05, 0.01))
     cost_o, d_cam, d_cap, d_tag = numpy_radial_first_step(oracle, m)
+    ls = ar_slam_b200.LINSOLVE_DENSE if solver == "dense" else ar_slam_b200.LINSOLVE_PCG
     s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, max_num_iterations=1, dense_max_dim=1 << 20,
+                                                             linear_solver=ls, pcg_tolerance=1e-13, pcg_max_iterations=5000,
                                                              function_tolerance=0.0, parameter_tolerance=0.0))
     s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
     s.set_params(m.cam0, m.cap0, m.tag0)
@@ -168,7 +173,7 @@ def test_config5_radial_first_step_at_full_shape(gpu_solver_cls, oracle):
     summ, log = s.solve()
     cam, cap, tag = s.get_params()
     s.close()
-    assert summ["linear_solver"] == ar_slam_b200.LINSOLVE_DENSE and summ["reduced_dim"] == 12003
+    assert summ["linear_solver"] == ls and summ["reduced_dim"] == 12003
     assert summ["iterations"] == 1 and summ["num_successful_steps"] == 2
     scale = max(np.abs(d_cap).max(), np.abs(d_tag).max())
     assert np.abs((cap - m.cap0) - d_cap).max() <= 1e-7 * scale
