@@ -68,8 +68,8 @@ typedef struct arslam_options {
   int32_t num_intrinsics;                    /* 1: focal only (the reference's live model,
                                                 ar_slam_util.cpp:160-162, l1 / l2 inert);
                                                 3: focal + l1 + l2 of the radial TODO model
-                                                (:164-171), evaluation, localisation and the
-                                                dense-Cholesky solve (PCG: ARSLAM_ERR_UNSUPPORTED) */
+                                                (:164-171): evaluation, localisation and the LM
+                                                solve with either linear solver */
   int32_t verbose;                           /* 0; 1 prints the per-iteration table like
                                                 minimizer_progress_to_stdout (:1012)          */
   double initial_trust_region_radius;        /* 1e4   */
@@ -274,7 +274,11 @@ int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch wit
  * reduction per product); "loc_chunk" (captures per chunk of arslam_localize_batch's upload / kernel / download pipeline, 0:
  * default 131072); "pcg_smem" (1: the PCG kernels that keep the
  * reduced matrix in shared memory, default); "pcg_pipelined" (1: one-barrier pipelined recurrence for
- * pcg_tolerance >= 1e-6, default; 0: always the classic two-barrier recurrence).
+ * pcg_tolerance >= 1e-6, default; 0: always the classic two-barrier recurrence);
+ * dense Cholesky: "chol_big" (1: asynchronous trailing update -- cp.async operand stream across tiles, C through TMA
+ * bulk reductions, default; 0: the synchronous round-1 kernel), "chol_chain" (1: back-substitution as one chained
+ * cooperative launch, default; 0: one launch per 64-block), "chol_nb" (outer panel width, default 256),
+ * "chol_free_sms" (SMs the persistent trailing update leaves to the factorisation chain, default 8).
  * Unknown key: ARSLAM_ERR_INVALID. */
 int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value);
 int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap); /* returns rows */
