@@ -722,7 +722,7 @@ struct CandArgs {
   double* out;             // [1]
 };
 template <int SIDE, int MODEL>
-__global__ void __launch_bounds__(256) candidate_kernel(const CandArgs a) {
+__global__ void __launch_bounds__(256, 4) candidate_kernel(const CandArgs a) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   double c2 = 0.0;
   if (pos < a.n_blk) {

@@ -127,7 +127,7 @@ __device__ __forceinline__ void loc_normal_eq(const LocArgs& a, int b0, int nb, 
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(128) localize_kernel(const LocArgs a) {
+__global__ void __launch_bounds__(128, 3) localize_kernel(const LocArgs a) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int cap = gid / kLocGroup;
   const int lane = threadIdx.x & 31, gl = lane & (kLocGroup - 1);

@@ -562,7 +562,9 @@ __device__ __forceinline__ void store_tag_prep(const double pose[6], double tag_
     for (int k = 0; k < 6; ++k) c[k] = make_double2(w[2 * k], w[2 * k + 1]);
   }
 }
-__global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
+// Six CTAs per SM (80 registers, a few spilled doubles): the kernel is a chain of dependent loads per pose, so
+// resident warps count for more than registers (4 CTAs at 128 registers: 125 us, 6 at 80: 105 us, 8 at 64: 125 us).
+__global__ void __launch_bounds__(128, 6) backsub_kernel(const BacksubArgs a) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int slot = gid / kBsGroup, gl = gid % kBsGroup;
   const bool valid = slot < a.sa.n_e;
@@ -570,12 +572,9 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   const int e = valid ? (a.e_order ? a.e_order[slot] : slot) : 0;
   const int beg = valid ? a.sa.e_off[e] : 0, k = valid ? a.sa.e_end[e] - beg : 0;
   double L[36], zt[6], hk[6], s[6];
-  if (k > 0) {
-    load_scaled_E(a.sa, e, L, zt, hk, s);
-    chol6(L);
-  }
   const size_t ps = a.sa.plane;
   double t[6] = {0, 0, 0, 0, 0, 0};
+  // the 36 W loads of a block are in flight before the pose record is fetched and factored
   for (int j = gl; j < k; j += kBsGroup) {
     const int blk = beg + j;
     const int f = a.sa.f_idx[blk];
@@ -586,6 +585,10 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
     for (int i = 0; i < 6; ++i)
 #pragma unroll
       for (int c = 0; c < 6; ++c) t[i] += a.sa.W[(size_t)(i * 6 + c) * ps + blk] * u[c];
+  }
+  if (k > 0) {
+    load_scaled_E(a.sa, e, L, zt, hk, s);
+    chol6(L);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) t[i] = group_sum(t[i]);
