@@ -278,6 +278,7 @@ struct arslam_solver {
   int cur = 0;
   // normal equations
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
+  DevBuf<int> check3;  // store_blocks: first bad block, capture range
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red, tri;  // tri: packed lower region of the dense system (multi-GPU sum)  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
   DenseCholesky::LookAhead lookahead;  // second stream + events of the dense factorisation
@@ -543,25 +544,49 @@ int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap) 
 namespace {
 
 // validates blocks [first, first + n_new) and moves them into the original-order arrays
+// range check of freshly uploaded indices + the capture range they span: out[0] = first bad block (or INT_MAX), out[1] / out[2] = min / max capture
+__global__ void validate_blocks_kernel(int n, const int32_t* __restrict__ cap, const int32_t* __restrict__ tag, int n_cap, int n_tag, int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0x7fffffff, lo = 0x7fffffff, hi = -1;
+  if (b < n) {
+    const int c = cap[b], t = tag[b];
+    if (c < 0 || c >= n_cap || t < 0 || t >= n_tag) bad = b;
+    lo = hi = c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad != 0x7fffffff) atomicMin(out, bad);
+    atomicMin(out + 1, lo);
+    atomicMax(out + 2, hi);
+  }
+}
+
+// Uploads blocks [first, first + n_new) and validates them ON THE DEVICE (a serial host loop over 800 k blocks cost
+// 0.6 ms per call at config 3).  The stream is drained before an error is returned, so no copy is left reading the
+// caller's (possibly pinned, possibly about to be freed) arrays; the blocks before `first` are untouched.
 int store_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t first, int64_t n_new, const int32_t* cap_idx,
                  const int32_t* tag_idx, const double* rect8, int32_t* lo_out, int32_t* hi_out) {
-  // validate BEFORE any copy is enqueued: an error return must not leave a DMA reading the caller's
-  // (possibly pinned, possibly about to be freed) arrays
-  int32_t lo = cap_idx[0], hi = cap_idx[0];
-  for (int64_t b = 0; b < n_new; ++b) {
-    if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
-      return s->fail(ARSLAM_ERR_INVALID, "block %lld has an index out of range", (long long)(first + b));
-    lo = std::min(lo, cap_idx[b]);
-    hi = std::max(hi, cap_idx[b]);
-  }
   CU(s->o_obs.grow_keep((size_t)(first + n_new) * 8, (size_t)first * 8, s->stream));
   CU(cudaMemcpyAsync(s->o_obs.p + 8 * first, rect8, sizeof(double) * 8 * n_new, cudaMemcpyHostToDevice, s->stream));
   CU(s->o_cap.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
   CU(s->o_tag.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
   CU(cudaMemcpyAsync(s->o_cap.p + first, cap_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_tag.p + first, tag_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
-  *lo_out = lo;
-  *hi_out = hi;
+  CU(s->check3.ensure(4));
+  CU(cudaMemsetAsync(s->check3.p, 0x7f, 2 * sizeof(int), s->stream));
+  CU(cudaMemsetAsync(s->check3.p + 2, 0xff, sizeof(int), s->stream));
+  validate_blocks_kernel<<<cdiv(n_new, 256), 256, 0, s->stream>>>((int)n_new, s->o_cap.p + first, s->o_tag.p + first, (int)n_cap, (int)n_tag, s->check3.p);
+  int* h = reinterpret_cast<int*>(s->h_sc);  // pinned
+  CU(cudaMemcpyAsync(h, s->check3.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (h[0] < (int)n_new) return s->fail(ARSLAM_ERR_INVALID, "block %lld has an index out of range", (long long)(first + h[0]));
+  *lo_out = h[1];
+  *hi_out = h[2];
   return ARSLAM_OK;
 }
 
@@ -703,7 +728,7 @@ int arslam_append_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t
   s->have_params = false;
   int32_t lo = 0, hi = 0;
   const int rc = store_blocks(s, n_cap, n_tag, s->n_blk, n_new, cap_idx, tag_idx, rect8, &lo, &hi);
-  if (rc) {  // nothing was enqueued: the earlier blocks and parameters are intact
+  if (rc) {  // the rejected blocks sit behind the n_blk the handle knows: the earlier blocks and parameters are intact
     s->have_problem = true;
     s->have_params = had_params;
     return rc;
