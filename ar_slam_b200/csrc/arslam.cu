@@ -571,12 +571,25 @@ __global__ void validate_blocks_kernel(int n, const int32_t* __restrict__ cap, c
 // caller's (possibly pinned, possibly about to be freed) arrays; the blocks before `first` are untouched.
 int store_blocks(arslam_solver* s, int64_t n_cap, int64_t n_tag, int64_t first, int64_t n_new, const int32_t* cap_idx,
                  const int32_t* tag_idx, const double* rect8, int32_t* lo_out, int32_t* hi_out) {
+  const bool on_host = n_new <= 4096;  // the incremental schedules append a handful of blocks: cheaper than a kernel + read-back
+  if (on_host) {
+    int32_t lo = cap_idx[0], hi = cap_idx[0];
+    for (int64_t b = 0; b < n_new; ++b) {
+      if (cap_idx[b] < 0 || cap_idx[b] >= n_cap || tag_idx[b] < 0 || tag_idx[b] >= n_tag)
+        return s->fail(ARSLAM_ERR_INVALID, "block %lld has an index out of range", (long long)(first + b));
+      lo = std::min(lo, cap_idx[b]);
+      hi = std::max(hi, cap_idx[b]);
+    }
+    *lo_out = lo;
+    *hi_out = hi;
+  }
   CU(s->o_obs.grow_keep((size_t)(first + n_new) * 8, (size_t)first * 8, s->stream));
   CU(cudaMemcpyAsync(s->o_obs.p + 8 * first, rect8, sizeof(double) * 8 * n_new, cudaMemcpyHostToDevice, s->stream));
   CU(s->o_cap.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
   CU(s->o_tag.grow_keep((size_t)(first + n_new), (size_t)first, s->stream));
   CU(cudaMemcpyAsync(s->o_cap.p + first, cap_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->o_tag.p + first, tag_idx, sizeof(int32_t) * n_new, cudaMemcpyHostToDevice, s->stream));
+  if (on_host) return ARSLAM_OK;
   CU(s->check3.ensure(4));
   CU(cudaMemsetAsync(s->check3.p, 0x7f, 2 * sizeof(int), s->stream));
   CU(cudaMemsetAsync(s->check3.p + 2, 0xff, sizeof(int), s->stream));

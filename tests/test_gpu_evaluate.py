@@ -97,6 +97,16 @@ def test_errors_are_reported(gpu_solver_cls):
         s.set_problem(2, 2, [0, 5], [0, 1], np.zeros((2, 8)))   # capture index out of range
     with pytest.raises(ar_slam_b200.ArslamError):
         s.evaluate()                                            # no problem set
+    # large uploads are validated on the device: the first bad block is named, the handle stays usable
+    from ar_slam_b200 import synth
+    m = synth.make_map(2000, 100, seed=5)
+    bad = m.tag_idx.copy()
+    bad[[7777, 12001]] = m.n_tag
+    with pytest.raises(ar_slam_b200.ArslamError, match="block 7777 has an index out of range"):
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, bad, m.obs)
+    s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+    s.set_params(m.cam0, m.cap0, m.tag0)
+    assert s.evaluate(jacobians=False)[0] > 0.0
     s.close()
 
 
