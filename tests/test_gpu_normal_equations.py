@@ -174,3 +174,29 @@ def test_set_constant_matches_oracle(gpu_solver_cls, oracle, elim):
             assert cam_g[0] == m.cam0[0]
         assert abs(cam_g[0] - cam_o[0]) <= 1e-6 * cam_o[0]
         assert np.abs(cap_g - cap_o).max() <= 1e-6 and np.abs(tag_g - tag_o).max() <= 1e-6
+
+
+@pytest.mark.parametrize("n_tag", [10, 11, 21, 22, 42, 43, 64, 107, 150])
+def test_dense_cholesky_sizes_match_numpy(gpu_solver_cls, oracle, n_tag):
+    """The dense DMMA Cholesky at the sizes where its tiling changes shape: one 64-block (n_pad = 64), exactly one
+    128-tile, a partial last 128-tile (n_pad = 192, 320, 448, 704), exactly one 256-wide outer panel and a second
+    panel of a single block; reduced dimension n = 6 n_tag + 1.  One LM step against a dense numpy solve of the
+    full normal equations; chained and stepwise back-substitution."""
+    import ar_slam_b200
+    from ar_slam_b200 import synth
+    m = synth.make_map(4 * n_tag, n_tag, seed=100 + n_tag)
+    cost, res, jc, jp, ja = oracle_pieces(oracle, m, m.cam0, m.cap0, m.tag0)
+    delta = numpy_lm_step(m, res, jc, jp, ja, 1e4)
+    for chain in (1, 0):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(elimination=ar_slam_b200.ELIM_CAPTURES,
+                                                                 linear_solver=ar_slam_b200.LINSOLVE_DENSE, max_num_iterations=1,
+                                                                 function_tolerance=0.0, parameter_tolerance=0.0))
+        s.set_tuning("chol_chain", chain)
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_params(m.cam0, m.cap0, m.tag0)
+        summ, log = s.solve()
+        cam, cap, tag = s.get_params()
+        s.close()
+        assert summ["reduced_dim"] == 6 * n_tag + 1 and summ["iterations"] == 1 and summ["num_successful_steps"] == 2
+        got = np.concatenate([[cam[0] - m.cam0[0]], (cap - m.cap0).ravel(), (tag - m.tag0).ravel()])
+        assert np.abs(got - delta).max() <= 2e-9 * np.abs(delta).max(), (chain, np.abs(got - delta).max() / np.abs(delta).max())

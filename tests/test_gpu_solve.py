@@ -476,7 +476,8 @@ def test_dense_cholesky_variants_agree(gpu_solver_cls):
     the same arithmetic as the synchronous round-1 kernel: every C element receives one contribution per launch,
     so the factor -- and with it the whole LM trajectory -- is bit-identical.  The one-launch chained
     back-substitution sums in a different (fixed) order than the stepwise one: agreement to rounding.
-    n = 6 * 420 + 1 = 2521: ten outer panels, a partial last tile, a partial last 64-block."""
+    n = 6 * 420 + 1 = 2521: ten outer panels, a partial last 64-block (the tiling's edge sizes:
+    test_gpu_normal_equations.py::test_dense_cholesky_sizes_match_numpy)."""
     import ar_slam_b200
     from ar_slam_b200 import synth
     m = synth.make_map(2500, 420, seed=23)
