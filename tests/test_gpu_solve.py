@@ -500,3 +500,32 @@ def test_dense_cholesky_variants_agree(gpu_solver_cls):
         assert np.allclose(runs[name][2][2], ref[2][2], rtol=0, atol=1e-9), name
     assert np.allclose(runs["stepwise"][1][:, 0], ref[1][:, 0], rtol=1e-10, atol=0)
     assert np.allclose(runs["stepwise"][2][2], ref[2][2], rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("shape", [(60, 12), (500, 90)])
+@pytest.mark.parametrize("cam_const", [False, True])
+def test_radial_pcg_small_and_constant_camera(gpu_solver_cls, oracle, shape, cam_const):
+    """Radial model on the sparse path at sizes where most CTAs of the persistent kernels own no row, and with the
+    three intrinsics held constant (sigma = 0: their 3 x 3 block is the damping alone, the border columns vanish)."""
+    import ar_slam_b200
+    m = _radial_map(oracle, shape[0], shape[1], seed=41)
+    res = {}
+    for name, ls, tol in (("dense", ar_slam_b200.LINSOLVE_DENSE, 0.1), ("pcg", ar_slam_b200.LINSOLVE_PCG, 1e-12),
+                          ("pipelined", ar_slam_b200.LINSOLVE_PCG, 1e-6)):
+        s = gpu_solver_cls(options=ar_slam_b200.default_options(num_intrinsics=3, linear_solver=ls, pcg_tolerance=tol,
+                                                                 pcg_max_iterations=3000, max_num_iterations=6))
+        s.set_problem(m.n_cap, m.n_tag, m.cap_idx, m.tag_idx, m.obs)
+        s.set_constant(camera=cam_const)
+        s.set_params(m.cam_true if cam_const else m.cam0, m.cap0, m.tag0)
+        summ, log = s.solve()
+        res[name] = (summ, log, s.get_params())
+        s.close()
+    sd, ld, pd = res["dense"]
+    # (an inexact first step from a far start moves the intermediate costs by ~1e-4; the end point is the same)
+    for name, rtol, rtol_end in (("pcg", 1e-8, 1e-8), ("pipelined", 1e-3, 1e-6)):
+        sp, lp, pp = res[name]
+        assert sp["linear_solver"] == ar_slam_b200.LINSOLVE_PCG
+        assert len(lp) == len(ld) and np.allclose(lp[:, 0], ld[:, 0], rtol=rtol), name
+        assert abs(lp[-1, 0] - ld[-1, 0]) <= rtol_end * ld[-1, 0], name
+        if cam_const:
+            assert np.array_equal(pp[0], m.cam_true)
