@@ -279,6 +279,9 @@ struct arslam_solver {
   // normal equations
   DevBuf<double> H[2], partial[2], W, Z, YB, seg_cam, seg_cross, warp_cam, warp_cand, warp_norm[2], warp_gmax[2];
   DevBuf<int> check3;  // store_blocks: first bad block, capture range
+  DevBuf<int32_t> straddle_list[2];  // per sorted copy: elimination CTAs with a segment that leaves them (schur.cuh)
+  DevBuf<int> straddle_count;
+  int n_straddle[2] = {0, 0};
   DevBuf<double> sigE, sigF, d_cam, d_pose[2], uF, yF, sc, cam_minus, red, tri;  // tri: packed lower region of the dense system (multi-GPU sum)  // red: S | cam_minus | HF | sc head
   DevBuf<double> eval_out, small, colsum_part, linv;
   DenseCholesky::LookAhead lookahead;  // second stream + events of the dense factorisation
@@ -353,13 +356,16 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // main launch + the launch for the products whose partner sits in another CTA (schur.cuh)
 template <typename Target, int NK>
 void launch_schur(arslam_solver* s, const SchurArgs& a, const Target& t, const int32_t* e_idx, double bytes, bool bulk = false) {
+  static_assert(kSchurThreads == kSchurCtaBlocks, "the straddle list is built for the elimination kernel's CTA size");
   const int grid = cdiv(s->n_blk, kSchurThreads);
   if (bulk) {
     LAUNCH("schur_eliminate", bytes, schur_eliminate_kernel<Target, NK, false, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
-    LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+    if (a.n_straddle > 0)
+      LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true, true><<<a.n_straddle, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
   } else {
     LAUNCH("schur_eliminate", bytes, schur_eliminate_kernel<Target, NK, false><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
-    LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true><<<grid, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
+    if (a.n_straddle > 0)
+      LAUNCH("schur_straddle", 0.0, schur_eliminate_kernel<Target, NK, true><<<a.n_straddle, kSchurThreads, kSchurSmem, s->stream>>>(a, t, s->n_blk, e_idx));
   }
 }
 template <typename Target, int NK>
@@ -655,8 +661,21 @@ int rebuild_views(arslam_solver* s) {
     CU(s->warp_norm[side].ensure((size_t)12 * cdiv(n_own, 128) + 12));
     CU(s->warp_gmax[side].ensure((size_t)4 * cdiv(n_own, 128) + 4));
   }
+  {
+    const int nc = cdiv(nb, kSchurCtaBlocks);
+    CU(s->straddle_count.ensure(2));
+    CU(cudaMemsetAsync(s->straddle_count.p, 0, 2 * sizeof(int), s->stream));
+    for (int side = 0; side < 2; ++side) {
+      CU(s->straddle_list[side].ensure(nc));
+      straddle_ctas_kernel<<<cdiv(nc, 256), 256, 0, s->stream>>>(nb, s->s_own[side].p, s->s_off[side].p, s->seg_end(side), s->straddle_list[side].p,
+                                                                 s->straddle_count.p + side);
+    }
+    CU(cudaMemcpyAsync(s->h_sc, s->straddle_count.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  }
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
+  s->n_straddle[0] = reinterpret_cast<const int*>(s->h_sc)[0];
+  s->n_straddle[1] = reinterpret_cast<const int*>(s->h_sc)[1];
   for (int k = 0; k < 2; ++k) {
     CU(s->cam[k].ensure(4));
     // the current parameter set survives a growing problem (arslam_append_blocks): poses that did not exist
@@ -1463,6 +1482,7 @@ int arslam_solve(arslam_solver* s, arslam_summary* summary, double* iter_log, in
       a.HE = s->H[sd.e].p; a.HEx = dist ? s->Hx[sd.e].p : nullptr; a.W = s->W.p; a.sig_e = s->sigE.p;
       a.radius = radius; a.inv_radius = 1.0 / radius; a.min_diag = o.min_lm_diagonal; a.max_diag = o.max_lm_diagonal;
       a.Z = s->Z.p; a.YB = s->YB.p; a.seg_cam = s->seg_cam.p; a.pair_off = nullptr; a.e_const = const_e;
+      a.straddle_ctas = s->straddle_list[sd.e].p; a.n_straddle = s->n_straddle[sd.e];
       schur_args = a;
       if (lin == ARSLAM_LINSOLVE_DENSE) {
         LAUNCH("dense_zero", 4.0 * s->n_pad * (double)s->n_pad,

@@ -31,7 +31,24 @@ struct SchurArgs {
   double* YB;             // [n_e][6 NK]: Ht_ee^-1 sig_e H_e,intrinsic_q
   double* seg_cam;        // [grid][12] CTA partials of M = hk^T yb (ff, f l1, f l2, l1l1, l1l2, l2l2) | hk^T z (3) | failed | max |g_e| | 0
   const unsigned char* e_const;  // [n_e] != 0: E pose held constant (left out of the gradient norm), or null
+  // second launch (products whose partner sits in another CTA): the CTAs that hold a part of a segment that leaves
+  // them, found once per problem; with equally long aligned segments (every capture sees 8 tags) there are none
+  const int32_t* straddle_ctas;  // [n_straddle]
+  int n_straddle;
 };
+
+// CTAs (of kSchurCtaBlocks consecutive E-sorted blocks) that hold a part of a segment leaving them
+constexpr int kSchurCtaBlocks = 128;
+__global__ void straddle_ctas_kernel(int n_blk, const int32_t* __restrict__ e_idx, const int32_t* __restrict__ e_off,
+                                     const int32_t* __restrict__ e_end, int32_t* __restrict__ list, int* __restrict__ count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int first = c * kSchurCtaBlocks;
+  if (first >= n_blk) return;
+  const int last = min(first + kSchurCtaBlocks, n_blk) - 1;
+  const bool open_head = e_off[e_idx[first]] < first;
+  const bool open_tail = e_end[e_idx[last]] > first + kSchurCtaBlocks;
+  if (open_head || open_tail) list[atomicAdd(count, 1)] = c;
+}
 
 // FP64 add to global memory without a return value.  atomicAdd through a pointer whose address
 // space the compiler cannot prove (e.g. one that went through a shuffle) becomes a generic ATOM
@@ -167,8 +184,9 @@ schur_eliminate_kernel(const SchurArgs a, const Target t, int n_blk, const int32
   extern __shared__ __align__(16) double schur_sm[];
   double(*Vs)[37] = reinterpret_cast<double(*)[37]>(schur_sm);                       // [128][37]
   double(*stage)[32][kSchurStageLd] = reinterpret_cast<double(*)[32][kSchurStageLd]>(schur_sm + kSchurThreads * 37);  // [4][32][38]
-  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  const int cta0 = blockIdx.x * blockDim.x;
+  const int cta = STRADDLE ? a.straddle_ctas[blockIdx.x] : (int)blockIdx.x;
+  const int pos = cta * blockDim.x + threadIdx.x;
+  const int cta0 = cta * blockDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   bool valid = pos < n_blk;
   const int e = valid ? e_idx[pos] : 0;
