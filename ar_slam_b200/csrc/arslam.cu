@@ -1190,7 +1190,7 @@ int pcg_launch_solve(arslam_solver* s, int n_f, double* Sraw, const double* HF, 
   LAUNCH("pcg_finalize_offdiag", 2.0 * 288.0 * w.nnzb,
          pcg_finalize_offdiag_kernel<<<cdiv((long long)w.nnzb * 6, 256), 256, 0, s->stream>>>(f, w.slot_row));
   LAUNCH("pcg_finalize", 8.0 * (NV + 36 + 36 + 36 + 24) * n_f,
-         pcg_finalize_kernel<<<cdiv(std::max(n_f, 1), 64), 64, 0, s->stream>>>(f, w.diag_slot));
+         pcg_finalize_kernel<<<cdiv((long long)std::max(n_f, 1) * kFinLanes, 128), 128, 0, s->stream>>>(f, w.diag_slot));
   PcgSmemArgs sa;
   PcgArgs& a = sa.a;
   a.n_f = n_f; a.max_iter = s->opt.pcg_max_iterations; a.tol = s->opt.pcg_tolerance; a.q_tol = s->opt.pcg_q_tolerance;

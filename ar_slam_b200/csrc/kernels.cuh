@@ -123,42 +123,67 @@ __device__ __forceinline__ void grid_reduce_last_cta(const double (&v)[M], doubl
 // kernels (six 128-bit loads instead of twelve scalar ones spread over the 384-byte record)
 // cap_rt (optional): R | t alone, 12 contiguous doubles per capture, for the passes that never form the
 // capture-rotation columns (accum_f_pipe_kernel)
+// A thread's records are 96 .. 384 contiguous bytes: written directly, every warp-wide store would touch 32 half-filled
+// sectors (ncu: lg_throttle 12 stall cycles per issue).  They go through a per-warp shared-memory stage instead, 32 consecutive
+// 16-byte pieces per store instruction.
+template <int N2, int STRIDE2>
+__device__ __forceinline__ void warp_store_records(double2* __restrict__ dst_warp, const double2 (&v)[N2], double2* stage, int lane, int n_valid) {
+#pragma unroll
+  for (int k = 0; k < N2; ++k) stage[lane * N2 + k] = v[k];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < N2; ++k) {
+    const int i = k * 32 + lane;
+    const int t = i / N2, j = i - t * N2;
+    if (t < n_valid) dst_warp[(size_t)t * STRIDE2 + j] = stage[i];
+  }
+  __syncwarp();
+}
 __global__ void __launch_bounds__(128) prep_poses_kernel(int n_cap, const double* __restrict__ cap_pose, double* __restrict__ cap_out,
                                                          int n_tag, const double* __restrict__ tag_pose, double tag_size,
                                                          double* __restrict__ tag_out, int cap_ctas, double* __restrict__ tag_cor,
                                                          double* __restrict__ cap_rt) {
+  __shared__ double2 stage_all[4][32 * 12];
+  const int lane = threadIdx.x & 31;
+  double2* stage = stage_all[threadIdx.x >> 5];
   if ((int)blockIdx.x < cap_ctas) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cap) return;
+    const int w0 = i - lane;                       // first capture of this warp
+    const int n_valid = min(32, n_cap - w0);
+    if (n_valid <= 0) return;
     double p[6], rec[kCapPre];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p[k] = cap_pose[6 * (size_t)i + k];
+    for (int k = 0; k < 6; ++k) p[k] = i < n_cap ? cap_pose[6 * (size_t)i + k] : 0.0;
     prep_capture(p, rec);
-    double2* o = reinterpret_cast<double2*>(cap_out + (size_t)kCapPre * i);
+    double2 v[kCapPre / 2];
 #pragma unroll
-    for (int k = 0; k < kCapPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    for (int k = 0; k < kCapPre / 2; ++k) v[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    warp_store_records<kCapPre / 2, kCapPre / 2>(reinterpret_cast<double2*>(cap_out + (size_t)kCapPre * w0), v, stage, lane, n_valid);
     if (cap_rt) {
-      double2* c = reinterpret_cast<double2*>(cap_rt + (size_t)12 * i);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) c[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
-      c[4] = make_double2(rec[8], rec[18]);
-      c[5] = make_double2(rec[19], rec[20]);
+      const double2 c[6] = {v[0], v[1], v[2], v[3], make_double2(rec[8], rec[18]), make_double2(rec[19], rec[20])};
+      warp_store_records<6, 6>(reinterpret_cast<double2*>(cap_rt + (size_t)12 * w0), c, stage, lane, n_valid);
     }
   } else {
     const int i = (blockIdx.x - cap_ctas) * blockDim.x + threadIdx.x;
-    if (i >= n_tag) return;
+    const int w0 = i - lane;
+    const int n_valid = min(32, n_tag - w0);
+    if (n_valid <= 0) return;
     double p[6], rec[kTagPre];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p[k] = tag_pose[6 * (size_t)i + k];
+    for (int k = 0; k < 6; ++k) p[k] = i < n_tag ? tag_pose[6 * (size_t)i + k] : 0.0;
     prep_tag(p, tag_size, rec);
-    double2* o = reinterpret_cast<double2*>(tag_out + (size_t)kTagPre * i);
+    double2* o = reinterpret_cast<double2*>(tag_out + (size_t)kTagPre * w0);
 #pragma unroll
-    for (int k = 0; k < kTagPre / 2; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+    for (int half = 0; half < 2; ++half) {
+      double2 v[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) v[k] = make_double2(rec[24 * half + 2 * k], rec[24 * half + 2 * k + 1]);
+      warp_store_records<12, kTagPre / 2>(o + 12 * half, v, stage, lane, n_valid);
+    }
     if (tag_cor) {
-      double2* c = reinterpret_cast<double2*>(tag_cor + (size_t)12 * i);
-      const double w[12] = {rec[0], rec[1], rec[2], rec[12], rec[13], rec[14], rec[24], rec[25], rec[26], rec[36], rec[37], rec[38]};
-#pragma unroll
-      for (int k = 0; k < 6; ++k) c[k] = make_double2(w[2 * k], w[2 * k + 1]);
+      const double2 c[6] = {make_double2(rec[0], rec[1]),   make_double2(rec[2], rec[12]),  make_double2(rec[13], rec[14]),
+                            make_double2(rec[24], rec[25]), make_double2(rec[26], rec[36]), make_double2(rec[37], rec[38])};
+      warp_store_records<6, 6>(reinterpret_cast<double2*>(tag_cor + (size_t)12 * w0), c, stage, lane, n_valid);
     }
   }
 }

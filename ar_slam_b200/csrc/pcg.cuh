@@ -464,9 +464,14 @@ __global__ void pcg_finalize_offdiag_kernel(const PcgFinalizeArgs a, const int32
 }
 
 // diagonal blocks, border, right-hand side and the block-Jacobi inverses: one thread per block row
+// Eight lanes per block row (six at work): lane c owns component c of the border / right-hand side, row c of the final
+// diagonal block and column c of its inverse; the 6 x 6 factorisation is repeated by the six lanes, which is cheaper than
+// the six dependent solves one thread per row used to walk.
+constexpr int kFinLanes = 8;
 __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __restrict__ diag_slot) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row == 0) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gid / kFinLanes, c = gid % kFinLanes;
+  if (gid == 0) {
     const double sf = a.sc->sigma_f;
     const double h = a.sc->cam_H * sf * sf;
     const double d = fmin(fmax(h, a.min_diag), a.max_diag) / a.radius;
@@ -500,20 +505,20 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __re
       a.scal[13] = (K[0] * K[5] - K[2] * K[2]) * id; a.scal[14] = (K[1] * K[2] - K[0] * K[4]) * id; a.scal[15] = m2 * id;
     }
   }
-  if (row >= a.n_f) return;
+  if (row >= a.n_f || c >= 6) return;
   double sr[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) sr[i] = a.sigF[6 * (size_t)row + i];
   const double scam = a.sigF[6 * (size_t)a.n_f];
   const double* rec = a.HF + (size_t)row * NV;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    a.border[6 * (size_t)row + i] = sr[i] * scam * (rec[27 + i] - a.borderm[6 * (size_t)row + i]);
-    a.rhs[6 * (size_t)row + i] = sr[i] * (rec[21 + i] - a.rhsm[6 * (size_t)row + i]);
+  {
+    const double sc_ = a.sigF[6 * (size_t)row + c];
+    a.border[6 * (size_t)row + c] = sc_ * scam * (rec[27 + c] - a.borderm[6 * (size_t)row + c]);
+    a.rhs[6 * (size_t)row + c] = sc_ * (rec[21 + c] - a.rhsm[6 * (size_t)row + c]);
     if (a.nk == 3) {
       const double* rx = a.HFx + (size_t)row * NVX;
-      a.border1[6 * (size_t)row + i] = sr[i] * a.sigF[6 * (size_t)a.n_f + 1] * (rx[i] - a.borderx[6 * (size_t)row + i]);
-      a.border2[6 * (size_t)row + i] = sr[i] * a.sigF[6 * (size_t)a.n_f + 2] * (rx[6 + i] - a.borderx[6 * (size_t)(a.n_f + row) + i]);
+      a.border1[6 * (size_t)row + c] = sc_ * a.sigF[6 * (size_t)a.n_f + 1] * (rx[c] - a.borderx[6 * (size_t)row + c]);
+      a.border2[6 * (size_t)row + c] = sc_ * a.sigF[6 * (size_t)a.n_f + 2] * (rx[6 + c] - a.borderx[6 * (size_t)(a.n_f + row) + c]);
     }
   }
   const int s = diag_slot[row];
@@ -529,18 +534,16 @@ __global__ void pcg_finalize_kernel(const PcgFinalizeArgs a, const int32_t* __re
       double v = sr[i] * sr[j] * (h - m);
       if (i == j) v += fmin(fmax(sr[i] * sr[i] * h, a.min_diag), a.max_diag) / a.radius;
       D[i * 6 + j] = v;
-      dst[i * 6 + j] = v;
+      if (i == c) dst[i * 6 + j] = v;
     }
   const bool ok = chol6(D);
-  if (!ok) a.scal[3] = 1.0;
+  if (!ok && c == 0) a.scal[3] = 1.0;
+  double e[6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    double e[6] = {0, 0, 0, 0, 0, 0};
-    e[c] = 1.0;
-    chol6_solve(D, e);
+  for (int i = 0; i < 6; ++i) e[i] = i == c ? 1.0 : 0.0;
+  chol6_solve(D, e);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) a.Minv[36 * (size_t)row + i * 6 + c] = e[i];
-  }
+  for (int i = 0; i < 6; ++i) a.Minv[36 * (size_t)row + i * 6 + c] = e[i];
 }
 
 // ---- the solver: persistent cooperative kernel ------------------------------
