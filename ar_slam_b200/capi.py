@@ -289,3 +289,124 @@ class Solver:
     def comm_init(self, rank, world, uid):
         buf = (C.c_char * 128).from_buffer_copy(uid)
         self._check(self._lib.arslam_comm_init(self._h, C.c_int(rank), C.c_int(world), buf))
+
+
+class DetectParams(C.Structure):
+    """arslam_detect_params: the cv::aruco::DetectorParameters fields the path reads."""
+    _fields_ = [("adaptive_thresh_win_size_min", C.c_int32), ("adaptive_thresh_win_size_max", C.c_int32),
+                ("adaptive_thresh_win_size_step", C.c_int32), ("min_distance_to_border", C.c_int32),
+                ("marker_border_bits", C.c_int32), ("perspective_remove_pixel_per_cell", C.c_int32),
+                ("adaptive_thresh_constant", C.c_double), ("min_marker_perimeter_rate", C.c_double),
+                ("max_marker_perimeter_rate", C.c_double), ("polygonal_approx_accuracy_rate", C.c_double),
+                ("min_corner_distance_rate", C.c_double), ("min_marker_distance_rate", C.c_double),
+                ("min_group_distance", C.c_double), ("perspective_remove_ignored_margin_per_cell", C.c_double),
+                ("max_erroneous_bits_in_border_rate", C.c_double), ("min_otsu_std_dev", C.c_double),
+                ("error_correction_rate", C.c_double)]
+
+
+def default_detect_params(**kw):
+    p = DetectParams()
+    load_library().arslam_detect_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class Detector:
+    """One `arslam_detector` handle: cv::aruco::detectMarkers for batches of equally sized frames on the GPU
+    (aruco_detector.cpp:106, ar_slam_util.cpp:268)."""
+
+    def __init__(self, max_images, max_width, max_height, device=0):
+        self._lib = lib = load_library()
+        lib.arslam_detector_last_error.restype = C.c_char_p
+        lib.arslam_detector_last_error.argtypes = [C.c_void_p]
+        lib.arslam_detector_create.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        lib.arslam_detector_destroy.argtypes = [C.c_void_p]
+        lib.arslam_detector_destroy.restype = None
+        lib.arslam_detector_set_dictionary.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
+        lib.arslam_detect_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                              C.POINTER(DetectParams), C.c_int32, C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        lib.arslam_detector_candidates.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                   C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                   C.POINTER(C.c_int32)]
+        lib.arslam_detector_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        self._h = C.c_void_p()
+        rc = lib.arslam_detector_create(device, max_images, max_width, max_height, C.byref(self._h))
+        if rc != 0:
+            raise ArslamError(rc, (lib.arslam_detector_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.arslam_detector_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise ArslamError(rc, (self._lib.arslam_detector_last_error(self._h) or b"").decode())
+        return rc
+
+    def set_dictionary(self, bits, max_correction_bits):
+        """bits: (n_markers, marker_size, marker_size) array of 0/1 (cv::aruco::Dictionary::getBitsFromByteList)."""
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        self._check(self._lib.arslam_detector_set_dictionary(self._h, b.shape[0], b.shape[1], int(max_correction_bits),
+                                                             _p(b, C.c_uint8)))
+
+    def detect(self, images, params=None, max_markers=256, device_ptr=None, shape=None):
+        """images: (n, h, w, 3) BGR or (n, h, w) grey uint8 array (host), or device_ptr + shape for frames already
+        in HBM.  Returns per frame (ids int32 array, corners (k, 4, 2) float32 array)."""
+        if device_ptr is None:
+            a = np.ascontiguousarray(images, dtype=np.uint8)
+            shape = a.shape
+            ptr, on_dev = a.ctypes.data, 0
+        else:
+            ptr, on_dev = int(device_ptr), 1
+        n, h, w = shape[0], shape[1], shape[2]
+        ch = shape[3] if len(shape) == 4 else 1
+        n_found = np.zeros(n, np.int32)
+        ids = np.zeros((n, max_markers), np.int32)
+        corners = np.zeros((n, max_markers, 4, 2), np.float32)
+        self._check(self._lib.arslam_detect_markers(self._h, C.c_void_p(ptr), n, w, h, ch, on_dev,
+                                                    C.byref(params) if params is not None else None, max_markers,
+                                                    _p(n_found, C.c_int32), _p(ids, C.c_int32), _p(corners, C.c_float)))
+        return [(ids[i, :n_found[i]].copy(), corners[i, :n_found[i]].copy()) for i in range(n)]
+
+    def candidates(self, cap=65536):
+        """Candidate quads of the last detect() before grouping, in cv::aruco's order."""
+        img = np.zeros(cap, np.int32)
+        win = np.zeros(cap, np.int32)
+        quad = np.zeros((cap, 4, 2), np.float32)
+        near = np.zeros(cap, np.int32)
+        mid = np.zeros(cap, np.int32)
+        rot = np.zeros(cap, np.int32)
+        n = self._check(self._lib.arslam_detector_candidates(self._h, cap, _p(img, C.c_int32), _p(win, C.c_int32),
+                                                             _p(quad, C.c_float), _p(near, C.c_int32),
+                                                             _p(mid, C.c_int32), _p(rot, C.c_int32)))
+        n = min(n, cap)
+        return dict(image=img[:n], window=win[:n], quad=quad[:n], near_border=near[:n], id=mid[:n], rotation=rot[:n])
+
+    def read_stage(self, what):
+        """0: grey frames, 1: threshold bits, 2: border table (n, 5) int32, 3: border points (x | y << 16) int32."""
+        f = self._lib.arslam_detector_read_stage
+        f.restype = C.c_int64
+        f.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+        need = self._check(f(self._h, what, None, 0))
+        out = np.zeros(max(need, 1), np.uint8)
+        self._check(f(self._h, what, C.c_void_p(out.ctypes.data), need))
+        out = out[:need]
+        return out if what < 2 else out.view(np.int32).reshape((-1, 5) if what == 2 else (-1,))
+
+    def times(self):
+        ms = (C.c_double * 5)()
+        launches = C.c_int64()
+        self._check(self._lib.arslam_detector_times(self._h, ms, C.byref(launches)))
+        return dict(threshold_ms=ms[0], borders_ms=ms[1], approx_ms=ms[2], identify_ms=ms[3], total_ms=ms[4],
+                    launches=launches.value)

@@ -179,3 +179,70 @@ def write_detections_yaml(m, path, width=IMG_W, height=IMG_H, f0=3000.0):
         for t in range(m.n_tag):
             f.write("  aruco_4X4_50_%d:\n    pose: [0, 0, 0, 0, 0, 0]\n" % t)
         f.write("camera:\n  params: [%r, 0, 0]\n  width: %d\n  height: %d\n" % (float(f0), width, height))
+
+
+# ---- camera frames for the marker detector ------------------------------------------
+def dict_4x4_50_bits():
+    """(50, 4, 4) uint8 cells of cv::aruco::DICT_4X4_50, read from the table the library embeds
+    (csrc/dict_4x4_50.inc, written by scripts/make_dictionary_table.py)."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "dict_4x4_50.inc")
+    codes = [int(c, 16) for c in re.findall(r"0x([0-9a-fA-F]{4})", open(path).read())]
+    assert len(codes) == 50
+    return np.array([[[(c >> (15 - (4 * y + x))) & 1 for x in range(4)] for y in range(4)] for c in codes], np.uint8)
+
+
+def render_marker_scene(h, w, dict_bits, n_markers, seed, noise=4.0, blur=True):
+    """Synthetic camera frame: dictionary markers (black border, white quiet zone) under random homographies on a
+    shaded background, box-blurred, with Gaussian pixel noise.  Pure numpy (no OpenCV), deterministic per seed.
+    Returns (bgr uint8 image (h, w, 3), list of the marker ids placed)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = 120 + 50 * np.sin(xx / w * 3.1 + rng.uniform(0, 6)) * np.cos(yy / h * 2.3 + rng.uniform(0, 6))
+    ids = []
+    placed = []
+    for _ in range(n_markers * 6):
+        if len(ids) >= n_markers:
+            break
+        side = rng.uniform(0.05, 0.16) * w
+        cx, cy = rng.uniform(side, w - side), rng.uniform(side, h - side)
+        if any((cx - px) ** 2 + (cy - py) ** 2 < (1.1 * (side + ps)) ** 2 for px, py, ps in placed):
+            continue
+        placed.append((cx, cy, side))
+        mid = int(rng.integers(0, dict_bits.shape[0]))
+        ids.append(mid)
+        ang = rng.uniform(0, 2 * np.pi)
+        tilt = rng.uniform(0.6, 1.0)
+        persp = rng.uniform(-0.15, 0.15, 2) / side
+        c, s = np.cos(ang), np.sin(ang)
+        # marker plane coordinates (u, v) in [-1, 1] cover the marker with its border; quiet zone out to 1.35
+        a = np.array([[c * side / 2, -s * side / 2 * tilt, cx], [s * side / 2, c * side / 2 * tilt, cy],
+                      [persp[0], persp[1], 1.0]])
+        inv = np.linalg.inv(a)
+        r = int(side * 1.2) + 2
+        x0, x1 = max(0, int(cx) - r), min(w, int(cx) + r)
+        y0, y1 = max(0, int(cy) - r), min(h, int(cy) + r)
+        sub_y, sub_x = np.mgrid[y0:y1, x0:x1].astype(np.float64)
+        den = inv[2, 0] * sub_x + inv[2, 1] * sub_y + inv[2, 2]
+        u = (inv[0, 0] * sub_x + inv[0, 1] * sub_y + inv[0, 2]) / den
+        v = (inv[1, 0] * sub_x + inv[1, 1] * sub_y + inv[1, 2]) / den
+        n = dict_bits.shape[1] + 2
+        cell_x = np.floor((u + 1) / 2 * n).astype(int)
+        cell_y = np.floor((v + 1) / 2 * n).astype(int)
+        full = np.zeros((n, n))
+        full[1:-1, 1:-1] = dict_bits[mid]
+        inside = (cell_x >= 0) & (cell_x < n) & (cell_y >= 0) & (cell_y < n)
+        quiet = (np.abs(u) < 1.35) & (np.abs(v) < 1.35)
+        val = np.where(inside, full[np.clip(cell_y, 0, n - 1), np.clip(cell_x, 0, n - 1)] * 200 + 30, 235.0)
+        region = img[y0:y1, x0:x1]
+        region[quiet] = val[quiet]
+    if blur:
+        pad = np.pad(img, 1, mode="edge")
+        img = (pad[:-2, 1:-1] + 2 * pad[1:-1, 1:-1] + pad[2:, 1:-1]) / 4
+        pad = np.pad(img, 1, mode="edge")
+        img = (pad[1:-1, :-2] + 2 * pad[1:-1, 1:-1] + pad[1:-1, 2:]) / 4
+    img = img + rng.normal(0, noise, img.shape)
+    g = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    bgr = np.stack([np.clip(g.astype(int) + d, 0, 255).astype(np.uint8) for d in (-3, 0, 4)], axis=-1)
+    return bgr, ids

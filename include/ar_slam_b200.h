@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ARSLAM_ABI_VERSION 3 /* 2: arslam_append_blocks, device-resident parameters; 3: arslam_set_constant,
+#define ARSLAM_ABI_VERSION 4 /* 4: marker detection (arslam_detector_*, arslam_detect_markers); 2: arslam_append_blocks, device-resident parameters; 3: arslam_set_constant,
                                 arslam_get_normal_equations, arslam_set_tuning, device-resident schedule entries
                                 (arslam_set_camera / set_poses / get_poses / seed_captures / seed_tags) */
 
@@ -282,6 +282,73 @@ int arslam_set_profiling(arslam_solver* s, int on); /* brackets every launch wit
  * Unknown key: ARSLAM_ERR_INVALID. */
 int arslam_set_tuning(arslam_solver* s, const char* key, int64_t value);
 int arslam_kernel_times(arslam_solver* s, arslam_kernel_time* out, int32_t cap); /* returns rows */
+
+/* ---- Marker detection: the step before the path --------------------------------
+ * Replaces cv::aruco::detectMarkers at ar_slam/src/aruco_detector.cpp:106 (ArucoDetector::image_callback) and
+ * ar_slam/src/ar_slam_util.cpp:268 (ArSlamSolver::loadImages): 8-bit BGR or grey frames in, marker ids and the
+ * four corners (pixel coordinates, marker's top-left first, clockwise, exactly cv::aruco's convention; the caller
+ * centres them like from_cv_img, ar_slam_util.hpp:257-263) out.  Everything that touches pixels runs on the GPU
+ * (grey conversion + three adaptive thresholds, border following, polygon approximation, perspective removal,
+ * Otsu, bit extraction, dictionary match); the grouping of near-duplicate candidates (tens of quads per frame) is
+ * host code, like the reference's schedules.  No corner refinement (cv's default CORNER_REFINE_NONE, which is
+ * what the reference uses), no inverted markers, no ArUco3 pyramid.
+ * Fields and defaults of cv::aruco::DetectorParameters that the path reads. */
+typedef struct arslam_detect_params {
+  int32_t adaptive_thresh_win_size_min;  /* 3  */
+  int32_t adaptive_thresh_win_size_max;  /* 23 */
+  int32_t adaptive_thresh_win_size_step; /* 10: windows 3, 13, 23 (at most 8 windows, each odd and <= 31) */
+  int32_t min_distance_to_border;        /* 3  */
+  int32_t marker_border_bits;            /* 1  */
+  int32_t perspective_remove_pixel_per_cell; /* 4 */
+  double adaptive_thresh_constant;       /* 7  */
+  double min_marker_perimeter_rate;      /* 0.03 */
+  double max_marker_perimeter_rate;      /* 4.0  */
+  double polygonal_approx_accuracy_rate; /* 0.03 */
+  double min_corner_distance_rate;       /* 0.05; ArSlamSolver::loadImages sets 0.1 (ar_slam_util.cpp:250) */
+  double min_marker_distance_rate;       /* 0.125 */
+  double min_group_distance;             /* 0.21 */
+  double perspective_remove_ignored_margin_per_cell; /* 0.13 */
+  double max_erroneous_bits_in_border_rate;          /* 0.35 */
+  double min_otsu_std_dev;               /* 5.0 */
+  double error_correction_rate;          /* 0.6 */
+} arslam_detect_params;
+void arslam_detect_default_params(arslam_detect_params* p);
+
+typedef struct arslam_detector arslam_detector; /* opaque; owns its device workspace and stream */
+
+/* Workspace for batches of up to max_images frames of up to max_width x max_height pixels.  The dictionary is
+ * DICT_4X4_50 (the reference's default, aruco_detector.cpp:71, ar_slam_util.cpp:251-252) until
+ * arslam_detector_set_dictionary replaces it.  ARSLAM_ERR_NO_DEVICE without an sm_100 GPU: no CPU path. */
+int arslam_detector_create(int device, int32_t max_images, int32_t max_width, int32_t max_height,
+                           arslam_detector** out);
+void arslam_detector_destroy(arslam_detector* d);
+const char* arslam_detector_last_error(const arslam_detector* d); /* d may be NULL: creation errors */
+/* Any square dictionary (aruco_detector.cpp:148-152 offers 4X4_50, 5X5_100, 6X6_250): n_markers codes of
+ * marker_size x marker_size bits, one byte per bit, row-major, rotation 0 (cv::aruco::Dictionary::getBitsFromByteList);
+ * max_correction_bits as in cv::aruco::Dictionary.  marker_size <= 6. */
+int arslam_detector_set_dictionary(arslam_detector* d, int32_t n_markers, int32_t marker_size,
+                                   int32_t max_correction_bits, const uint8_t* bits);
+/* n_images frames of width x height pixels, channels = 1 (grey) or 3 (BGR, cv::imread / cv_bridge order),
+ * tightly packed one after the other; on_device != 0: `images` is a device pointer (frames already in HBM).
+ * Per image i: n_found[i] markers, written to ids[i * max_markers ...] and corners[(i * max_markers + k) * 8 ...]
+ * as x0,y0,...,x3,y3 in cv::aruco's order of detection.  More than max_markers detections in a frame:
+ * ARSLAM_ERR_INVALID.  The contour workspace grows on demand (a batch of pure noise costs one re-run). */
+int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_images, int32_t width,
+                          int32_t height, int32_t channels, int32_t on_device, const arslam_detect_params* params,
+                          int32_t max_markers, int32_t* n_found, int32_t* ids, float* corners);
+/* Candidate quads of the last call before grouping (parity tests and debugging): per candidate image index,
+ * threshold window index, 8 corner coordinates (clockwise), too-near-border flag, identified id (-1: none) and
+ * rotation; in cv::aruco's candidate order.  Returns the number of candidates (<= cap rows are written). */
+int arslam_detector_candidates(arslam_detector* d, int32_t cap, int32_t* image, int32_t* window, float* corners,
+                               int32_t* near_border, int32_t* id, int32_t* rotation);
+/* Intermediate results of the last call, for the stage-by-stage parity tests: what = 0 grey frames (n x h x w bytes),
+ * 1 threshold bits (n x h x w bytes, bit k = window k), 2 the traced borders (5 int32 each: image, window, raster
+ * index of discovery in the frame padded to pitch ((w + 2 + 15) / 16) * 16, length, offset into the points), 3 border
+ * points (int32 x | y << 16).  Returns the bytes written; out == NULL: the bytes needed. */
+int64_t arslam_detector_read_stage(arslam_detector* d, int32_t what, void* out, int64_t cap_bytes);
+/* Device time of the stages of the last arslam_detect_markers in ms: [0] grey + thresholds, [1] border following,
+ * [2] polygon approximation, [3] identification, [4] whole call on the device incl. copies; kernel launches. */
+int arslam_detector_times(arslam_detector* d, double* ms5, int64_t* launches);
 
 #ifdef __cplusplus
 }

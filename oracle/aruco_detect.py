@@ -190,7 +190,7 @@ def approx_poly_dp(contour, eps, closed=True):
                 px = float(pt[0] - start_pt[0])
                 py = float(pt[1] - start_pt[1])
                 proj = px * dx + py * dy
-                if proj < 0:                      # before the chord's start: distance to the start point
+                if proj < 0 or len2 == 0:         # before the chord's start (or a chord of no length): distance to the start
                     dist = px * px + py * py
                 elif proj > len2:                 # beyond its end
                     ex = float(pt[0] - end_pt[0])
