@@ -31,8 +31,9 @@ namespace ard {
 
 constexpr int MAX_WIN = 8;        // adaptive-threshold windows per call
 constexpr int MAX_RADIUS = 15;    // window <= 31
-constexpr int TX = 64, TY = 32;   // output tile of the threshold kernel
+constexpr int TX = 64, TY = 64;   // output tile of the threshold kernel
 constexpr int MAX_MARKER = 6;     // marker_size <= 6: (6 + 2) * 4 = 32 pixel wide canonical image at 4 pixels per cell
+constexpr int LPAD = 16;          // zero bytes left of every row of the threshold-bit frames (keeps 8-byte loads aligned)
 constexpr int CANON_SIDE = 48;     // canonical image side limit ((marker_size + 2 border) * pixels per cell)
 
 struct Windows {
@@ -51,14 +52,16 @@ __device__ __forceinline__ int grey_at(const uint8_t* img, size_t idx) {
 }
 
 // One CTA per TX x TY tile of one frame.  Shared memory: the integral image of the tile with its halo (replicated
-// image borders, like BORDER_REPLICATE), built by a warp scan along rows and a thread per column.
-template <int CH>
+// image borders, like BORDER_REPLICATE) and the grey tile itself.  A warp loads a row, converts it to grey and scans it
+// in the same pass; columns are then summed by a thread each; every thread finishes four neighbouring pixels.
+// R = halo = the largest window radius the kernel serves (11 for the default windows 3 / 13 / 23, 15 in general).
+template <int CH, int R>
 __global__ void __launch_bounds__(256) gray_threshold_kernel(const uint8_t* __restrict__ images, int W, int H,
                                                              uint8_t* __restrict__ gray, uint8_t* __restrict__ mask,
                                                              int P, Windows wins) {
-  extern __shared__ uint32_t integ[];          // (TY + 2R + 1) x (TX + 2R + 1)
-  const int R = wins.rmax;
-  const int tw = TX + 2 * R, th = TY + 2 * R, ld = tw + 1;
+  constexpr int TW = TX + 2 * R, TH = TY + 2 * R, LD = TW + 1, GP = (TW + 3) / 4 * 4;
+  extern __shared__ uint32_t integ[];          // (TH + 1) x LD, then the grey tile TH x GP bytes
+  uint8_t* gt = reinterpret_cast<uint8_t*>(integ + (TH + 1) * LD);
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const uint8_t* img = images + (size_t)b * W * H * CH;
@@ -66,57 +69,77 @@ __global__ void __launch_bounds__(256) gray_threshold_kernel(const uint8_t* __re
   uint8_t* m_out = mask + (size_t)b * (H + 2) * P;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < ld; i += 256) integ[i] = 0;
-  for (int j = tid; j < th + 1; j += 256) integ[j * ld] = 0;
-  for (int i = tid; i < tw * th; i += 256) {
-    int jy = i / tw, jx = i - jy * tw;
-    int gy = min(max(y0 + jy - R, 0), H - 1), gx = min(max(x0 + jx - R, 0), W - 1);
-    integ[(jy + 1) * ld + jx + 1] = grey_at<CH>(img, (size_t)gy * W + gx);
-  }
-  __syncthreads();
-  // rows: inclusive prefix sums, a warp per row
-  for (int j = warp; j < th; j += 8) {
-    uint32_t* row = integ + (j + 1) * ld + 1;
+  for (int i = tid; i < LD; i += 256) integ[i] = 0;
+  for (int j = tid; j < TH + 1; j += 256) integ[j * LD] = 0;
+  for (int j = warp; j < TH; j += 8) {
+    const int gy = min(max(y0 + j - R, 0), H - 1);
+    const size_t row = (size_t)gy * W;
     uint32_t carry = 0;
-    for (int c = 0; c < tw; c += 32) {
-      uint32_t v = (c + lane < tw) ? row[c + lane] : 0;
+#pragma unroll
+    for (int c = 0; c < TW; c += 32) {
+      const int i = c + lane;
+      uint32_t v = 0;
+      if (i < TW) {
+        const int gx = min(max(x0 + i - R, 0), W - 1);
+        v = (uint32_t)grey_at<CH>(img, row + gx);
+        gt[j * GP + i] = (uint8_t)v;
+      }
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
         if (lane >= d) v += u;
       }
       v += carry;
-      if (c + lane < tw) row[c + lane] = v;
+      if (i < TW) integ[(j + 1) * LD + i + 1] = v;
       carry = __shfl_sync(0xffffffffu, v, 31);
     }
   }
   __syncthreads();
-  // columns
-  for (int i = tid; i < tw; i += 256) {
+  for (int i = tid; i < TW; i += 256) {       // columns
     uint32_t acc = 0;
-    for (int j = 0; j < th; ++j) {
-      acc += integ[(j + 1) * ld + i + 1];
-      integ[(j + 1) * ld + i + 1] = acc;
+#pragma unroll 8
+    for (int j = 0; j < TH; ++j) {
+      acc += integ[(j + 1) * LD + i + 1];
+      integ[(j + 1) * LD + i + 1] = acc;
     }
   }
   __syncthreads();
-  for (int i = tid; i < TX * TY; i += 256) {
-    int ty = i / TX, tx = i - ty * TX;
-    int gx = x0 + tx, gy = y0 + ty;
+  int radius[MAX_WIN], w2[MAX_WIN];
+#pragma unroll
+  for (int k = 0; k < MAX_WIN; ++k) { radius[k] = k < wins.n ? wins.radius[k] : 0; w2[k] = (2 * radius[k] + 1) * (2 * radius[k] + 1); }
+  const bool vec_grey = (W & 3) == 0;
+  for (int q = tid; q < TX * TY / 4; q += 256) {
+    const int ty = q / (TX / 4), tx = (q - ty * (TX / 4)) * 4;
+    const int gx = x0 + tx, gy = y0 + ty;
     if (gx >= W || gy >= H) continue;
-    int cy = ty + R, cx = tx + R;     // tile coordinates; integral index = +1
-    int g = (int)(integ[(cy + 1) * ld + cx + 1] - integ[cy * ld + cx + 1] - integ[(cy + 1) * ld + cx] + integ[cy * ld + cx]);
-    unsigned bits = 0;
-    for (int k = 0; k < wins.n; ++k) {
-      int r = wins.radius[k];
-      int w2 = (2 * r + 1) * (2 * r + 1);
-      int s = (int)(integ[(cy + r + 1) * ld + cx + r + 1] - integ[(cy - r) * ld + cx + r + 1] -
-                    integ[(cy + r + 1) * ld + cx - r] + integ[(cy - r) * ld + cx - r]);
-      int mean = (2 * s + w2) / (2 * w2);                // rounded box mean; w2 is odd: no ties
-      if (g - mean <= -wins.idelta) bits |= 1u << k;      // THRESH_BINARY_INV
+    uint32_t gpack = 0, mpack = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int cy = ty + R, cx = tx + e + R;     // tile coordinates; integral index = +1
+      const int g = gt[cy * GP + cx];
+      unsigned bits = 0;
+#pragma unroll
+      for (int k = 0; k < MAX_WIN; ++k) {
+        if (k < wins.n) {
+          const int r = radius[k];
+          const int sum = (int)(integ[(cy + r + 1) * LD + cx + r + 1] - integ[(cy - r) * LD + cx + r + 1] -
+                                integ[(cy + r + 1) * LD + cx - r] + integ[(cy - r) * LD + cx - r]);
+          const int mean = (2 * sum + w2[k]) / (2 * w2[k]);       // rounded box mean; w2 is odd: no ties
+          if (g - mean <= -wins.idelta) bits |= 1u << k;           // THRESH_BINARY_INV
+        }
+      }
+      gpack |= (uint32_t)g << (8 * e);
+      mpack |= bits << (8 * e);
     }
-    g_out[(size_t)gy * W + gx] = (uint8_t)g;
-    m_out[(size_t)(gy + 1) * P + gx + 1] = (uint8_t)bits;
+    uint8_t* gp_ = g_out + (size_t)gy * W + gx;
+    uint8_t* mp_ = m_out + (size_t)(gy + 1) * P + LPAD + gx;
+    if (gx + 3 < W) {
+      *reinterpret_cast<uint32_t*>(mp_) = mpack;                    // P and LPAD are multiples of 16, gx of 4
+      if (vec_grey) *reinterpret_cast<uint32_t*>(gp_) = gpack;
+      else { gp_[0] = gpack; gp_[1] = gpack >> 8; gp_[2] = gpack >> 16; gp_[3] = gpack >> 24; }
+    } else {
+      for (int e = 0; gx + e < W; ++e) { gp_[e] = gpack >> (8 * e); mp_[e] = mpack >> (8 * e); }
+    }
   }
 }
 
@@ -126,22 +149,32 @@ __global__ void __launch_bounds__(256) gray_threshold_kernel(const uint8_t* __re
 __global__ void __launch_bounds__(256) border_starts_kernel(const uint8_t* __restrict__ mask, int W, int H, int P, int n_img,
                                                             int nwin, unsigned long long* __restrict__ starts,
                                                             unsigned long long cap, unsigned long long* __restrict__ n_starts) {
-  size_t total = (size_t)n_img * H * W;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned outer = 0, hole = 0;
+  // a thread per 8 consecutive pixels: the tests are bitwise inside every byte, so they run on 64-bit words
+  const int gpr = (W + 7) / 8;                      // groups per row; the last one may reach into the zero padding
+  const size_t total = (size_t)n_img * H * gpr;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long outer = 0, hole = 0;
   size_t gp = 0;
   if (i < total) {
-    int b = (int)(i / ((size_t)H * W));
-    size_t r = i - (size_t)b * H * W;
-    int y = (int)(r / W), x = (int)(r - (size_t)y * W);
-    gp = (size_t)b * (H + 2) * P + (size_t)(y + 1) * P + x + 1;
-    unsigned m = mask[gp];
-    if (m) {
-      outer = m & ~(unsigned)mask[gp - 1];
-      hole = m & ~(unsigned)mask[gp + 1];
+    const int b = (int)(i / ((size_t)H * gpr));
+    const size_t r = i - (size_t)b * H * gpr;
+    const int y = (int)(r / gpr), x = 8 * (int)(r - (size_t)y * gpr);
+    gp = (size_t)b * (H + 2) * P + (size_t)(y + 1) * P + LPAD + x;
+    const unsigned long long cur = *reinterpret_cast<const unsigned long long*>(mask + gp);
+    if (cur) {
+      // The start the sequential scan uses for an outer border is the raster-first pixel of its 8-connected
+      // component: nothing set at W, NW, N, NE.  For a hole it is the pixel left of the raster-first pixel of a
+      // 4-connected background region: E is clear and the pixel above E is set.  Necessary, not sufficient: the
+      // border following below still stops at any raster-earlier start of the same border.
+      const unsigned long long up = *reinterpret_cast<const unsigned long long*>(mask + gp - P);
+      const unsigned long long l = mask[gp - 1], rr = mask[gp + 8], ul = mask[gp - P - 1], ur = mask[gp - P + 8];
+      const unsigned long long west = cur << 8 | l, east = cur >> 8 | rr << 56;
+      const unsigned long long upw = up << 8 | ul, upe = up >> 8 | ur << 56;
+      outer = cur & ~(west | upw | up | upe);
+      hole = cur & ~east & upe;
     }
   }
-  int cnt = __popc(outer) + __popc(hole);
+  int cnt = __popcll(outer) + __popcll(hole);
   int incl = cnt;
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -155,9 +188,17 @@ __global__ void __launch_bounds__(256) border_starts_kernel(const uint8_t* __res
   base = __shfl_sync(0xffffffffu, base, 31);
   if (!cnt) return;
   unsigned long long o = base + incl - cnt;
-  for (int k = 0; k < nwin; ++k) {
-    if (outer >> k & 1) { if (o < cap) starts[o] = ((unsigned long long)gp << 4) | (k << 1); ++o; }
-    if (hole >> k & 1) { if (o < cap) starts[o] = ((unsigned long long)gp << 4) | (k << 1) | 1; ++o; }
+  while (outer) {
+    int bit = __ffsll((long long)outer) - 1;
+    outer &= outer - 1;
+    if (o < cap) starts[o] = ((unsigned long long)(gp + (bit >> 3)) << 4) | ((bit & 7) << 1);
+    ++o;
+  }
+  while (hole) {
+    int bit = __ffsll((long long)hole) - 1;
+    hole &= hole - 1;
+    if (o < cap) starts[o] = ((unsigned long long)(gp + (bit >> 3)) << 4) | ((bit & 7) << 1) | 1;
+    ++o;
   }
 }
 
@@ -176,6 +217,7 @@ struct FollowArgs {
   int W, H, P, n_img;
   const unsigned long long* starts;
   unsigned long long n_starts;
+  unsigned long long* next;          // work counter: warps take chunks of starts from it
   int min_len, max_len;
   Border* borders;
   int border_cap;
@@ -186,74 +228,139 @@ struct FollowArgs {
   int* overflow;
 };
 
-// Follows the border from (p0, kind); returns its length, or -1 when this start is not the one the raster scan
-// would have used (a smaller start key lies on the same border) or the border is longer than max_len.
-__device__ __forceinline__ int follow(const uint8_t* __restrict__ m, int P, int p0, int kind, int k, int max_len, int* out) {
-  const int off[8] = {1, 1 - P, -P, -1 - P, -1, -1 + P, P, 1 + P};
-  int s_end = kind ? 0 : 4, s = s_end;
-  bool found = false;
-  do {
-    s = (s - 1) & 7;
-    if (m[p0 + off[s]] >> k & 1) { found = true; break; }
-  } while (s != s_end);
-  if (!found) {                      // isolated pixel: belongs to the outer-kind start
-    if (kind) return -1;
-    if (out) out[0] = ((p0 % P) - 1) | (((p0 / P) - 1) << 16);
-    return 1;
-  }
-  const int p1 = p0 + off[s];
-  const long long key0 = (long long)p0 * 2 + kind;
-  int p3 = p0, len = 0;
-  for (;;) {
-    bool west = false, east = false;
-    int p4;
-    for (;;) {
-      ++s;
-      int d = s & 7;
-      p4 = p3 + off[d];
-      if (m[p4] >> k & 1) break;
-      west |= d == 4;
-      east |= d == 0;
-    }
-    s &= 7;
-    if (west && (long long)p3 * 2 < key0) return -1;
-    if (east && (long long)p3 * 2 + 1 < key0) return -1;
-    if (len >= max_len) return -1;
-    if (out) out[len] = ((p3 % P) - 1) | (((p3 / P) - 1) << 16);
-    ++len;
-    if (p4 == p0 && p3 == p1) break;
-    p3 = p4;
-    s = (s + 4) & 7;
-  }
-  return len;
+// Offsets of the eight Freeman directions (0 = east, counter-clockwise on the screen) from two packed tables.
+__device__ __forceinline__ int dir_off(int d, int P) {
+  const int dx = (int)((0x901au >> (2 * d)) & 3u) - 1;     // {1, 1, 0, -1, -1, -1, 0, 1} + 1, two bits each
+  const int dy = (int)((0xa901u >> (2 * d)) & 3u) - 1;     // {0, -1, -1, -1, 0, 1, 1, 1} + 1
+  return dx + dy * P;
+}
+__device__ __forceinline__ unsigned neighbours(const uint8_t* __restrict__ m, int p, int P, int k) {
+  // bit d = the neighbour in direction d is set; eight independent byte loads in flight, then the window's bit of
+  // each is gathered with one multiply per four bytes
+  const unsigned lo = (unsigned)m[p + 1] | (unsigned)m[p + 1 - P] << 8 | (unsigned)m[p - P] << 16 | (unsigned)m[p - 1 - P] << 24;
+  const unsigned hi = (unsigned)m[p - 1] | (unsigned)m[p - 1 + P] << 8 | (unsigned)m[p + P] << 16 | (unsigned)m[p + 1 + P] << 24;
+  const unsigned a = (((lo >> k) & 0x01010101u) * 0x01020408u) >> 24;
+  const unsigned b = (((hi >> k) & 0x01010101u) * 0x01020408u) >> 24;
+  return (a & 15u) | (b & 15u) << 4;
 }
 
+// Follows borders as cv::findContours does (Suzuki-Abe): from a start pixel, first set neighbour clockwise from west
+// (outer) or east (hole), then counter-clockwise from the direction after the one we came from.  A start survives only
+// if no raster-earlier start lies on its border (`key`), so every border is reported once, from the pixel the
+// sequential scan would have started at.  Survivors of admissible length are followed a second time to write their
+// points.  Persistent warps: a lane whose border ends (or whose start loses) takes the next start at once.
 __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_starts) return;
-  unsigned long long st = a.starts[i];
-  int kind = (int)(st & 1), k = (int)(st >> 1 & 7);
-  size_t gp = (size_t)(st >> 4);
-  size_t frame = (size_t)(a.H + 2) * a.P;
-  int b = (int)(gp / frame);
-  int p0 = (int)(gp - (size_t)b * frame);
-  const uint8_t* m = a.mask + (size_t)b * frame;
-  int len = follow(m, a.P, p0, kind, k, a.max_len, nullptr);
-  if (len < a.min_len) return;       // also the -1 cases
-  int slot = atomicAdd(a.n_borders, 1);
-  unsigned long long po = atomicAdd(a.n_pts, (unsigned long long)len);
-  if (slot >= a.border_cap || po + len > a.pts_cap) { atomicExch(a.overflow, 1); return; }
-  follow(m, a.P, p0, kind, k, a.max_len, a.pts + po);
-  Border& br = a.borders[slot];
-  br.img = b;
-  br.win = k;
-  br.disc = p0 + kind;               // a hole is discovered at the zero pixel right of its first border pixel
-  br.len = len;
-  br.pts_off = (int)po;
-  br.valid = 0;
-  br.near_border = 0;
-  br.id = -1;
-  br.rot = 0;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int CHUNK = 256;
+  const int lane = threadIdx.x & 31, P = a.P;
+  const size_t frame = (size_t)(a.H + 2) * P;
+  unsigned long long w_next = 0, w_end = 0;      // the warp's current chunk of starts (uniform)
+  bool exhausted = false;
+  // lane state
+  bool active = false;
+  const uint8_t* m = a.mask;
+  int img = 0, p0 = 0, p1 = 0, p3 = 0, kind = 0, k = 0, s = 0, s0 = 0, len = 0;
+  unsigned nb = 0;
+  long long key0 = 0;
+  int* out = nullptr;
+  for (;;) {
+    // idle lanes take the next starts of the warp's chunk (all control flow here is warp-uniform)
+    for (;;) {
+      const unsigned need = __ballot_sync(FULL, !active);
+      if (!need || exhausted) break;
+      if (w_next >= w_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.next, (unsigned long long)CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= a.n_starts) { exhausted = true; break; }
+        w_next = base;
+        w_end = base + CHUNK < a.n_starts ? base + CHUNK : a.n_starts;
+      }
+      const unsigned long long avail = w_end - w_next;
+      const int rank = __popc(need & ((1u << lane) - 1u));
+      if (!active && (unsigned long long)rank < avail) {
+        const unsigned long long st = a.starts[w_next + rank];
+        kind = (int)(st & 1);
+        k = (int)(st >> 1 & 7);
+        const size_t gp = (size_t)(st >> 4);
+        img = (int)(gp / frame);
+        p0 = (int)(gp - (size_t)img * frame);
+        m = a.mask + (size_t)img * frame;
+        nb = neighbours(m, p0, P, k);
+        out = nullptr;
+        len = 0;
+        p3 = p0;
+        key0 = (long long)p0 * 2 + kind;
+        if (nb) {
+          const int s_end = kind ? 0 : 4;
+          unsigned r = 0;                          // bit j = direction (s_end - 1 - j) & 7: the clockwise search
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r |= ((nb >> ((s_end - 1 - j) & 7)) & 1u) << j;
+          s0 = s = (s_end - 1 - (__ffs(r) - 1)) & 7;
+          p1 = p0 + dir_off(s, P);
+          active = true;
+        } else if (kind == 0 && a.min_len <= 1 && a.max_len >= 1) {
+          // an isolated pixel is a border of one point (it only matters for images under 34 pixels)
+          int slot = atomicAdd(a.n_borders, 1);
+          unsigned long long po = atomicAdd(a.n_pts, 1ull);
+          if (slot >= a.border_cap || po + 1 > a.pts_cap) atomicExch(a.overflow, 1);
+          else {
+            a.pts[po] = ((p0 % P) - LPAD) | (((p0 / P) - 1) << 16);
+            Border& br = a.borders[slot];
+            br.img = img; br.win = k; br.disc = p0; br.len = 1; br.pts_off = (int)po;
+            br.valid = 0; br.near_border = 0; br.id = -1; br.rot = 0;
+          }
+        }
+      }
+      const unsigned long long asked = (unsigned long long)__popc(need);
+      w_next += asked < avail ? asked : avail;
+    }
+    if (!__any_sync(FULL, active)) break;          // only possible once the starts are exhausted
+    if (active) {
+      // one step: counter-clockwise from the direction after the one we came from: dir, dir + 1, ...
+      const int dir = (s + 1) & 7;
+      const unsigned rot = ((nb >> dir) | (nb << (8 - dir))) & 0xffu;
+      const int t = __ffs(rot) - 1;            // clear directions passed; the pixel we came from ends the search at the latest
+      s = (dir + t) & 7;
+      const bool west = ((4 - dir) & 7) < t, east = ((8 - dir) & 7) < t;
+      bool lost = (west && (long long)p3 * 2 < key0) || (east && (long long)p3 * 2 + 1 < key0) || len >= a.max_len;
+      if (lost) {
+        active = false;
+      } else {
+        if (out) out[len] = ((p3 % P) - LPAD) | (((p3 / P) - 1) << 16);
+        ++len;
+        const int p4 = p3 + dir_off(s, P);
+        if (p4 == p0 && p3 == p1) {            // closed
+          if (!out) {
+            active = false;
+            if (len >= a.min_len) {
+              int slot = atomicAdd(a.n_borders, 1);
+              unsigned long long po = atomicAdd(a.n_pts, (unsigned long long)len);
+              if (slot >= a.border_cap || po + len > a.pts_cap) atomicExch(a.overflow, 1);
+              else {                           // follow it again, this time writing the points
+                Border& br = a.borders[slot];
+                br.img = img; br.win = k; br.disc = p0 + kind;   // a hole is discovered at the clear pixel right of its first pixel
+                br.len = len; br.pts_off = (int)po;
+                br.valid = 0; br.near_border = 0; br.id = -1; br.rot = 0;
+                out = a.pts + po;
+                len = 0;
+                p3 = p0;
+                s = s0;
+                nb = neighbours(m, p0, P, k);
+                active = true;
+              }
+            }
+          } else {
+            active = false;
+          }
+        } else {
+          p3 = p4;
+          nb = neighbours(m, p3, P, k);
+          s = (s + 4) & 7;
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- (d3)
@@ -593,7 +700,7 @@ __global__ void __launch_bounds__(128) identify_kernel(IdentifyArgs a) {
 using ard::Border;
 
 struct arslam_detector {
-  int device = 0;
+  int device = 0, sm_count = 148;
   int max_images = 0, max_w = 0, max_h = 0;
   cudaStream_t stream = nullptr;
   uint8_t* d_images = nullptr;
@@ -717,13 +824,14 @@ int arslam_detector_create(int device, int32_t max_images, int32_t max_width, in
     return dfail(nullptr, ARSLAM_ERR_NO_DEVICE, "device is not sm_100 (the library is built for sm_100a only)");
   arslam_detector* d = new arslam_detector;
   d->device = device;
+  d->sm_count = prop.multiProcessorCount;
   d->max_images = max_images; d->max_w = max_width; d->max_h = max_height;
   auto bail = [&](int rc) { std::string m = d->err; arslam_detector_destroy(d); g_detect_create_error = m; return rc; };
 #define DC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { d->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(ARSLAM_ERR_CUDA); } } while (0)
   DC(cudaSetDevice(device));
   DC(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   const size_t px = (size_t)max_images * max_width * max_height;
-  const int P = (max_width + 2 + 15) / 16 * 16;
+  const int P = (max_width + 2 * ard::LPAD + 15) / 16 * 16;
   d->mask_bytes = (size_t)max_images * (max_height + 2) * P;
   d->starts_cap = std::max<unsigned long long>(px / 2, 1 << 16);          // grown on demand, like the two below
   d->border_cap = (int)std::min<size_t>((size_t)max_images * 4096, (size_t)1 << 24);
@@ -796,7 +904,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
   if (!images || !n_found || !ids || !corners || max_markers < 1)
     return dfail(d, ARSLAM_ERR_INVALID, "arslam_detect_markers: NULL argument or max_markers < 1");
   if (n_images < 1 || n_images > d->max_images || W < 8 || H < 8 || W > d->max_w || H > d->max_h ||
-      (size_t)n_images * (H + 2) * ((W + 2 + 15) / 16 * 16) > d->mask_bytes)
+      (size_t)n_images * (H + 2) * ((W + 2 * ard::LPAD + 15) / 16 * 16) > d->mask_bytes)
     return dfail(d, ARSLAM_ERR_INVALID, "arslam_detect_markers: batch or frame size exceeds what arslam_detector_create reserved");
   if (channels != 1 && channels != 3) return dfail(d, ARSLAM_ERR_INVALID, "arslam_detect_markers: channels must be 1 (grey) or 3 (BGR)");
   ard::Windows wins;
@@ -822,7 +930,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
 
   DCUDA(d, cudaSetDevice(d->device));
   cudaStream_t st = d->stream;
-  const int P = (W + 2 + 15) / 16 * 16;
+  const int P = (W + 2 * ard::LPAD + 15) / 16 * 16;
   const size_t px = (size_t)n_images * W * H;
   d->launches = 0;
   DCUDA(d, cudaEventRecord(d->ev[0], st));
@@ -839,15 +947,19 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
   DCUDA(d, cudaEventRecord(d->ev[1], st));
   {
     dim3 grid((W + ard::TX - 1) / ard::TX, (H + ard::TY - 1) / ard::TY, n_images);
-    size_t smem = (size_t)(ard::TY + 2 * wins.rmax + 1) * (ard::TX + 2 * wins.rmax + 1) * sizeof(uint32_t);
-    if (channels == 3) ard::gray_threshold_kernel<3><<<grid, 256, smem, st>>>(d_in, W, H, d->d_gray, d->d_mask, P, wins);
-    else ard::gray_threshold_kernel<1><<<grid, 256, smem, st>>>(d_in, W, H, d->d_gray, d->d_mask, P, wins);
+    const int R = wins.rmax <= 11 ? 11 : 15;
+    const int tw = ard::TX + 2 * R, th = ard::TY + 2 * R;
+    size_t smem = (size_t)(th + 1) * (tw + 1) * sizeof(uint32_t) + (size_t)th * ((tw + 3) / 4 * 4);
+    if (channels == 3 && R == 11) ard::gray_threshold_kernel<3, 11><<<grid, 256, smem, st>>>(d_in, W, H, d->d_gray, d->d_mask, P, wins);
+    else if (channels == 3) ard::gray_threshold_kernel<3, 15><<<grid, 256, smem, st>>>(d_in, W, H, d->d_gray, d->d_mask, P, wins);
+    else if (R == 11) ard::gray_threshold_kernel<1, 11><<<grid, 256, smem, st>>>(d_in, W, H, d->d_gray, d->d_mask, P, wins);
+    else ard::gray_threshold_kernel<1, 15><<<grid, 256, smem, st>>>(d_in, W, H, d->d_gray, d->d_mask, P, wins);
     ++d->launches;
   }
   DCUDA(d, cudaEventRecord(d->ev[2], st));
   unsigned long long n_starts = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {      // a frame of pure noise has more starts than reserved: grow once
-    unsigned blocks = (unsigned)((px + 255) / 256);
+    unsigned blocks = (unsigned)(((size_t)n_images * H * ((W + 7) / 8) + 255) / 256);
     ard::border_starts_kernel<<<blocks, 256, 0, st>>>(d->d_mask, W, H, P, n_images, wins.n, d->d_starts, d->starts_cap, d->d_counters);
     ++d->launches;
     DCUDA(d, cudaMemcpyAsync(d->h_counters, d->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -876,7 +988,9 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     fa.min_len = std::max(min_len, 1); fa.max_len = max_len;
     fa.borders = d->d_borders; fa.border_cap = d->border_cap; fa.n_borders = d_nb;
     fa.pts = d->d_pts; fa.pts_cap = d->pts_cap; fa.n_pts = d->d_counters + 1; fa.overflow = d_nb + 1;
-    ard::border_follow_kernel<<<(unsigned)((n_starts + 127) / 128), 128, 0, st>>>(fa);
+    fa.next = d->d_counters + 3;
+    const unsigned want = (unsigned)((n_starts + 127) / 128);
+    ard::border_follow_kernel<<<std::min(want, (unsigned)d->sm_count * 12u), 128, 0, st>>>(fa);
     ++d->launches;
     if (attempt == 0) DCUDA(d, cudaEventRecord(d->ev[3], st));
     DCUDA(d, cudaMemcpyAsync(d->h_counters, d->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1021,7 +1135,7 @@ int arslam_detector_candidates(arslam_detector* d, int32_t cap, int32_t* image, 
 int64_t arslam_detector_read_stage(arslam_detector* d, int32_t what, void* out, int64_t cap_bytes) {
   if (!d) return ARSLAM_ERR_INVALID;
   if (cudaSetDevice(d->device) != cudaSuccess) return dfail(d, ARSLAM_ERR_CUDA, "cudaSetDevice");
-  const int n = d->call_n, W = d->call_w, H = d->call_h, P = (W + 2 + 15) / 16 * 16;
+  const int n = d->call_n, W = d->call_w, H = d->call_h, P = (W + 2 * ard::LPAD + 15) / 16 * 16;
   if (n == 0) return dfail(d, ARSLAM_ERR_INVALID, "arslam_detector_read_stage: no arslam_detect_markers call yet");
   int64_t need = 0;
   if (what == 0 || what == 1) need = (int64_t)n * W * H;
@@ -1034,7 +1148,7 @@ int64_t arslam_detector_read_stage(arslam_detector* d, int32_t what, void* out, 
     DCUDA(d, cudaMemcpy(out, d->d_gray, need, cudaMemcpyDeviceToHost));
   } else if (what == 1) {
     for (int b = 0; b < n; ++b)
-      DCUDA(d, cudaMemcpy2D((uint8_t*)out + (size_t)b * W * H, W, d->d_mask + (size_t)b * (H + 2) * P + P + 1, P, W, H,
+      DCUDA(d, cudaMemcpy2D((uint8_t*)out + (size_t)b * W * H, W, d->d_mask + (size_t)b * (H + 2) * P + P + ard::LPAD, P, W, H,
                             cudaMemcpyDeviceToHost));
   } else if (what == 2) {
     std::vector<Border> tmp(d->call_borders);

@@ -343,7 +343,8 @@ int arslam_detector_candidates(arslam_detector* d, int32_t cap, int32_t* image, 
                                int32_t* near_border, int32_t* id, int32_t* rotation);
 /* Intermediate results of the last call, for the stage-by-stage parity tests: what = 0 grey frames (n x h x w bytes),
  * 1 threshold bits (n x h x w bytes, bit k = window k), 2 the traced borders (5 int32 each: image, window, raster
- * index of discovery in the frame padded to pitch ((w + 2 + 15) / 16) * 16, length, offset into the points), 3 border
+ * index of discovery in the zero-padded frame -- pitch ((w + 32 + 15) / 16) * 16, pixel (x, y) at (y + 1) * pitch + 16 + x --,
+ * length, offset into the points), 3 border
  * points (int32 x | y << 16).  Returns the bytes written; out == NULL: the bytes needed. */
 int64_t arslam_detector_read_stage(arslam_detector* d, int32_t what, void* out, int64_t cap_bytes);
 /* Device time of the stages of the last arslam_detect_markers in ms: [0] grey + thresholds, [1] border following,
