@@ -13,7 +13,7 @@ LIB = os.path.join(LIB_DIR, "libar_slam_b200.so")
 SOURCES = {
     "arslam.cu": (["model.cuh", "kernels.cuh", "accum_pipe.cuh", "schur.cuh", "schur_local.cuh", "cholesky.cuh",
                    "localize.cuh", "pcg.cuh"], []),
-    "detect.cu": (["dict_4x4_50.inc"], ["-fmad=false"]),
+    "detect.cu": (["dict_4x4_50.inc", "aruco_dictionaries.inc"], ["-fmad=false"]),
 }
 COMMON_HEADERS = [os.path.join("..", "..", "include", "ar_slam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -360,6 +360,11 @@ class Detector:
         self._check(self._lib.arslam_detector_set_dictionary(self._h, b.shape[0], b.shape[1], int(max_correction_bits),
                                                              _p(b, C.c_uint8)))
 
+    def set_predefined_dictionary(self, name):
+        """"4X4_50" (default), "5X5_100" or "6X6_250" (aruco_detector.cpp:148-152)."""
+        self._lib.arslam_detector_set_predefined_dictionary.argtypes = [C.c_void_p, C.c_char_p]
+        self._check(self._lib.arslam_detector_set_predefined_dictionary(self._h, name.encode()))
+
     def detect(self, images, params=None, max_markers=256, device_ptr=None, shape=None):
         """images: (n, h, w, 3) BGR or (n, h, w) grey uint8 array (host), or device_ptr + shape for frames already
         in HBM.  Returns per frame (ids int32 array, corners (k, 4, 2) float32 array)."""
@@ -405,8 +410,8 @@ class Detector:
         return out if what < 2 else out.view(np.int32).reshape((-1, 5) if what == 2 else (-1,))
 
     def times(self):
-        ms = (C.c_double * 5)()
+        ms = (C.c_double * 6)()
         launches = C.c_int64()
         self._check(self._lib.arslam_detector_times(self._h, ms, C.byref(launches)))
-        return dict(threshold_ms=ms[0], borders_ms=ms[1], approx_ms=ms[2], identify_ms=ms[3], total_ms=ms[4],
-                    launches=launches.value)
+        return dict(threshold_ms=ms[0], starts_ms=ms[1], follow_ms=ms[2], approx_ms=ms[3], identify_ms=ms[4],
+                    total_ms=ms[5], launches=launches.value)

@@ -720,8 +720,8 @@ struct arslam_detector {
   Border* h_borders = nullptr;                // pinned
   unsigned long long* d_codes = nullptr;
   int n_markers = 0, marker_size = 0, max_correction_bits = 0;
-  cudaEvent_t ev[6] = {};
-  double ms[5] = {};
+  cudaEvent_t ev[7] = {};
+  double ms[6] = {};
   long long launches = 0;
   // candidates of the last call, in cv::aruco's order
   std::vector<Border> cand;
@@ -743,6 +743,7 @@ static int dfail(arslam_detector* d, int code, const std::string& msg) {
 static const uint16_t kDict4x4_50[50] = {
 #include "dict_4x4_50.inc"
 };
+#include "aruco_dictionaries.inc"
 
 static unsigned long long rotate_code_ccw(unsigned long long code, int ms) {   // np.rot90(bits, 1)
   unsigned long long out = 0;
@@ -872,6 +873,21 @@ int arslam_detector_set_dictionary(arslam_detector* d, int32_t n_markers, int32_
   return upload_dictionary(d, n_markers, marker_size, max_correction_bits, codes);
 }
 
+/* The three names the reference's detector node accepts (aruco_detector.cpp:148-152). */
+int arslam_detector_set_predefined_dictionary(arslam_detector* d, const char* name) {
+  if (!d) return ARSLAM_ERR_INVALID;
+  const std::string n = name ? name : "";
+  std::vector<unsigned long long> codes;
+  int ms = 0, mc = 0;
+  if (n == "4X4_50") { codes.assign(kDict4x4_50, kDict4x4_50 + 50); ms = 4; mc = 1; }
+  else if (n == "5X5_100") { codes.assign(kDICT_5X5_100, kDICT_5X5_100 + 100); ms = 5; mc = kDICT_5X5_100_max_correction; }
+  else if (n == "6X6_250") { codes.assign(kDICT_6X6_250, kDICT_6X6_250 + 250); ms = 6; mc = kDICT_6X6_250_max_correction; }
+  else return dfail(d, ARSLAM_ERR_INVALID, "invalid aruco_dict " + n + " (4X4_50, 5X5_100, 6X6_250)");
+  DCUDA(d, cudaSetDevice(d->device));
+  DCUDA(d, cudaStreamSynchronize(d->stream));
+  return upload_dictionary(d, (int)codes.size(), ms, mc, codes);
+}
+
 static float side_sum(const float* q) {          // float32 like OpenCV's MarkerCandidateTree perimeter
   float s = 0.f;
   for (int i = 0; i < 4; ++i) {
@@ -962,6 +978,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     unsigned blocks = (unsigned)(((size_t)n_images * H * ((W + 7) / 8) + 255) / 256);
     ard::border_starts_kernel<<<blocks, 256, 0, st>>>(d->d_mask, W, H, P, n_images, wins.n, d->d_starts, d->starts_cap, d->d_counters);
     ++d->launches;
+    if (attempt == 0) DCUDA(d, cudaEventRecord(d->ev[3], st));
     DCUDA(d, cudaMemcpyAsync(d->h_counters, d->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     DCUDA(d, cudaStreamSynchronize(st));
     n_starts = d->h_counters[0];
@@ -992,7 +1009,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     const unsigned want = (unsigned)((n_starts + 127) / 128);
     ard::border_follow_kernel<<<std::min(want, (unsigned)d->sm_count * 12u), 128, 0, st>>>(fa);
     ++d->launches;
-    if (attempt == 0) DCUDA(d, cudaEventRecord(d->ev[3], st));
+    if (attempt == 0) DCUDA(d, cudaEventRecord(d->ev[4], st));
     DCUDA(d, cudaMemcpyAsync(d->h_counters, d->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     DCUDA(d, cudaStreamSynchronize(st));
     n_borders = h_nb[0];
@@ -1013,7 +1030,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     }
     DCUDA(d, cudaMemsetAsync(d->d_counters + 1, 0, 3 * sizeof(unsigned long long), st));
   }
-  if (!n_starts) DCUDA(d, cudaEventRecord(d->ev[3], st));
+  if (!n_starts) DCUDA(d, cudaEventRecord(d->ev[4], st));
   d->call_borders = n_borders;
   if (n_borders) {
     ard::ApproxArgs aa;
@@ -1023,7 +1040,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     ard::approx_quad_kernel<<<(n_borders + 3) / 4, 128, 0, st>>>(aa);
     ++d->launches;
   }
-  DCUDA(d, cudaEventRecord(d->ev[4], st));
+  DCUDA(d, cudaEventRecord(d->ev[5], st));
   if (n_borders) {
     ard::IdentifyArgs ia;
     ia.borders = d->d_borders; ia.n_borders = n_borders; ia.gray = d->d_gray; ia.W = W; ia.H = H;
@@ -1036,15 +1053,15 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     ++d->launches;
     DCUDA(d, cudaMemcpyAsync(d->h_borders, d->d_borders, (size_t)n_borders * sizeof(Border), cudaMemcpyDeviceToHost, st));
   }
-  DCUDA(d, cudaEventRecord(d->ev[5], st));
+  DCUDA(d, cudaEventRecord(d->ev[6], st));
   DCUDA(d, cudaStreamSynchronize(st));
   DCUDA(d, cudaGetLastError());
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     float t = 0.f;
     cudaEventElapsedTime(&t, d->ev[i + 1], d->ev[i + 2]);
     d->ms[i] = t;
   }
-  { float t = 0.f; cudaEventElapsedTime(&t, d->ev[0], d->ev[5]); d->ms[4] = t; }
+  { float t = 0.f; cudaEventElapsedTime(&t, d->ev[0], d->ev[6]); d->ms[5] = t; }
 
   // ---- host: candidates in cv::aruco's order, grouping (_filterTooCloseCandidates), output
   d->cand.clear();
@@ -1163,9 +1180,9 @@ int64_t arslam_detector_read_stage(arslam_detector* d, int32_t what, void* out, 
   return need;
 }
 
-int arslam_detector_times(arslam_detector* d, double* ms5, int64_t* launches) {
+int arslam_detector_times(arslam_detector* d, double* ms6, int64_t* launches) {
   if (!d) return ARSLAM_ERR_INVALID;
-  if (ms5) for (int i = 0; i < 5; ++i) ms5[i] = d->ms[i];
+  if (ms6) for (int i = 0; i < 6; ++i) ms6[i] = d->ms[i];
   if (launches) *launches = d->launches;
   return ARSLAM_OK;
 }

@@ -18,8 +18,9 @@
 int main(int argc, char** argv) {
   if (argc < 2) {
     std::cerr << "Need to provide a .yaml of detections for processing" << std::endl;
-    std::cerr << "Usage:  ar_slam_cli [fn1.yaml] [fn2.yaml] ...\n"
-                 "Description run slam on pre-processed detections (yaml written by a previous run or by a detector)\n";
+    std::cerr << "Usage:  ar_slam_cli [fn1.yaml | img1.ppm] [fn2.yaml | img2.pgm] ...\n"
+                 "Description run slam on pre-processed detections (yaml) or on images (binary netpbm; the markers are "
+                 "detected on the GPU)\n";
     return 1;
   }
   try {
@@ -40,14 +41,14 @@ int main(int argc, char** argv) {
     std::streambuf* cout_buf = std::cout.rdbuf();
     std::ostringstream sink;
     if (quiet) std::cout.rdbuf(sink.rdbuf());
+    // ar_slam_cli.cpp:58-70 of the reference: .yaml files are detections, everything else is an image
+    std::vector<std::string> img_fns;
     for (int i = first_file; i < argc; ++i) {
       const std::string fn = argv[i];
-      if (!endswith(fn, ".yaml")) {
-        std::cerr << "error loading image " << fn << " : image ingest (cv::aruco) is not part of this build, pass detections as .yaml" << std::endl;
-        return 2;
-      }
-      solver.loadYaml(fn);
+      if (endswith(fn, ".yaml")) solver.loadYaml(fn);
+      else img_fns.push_back(fn);
     }
+    if (!img_fns.empty()) solver.loadImages(img_fns);   // netpbm frames, markers detected on the GPU
     solver.prepareDevice();  // context creation is not part of the schedule
     const auto t0 = std::chrono::steady_clock::now();
     solver.solve();

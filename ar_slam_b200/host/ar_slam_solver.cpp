@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cctype>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -129,6 +130,95 @@ Block& ArSlamSolver::addBlock(const ArucoRect& rect, CaptureHandle c, ArucoHandl
   at(c).blocks.emplace_back(h);
   at(a).blocks.emplace_back(h);
   return blocks_.back();
+}
+
+// ---- image ingest (reference ar_slam_util.cpp:218-286) ----------------------------------------------------
+namespace {
+struct Netpbm { int width = 0, height = 0, channels = 0; std::vector<uint8_t> data; };   // data: BGR or grey
+Netpbm read_netpbm(const std::string& fn) {
+  std::ifstream in(fn, std::ios::binary);
+  if (!in) throw std::runtime_error("error loading image " + fn);
+  std::string magic;
+  in >> magic;
+  if (magic != "P5" && magic != "P6") throw std::runtime_error("error loading image " + fn + " (binary netpbm P5 / P6 only)");
+  int vals[3], got = 0;
+  while (got < 3) {
+    int c = in.peek();
+    if (c == '#') { std::string skip; std::getline(in, skip); continue; }
+    if (std::isspace(c)) { in.get(); continue; }
+    if (!(in >> vals[got++])) throw std::runtime_error("error loading image " + fn);
+  }
+  in.get();                                     // the single whitespace before the raster
+  if (vals[2] != 255 || vals[0] < 1 || vals[1] < 1) throw std::runtime_error("error loading image " + fn + " (8-bit only)");
+  Netpbm img;
+  img.width = vals[0]; img.height = vals[1]; img.channels = magic == "P6" ? 3 : 1;
+  img.data.resize((size_t)img.width * img.height * img.channels);
+  in.read(reinterpret_cast<char*>(img.data.data()), (std::streamsize)img.data.size());
+  if ((size_t)in.gcount() != img.data.size()) throw std::runtime_error("error loading image " + fn + " (truncated)");
+  if (img.channels == 3)                        // netpbm is RGB, the detector takes cv::imread's BGR
+    for (size_t i = 0; i < img.data.size(); i += 3) std::swap(img.data[i], img.data[i + 2]);
+  return img;
+}
+Netpbm rotate_90_clockwise(const Netpbm& a) {   // cv::rotate(ROTATE_90_CLOCKWISE)
+  Netpbm r;
+  r.width = a.height; r.height = a.width; r.channels = a.channels;
+  r.data.resize(a.data.size());
+  for (int y = 0; y < a.height; ++y)
+    for (int x = 0; x < a.width; ++x)
+      for (int c = 0; c < a.channels; ++c)
+        r.data[((size_t)x * r.width + (a.height - 1 - y)) * a.channels + c] = a.data[((size_t)y * a.width + x) * a.channels + c];
+  return r;
+}
+}  // namespace
+
+void ArSlamSolver::loadImages(const std::vector<std::string>& img_fns) {
+  arslam_detect_params params;
+  arslam_detect_default_params(&params);
+  params.min_corner_distance_rate = 0.1;        // :250
+  arslam_detector* det = nullptr;
+  for (const auto& img_fn : img_fns) {
+    Netpbm img = read_netpbm(img_fn);
+    // checkAndFixImageSize (:218-245)
+    if (camera_.size.has_value()) {
+      if (img.width == camera_.size->second && img.height == camera_.size->first && img.width != img.height) {
+        std::cerr << "WARNING : some images are rotated relative to others fixing by rotating 90 degrees" << std::endl;
+        img = rotate_90_clockwise(img);
+      }
+      if (std::make_pair(img.width, img.height) != camera_.size.value()) {
+        if (det) arslam_detector_destroy(det);
+        std::ostringstream ss;
+        ss << "Loaded images should all be same size :  expected [" << camera_.size->first << " x " << camera_.size->second
+           << "] got [" << img.width << " x " << img.height << "]";
+        throw std::runtime_error(ss.str());
+      }
+    } else {
+      camera_.size = std::make_pair(img.width, img.height);
+    }
+    if (!det && arslam_detector_create(0, 1, camera_.size->first, camera_.size->second, &det) != ARSLAM_OK)
+      throw std::runtime_error(std::string("arslam_detector_create: ") + arslam_detector_last_error(nullptr));
+    const int cap = 1024;
+    int32_t n = 0;
+    std::vector<int32_t> ids(cap);
+    std::vector<float> corners((size_t)cap * 8);
+    if (arslam_detect_markers(det, img.data.data(), 1, img.width, img.height, img.channels, 0, &params, cap, &n, ids.data(),
+                              corners.data()) != ARSLAM_OK) {
+      std::string msg = std::string("arslam_detect_markers: ") + arslam_detector_last_error(det);
+      arslam_detector_destroy(det);
+      throw std::runtime_error(msg);
+    }
+    if (n <= 2) std::cout << "Warning not enough AR tags detected in " << img_fn << std::endl;   // :270-272
+    Capture& capture = addCapture(genUniqueCaptureUid(), img_fn);
+    for (int k = 0; k < n; ++k) {
+      Aruco& aruco = getOrAddAruco(ArucoId("aruco_4X4_50_" + std::to_string(ids[k])));
+      ArucoRect rect;                           // ArucoRect(rects, img.size()): from_cv_img in double (hpp:257-282)
+      for (int j = 0; j < 4; ++j) {
+        rect.corners[j].x = corners[(size_t)k * 8 + 2 * j] - 0.5 * img.width;
+        rect.corners[j].y = corners[(size_t)k * 8 + 2 * j + 1] - 0.5 * img.height;
+      }
+      addBlock(rect, capture.handle, aruco.handle);
+    }
+  }
+  if (det) arslam_detector_destroy(det);
 }
 
 CaptureUid ArSlamSolver::genUniqueCaptureUid() const {

@@ -10,8 +10,9 @@
 // keeps the data store, the schedules and map.yaml.
 //
 // Built without ROS2 / OpenCV / yaml-cpp / Ceres (none exist in this
-// environment): image ingest and the debug display (loadImages, displayDebug;
-// SURVEY.md section 2 rows 10-11) are outside the hot path and not provided.
+// environment): the debug display (displayDebug) is
+// outside the hot path and not provided; loadImages reads netpbm files instead
+// of going through cv::imread and detects the markers on the GPU.
 // The ROS output getters (getTransforms, getCameraInfo, appendArucoMarkers;
 // reference ar_slam_util.cpp:1027-1162, called at ar_slam.cpp:133,145,154) ARE
 // provided: they fill the real ROS2 messages when built with -DARSLAM_WITH_ROS
@@ -108,6 +109,10 @@ public:
   ArSlamSolver(const ArSlamSolver&) = delete;
   ArSlamSolver& operator=(const ArSlamSolver&) = delete;
 
+  // Image ingest (reference loadImages, ar_slam_util.cpp:247-286): marker detection on the GPU
+  // (arslam_detect_markers, DICT_4X4_50, minCornerDistanceRate = 0.1), one capture per image, ids
+  // "aruco_4X4_50_<n>".  Without OpenCV there is no cv::imread: the files are binary netpbm (P5 grey / P6 colour).
+  void loadImages(const std::vector<std::string>& img_fns);
   void loadYaml(const std::string& fn);
   void saveYaml(std::ostream& output) const;
   void printCameras() const;

@@ -3,7 +3,10 @@
 #include <iostream>
 #include <sstream>
 
+#include <fstream>
+
 #include "ar_slam_solver.hpp"
+#include "aruco_detector.hpp"
 
 int main(int argc, char** argv) {
   if (argc < 2 || ((std::string(argv[1]) == "roundtrip" || std::string(argv[1]) == "rosout") && argc < 3)) {
@@ -12,6 +15,31 @@ int main(int argc, char** argv) {
   }
   const std::string mode = argv[1];
   try {
+    if (mode == "detect" && argc >= 4) {
+      // host_selftest detect <dict> frame.pgm: the detector node's message for one grey netpbm frame (needs a GPU)
+      std::ifstream in(argv[3], std::ios::binary);
+      std::string magic;
+      int w = 0, h = 0, maxv = 0;
+      in >> magic >> w >> h >> maxv;
+      in.get();
+      if (magic != "P5" || maxv != 255) { std::cerr << "detect: binary 8-bit PGM only" << std::endl; return 1; }
+      std::vector<uint8_t> px((size_t)w * h);
+      in.read(reinterpret_cast<char*>(px.data()), (std::streamsize)px.size());
+      ar_slam::ArucoDetector det(argv[2], 0, 1, w, h);
+      det.params().min_corner_distance_rate = 0.1;
+      ar_slam::Frame f;
+      f.data = px.data(); f.width = w; f.height = h; f.channels = 1; f.capture_uid = "cap_test"; f.image_path = argv[3];
+      const auto msg = det.detect(f);
+      std::cout.precision(9);
+      std::cout << "detections " << msg.capture_uid << " " << msg.image_width << " " << msg.image_height << " "
+                << msg.detector_types.at(0) << " " << msg.detections.size() << "\n";
+      for (const auto& d : msg.detections) {
+        std::cout << d.id;
+        for (const auto& c : d.corners) std::cout << " " << c.x << " " << c.y;
+        std::cout << "\n";
+      }
+      return 0;
+    }
     if (mode == "roundtrip") {
       ArSlamSolver s;
       s.loadYaml(argv[2]);

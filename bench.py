@@ -644,7 +644,7 @@ def bench_detection(ctx, workload, steps, warmup, cpu=True, clocks=True):
     if rank == 0 and clocks:
         sampler.start()
     # ---- value: frames already in HBM, device time of the whole call (all stages + the candidate table's D2H)
-    stage = {"threshold_ms": 0.0, "borders_ms": 0.0, "approx_ms": 0.0, "identify_ms": 0.0, "total_ms": 0.0}
+    stage = {"threshold_ms": 0.0, "starts_ms": 0.0, "follow_ms": 0.0, "approx_ms": 0.0, "identify_ms": 0.0, "total_ms": 0.0}
     launches = 0
     ctx.barrier()
     for _ in range(steps):

@@ -328,6 +328,8 @@ const char* arslam_detector_last_error(const arslam_detector* d); /* d may be NU
  * max_correction_bits as in cv::aruco::Dictionary.  marker_size <= 6. */
 int arslam_detector_set_dictionary(arslam_detector* d, int32_t n_markers, int32_t marker_size,
                                    int32_t max_correction_bits, const uint8_t* bits);
+/* The embedded tables by the names of aruco_detector.cpp:148-152: "4X4_50", "5X5_100", "6X6_250". */
+int arslam_detector_set_predefined_dictionary(arslam_detector* d, const char* name);
 /* n_images frames of width x height pixels, channels = 1 (grey) or 3 (BGR, cv::imread / cv_bridge order),
  * tightly packed one after the other; on_device != 0: `images` is a device pointer (frames already in HBM).
  * Per image i: n_found[i] markers, written to ids[i * max_markers ...] and corners[(i * max_markers + k) * 8 ...]
@@ -347,9 +349,10 @@ int arslam_detector_candidates(arslam_detector* d, int32_t cap, int32_t* image, 
  * length, offset into the points), 3 border
  * points (int32 x | y << 16).  Returns the bytes written; out == NULL: the bytes needed. */
 int64_t arslam_detector_read_stage(arslam_detector* d, int32_t what, void* out, int64_t cap_bytes);
-/* Device time of the stages of the last arslam_detect_markers in ms: [0] grey + thresholds, [1] border following,
- * [2] polygon approximation, [3] identification, [4] whole call on the device incl. copies; kernel launches. */
-int arslam_detector_times(arslam_detector* d, double* ms5, int64_t* launches);
+/* Device time of the stages of the last arslam_detect_markers in ms: [0] grey + thresholds, [1] border starts,
+ * [2] border following (incl. the host's read of the start count before it), [3] polygon approximation,
+ * [4] identification + candidate table download, [5] whole call on the device incl. copies; kernel launches. */
+int arslam_detector_times(arslam_detector* d, double* ms6, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -52,8 +52,9 @@ def test_add_detections_semantics(host_tools):
 def test_cli_usage_errors(host_tools):
     assert subprocess.run([os.path.join(host_tools, "ar_slam_cli")], capture_output=True).returncode == 1
     assert subprocess.run([os.path.join(host_tools, "ar_loc")], capture_output=True).returncode == 1
+    # images go to loadImages (netpbm only, there is no cv::imread here): a missing file is the reference's error text
     r = subprocess.run([os.path.join(host_tools, "ar_slam_cli"), "img1.jpg"], capture_output=True, text=True)
-    assert r.returncode == 2 and "image ingest" in r.stderr
+    assert r.returncode == 3 and "error loading image img1.jpg" in r.stderr
 
 
 @pytest.mark.gpu
@@ -210,3 +211,44 @@ def test_device_resident_schedule_equals_host_round_trips(host_tools, tmp_path, 
     # batched schedule: another trajectory, the same map (cost within the solver's function tolerance, focal 760)
     assert abs(c["k4"] - c["host"]) <= 1e-4 * c["host"]
     assert abs(maps["k4"].cam[0] - 760.0) < 5.0
+
+
+def _write_pgm(path, grey):
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (grey.shape[1], grey.shape[0]))
+        f.write(np.ascontiguousarray(grey, np.uint8).tobytes())
+
+
+@pytest.mark.gpu
+def test_detector_node_and_image_ingest_on_the_demo_frames(host_tools, tmp_path):
+    """The host side of SURVEY 8 row f4: ar_slam::ArucoDetector (aruco_detector.cpp:95-140 -> Detections message) and
+    ArSlamSolver::loadImages through ar_slam_cli (ar_slam_util.cpp:247-286), on the reference's own demo frames (grey,
+    as netpbm), against cv2's corners for those frames (tests/golden/marker_golden.json)."""
+    import json
+    gold = json.load(open(os.path.join(GOLD, "marker_golden.json")))["demo"]
+    frames = np.load(os.path.join(GOLD, "demo_gray.npz"))
+    for name in ("img1", "img4"):
+        _write_pgm(tmp_path / (name + ".pgm"), frames[name])
+    # the detector node's message: ids "aruco_4X4_50_<n>", corners centred (x - w / 2, y - h / 2), float32
+    out = subprocess.check_output([os.path.join(host_tools, "host_selftest"), "detect", "4X4_50", str(tmp_path / "img1.pgm")],
+                                  text=True).splitlines()
+    assert out[0].split() == ["detections", "cap_test", "1020", "768", "aruco_4X4_50", str(len(gold["img1"]["ids"]))]
+    for line, mid, quad in zip(out[1:], gold["img1"]["ids"], gold["img1"]["corners"]):
+        tok = line.split()
+        assert tok[0] == "aruco_4X4_50_%d" % mid
+        want = (np.array(quad, np.float64) - [510.0, 384.0]).astype(np.float32).ravel()
+        assert np.array_equal(np.array(tok[1:], np.float32), want)
+    r = subprocess.run([os.path.join(host_tools, "host_selftest"), "detect", "7X7_1000", str(tmp_path / "img1.pgm")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "invalid aruco_dict" in r.stderr
+    # image ingest + map build: two real views (5 and 3 tags, 3 shared) through the drop-in CLI
+    r = subprocess.run([os.path.join(host_tools, "ar_slam_cli"), "--output", "map.yaml", "img1.pgm", "img4.pgm"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    m = yaml.safe_load(open(tmp_path / "map.yaml"))
+    assert m["camera"]["width"] == 1020 and m["camera"]["height"] == 768
+    blocks = m["blocks"]
+    assert [b["aruco"] for b in blocks] == ["aruco_4X4_50_%d" % i for i in gold["img1"]["ids"] + gold["img4"]["ids"]]
+    assert [b["capture"] for b in blocks] == ["cap_0"] * 5 + ["cap_1"] * 3
+    for b, quad in zip(blocks, gold["img1"]["corners"] + gold["img4"]["corners"]):
+        assert np.array_equal(np.array(b["aruco_rect"]), (np.array(quad) - [510.0, 384.0]).ravel())
