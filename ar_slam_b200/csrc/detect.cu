@@ -246,23 +246,29 @@ __device__ __forceinline__ unsigned neighbours(const uint8_t* __restrict__ m, in
 
 // Follows borders as cv::findContours does (Suzuki-Abe): from a start pixel, first set neighbour clockwise from west
 // (outer) or east (hole), then counter-clockwise from the direction after the one we came from.  A start survives only
-// if no raster-earlier start lies on its border (`key`), so every border is reported once, from the pixel the
-// sequential scan would have started at.  Survivors of admissible length are followed a second time to write their
-// points.  Persistent warps: a lane whose border ends (or whose start loses) takes the next start at once.
+// if no raster-earlier start lies on its border, so every border is reported once, from the pixel the sequential scan
+// would have started at.  Persistent warps: a lane whose border ends (or whose start loses) takes the next start at
+// once.  While following, a lane leaves a checkpoint (pixel, direction) every SEG = max_len / 32 steps (a power of two); when a border of admissible
+// length closes, the whole warp writes its points: lane i replays segment i from checkpoint i, so the second pass
+// over a border of L points is a chain of at most SEG steps instead of L.
 __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int CHUNK = 256;
-  const int lane = threadIdx.x & 31, P = a.P;
+  __shared__ unsigned ckpt[4][32][32];            // [warp][lane][checkpoint] = pixel | direction << 29
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, P = a.P;
   const size_t frame = (size_t)(a.H + 2) * P;
+  const int max_len = a.max_len;
+  int seg_shift = 0;
+  while ((32 << seg_shift) < max_len) ++seg_shift;
+  const int SEG = 1 << seg_shift;
   unsigned long long w_next = 0, w_end = 0;      // the warp's current chunk of starts (uniform)
   bool exhausted = false;
   // lane state
-  bool active = false;
+  bool active = false, finished = false;
   const uint8_t* m = a.mask;
-  int img = 0, p0 = 0, p1 = 0, p3 = 0, kind = 0, k = 0, s = 0, s0 = 0, len = 0;
+  int p0 = 0, p1 = 0, p3 = 0, kind = 0, k = 0, s = 0, len = 0;
   unsigned nb = 0;
-  long long key0 = 0;
-  int* out = nullptr;
+  unsigned long long done_po = 0;
   for (;;) {
     // idle lanes take the next starts of the warp's chunk (all control flow here is warp-uniform)
     for (;;) {
@@ -283,23 +289,21 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
         kind = (int)(st & 1);
         k = (int)(st >> 1 & 7);
         const size_t gp = (size_t)(st >> 4);
-        img = (int)(gp / frame);
+        const int img = (int)(gp / frame);
         p0 = (int)(gp - (size_t)img * frame);
         m = a.mask + (size_t)img * frame;
         nb = neighbours(m, p0, P, k);
-        out = nullptr;
         len = 0;
         p3 = p0;
-        key0 = (long long)p0 * 2 + kind;
         if (nb) {
           const int s_end = kind ? 0 : 4;
           unsigned r = 0;                          // bit j = direction (s_end - 1 - j) & 7: the clockwise search
 #pragma unroll
           for (int j = 0; j < 8; ++j) r |= ((nb >> ((s_end - 1 - j) & 7)) & 1u) << j;
-          s0 = s = (s_end - 1 - (__ffs(r) - 1)) & 7;
+          s = (s_end - 1 - (__ffs(r) - 1)) & 7;
           p1 = p0 + dir_off(s, P);
           active = true;
-        } else if (kind == 0 && a.min_len <= 1 && a.max_len >= 1) {
+        } else if (kind == 0 && a.min_len <= 1 && max_len >= 1) {
           // an isolated pixel is a border of one point (it only matters for images under 34 pixels)
           int slot = atomicAdd(a.n_borders, 1);
           unsigned long long po = atomicAdd(a.n_pts, 1ull);
@@ -317,41 +321,34 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
     }
     if (!__any_sync(FULL, active)) break;          // only possible once the starts are exhausted
     if (active) {
+      if ((len & (SEG - 1)) == 0) ckpt[wl][lane][len >> seg_shift] = (unsigned)p3 | (unsigned)s << 29;
       // one step: counter-clockwise from the direction after the one we came from: dir, dir + 1, ...
       const int dir = (s + 1) & 7;
       const unsigned rot = ((nb >> dir) | (nb << (8 - dir))) & 0xffu;
       const int t = __ffs(rot) - 1;            // clear directions passed; the pixel we came from ends the search at the latest
       s = (dir + t) & 7;
       const bool west = ((4 - dir) & 7) < t, east = ((8 - dir) & 7) < t;
-      bool lost = (west && (long long)p3 * 2 < key0) || (east && (long long)p3 * 2 + 1 < key0) || len >= a.max_len;
-      if (lost) {
+      // a start with a smaller key (2 * pixel + kind) on this border: this one is not the scan's
+      if ((west && p3 < p0 + kind) || (east && p3 < p0) || len >= max_len) {
         active = false;
       } else {
-        if (out) out[len] = ((p3 % P) - LPAD) | (((p3 / P) - 1) << 16);
         ++len;
         const int p4 = p3 + dir_off(s, P);
         if (p4 == p0 && p3 == p1) {            // closed
-          if (!out) {
-            active = false;
-            if (len >= a.min_len) {
-              int slot = atomicAdd(a.n_borders, 1);
-              unsigned long long po = atomicAdd(a.n_pts, (unsigned long long)len);
-              if (slot >= a.border_cap || po + len > a.pts_cap) atomicExch(a.overflow, 1);
-              else {                           // follow it again, this time writing the points
-                Border& br = a.borders[slot];
-                br.img = img; br.win = k; br.disc = p0 + kind;   // a hole is discovered at the clear pixel right of its first pixel
-                br.len = len; br.pts_off = (int)po;
-                br.valid = 0; br.near_border = 0; br.id = -1; br.rot = 0;
-                out = a.pts + po;
-                len = 0;
-                p3 = p0;
-                s = s0;
-                nb = neighbours(m, p0, P, k);
-                active = true;
-              }
+          active = false;
+          if (len >= a.min_len) {
+            int slot = atomicAdd(a.n_borders, 1);
+            unsigned long long po = atomicAdd(a.n_pts, (unsigned long long)len);
+            if (slot >= a.border_cap || po + len > a.pts_cap) atomicExch(a.overflow, 1);
+            else {
+              Border& br = a.borders[slot];
+              br.img = (int)((size_t)(m - a.mask) / frame); br.win = k;
+              br.disc = p0 + kind;             // a hole is discovered at the clear pixel right of its first pixel
+              br.len = len; br.pts_off = (int)po;
+              br.valid = 0; br.near_border = 0; br.id = -1; br.rot = 0;
+              done_po = po;
+              finished = true;
             }
-          } else {
-            active = false;
           }
         } else {
           p3 = p4;
@@ -359,6 +356,36 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
           s = (s + 4) & 7;
         }
       }
+    }
+    // borders that closed in this round: the warp writes their points, a segment per lane
+    unsigned fin = __ballot_sync(FULL, finished);
+    while (fin) {
+      const int src = __ffs(fin) - 1;
+      fin &= fin - 1;
+      const int L = __shfl_sync(FULL, len, src);
+      const int kk = __shfl_sync(FULL, k, src);
+      const unsigned long long po = __shfl_sync(FULL, done_po, src);
+      const uint8_t* mm = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(m), src));
+      __syncwarp();
+      const int first = lane * SEG;
+      if (first < L) {
+        const unsigned c = ckpt[wl][src][lane];
+        int q = (int)(c & 0x1fffffffu), sd = (int)(c >> 29);
+        int* out = a.pts + po + first;
+        const int cnt = min(SEG, L - first);
+        unsigned nq = neighbours(mm, q, P, kk);
+        for (int j = 0; j < cnt; ++j) {
+          const int dir = (sd + 1) & 7;
+          const unsigned rot = ((nq >> dir) | (nq << (8 - dir))) & 0xffu;
+          sd = (dir + __ffs(rot) - 1) & 7;
+          out[j] = ((q % P) - LPAD) | (((q / P) - 1) << 16);
+          q += dir_off(sd, P);
+          nq = neighbours(mm, q, P, kk);
+          sd = (sd + 4) & 7;
+        }
+      }
+      if (lane == src) finished = false;
+      __syncwarp();
     }
   }
 }

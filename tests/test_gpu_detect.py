@@ -176,6 +176,26 @@ def test_live_cv2_and_other_dictionaries(capi):
         assert found >= 8, name
 
 
+def test_large_frame_with_long_borders_matches_live_cv2(capi):
+    """1600 x 1200: borders of up to 6400 points are admissible, so the checkpoints of the border following are
+    256 steps apart instead of 128; big markers give borders of a few thousand points."""
+    cv2 = pytest.importorskip("cv2")
+    bits = synth.dict_4x4_50_bits()
+    img = synth.render_marker_scene(1200, 1600, bits, 6, 77, noise=2.0)[0]
+    big = np.kron(bits[7], np.ones((150, 150), np.uint8))                       # one marker 900 pixels wide
+    img[100:1300 - 100, 200:1300] = 235
+    img[250:1150, 300:1200] = 30
+    img[400:1000, 450:1050] = np.where(big[..., None] > 0, 230, 30)
+    det = capi.Detector(1, 1600, 1200)
+    ids, corners = det.detect(img[None], capi.default_detect_params())[0]
+    r, i, _ = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50),
+                                      cv2.aruco.DetectorParameters()).detectMarkers(img)
+    assert 7 in list(ids)
+    assert as_pairs(ids, corners) == as_pairs(i.ravel(), r)
+    table = det.read_stage(2)
+    assert table[:, 3].max() > 3000                                             # the big marker's border
+
+
 def test_frames_already_on_the_device_and_errors(capi):
     import torch
     sc = golden()["scenes"][0]
