@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(256) gray_threshold_kernel(const uint8_t* __re
           const int r = radius[k];
           const int sum = (int)(integ[(cy + r + 1) * LD + cx + r + 1] - integ[(cy - r) * LD + cx + r + 1] -
                                 integ[(cy + r + 1) * LD + cx - r] + integ[(cy - r) * LD + cx - r]);
-          const int mean = (2 * sum + w2[k]) / (2 * w2[k]);       // rounded box mean; w2 is odd: no ties
-          if (g - mean <= -wins.idelta) bits |= 1u << k;           // THRESH_BINARY_INV
+          // THRESH_BINARY_INV: g - mean <= -delta with mean = floor((2 sum + w2) / (2 w2)), the rounded box mean
+          // (w2 is odd: no ties); floor(a / b) >= c  <=>  a >= c b, so no division
+          if (2 * sum + w2[k] >= (g + wins.idelta) * 2 * w2[k]) bits |= 1u << k;
         }
       }
       gpack |= (uint32_t)g << (8 * e);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) gray_threshold_kernel(const uint8_t* __re
 // A border start: pixel index inside the padded frame, window k, kind 0 (its west neighbour is a zero of the
 // border: outer borders start there) or 1 (east neighbour: hole borders).  Key order = raster order, kind 0 first.
 __global__ void __launch_bounds__(256) border_starts_kernel(const uint8_t* __restrict__ mask, int W, int H, int P, int n_img,
-                                                            int nwin, unsigned long long* __restrict__ starts,
+                                                            int drop_isolated, unsigned long long* __restrict__ starts,
                                                             unsigned long long cap, unsigned long long* __restrict__ n_starts) {
   // a thread per 8 consecutive pixels: the tests are bitwise inside every byte, so they run on 64-bit words
   const int gpr = (W + 7) / 8;                      // groups per row; the last one may reach into the zero padding
@@ -155,11 +156,13 @@ __global__ void __launch_bounds__(256) border_starts_kernel(const uint8_t* __res
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long outer = 0, hole = 0;
   size_t gp = 0;
+  unsigned long long rec = 0;                       // image << 36 | pixel inside the padded frame << 4
   if (i < total) {
     const int b = (int)(i / ((size_t)H * gpr));
     const size_t r = i - (size_t)b * H * gpr;
     const int y = (int)(r / gpr), x = 8 * (int)(r - (size_t)y * gpr);
     gp = (size_t)b * (H + 2) * P + (size_t)(y + 1) * P + LPAD + x;
+    rec = (unsigned long long)b << 36 | (unsigned long long)((y + 1) * P + LPAD + x) << 4;
     const unsigned long long cur = *reinterpret_cast<const unsigned long long*>(mask + gp);
     if (cur) {
       // The start the sequential scan uses for an outer border is the raster-first pixel of its 8-connected
@@ -172,6 +175,13 @@ __global__ void __launch_bounds__(256) border_starts_kernel(const uint8_t* __res
       const unsigned long long upw = up << 8 | ul, upe = up >> 8 | ur << 56;
       outer = cur & ~(west | upw | up | upe);
       hole = cur & ~east & upe;
+      if (drop_isolated && outer) {
+        // a pixel without any set neighbour is a border of one point: most of what noise produces, and never a
+        // marker unless one-point borders are admissible (frames under 34 pixels)
+        const unsigned long long dn = *reinterpret_cast<const unsigned long long*>(mask + gp + P);
+        const unsigned long long dl = mask[gp + P - 1], dr = mask[gp + P + 8];
+        outer &= east | dn | (dn << 8 | dl) | (dn >> 8 | dr << 56);
+      }
     }
   }
   int cnt = __popcll(outer) + __popcll(hole);
@@ -191,13 +201,13 @@ __global__ void __launch_bounds__(256) border_starts_kernel(const uint8_t* __res
   while (outer) {
     int bit = __ffsll((long long)outer) - 1;
     outer &= outer - 1;
-    if (o < cap) starts[o] = ((unsigned long long)(gp + (bit >> 3)) << 4) | ((bit & 7) << 1);
+    if (o < cap) starts[o] = (rec + ((unsigned long long)(bit >> 3) << 4)) | ((bit & 7) << 1);
     ++o;
   }
   while (hole) {
     int bit = __ffsll((long long)hole) - 1;
     hole &= hole - 1;
-    if (o < cap) starts[o] = ((unsigned long long)(gp + (bit >> 3)) << 4) | ((bit & 7) << 1) | 1;
+    if (o < cap) starts[o] = (rec + ((unsigned long long)(bit >> 3) << 4)) | ((bit & 7) << 1) | 1;
     ++o;
   }
 }
@@ -253,7 +263,8 @@ __device__ __forceinline__ unsigned neighbours(const uint8_t* __restrict__ m, in
 // over a border of L points is a chain of at most SEG steps instead of L.
 __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int CHUNK = 256;
+  constexpr int CHUNK = 32;           // starts a warp takes from the global pool at a time: small, so that every warp keeps
+                                      // refilling its idle lanes until the pool is empty and the tails of all warps coincide
   __shared__ unsigned ckpt[4][32][32];            // [warp][lane][checkpoint] = pixel | direction << 29
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, P = a.P;
   const size_t frame = (size_t)(a.H + 2) * P;
@@ -288,9 +299,8 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
         const unsigned long long st = a.starts[w_next + rank];
         kind = (int)(st & 1);
         k = (int)(st >> 1 & 7);
-        const size_t gp = (size_t)(st >> 4);
-        const int img = (int)(gp / frame);
-        p0 = (int)(gp - (size_t)img * frame);
+        const int img = (int)(st >> 36);
+        p0 = (int)(st >> 4);                       // 32 bits: pixel inside the padded frame
         m = a.mask + (size_t)img * frame;
         nb = neighbours(m, p0, P, k);
         len = 0;
@@ -1000,10 +1010,13 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     ++d->launches;
   }
   DCUDA(d, cudaEventRecord(d->ev[2], st));
+  const int big = std::max(W, H);
+  const int min_len = (int)(unsigned)(p.min_marker_perimeter_rate * big);
+  const int max_len = (int)(unsigned)(p.max_marker_perimeter_rate * big);
   unsigned long long n_starts = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {      // a frame of pure noise has more starts than reserved: grow once
     unsigned blocks = (unsigned)(((size_t)n_images * H * ((W + 7) / 8) + 255) / 256);
-    ard::border_starts_kernel<<<blocks, 256, 0, st>>>(d->d_mask, W, H, P, n_images, wins.n, d->d_starts, d->starts_cap, d->d_counters);
+    ard::border_starts_kernel<<<blocks, 256, 0, st>>>(d->d_mask, W, H, P, n_images, min_len > 1 ? 1 : 0, d->d_starts, d->starts_cap, d->d_counters);
     ++d->launches;
     if (attempt == 0) DCUDA(d, cudaEventRecord(d->ev[3], st));
     DCUDA(d, cudaMemcpyAsync(d->h_counters, d->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1017,9 +1030,6 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     DCUDA(d, cudaMalloc(&d->d_starts, d->starts_cap * sizeof(unsigned long long)));
     DCUDA(d, cudaMemsetAsync(d->d_counters, 0, 4 * sizeof(unsigned long long), st));
   }
-  const int big = std::max(W, H);
-  const int min_len = (int)(unsigned)(p.min_marker_perimeter_rate * big);
-  const int max_len = (int)(unsigned)(p.max_marker_perimeter_rate * big);
   int* d_nb = reinterpret_cast<int*>(d->d_counters + 2);
   const int* h_nb = reinterpret_cast<const int*>(d->h_counters + 2);
   int n_borders = 0;
@@ -1033,7 +1043,7 @@ int arslam_detect_markers(arslam_detector* d, const uint8_t* images, int32_t n_i
     fa.borders = d->d_borders; fa.border_cap = d->border_cap; fa.n_borders = d_nb;
     fa.pts = d->d_pts; fa.pts_cap = d->pts_cap; fa.n_pts = d->d_counters + 1; fa.overflow = d_nb + 1;
     fa.next = d->d_counters + 3;
-    const unsigned want = (unsigned)((n_starts + 127) / 128);
+    const unsigned want = (unsigned)((n_starts + 127) / 128);      // a lane per start at most
     ard::border_follow_kernel<<<std::min(want, (unsigned)d->sm_count * 12u), 128, 0, st>>>(fa);
     ++d->launches;
     if (attempt == 0) DCUDA(d, cudaEventRecord(d->ev[4], st));
