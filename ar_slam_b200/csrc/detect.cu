@@ -263,6 +263,7 @@ __device__ __forceinline__ unsigned neighbours(const uint8_t* __restrict__ m, in
 // over a border of L points is a chain of at most SEG steps instead of L.
 __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr int PROBE_AFTER = 8, PROBE_STEPS = 16;
   constexpr int CHUNK = 32;           // starts a warp takes from the global pool at a time: small, so that every warp keeps
                                       // refilling its idle lanes until the pool is empty and the tails of all warps coincide
   __shared__ unsigned ckpt[4][32][32];            // [warp][lane][checkpoint] = pixel | direction << 29
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
   // lane state
   bool active = false, finished = false;
   const uint8_t* m = a.mask;
-  int p0 = 0, p1 = 0, p3 = 0, kind = 0, k = 0, s = 0, len = 0;
+  int p0 = 0, p1 = 0, p3 = 0, kind = 0, k = 0, s = 0, s0 = 0, len = 0;
+  int probe = 0, q = 0, c = 0;                   // the backward probe: steps left, pixel, direction we came from
   unsigned nb = 0;
   unsigned long long done_po = 0;
   for (;;) {
@@ -310,8 +312,9 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
           unsigned r = 0;                          // bit j = direction (s_end - 1 - j) & 7: the clockwise search
 #pragma unroll
           for (int j = 0; j < 8; ++j) r |= ((nb >> ((s_end - 1 - j) & 7)) & 1u) << j;
-          s = (s_end - 1 - (__ffs(r) - 1)) & 7;
+          s0 = s = (s_end - 1 - (__ffs(r) - 1)) & 7;
           p1 = p0 + dir_off(s, P);
+          probe = -1;
           active = true;
         } else if (kind == 0 && a.min_len <= 1 && max_len >= 1) {
           // an isolated pixel is a border of one point (it only matters for images under 34 pixels)
@@ -364,6 +367,35 @@ __global__ void __launch_bounds__(128) border_follow_kernel(FollowArgs a) {
           p3 = p4;
           nb = neighbours(m, p3, P, k);
           s = (s + 4) & 7;
+        }
+      }
+      // Most starts that lose do so only after most of the border (a local top on a jagged edge walks away from
+      // the rows above it).  The same border followed BACKWARDS from the start climbs towards them at once, so a
+      // start that is still alive after PROBE_AFTER steps also walks PROBE_STEPS steps backwards (the mirrored rule:
+      // clockwise from the direction before the one we came from visits the same (pixel, clear neighbour) states in
+      // reverse order) and gives up as soon as either walk meets a smaller start key.
+      if (active) {
+        if (probe < 0 && len >= PROBE_AFTER) {
+          const unsigned n0 = neighbours(m, p0, P, k);
+          const int d0 = (s0 + 1) & 7;
+          const unsigned r0 = ((n0 >> d0) | (n0 << (8 - d0))) & 0xffu;
+          c = (d0 + __ffs(r0) - 1) & 7;          // the first forward direction: where the backward walk "comes from"
+          q = p0;
+          probe = PROBE_STEPS;
+        }
+        if (probe > 0) {
+          const unsigned nq = neighbours(m, q, P, k);
+          const unsigned rq = ((nq >> c) | (nq << (8 - c))) & 0xffu;     // bit i = direction c + i; bit 0 is set
+          const int hb = 31 - __clz(rq);         // clockwise from c - 1 = c + 7 down to the first set direction
+          const bool westq = ((4 - c) & 7) > hb, eastq = ((8 - c) & 7) > hb;
+          if ((westq && q < p0 + kind) || (eastq && q < p0)) {
+            active = false;
+          } else {
+            const int d = (c + hb) & 7;
+            q += dir_off(d, P);
+            c = (d + 4) & 7;
+            probe = q == p0 ? 0 : probe - 1;      // all the way round: a small border, nothing more to learn
+          }
         }
       }
     }
