@@ -630,33 +630,57 @@ __global__ void __launch_bounds__(128) identify_kernel(IdentifyArgs a) {
   // cv::getPerspectiveTransform(quad -> canonical square), then its inverse (what cv::warpPerspective maps with)
   double inv[9];
   {
-    double A[8][9];
-    const double c = (double)(size - 1);
-    const double ddx[4] = {0.0, c, c, 0.0}, ddy[4] = {0.0, 0.0, c, c};
-    for (int i = 0; i < 4; ++i) {
-      double sx = br.quad[2 * i], sy = br.quad[2 * i + 1];
-      double r0[9] = {sx, sy, 1, 0, 0, 0, -sx * ddx[i], -sy * ddx[i], ddx[i]};
-      double r1[9] = {0, 0, 0, sx, sy, 1, -sx * ddy[i], -sy * ddy[i], ddy[i]};
-      for (int j = 0; j < 9; ++j) { A[i][j] = r0[j]; A[i + 4][j] = r1[j]; }
+    // lanes 0..7 hold one row of the 8 x 9 system each, in registers; pivots and rows travel by shuffles
+    double row[9];
+    {
+      const double c = (double)(size - 1);
+      const int i = lane & 3;
+      const double ddx = (i == 1 || i == 2) ? c : 0.0, ddy = i >= 2 ? c : 0.0;
+      const double sx = br.quad[2 * i], sy = br.quad[2 * i + 1];
+      const bool second = (lane & 7) >= 4;           // rows 4..7: the y equations
+      row[0] = second ? 0.0 : sx; row[1] = second ? 0.0 : sy; row[2] = second ? 0.0 : 1.0;
+      row[3] = second ? sx : 0.0; row[4] = second ? sy : 0.0; row[5] = second ? 1.0 : 0.0;
+      const double dd = second ? ddy : ddx;
+      row[6] = -sx * dd; row[7] = -sy * dd; row[8] = dd;
     }
-    for (int col = 0; col < 8; ++col) {           // Gaussian elimination with partial pivoting
-      int piv = col;
-      for (int r = col + 1; r < 8; ++r) if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
-      if (piv != col) for (int j = 0; j < 9; ++j) { double t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
-      double d = A[col][col];
-      if (d == 0.0) return;
-      for (int r = col + 1; r < 8; ++r) {
-        double f = A[r][col] / d;
-        for (int j = col; j < 9; ++j) A[r][j] -= f * A[col][j];
+    bool singular = false;
+#pragma unroll
+    for (int col = 0; col < 8; ++col) {             // Gaussian elimination with partial pivoting
+      // pivot: the row >= col with the largest |a[col]|, first one on ties
+      double best = (lane >= col && lane < 8) ? fabs(row[col]) : -1.0;
+      int piv = lane;
+#pragma unroll
+      for (int d = 4; d; d >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, d);
+        int op = __shfl_xor_sync(0xffffffffu, piv, d);
+        if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+      }
+      piv = __shfl_sync(0xffffffffu, piv, 0);
+      // swap rows col and piv
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const double from_piv = __shfl_sync(0xffffffffu, row[j], piv), from_col = __shfl_sync(0xffffffffu, row[j], col);
+        if (piv != col) { if (lane == col) row[j] = from_piv; else if (lane == piv) row[j] = from_col; }
+      }
+      const double dgl = __shfl_sync(0xffffffffu, row[col], col);
+      if (dgl == 0.0) singular = true;
+      const double f = row[col] / dgl;
+#pragma unroll
+      for (int j = col; j < 9; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, row[j], col);
+        if (lane > col && lane < 8) row[j] -= f * pj;
       }
     }
+    if (singular) return;
     double m[9];
-    for (int r = 7; r >= 0; --r) {
-      double s = A[r][8];
-      for (int j = r + 1; j < 8; ++j) s -= A[r][j] * m[j];
-      m[r] = s / A[r][r];
-    }
     m[8] = 1.0;
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+      double sacc = row[8];
+#pragma unroll
+      for (int j = r + 1; j < 8; ++j) sacc -= row[j] * m[j];
+      m[r] = __shfl_sync(0xffffffffu, sacc / row[r], r);
+    }
     double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
     double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
     if (det == 0.0) return;
