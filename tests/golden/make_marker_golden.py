@@ -21,7 +21,9 @@ from ar_slam_b200 import synth  # noqa: E402
 
 REF = "/root/reference/ar_slam/resources/images"
 SCENES = [dict(seed=s, h=[480, 768, 360][s % 3], w=[640, 1020, 500][s % 3], n_markers=8,
-               noise=[2.0, 5.0, 9.0][s % 3]) for s in range(9)]
+               noise=[2.0, 5.0, 9.0][s % 3]) for s in list(range(9)) + [14, 17, 20]]
+# seed 14: a marker whose quiet zone touches the image border (the enclosing quad is too near the border and takes the
+# marker's own quads with it: cv2 reports nothing there)
 
 
 def detector(rate=0.1):

@@ -55,6 +55,26 @@ def test_struct_layout_matches_header_field_order():
     assert fields("arslam_options") == [n for n, _ in capi.Options._fields_]
     assert fields("arslam_summary") == [n for n, _ in capi.Summary._fields_]
     assert fields("arslam_kernel_time") == [n for n, _ in capi.KernelTime._fields_]
+    assert fields("arslam_detect_params") == [n for n, _ in capi.DetectParams._fields_]
+
+
+def test_detector_defaults_are_opencvs():
+    """cv::aruco::DetectorParameters defaults (the reference only overrides minCornerDistanceRate, ar_slam_util.cpp:250)."""
+    from ar_slam_b200 import capi
+    p = capi.default_detect_params()
+    assert (p.adaptive_thresh_win_size_min, p.adaptive_thresh_win_size_max, p.adaptive_thresh_win_size_step) == (3, 23, 10)
+    assert p.adaptive_thresh_constant == 7.0 and p.min_distance_to_border == 3 and p.marker_border_bits == 1
+    assert (p.min_marker_perimeter_rate, p.max_marker_perimeter_rate, p.polygonal_approx_accuracy_rate) == (0.03, 4.0, 0.03)
+    assert p.min_corner_distance_rate == 0.05 and p.min_marker_distance_rate == 0.125
+    assert p.perspective_remove_pixel_per_cell == 4 and p.perspective_remove_ignored_margin_per_cell == 0.13
+    assert p.max_erroneous_bits_in_border_rate == 0.35 and p.min_otsu_std_dev == 5.0 and p.error_correction_rate == 0.6
+    try:
+        import cv2
+    except ImportError:
+        return
+    q = cv2.aruco.DetectorParameters()
+    assert p.min_group_distance == q.minGroupDistance and p.min_marker_distance_rate == q.minMarkerDistanceRate
+    assert p.min_corner_distance_rate == q.minCornerDistanceRate and p.min_otsu_std_dev == q.minOtsuStdDev
 
 
 def test_no_cpu_fallback():

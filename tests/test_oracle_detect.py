@@ -118,6 +118,17 @@ def test_pipeline_reproduces_cv2_on_rendered_scenes():
     assert n >= 40
 
 
+def test_quad_too_near_the_border_takes_its_group_with_it():
+    """Golden scene 14: marker 49 sits at the top edge; the quad around its quiet zone is too near the image border,
+    and cv2 4.13 drops that quad only AFTER it has absorbed the marker's own quads, so nothing is reported there.
+    Dropping it before the grouping (as the 4.5.4 sources read) would report the marker."""
+    sc = [s for s in golden()["scenes"] if s["seed"] == 14][0]
+    assert 49 in sc["placed"] and 49 not in sc["ids"]
+    bits = synth.dict_4x4_50_bits()
+    corners, ids = A.detect_markers(scene_image(sc), bits, 1)
+    assert as_pairs(ids, corners) == as_pairs(sc["ids"], sc["corners"])
+
+
 def test_pipeline_against_live_cv2_with_default_parameters():
     """Not the reference's 0.1 but cv2's default minCornerDistanceRate, on scenes that are not in the golden file."""
     cv2 = pytest.importorskip("cv2")
