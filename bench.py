@@ -713,7 +713,9 @@ def bench_detection(ctx, workload, steps, warmup, cpu=True, clocks=True):
                        "what": "arslam_detect_markers on pinned host frames (H2D, five kernels, candidate table D2H, "
                                "host-side grouping), wall clock"},
                "roofline": {"bound": "hbm", "kernel": "gray_threshold", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "peak_source": how, "algorithmic_bytes": alg,
+                            "frac": ach / peak, "traffic": (static_traffic(workload, "gray_threshold")[0] or 0) * len(mine) / 64.0 or None,
+                            "traffic_source": "profiles/r2_traffic.json (ncu --set full of a 64-frame launch, static)",
+                            "peak_source": how, "algorithmic_bytes": alg,
                             "us_per_launch": 1e3 * stage["threshold_ms"] / steps,
                             "share_of_step": stage["threshold_ms"] / stage["total_ms"],
                             "note": "grey conversion + three adaptive thresholds from one shared-memory integral tile: "
@@ -821,13 +823,20 @@ def main():
         if extra_on and ctx.world == 1 and args.workload == "ba_100k_5k":
             # the other BASELINE configurations, short runs, so that one invocation witnesses them all
             ex = {}
-            ex["ba_1k_200"] = short(bench_ba(ctx, "ba_1k_200", 40, 10, e2e=True, clocks=False, converge=True))
-            ex["ba_20k_2k_radial_dense"] = short(bench_ba(ctx, "ba_20k_2k", 5, 3, linear_solver="dense", num_intrinsics=3, e2e=False, converge=True,
-                                                          clocks=False))
-            ex["ba_20k_2k_radial_pcg"] = short(bench_ba(ctx, "ba_20k_2k", 20, 5, linear_solver="pcg", num_intrinsics=3, e2e=False,
-                                                        clocks=False, converge=True))
-            ex["loc_1m_5k"] = short(bench_localization(ctx, "loc_1m_5k", 3, 2, cpu=False, clocks=False))
-            ex["detect_1020x768"] = short(bench_detection(ctx, "detect_1020x768", 5, 2, cpu=True, clocks=False))
+
+            def extra(name, fn):
+                # an extra workload must never take the headline line down with it
+                try:
+                    ex[name] = short(fn())
+                except Exception as e:  # noqa: BLE001
+                    ex[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            extra("ba_1k_200", lambda: bench_ba(ctx, "ba_1k_200", 40, 10, e2e=True, clocks=False, converge=True))
+            extra("ba_20k_2k_radial_dense", lambda: bench_ba(ctx, "ba_20k_2k", 5, 3, linear_solver="dense", num_intrinsics=3,
+                                                             e2e=False, converge=True, clocks=False))
+            extra("ba_20k_2k_radial_pcg", lambda: bench_ba(ctx, "ba_20k_2k", 20, 5, linear_solver="pcg", num_intrinsics=3,
+                                                           e2e=False, clocks=False, converge=True))
+            extra("loc_1m_5k", lambda: bench_localization(ctx, "loc_1m_5k", 3, 2, cpu=False, clocks=False))
+            extra("detect_1020x768", lambda: bench_detection(ctx, "detect_1020x768", 5, 2, cpu=True, clocks=False))
             line["extra_workloads"] = ex
     if ctx.rank == 0:
         print(json.dumps(line))

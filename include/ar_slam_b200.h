@@ -331,7 +331,8 @@ int arslam_detector_set_dictionary(arslam_detector* d, int32_t n_markers, int32_
 /* The embedded tables by the names of aruco_detector.cpp:148-152: "4X4_50", "5X5_100", "6X6_250". */
 int arslam_detector_set_predefined_dictionary(arslam_detector* d, const char* name);
 /* n_images frames of width x height pixels, channels = 1 (grey) or 3 (BGR, cv::imread / cv_bridge order),
- * tightly packed one after the other; on_device != 0: `images` is a device pointer (frames already in HBM).
+ * tightly packed one after the other; on_device != 0: `images` is a device pointer (frames already in HBM, complete
+ * before the call: the detector works on its own stream).
  * Per image i: n_found[i] markers, written to ids[i * max_markers ...] and corners[(i * max_markers + k) * 8 ...]
  * as x0,y0,...,x3,y3 in cv::aruco's order of detection.  More than max_markers detections in a frame:
  * ARSLAM_ERR_INVALID.  The contour workspace grows on demand (a batch of pure noise costs one re-run). */
