@@ -476,11 +476,16 @@ def extract_bits(gray, quad, params, marker_size=4):
 def dictionary_bits(byte_list, marker_size):
     """Bits (marker_size x marker_size) of every marker of a cv::aruco::Dictionary bytesList, rotation 0."""
     out = []
-    nbytes = (marker_size * marker_size + 7) // 8
+    nbits = marker_size * marker_size
+    nbytes = (nbits + 7) // 8
     flat = np.asarray(byte_list, np.uint8).reshape(byte_list.shape[0], -1)      # per marker: 4 rotations x nbytes
     for m in range(flat.shape[0]):
-        bits = np.unpackbits(flat[m, :nbytes])[:marker_size * marker_size]
-        out.append(bits.reshape(marker_size, marker_size))
+        # cv::aruco::Dictionary::getByteListFromBits fills bytes most significant bit first; the last, partial byte
+        # keeps its bits in the LOW positions
+        full = np.unpackbits(flat[m, :nbytes - 1])
+        rem = nbits - 8 * (nbytes - 1)
+        last = np.unpackbits(flat[m, nbytes - 1:nbytes])[8 - rem:]
+        out.append(np.concatenate([full, last]).reshape(marker_size, marker_size))
     return np.array(out, np.uint8)
 
 

@@ -45,6 +45,22 @@ def test_dictionary_table_is_cv2s():
             assert ok and (idx, rot) == A.identify(full, bits, d.maxCorrectionBits, A.REFERENCE_PARAMS)
 
 
+def test_embedded_tables_of_the_other_dictionaries_are_cv2s():
+    """csrc/aruco_dictionaries.inc (arslam_detector_set_predefined_dictionary "5X5_100" / "6X6_250") against cv2."""
+    cv2 = pytest.importorskip("cv2")
+    import re
+    text = open(os.path.join(os.path.dirname(GOLD), "..", "ar_slam_b200", "csrc", "aruco_dictionaries.inc")).read()
+    for name, size in (("DICT_5X5_100", 5), ("DICT_6X6_250", 6)):
+        d = cv2.aruco.getPredefinedDictionary(getattr(cv2.aruco, name))
+        body = re.search(r"k%s\[(\d+)\] = \{(.*?)\};" % name, text, re.S)
+        codes = [int(c, 16) for c in re.findall(r"0x([0-9a-f]+)ull", body.group(2))]
+        assert len(codes) == int(body.group(1)) == d.bytesList.shape[0]
+        assert int(re.search(r"k%s_max_correction = (\d+)" % name, text).group(1)) == d.maxCorrectionBits
+        for m, c in enumerate(codes):
+            want = cv2.aruco.Dictionary.getBitsFromByteList(d.bytesList[m:m + 1], size).ravel()
+            assert c == int("".join(str(int(b)) for b in want), 2)
+
+
 def test_grey_threshold_contours_polygons_match_cv2():
     cv2 = pytest.importorskip("cv2")
     sc = golden()["scenes"][2]
@@ -127,6 +143,22 @@ def test_quad_too_near_the_border_takes_its_group_with_it():
     bits = synth.dict_4x4_50_bits()
     corners, ids = A.detect_markers(scene_image(sc), bits, 1)
     assert as_pairs(ids, corners) == as_pairs(sc["ids"], sc["corners"])
+
+
+def test_other_dictionaries_against_live_cv2():
+    """DICT_5X5_100 and DICT_6X6_250 (aruco_detector.cpp:148-152): 28 and 32 pixel canonical images, error correction
+    allowed (maxCorrectionBits 3 and 5 at errorCorrectionRate 0.6)."""
+    cv2 = pytest.importorskip("cv2")
+    for name, size in (("DICT_5X5_100", 5), ("DICT_6X6_250", 6)):
+        d = cv2.aruco.getPredefinedDictionary(getattr(cv2.aruco, name))
+        bits = A.dictionary_bits(d.bytesList, size)
+        for m in range(0, bits.shape[0], 7):
+            assert (bits[m] == cv2.aruco.Dictionary.getBitsFromByteList(d.bytesList[m:m + 1], size)).all()
+        img = synth.render_marker_scene(360, 500, bits, 5, 300 + size, noise=3.0)[0]
+        r, i, _ = cv2.aruco.ArucoDetector(d, cv2.aruco.DetectorParameters()).detectMarkers(img)
+        corners, ids = A.detect_markers(img, bits, d.maxCorrectionBits, A.DEFAULTS, marker_size=size)
+        assert len(ids) >= 3
+        assert as_pairs(ids, corners) == as_pairs(i.ravel(), r)
 
 
 def test_pipeline_against_live_cv2_with_default_parameters():
