@@ -174,6 +174,12 @@ def test_live_cv2_and_other_dictionaries(capi):
             assert as_pairs(ids, corners) == as_pairs([] if i is None else i.ravel(), r), name
             found += len(ids)
         assert found >= 8, name
+        det2 = capi.Detector(2, 640, 480)                  # the same dictionary from the tables the library embeds
+        det2.set_predefined_dictionary(name[5:])
+        res2 = det2.detect(imgs, capi.default_detect_params())
+        assert [as_pairs(*a) for a in res2] == [as_pairs(*a) for a in res], name
+    with pytest.raises(capi.ArslamError):
+        det2.set_predefined_dictionary("7X7_1000")
 
 
 def test_large_frame_with_long_borders_matches_live_cv2(capi):
