@@ -57,6 +57,23 @@ def test_cli_usage_errors(host_tools):
     assert r.returncode == 3 and "error loading image img1.jpg" in r.stderr
 
 
+def test_image_ingest_reads_netpbm_and_needs_the_gpu(host_tools, tmp_path):
+    """loadImages without a GPU: malformed netpbm files are refused with the reference's error text, and a well-formed
+    frame gets as far as the detector, which refuses to exist without a device (no CPU detection path)."""
+    import torch
+    cli = os.path.join(host_tools, "ar_slam_cli")
+    (tmp_path / "jpeg.ppm").write_bytes(b"\xff\xd8\xff\xe0 not a netpbm file")
+    (tmp_path / "short.pgm").write_bytes(b"P5\n# a comment\n8 8\n255\n" + bytes(10))
+    (tmp_path / "deep.pgm").write_bytes(b"P5\n8 8\n65535\n" + bytes(128))
+    for fn, what in (("jpeg.ppm", "binary netpbm"), ("short.pgm", "truncated"), ("deep.pgm", "8-bit only")):
+        r = subprocess.run([cli, fn], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 3 and "error loading image " + fn in r.stderr and what in r.stderr, r.stderr
+    (tmp_path / "ok.ppm").write_bytes(b"P6\n16 16\n255\n" + bytes(16 * 16 * 3))
+    r = subprocess.run([cli, "ok.ppm"], cwd=tmp_path, capture_output=True, text=True)
+    if not torch.cuda.is_available():
+        assert r.returncode == 3 and "arslam_detector_create" in r.stderr and "no CPU path" in r.stderr, r.stderr
+
+
 @pytest.mark.gpu
 def test_cli_map_build_and_ar_loc_match_oracle(host_tools, tmp_path, oracle):
     """BASELINE config 1 through the drop-in CLIs: ar_slam_cli -> map.yaml, ar_loc -> localize.yaml."""
