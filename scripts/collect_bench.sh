@@ -14,4 +14,5 @@ run r1_bench_ba_20k_2k_pcg --workload ba_20k_2k
 run r1_bench_ba_20k_2k_dense --workload ba_20k_2k --linear-solver dense --steps 5 --warmup 3 --no-cpu-baseline
 run r1_bench_ba_20k_2k_radial_dense --workload ba_20k_2k --num-intrinsics 3 --steps 5 --warmup 3 --no-cpu-baseline
 run r1_bench_loc_1m_5k --workload loc_1m_5k --steps 5 --warmup 3
+run r2_bench_detect_1020x768 --workload detect_1020x768 --steps 20 --warmup 3
 python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/r1_bench_reference.err | tail -1 > gpurun_out/r1_bench_reference.json
