@@ -202,6 +202,23 @@ def test_large_frame_with_long_borders_matches_live_cv2(capi):
     assert table[:, 3].max() > 3000                                             # the big marker's border
 
 
+def test_frame_sizes_that_are_not_multiples_of_the_vector_widths(capi, A):
+    """333 x 251 and 131 x 97: the threshold kernel's 4-pixel stores and the start scan's 8-pixel words end inside
+    the zero padding; grey, threshold bits, ids and corners against the restatement (cv2's default parameters)."""
+    bits = synth.dict_4x4_50_bits()
+    for h, w in ((251, 333), (97, 131)):
+        img = synth.render_marker_scene(h, w, bits, 3, 5, noise=3.0)[0]
+        det = capi.Detector(1, w, h)
+        ids, corners = det.detect(img[None], capi.default_detect_params())[0]
+        grey = A.to_gray(img)
+        assert (det.read_stage(0).reshape(h, w) == grey).all()
+        m = det.read_stage(1).reshape(h, w)
+        for k, win in enumerate(WINDOWS):
+            assert (((m >> k & 1) != 0) == (A.adaptive_threshold(grey, win, 7.0) != 0)).all()
+        ocorners, oids = A.detect_markers(img, bits, 1, A.DEFAULTS)
+        assert len(oids) == 3 and as_pairs(ids, corners) == as_pairs(oids, ocorners)
+
+
 def test_frames_already_on_the_device_and_errors(capi):
     import torch
     sc = golden()["scenes"][0]
